@@ -1,0 +1,105 @@
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE.  Run on a B200 box:
+
+    python oracle/gen_golden.py gpurun_out/reference_b200.npz
+
+Executes the reference's own compiled kernels / entry points (oracle/_ref/libref_*.so, built from
+/root/reference by oracle/Makefile) on the deterministic cases of oracle/golden_cases.py and stores their
+outputs.  The result is committed as tests/golden/reference_b200.npz; tests replay the same cases through
+the oracle (CPU, `-m "not gpu"`) and through libresnet_b200.so (`-m gpu`).
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import golden_cases as G  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from oracle.ref import Ref, available  # noqa: E402
+
+
+def main(out_path):
+    out = {}
+    notes = []
+    naive = Ref("naive")
+    # ---- single kernels of resnet.cu
+    for i in range(len(G.CONV_CASES)):
+        S, k, cin, cout, stride, N = G.CONV_CASES[i]
+        x, w, dy, base = G.conv_inputs(i)
+        out["conv%d.y" % i] = naive.op_conv_fwd(x, w, stride)
+        din, dw = naive.op_conv_bwd(x, w, dy, stride)
+        out["conv%d.din" % i], out["conv%d.dw" % i] = din, dw
+        din_add, _ = naive.op_conv_bwd(x, w, dy, stride, din_base=base)
+        out["conv%d.din_add" % i] = din_add
+    for i in range(len(G.BN_CASES)):
+        x, g, b, dy, relu = G.bn_inputs(i)
+        mu, var, xh, nv, act = naive.op_bn_fwd(x, g, b, 1e-7, relu)
+        out["bn%d.means" % i], out["bn%d.vars" % i], out["bn%d.xhat" % i] = mu, var, xh
+        out["bn%d.normalized" % i], out["bn%d.activated" % i] = nv, act
+        dg, db, dx = naive.op_bn_bwd(x, g, b, 1e-7, relu, mu, var, xh, act, dy)
+        out["bn%d.dgamma" % i], out["bn%d.dbeta" % i], out["bn%d.dx" % i] = dg, db, dx
+    mp, inds = naive.op_maxpool_fwd(G.maxpool_input(), 3, 2)
+    out["maxpool.out"], out["maxpool.inds"] = mp, inds
+    p, g1, g2 = G.adam_inputs()
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    naive.op_adam(p, g1, m, v, 1e-3, 0.0, 0.9, 0.999, 0.9, 0.999, 1e-7)
+    out["adam.p1"], out["adam.m1"], out["adam.v1"] = p.copy(), m.copy(), v.copy()
+    naive.op_adam(p, g2, m, v, 1e-3, 0.01, 0.9, 0.999, 0.81, 0.998001, 1e-7)
+    out["adam.p2"], out["adam.m2"], out["adam.v2"] = p.copy(), m.copy(), v.copy()
+    notes.append("naive single kernels: " + naive.cuda_error())
+
+    # ---- whole-network runs on numpy-seeded weights
+    for tag, cfg in (("mini", G.MINI), ("mini4", G.MINI4)):
+        shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
+        W = G.mini_weights(shapes)
+        img, lab = G.mini_batch(cfg)
+        for variant in ("naive", "clean", "cudnn"):
+            if not available(variant):
+                continue
+            r = Ref(variant).create(seed=1234, **cfg)
+            if tag == "mini" and variant == "naive":
+                # the reference's own cuRAND init (seed 1234): fingerprint per location
+                out["mini.curand_init"] = np.stack([G.summary(a) for a in r.get_params()])
+            r.set_params(W)
+            r.set_batch(img, lab)
+            pred = r.forward()
+            key = "%s.%s" % (tag, variant)
+            out[key + ".pred"] = pred
+            if variant == "naive":
+                for nm in G.ACT_NAMES_FWD:
+                    out[key + ".act." + nm] = G.summary(r.activation(nm))
+                out[key + ".max_inds"] = r.activation("max_inds", dtype=np.int32)
+                for bi in range(cfg["n_blocks"]):
+                    for f in G.BLOCK_FIELDS_FWD:
+                        a = r.activation("b%d.%s" % (bi, f))
+                        if a is not None:
+                            out[key + ".act.b%d.%s" % (bi, f)] = G.summary(a)
+                notes.append(key + " fwd: " + r.cuda_error())
+                continue  # resnet.cu's block backward is incomplete (resnet.cu:2060-2083)
+            r.backward()
+            out[key + ".grads"] = np.stack([G.summary(a) for a in r.get_params(1)])
+            if variant == "cudnn":
+                for nm in ("init_convblock_input", "init_conv_applied", "b0.post_reduced", "b1.post_expanded",
+                           "b1.transformed_residual", "b1.post_spatial", "b0.output_activated"):
+                    a = r.activation(nm, deriv=True)
+                    if a is not None:
+                        out[key + ".dact." + nm] = G.summary(a)
+            r.update()
+            out[key + ".params1"] = np.stack([G.summary(a) for a in r.get_params(0)])
+            out[key + ".m1"] = np.stack([G.summary(a) for a in r.get_params(2)])
+            # second step on the same batch (reference zeroes grads and the batch; feed it again)
+            r.set_batch(img, lab)
+            out[key + ".pred2"] = r.forward()
+            r.backward()
+            r.update()
+            out[key + ".params2"] = np.stack([G.summary(a) for a in r.get_params(0)])
+            notes.append(key + " step: " + r.cuda_error())
+    out["notes"] = np.array("; ".join(notes))
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
+    np.savez_compressed(out_path, **out)
+    print("wrote", out_path, "keys:", len(out))
+    print(out["notes"])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/reference_b200.npz")

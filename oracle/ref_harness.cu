@@ -1,0 +1,389 @@
+/*
+ * oracle/ref_harness.cu -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Wraps ONE of the reference's translation units (selected by -DREF_VARIANT, #include'd from
+ * where it lies under REF_DIR -- the sources are never copied into this repository) behind a
+ * tiny C ABI so that tests and bench.py can drive the reference's own, unmodified entry points
+ * (init_dimensions / init_resnet / init_general_batch / init_trainer / forward_pass /
+ * backwards_pass / update_parameters) and its own kernels on synthetic inputs.  The reference's
+ * main() is renamed and never called (it needs /mnt/storage/... files, reference:
+ * resnet.cu:3235-3237,1275).
+ *
+ *   REF_VARIANT 0  resnet.cu             hand-written naive kernels (forward + per-kernel oracle;
+ *                                        its block backward lacks the spatial-BN call, resnet.cu:2060-2083)
+ *   REF_VARIANT 1  resnet_clean.cu       complete hand-written step (weights are [Cout][kh][kw][Cin])
+ *   REF_VARIANT 2  resnet_cudnn.cu       cuDNN fp32 fixed-algo step
+ *   REF_VARIANT 3  resnet_cudnn_fast.cu  cuDNN autotuned NCHW step -- THROUGHPUT BASELINE ONLY
+ *                                        (its residual add is inverted, resnet_cudnn_fast.cu:1098-1104)
+ */
+#ifndef REF_VARIANT
+#error "define REF_VARIANT"
+#endif
+
+#include <string.h>
+#include <stdio.h>
+
+#define main ref_main_unused
+#if REF_VARIANT == 0
+#include "resnet.cu"
+#elif REF_VARIANT == 1
+#include "resnet_clean.cu"
+#elif REF_VARIANT == 2
+#include "resnet_cudnn.cu"
+#elif REF_VARIANT == 3
+#include "resnet_cudnn_fast.cu"
+#endif
+#undef main
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+struct RefHandle {
+	Dims *dims;
+	ResNet *model;
+	Batch *batch;
+	Train_ResNet *trainer;
+	curandGenerator_t gen;
+#if REF_VARIANT >= 2
+	cudnnHandle_t cudnn;
+#endif
+	int batch_size, input_dim, output;
+	float *stage_images;  /* device copy of the synthetic batch in the variant's layout */
+	int *stage_labels;
+	float *host_images;   /* pinned, variant layout */
+};
+
+REF_API int ref_variant(void) { return REF_VARIANT; }
+
+REF_API void *ref_create(int input_dim, int n_blocks, const int *reductions, int batch, int output, float lr, float wd,
+                         float b1, float b2, float eps, unsigned long long seed) {
+	RefHandle *h = (RefHandle *)calloc(1, sizeof(RefHandle));
+	int *red = (int *)calloc(n_blocks, sizeof(int));
+	int final_depth = 256;
+	for (int i = 0; i < n_blocks; i++) { red[i] = reductions[i]; if (red[i]) final_depth *= 2; }
+	h->dims = init_dimensions(input_dim, 7, 64, 2, 3, 2, n_blocks, red, final_depth, output);
+	curandCreateGenerator(&h->gen, CURAND_RNG_PSEUDO_DEFAULT);
+	curandSetPseudoRandomGeneratorSeed(h->gen, seed);
+	h->model = init_resnet(h->dims, &h->gen);
+	/* shard_n_images = batch: the shard buffers are only host staging for load_new_batch, unused here */
+	h->batch = init_general_batch(batch, input_dim * input_dim * 3, input_dim, batch);
+#if REF_VARIANT == 0
+	h->trainer = init_trainer(h->model, h->batch, batch, lr, wd, b1, b2, eps, 1, "ref_naive");
+#elif REF_VARIANT == 1
+	h->trainer = init_trainer(h->model, h->batch, batch, lr, wd, b1, b2, eps, 1, batch);
+#elif REF_VARIANT == 2
+	cudnnCreate(&h->cudnn);
+	h->trainer = init_trainer(h->model, h->batch, batch, lr, wd, b1, b2, eps, 1, &h->cudnn, "ref_cudnn");
+#else
+	cudnnCreate(&h->cudnn);
+	h->trainer = init_trainer(h->model, h->batch, batch, lr, wd, b1, b2, eps, 1, &h->cudnn, "ref_fast");
+#endif
+	h->batch_size = batch;
+	h->input_dim = input_dim;
+	h->output = output;
+	size_t npix = (size_t)batch * input_dim * input_dim * 3;
+	cudaMalloc(&h->stage_images, npix * sizeof(float));
+	cudaMalloc(&h->stage_labels, batch * sizeof(int));
+	cudaMallocHost(&h->host_images, npix * sizeof(float));
+	cudaDeviceSynchronize();
+	return h;
+}
+
+REF_API const char *ref_last_cuda_error(void) { return cudaGetErrorString(cudaGetLastError()); }
+REF_API int ref_n_locations(void *hv) { return ((RefHandle *)hv)->model->params->n_locations; }
+REF_API int ref_location_size(void *hv, int i) { return ((RefHandle *)hv)->model->params->sizes[i]; }
+
+static Params *which_params(RefHandle *h, int which) {
+	switch (which) {
+		case 0: return h->model->params;
+		case 1: return h->trainer->backprop_buffer->param_derivs;
+		case 2: return h->trainer->backprop_buffer->prev_means;
+		default: return h->trainer->backprop_buffer->prev_vars;
+	}
+}
+
+/* Kernel shape of location i when it is a conv weight ([Cout][Cin][k][k] as seen by callers), else k = 0. */
+static void conv_shape_of(RefHandle *h, int loc, int *cout, int *cin, int *k) {
+	*k = 0;
+	if (loc == 0) { *cout = 64; *cin = 3; *k = 7; return; }
+	int li = 3;
+	ConvBlock **cb = h->model->params->conv_blocks;
+	for (int b = 0; b < h->dims->n_conv_blocks; b++) {
+		ConvBlock *c = cb[b];
+		if (loc == li) { *cout = c->reduced_depth; *cin = c->incoming_filters; *k = 1; return; }
+		if (loc == li + 3) { *cout = c->reduced_depth; *cin = c->reduced_depth; *k = 3; return; }
+		if (loc == li + 6) { *cout = c->expanded_depth; *cin = c->reduced_depth; *k = 1; return; }
+		if (c->projection) {
+			if (loc == li + 9) { *cout = c->expanded_depth; *cin = c->incoming_filters; *k = (c->stride == 2) ? 3 : 1; return; }
+			li += 12;
+		} else li += 9;
+	}
+}
+
+/* All variants are presented to the caller in the resnet.cu layout [Cout][Cin][kh][kw]. */
+REF_API void ref_get_param(void *hv, int which, int i, float *host) {
+	RefHandle *h = (RefHandle *)hv;
+	Params *p = which_params(h, which);
+	size_t n = p->sizes[i];
+	cudaMemcpy(host, p->locations[i], n * sizeof(float), cudaMemcpyDeviceToHost);
+#if REF_VARIANT == 1
+	int cout, cin, k;
+	conv_shape_of(h, i, &cout, &cin, &k);
+	if (k > 1) { /* [co][kh][kw][ci] -> [co][ci][kh][kw] */
+		float *tmp = (float *)malloc(n * sizeof(float));
+		memcpy(tmp, host, n * sizeof(float));
+		for (int co = 0; co < cout; co++) for (int r = 0; r < k; r++) for (int c = 0; c < k; c++) for (int ci = 0; ci < cin; ci++)
+			host[(((size_t)co * cin + ci) * k + r) * k + c] = tmp[(((size_t)co * k + r) * k + c) * cin + ci];
+		free(tmp);
+	}
+#endif
+}
+
+REF_API void ref_set_param(void *hv, int which, int i, const float *host) {
+	RefHandle *h = (RefHandle *)hv;
+	Params *p = which_params(h, which);
+	size_t n = p->sizes[i];
+	const float *src = host;
+#if REF_VARIANT == 1
+	int cout, cin, k;
+	conv_shape_of(h, i, &cout, &cin, &k);
+	float *tmp = NULL;
+	if (k > 1) {
+		tmp = (float *)malloc(n * sizeof(float));
+		for (int co = 0; co < cout; co++) for (int r = 0; r < k; r++) for (int c = 0; c < k; c++) for (int ci = 0; ci < cin; ci++)
+			tmp[(((size_t)co * k + r) * k + c) * cin + ci] = host[(((size_t)co * cin + ci) * k + r) * k + c];
+		src = tmp;
+	}
+#endif
+	cudaMemcpy(p->locations[i], src, n * sizeof(float), cudaMemcpyHostToDevice);
+#if REF_VARIANT == 1
+	free(tmp);
+#endif
+}
+
+/* images arrive NHWC (the resnet.h family's layout); the fast variant wants NCHW. */
+REF_API void ref_set_batch(void *hv, const float *images_nhwc, const int *labels) {
+	RefHandle *h = (RefHandle *)hv;
+	int N = h->batch_size, S = h->input_dim;
+	size_t npix = (size_t)N * S * S * 3;
+#if REF_VARIANT == 3
+	for (int n = 0; n < N; n++) for (int y = 0; y < S; y++) for (int x = 0; x < S; x++) for (int c = 0; c < 3; c++)
+		h->host_images[(((size_t)n * 3 + c) * S + y) * S + x] = images_nhwc[(((size_t)n * S + y) * S + x) * 3 + c];
+#else
+	memcpy(h->host_images, images_nhwc, npix * sizeof(float));
+#endif
+	cudaMemcpy(h->stage_images, h->host_images, npix * sizeof(float), cudaMemcpyHostToDevice);
+	cudaMemcpy(h->stage_labels, labels, N * sizeof(int), cudaMemcpyHostToDevice);
+	memcpy(h->batch->correct_classes_cpu, labels, N * sizeof(int));
+	cudaMemcpy(h->batch->images, h->stage_images, npix * sizeof(float), cudaMemcpyDeviceToDevice);
+	cudaMemcpy(h->batch->correct_classes, h->stage_labels, N * sizeof(int), cudaMemcpyDeviceToDevice);
+}
+
+REF_API void ref_forward(void *hv) { forward_pass(((RefHandle *)hv)->trainer); cudaDeviceSynchronize(); }
+REF_API void ref_backward(void *hv) { backwards_pass(((RefHandle *)hv)->trainer); cudaDeviceSynchronize(); }
+REF_API void ref_update(void *hv) { update_parameters(((RefHandle *)hv)->trainer); cudaDeviceSynchronize(); }
+REF_API void ref_get_pred(void *hv, float *host) {
+	RefHandle *h = (RefHandle *)hv;
+	memcpy(host, h->trainer->forward_buffer->pred_cpu, (size_t)h->batch_size * h->output * sizeof(float));
+}
+
+/* One timed "step" exactly as the reference's main loop drives it (reference: resnet.cu:3340-3404,
+ * resnet_cudnn_fast.cu:3330-3420): batch in (D2D from a resident copy, or H2D from pinned memory
+ * when e2e != 0), forward_pass, sync + host read of pred_cpu, backwards_pass, update_parameters.
+ * Returns average milliseconds per step over `steps` (CUDA events on the legacy default stream the
+ * reference launches on). */
+REF_API double ref_time_steps(void *hv, int warmup, int steps, int e2e, int forward_only) {
+	RefHandle *h = (RefHandle *)hv;
+	size_t npix = (size_t)h->batch_size * h->input_dim * h->input_dim * 3;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	float ms = 0;
+	for (int it = 0; it < warmup + steps; it++) {
+		if (it == warmup) { cudaDeviceSynchronize(); cudaEventRecord(e0, 0); }
+		if (e2e) {
+			cudaMemcpy(h->batch->images, h->host_images, npix * sizeof(float), cudaMemcpyHostToDevice);
+			cudaMemcpy(h->batch->correct_classes, h->batch->correct_classes_cpu, h->batch_size * sizeof(int), cudaMemcpyHostToDevice);
+		} else {
+			cudaMemcpyAsync(h->batch->images, h->stage_images, npix * sizeof(float), cudaMemcpyDeviceToDevice, 0);
+			cudaMemcpyAsync(h->batch->correct_classes, h->stage_labels, h->batch_size * sizeof(int), cudaMemcpyDeviceToDevice, 0);
+		}
+		forward_pass(h->trainer);
+		cudaDeviceSynchronize();
+		volatile float sink = h->trainer->forward_buffer->pred_cpu[0];
+		(void)sink;
+		if (!forward_only) {
+			backwards_pass(h->trainer);
+			update_parameters(h->trainer);
+		}
+	}
+	cudaEventRecord(e1, 0);
+	cudaEventSynchronize(e1);
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return (double)ms / steps;
+}
+
+/* ---- named activation access (variants 0-2) ------------------------------------------------- */
+#if REF_VARIANT != 3
+static float *act_field(Activations *a, Dims *d, int N, const char *name, size_t *n) {
+	int S1 = d->input / d->init_conv_stride, S2 = S1 / d->init_maxpool_stride, F = d->init_conv_filters;
+	if (!strcmp(name, "init_conv_applied")) { *n = (size_t)N * S1 * S1 * F; return a->init_conv_applied; }
+	if (!strcmp(name, "init_convblock_input")) { *n = (size_t)N * S2 * S2 * F; return a->init_convblock_input; }
+	if (!strcmp(name, "max_inds")) { *n = (size_t)N * S2 * S2 * F; return (float *)a->max_inds; }
+	if (!strcmp(name, "norm_init_conv.means")) { *n = F; return a->norm_init_conv->means; }
+#if REF_VARIANT != 2
+	if (!strcmp(name, "norm_init_conv.vars")) { *n = F; return a->norm_init_conv->vars; }
+#else
+	if (!strcmp(name, "norm_init_conv.inv_vars")) { *n = F; return a->norm_init_conv->inv_vars; }
+#endif
+#if REF_VARIANT != 1
+	if (!strcmp(name, "init_conv_activated")) { *n = (size_t)N * S1 * S1 * F; return a->init_conv_activated; }
+#endif
+	if (!strcmp(name, "final_conv_output_pooled")) { *n = (size_t)N * d->final_depth; return a->final_conv_output_pooled; }
+	if (!strcmp(name, "linear_output")) { *n = (size_t)N * d->output; return a->linear_output; }
+	if (name[0] == 'b') {
+		int bi = atoi(name + 1);
+		const char *dot = strchr(name, '.');
+		if (!dot || bi < 0 || bi >= a->n_conv_blocks) return NULL;
+		const char *f = dot + 1;
+		Activation_ConvBlock *b = a->activation_conv_blocks[bi];
+		size_t s_in = (size_t)b->incoming_spatial_dim, s_out = s_in / b->stride;
+		size_t red_in = (size_t)N * s_in * s_in * b->reduced_depth, red_out = (size_t)N * s_out * s_out * b->reduced_depth;
+		size_t exp_out = (size_t)N * s_out * s_out * b->expanded_depth;
+		if (!strcmp(f, "post_reduced")) { *n = red_in; return b->post_reduced; }
+		if (!strcmp(f, "post_spatial")) { *n = red_out; return b->post_spatial; }
+		if (!strcmp(f, "post_expanded")) { *n = exp_out; return b->post_expanded; }
+		if (!strcmp(f, "transformed_residual")) { *n = exp_out; return b->transformed_residual; }
+		if (!strcmp(f, "output_activated")) { *n = exp_out; return b->output_activated; }
+		if (!strcmp(f, "norm_post_reduced.means")) { *n = b->reduced_depth; return b->norm_post_reduced->means; }
+		if (!strcmp(f, "norm_post_spatial.means")) { *n = b->reduced_depth; return b->norm_post_spatial->means; }
+		if (!strcmp(f, "norm_post_expanded.means")) { *n = b->expanded_depth; return b->norm_post_expanded->means; }
+#if REF_VARIANT != 2
+		if (!strcmp(f, "norm_post_reduced.vars")) { *n = b->reduced_depth; return b->norm_post_reduced->vars; }
+		if (!strcmp(f, "norm_post_spatial.vars")) { *n = b->reduced_depth; return b->norm_post_spatial->vars; }
+		if (!strcmp(f, "norm_post_expanded.vars")) { *n = b->expanded_depth; return b->norm_post_expanded->vars; }
+#endif
+#if REF_VARIANT != 1
+		if (!strcmp(f, "post_reduced_activated")) { *n = red_in; return b->post_reduced_activated; }
+		if (!strcmp(f, "post_spatial_activated")) { *n = red_out; return b->post_spatial_activated; }
+		if (!strcmp(f, "post_expanded_norm_vals")) { *n = exp_out; return b->post_expanded_norm_vals; }
+		if (!strcmp(f, "output")) { *n = exp_out; return b->output; }
+#endif
+	}
+	return NULL;
+}
+
+/* returns the element count (0 when the variant has no such tensor); copies min(count, max_elems) */
+REF_API size_t ref_get_activation(void *hv, const char *name, int is_deriv, float *host, size_t max_elems) {
+	RefHandle *h = (RefHandle *)hv;
+	Activations *a = h->trainer->forward_buffer->activations;
+	if (is_deriv) {
+#if REF_VARIANT == 1
+		return 0;
+#else
+		a = h->trainer->backprop_buffer->activation_derivs;
+#endif
+	}
+	size_t n = 0;
+	float *p = act_field(a, h->dims, h->batch_size, name, &n);
+	if (!p) return 0;
+	if (host) cudaMemcpy(host, p, (n < max_elems ? n : max_elems) * sizeof(float), cudaMemcpyDeviceToHost);
+	return n;
+}
+#else
+REF_API size_t ref_get_activation(void *, const char *, int, float *, size_t) { return 0; }
+#endif
+
+/* ---- single-kernel entry points: the reference's own launch wrappers on caller data (variant 0) ---- */
+#if REF_VARIANT == 0
+static float *to_dev(const float *h, size_t n) {
+	float *d;
+	cudaMalloc(&d, n * sizeof(float));
+	if (h) cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice); else cudaMemset(d, 0, n * sizeof(float));
+	return d;
+}
+static void to_host(float *h, float *d, size_t n) { cudaMemcpy(h, d, n * sizeof(float), cudaMemcpyDeviceToHost); cudaFree(d); }
+
+/* reference: resnet.cu:1386 prepareAndDoConvolution */
+REF_API void ref_op_conv_fwd(const float *in, const float *w, int S, int k, int cin, int cout, int stride, int N, float *out) {
+	size_t ni = (size_t)N * S * S * cin, nw = (size_t)cout * cin * k * k, no = (size_t)N * (S / stride) * (S / stride) * cout;
+	float *di = to_dev(in, ni), *dw = to_dev(w, nw), *dout = to_dev(NULL, no);
+	prepareAndDoConvolution(S, k, cin, cout, stride, N, di, dw, dout);
+	cudaDeviceSynchronize();
+	to_host(out, dout, no);
+	cudaFree(di); cudaFree(dw);
+}
+
+/* reference: resnet.cu:1399 prepreAndDoConvolutionDeriv (din_inout is both the to_add base and the result) */
+REF_API void ref_op_conv_bwd(const float *in, const float *w, const float *dout, int S, int k, int cin, int cout, int stride,
+                             int N, int to_add, float *din_inout, float *dw_out) {
+	size_t ni = (size_t)N * S * S * cin, nw = (size_t)cout * cin * k * k, no = (size_t)N * (S / stride) * (S / stride) * cout;
+	float *di = to_dev(in, ni), *dwt = to_dev(w, nw), *dd = to_dev(dout, no);
+	float *ddin = to_dev(to_add ? din_inout : NULL, ni), *ddw = to_dev(NULL, nw);
+	prepreAndDoConvolutionDeriv(S, k, cin, cout, stride, N, to_add != 0, di, dwt, dd, ddin, ddw, din_inout != NULL);
+	cudaDeviceSynchronize();
+	if (din_inout) to_host(din_inout, ddin, ni); else cudaFree(ddin);
+	to_host(dw_out, ddw, nw);
+	cudaFree(di); cudaFree(dwt); cudaFree(dd);
+}
+
+/* reference: resnet.cu:1431 prepareAndDoBatchNormAndActivate */
+REF_API void ref_op_bn_fwd(const float *x, const float *gamma, const float *beta, int S, int C, int N, float eps, int relu,
+                           float *means, float *vars, float *xhat, float *normalized, float *activated) {
+	size_t n = (size_t)N * S * S * C;
+	BatchNorm bn = {S, C, to_dev(gamma, C), to_dev(beta, C)};
+	Cache_BatchNorm cache = {(int)n, C, to_dev(NULL, C), to_dev(NULL, C), to_dev(NULL, n), to_dev(NULL, n)};
+	float *dx = to_dev(x, n), *dact = to_dev(NULL, n);
+	prepareAndDoBatchNormAndActivate(&bn, &cache, N, eps, dx, dact, relu != 0);
+	cudaDeviceSynchronize();
+	to_host(means, cache.means, C); to_host(vars, cache.vars, C);
+	to_host(xhat, cache.normalized_temp, n); to_host(normalized, cache.normalized, n); to_host(activated, dact, n);
+	cudaFree(dx); cudaFree(bn.gamma); cudaFree(bn.beta);
+}
+
+/* reference: resnet.cu:1455 prepareAndDoActivationAndBatchNormDeriv */
+REF_API void ref_op_bn_bwd(const float *x, const float *gamma, const float *beta, int S, int C, int N, float eps, int relu,
+                           const float *means, const float *vars, const float *xhat, const float *activated, const float *dy,
+                           float *dgamma, float *dbeta, float *dx_out) {
+	size_t n = (size_t)N * S * S * C;
+	BatchNorm bn = {S, C, to_dev(gamma, C), to_dev(beta, C)};
+	BatchNorm dbn = {S, C, to_dev(NULL, C), to_dev(NULL, C)};
+	Cache_BatchNorm cache = {(int)n, C, to_dev(means, C), to_dev(vars, C), to_dev(xhat, n), to_dev(NULL, 1)};
+	Cache_BatchNorm dcache = {(int)n, C, to_dev(NULL, C), to_dev(NULL, C), to_dev(NULL, n), to_dev(NULL, 1)};
+	float *dx = to_dev(x, n), *dact = to_dev(activated, n), *ddy = to_dev(dy, n), *ddx = to_dev(NULL, n);
+	prepareAndDoActivationAndBatchNormDeriv(&bn, &cache, &dbn, &dcache, N, eps, dx, dact, ddy, ddx, relu != 0);
+	cudaDeviceSynchronize();
+	to_host(dgamma, dbn.gamma, C); to_host(dbeta, dbn.beta, C); to_host(dx_out, ddx, n);
+	cudaFree(bn.gamma); cudaFree(bn.beta); cudaFree(cache.means); cudaFree(cache.vars); cudaFree(cache.normalized_temp);
+	cudaFree(cache.normalized); cudaFree(dcache.means); cudaFree(dcache.vars); cudaFree(dcache.normalized_temp);
+	cudaFree(dcache.normalized); cudaFree(dx); cudaFree(dact); cudaFree(ddy);
+}
+
+/* reference: resnet.cu:1567-1569 doMaxPool launch */
+REF_API void ref_op_maxpool_fwd(const float *x, int k, int stride, int S, int C, int N, int *max_inds, float *out) {
+	size_t ni = (size_t)N * S * S * C, no = (size_t)N * (S / stride) * (S / stride) * C;
+	float *dx = to_dev(x, ni), *dout = to_dev(NULL, no);
+	int *dinds;
+	cudaMalloc(&dinds, no * sizeof(int));
+	dim3 g(S / stride, S / stride);
+	doMaxPool<<<g, C>>>(dx, k, stride, N, dinds, dout);
+	cudaDeviceSynchronize();
+	cudaMemcpy(max_inds, dinds, no * sizeof(int), cudaMemcpyDeviceToHost);
+	to_host(out, dout, no);
+	cudaFree(dx); cudaFree(dinds);
+}
+
+/* reference: resnet.cu:605-662 + launch loop 2961-2965 */
+REF_API void ref_op_adam(float *p, const float *g, float *m, float *v, int n, float lr, float wd, float b1, float b2,
+                         float cur_b1, float cur_b2, float eps) {
+	float *dp = to_dev(p, n), *dg = to_dev(g, n), *dm = to_dev(m, n), *dv = to_dev(v, n);
+	dim3 grid(ceil((float)n / MAX_THREAD_PER_BLOCK)), block(MAX_THREAD_PER_BLOCK);
+	updateMeans<<<grid, block>>>(n, dg, dp, b1, wd, dm, 0);
+	updateVars<<<grid, block>>>(n, dg, dp, b2, wd, dv, 0);
+	updateParams<<<grid, block>>>(n, dp, dm, dv, lr, wd, cur_b1, cur_b2, eps, 0);
+	cudaDeviceSynchronize();
+	to_host(p, dp, n); to_host(m, dm, n); to_host(v, dv, n);
+	cudaFree(dg);
+}
+#endif
