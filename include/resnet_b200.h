@@ -1,0 +1,101 @@
+/*
+ * resnet_b200.h -- extra C-ABI entry points of libresnet_b200.so, beyond the reference's own surface (resnet.h).
+ *
+ * (1) The reference's launch wrappers, one per kernel family, on caller-supplied DEVICE buffers.  These are what
+ *     the reference's embedded self-tests call (reference: resnet.cu:3109-3218 testConvolution -> resnet.cu:1386
+ *     prepareAndDoConvolution, etc.); the parity tests in tests/ go through them.
+ * (2) Small runtime services a host driver needs because the library owns its stream: device malloc/copy helpers
+ *     for FFI callers without a CUDA binding, synchronisation, error string, step timers.
+ * (3) Data-parallel control (new; the reference is single-GPU).
+ *
+ * Plain pointers and sizes only; every function returns 0 on success (or the requested value) and records the
+ * first failure for resnet_b200_last_error().
+ */
+#ifndef RESNET_B200_EXTRA_H
+#define RESNET_B200_EXTRA_H
+
+#include "resnet.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime services ---------------------------------------------------------------------- */
+const char * resnet_b200_last_error(void);              /* "" when no error was recorded */
+void resnet_b200_clear_error(void);
+int resnet_b200_set_device(int device);                 /* cudaSetDevice */
+void * resnet_b200_malloc(size_t bytes);                /* device memory */
+void resnet_b200_free(void * dev_ptr);
+void * resnet_b200_malloc_host(size_t bytes);           /* pinned host memory */
+void resnet_b200_free_host(void * host_ptr);
+int resnet_b200_memcpy_h2d(void * dev_dst, const void * host_src, size_t bytes);
+int resnet_b200_memcpy_d2h(void * host_dst, const void * dev_src, size_t bytes);
+int resnet_b200_memcpy_d2d(void * dev_dst, const void * dev_src, size_t bytes);
+int resnet_b200_memset(void * dev_dst, int value, size_t bytes);
+int resnet_b200_sync(void);                             /* cudaDeviceSynchronize */
+/* curandGenerator_t (CURAND_RNG_PSEUDO_DEFAULT) seeded like the reference's main (resnet.cu:3264-3267) */
+void * resnet_b200_rng_create(unsigned long long seed);
+void resnet_b200_rng_destroy(void * gen);
+
+/* ---- trainer services ---------------------------------------------------------------------- */
+/* asynchronous copies on the trainer's stream: host (pinned) -> cur_batch->images / correct_classes */
+int resnet_b200_stage_batch(Train_ResNet * trainer, const float * images_host, const int * labels_host);
+int resnet_b200_stage_batch_device(Train_ResNet * trainer, const float * images_dev, const int * labels_dev);
+int resnet_b200_trainer_sync(Train_ResNet * trainer);   /* waits for the trainer's stream */
+/* CUDA-event bracket on the trainer's stream: begin / end-and-return-milliseconds */
+int resnet_b200_timer_begin(Train_ResNet * trainer);
+float resnet_b200_timer_end_ms(Train_ResNet * trainer);
+/* on-device loss / accuracy of the last forward_pass (same definitions as reference resnet.cu:3363-3383) */
+int resnet_b200_loss_accuracy(Train_ResNet * trainer, float * loss_sum, int * n_wrong);
+/* number of kernels this library launched since process start (bench.py's gpu_launches) */
+long long resnet_b200_launch_count(void);
+/* 1 when conv layers of this trainer run on the tcgen05 path, 0 when on the fp32 SIMT path */
+int resnet_b200_uses_tensor_cores(Train_ResNet * trainer);
+void resnet_b200_destroy_trainer(Train_ResNet * trainer);
+
+/* ---- single-operator entry points (device pointers, fp32, NHWC, weights [Cout][Cin][k][k]) -- */
+/* impl: 0 = tcgen05/TMA implicit GEMM (product path), 1 = fp32 SIMT */
+/* reference: resnet.cu:1386 prepareAndDoConvolution */
+int resnet_b200_conv_forward(int in_spatial_dim, int kern_dim, int in_filters, int out_filters, int stride, int batch_size,
+                             const float * input, const float * weights, float * output, int impl);
+/* reference: resnet.cu:1399 prepreAndDoConvolutionDeriv (input_deriv may be NULL == toComputeInputDeriv false) */
+int resnet_b200_conv_backward(int in_spatial_dim, int kern_dim, int in_filters, int out_filters, int stride, int batch_size, int to_add,
+                              const float * input, const float * weights, const float * out_deriv, float * input_deriv,
+                              float * weight_deriv, int impl);
+/* reference: resnet.cu:1431 prepareAndDoBatchNormAndActivate (normalized_temp / normalized outputs may be NULL) */
+int resnet_b200_batchnorm_forward(int spatial_dim, int filters, int batch_size, float eps, const float * input, const float * gamma,
+                                  const float * beta, float * means, float * vars, float * activated, int to_activate,
+                                  const float * residual, int round_tf32);
+/* reference: resnet.cu:1455 prepareAndDoActivationAndBatchNormDeriv */
+int resnet_b200_batchnorm_backward(int spatial_dim, int filters, int batch_size, float eps, const float * input, const float * gamma,
+                                   const float * means, const float * vars, const float * activated, const float * out_layer_deriv,
+                                   float * gamma_deriv, float * beta_deriv, float * input_deriv, int to_activate_deriv);
+/* reference: resnet.cu:433 doMaxPool / 476 maxPoolDeriv */
+int resnet_b200_maxpool_forward(const float * input, int kern_dim, int stride, int in_spatial_dim, int filters, int batch_size,
+                                int * max_inds, float * out);
+int resnet_b200_maxpool_backward(const int * max_inds, const float * out_deriv, int kern_dim, int in_spatial_dim, int stride, int filters,
+                                 int batch_size, float * input_deriv);
+/* reference: resnet.cu:500 doFilterAvgPool / 522 filterAvgPoolDeriv */
+int resnet_b200_avgpool_forward(const float * input, int spatial_dim, int filters, int batch_size, float * out);
+int resnet_b200_avgpool_backward(const float * pooled_deriv, int filters, int batch_size, int spatial_dim, float * out);
+/* reference: resnet.cu:70 matMul, 1482/1496 prepareAndDoMatMul{Left,Right}Transpose */
+int resnet_b200_matmul(const float * A, const float * B, int m, int k, int n, int transpose_a, int transpose_b, float * out);
+/* reference: resnet.cu:569 softMax + 597 crossEntropyDeriv (output_deriv may be NULL) */
+int resnet_b200_softmax_ce(const float * logits, const int * labels, int batch_size, int output_len, float * pred, float * output_deriv);
+/* reference: resnet.cu:605-662 updateMeans/updateVars/updateParams, fused; n must be a multiple of 4 */
+int resnet_b200_adam(float * params, float * grads, float * means, float * vars, long long n, float learning_rate, float weight_decay,
+                     float base_mean_decay, float base_var_decay, float cur_mean_decay, float cur_var_decay, float eps);
+
+/* ---- data parallel (new) -------------------------------------------------------------------- */
+/* 128-byte NCCL unique id, created on rank 0 and passed to every rank by the launcher (torch.distributed) */
+int resnet_b200_dp_unique_id(void * out_id_128_bytes);
+/* joins `trainer` to a world of `world_size` replicas: gradients are all-reduced (sum) in buckets on a side
+ * stream, overlapped with backwards_pass; update_parameters waits per bucket.  bucket_bytes <= 0: default. */
+int resnet_b200_dp_init(Train_ResNet * trainer, const void * id_128_bytes, int rank, int world_size, long long bucket_bytes);
+int resnet_b200_dp_world_size(Train_ResNet * trainer);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RESNET_B200_EXTRA_H */

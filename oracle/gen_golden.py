@@ -18,6 +18,13 @@ from oracle import oracle as O  # noqa: E402
 from oracle.ref import Ref, available  # noqa: E402
 
 
+def _save(out_path, out, notes):
+    # saved after every stage: a crash inside a later reference variant must not lose the earlier results
+    out["notes"] = np.array("; ".join(notes))
+    os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
+    np.savez_compressed(out_path, **out)
+
+
 def main(out_path):
     out = {}
     notes = []
@@ -75,6 +82,7 @@ def main(out_path):
                         if a is not None:
                             out[key + ".act.b%d.%s" % (bi, f)] = G.summary(a)
                 notes.append(key + " fwd: " + r.cuda_error())
+                _save(out_path, out, notes)
                 continue  # resnet.cu's block backward is incomplete (resnet.cu:2060-2083)
             r.backward()
             out[key + ".grads"] = np.stack([G.summary(a) for a in r.get_params(1)])
@@ -94,9 +102,8 @@ def main(out_path):
             r.update()
             out[key + ".params2"] = np.stack([G.summary(a) for a in r.get_params(0)])
             notes.append(key + " step: " + r.cuda_error())
-    out["notes"] = np.array("; ".join(notes))
-    os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
-    np.savez_compressed(out_path, **out)
+            _save(out_path, out, notes)
+    _save(out_path, out, notes)
     print("wrote", out_path, "keys:", len(out))
     print(out["notes"])
 

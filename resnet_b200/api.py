@@ -1,0 +1,289 @@
+"""Host-side mirror of the reference's driver API over libresnet_b200.so.
+
+The calls are the reference's own (`init_dimensions`, `init_resnet`, `init_general_batch`, `init_trainer`,
+`forward_pass`, `backwards_pass`, `update_parameters`; reference: resnet.cu:3259-3402) -- this module only adds
+numpy <-> device conveniences so that tests and bench.py read like the reference's main loop.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+
+f32p = _lib.f32p
+i32p = _lib.i32p
+
+
+def L():
+    return _lib.load()
+
+
+def check():
+    err = L().resnet_b200_last_error().decode()
+    if err:
+        raise RuntimeError("libresnet_b200: " + err)
+
+
+class DevBuf:
+    """A device allocation owned by Python (single-operator tests)."""
+
+    def __init__(self, arr=None, nbytes=None, zero=False):
+        self.nbytes = int(arr.nbytes if arr is not None else nbytes)
+        self.ptr = L().resnet_b200_malloc(self.nbytes)
+        if arr is not None:
+            a = np.ascontiguousarray(arr)
+            L().resnet_b200_memcpy_h2d(self.ptr, a.ctypes.data_as(C.c_void_p), self.nbytes)
+        elif zero:
+            L().resnet_b200_memset(self.ptr, 0, self.nbytes)
+
+    def get(self, shape, dtype=np.float32):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        L().resnet_b200_memcpy_d2h(out.ctypes.data_as(C.c_void_p), self.ptr, out.nbytes)
+        return out
+
+    def free(self):
+        if self.ptr:
+            L().resnet_b200_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def d2h(ptr, n, dtype=np.float32):
+    """copy n elements from a device pointer (ctypes pointer or int)"""
+    out = np.empty(int(n), dtype)
+    addr = C.cast(ptr, C.c_void_p)
+    L().resnet_b200_memcpy_d2h(out.ctypes.data_as(C.c_void_p), addr, out.nbytes)
+    return out
+
+
+def h2d(ptr, arr):
+    a = np.ascontiguousarray(arr)
+    L().resnet_b200_memcpy_h2d(C.cast(ptr, C.c_void_p), a.ctypes.data_as(C.c_void_p), a.nbytes)
+
+
+class Trainer:
+    """ResNet trainer driven through the reference's entry points."""
+
+    def __init__(self, input_dim=224, n_blocks=16, reductions=None, batch=32, output=1000, lr=1e-4, wd=0.0, b1=0.9, b2=0.999,
+                 eps=1e-7, seed=1234, init_filters=64, device=None):
+        lib = L()
+        if device is not None:
+            lib.resnet_b200_set_device(int(device))
+        if reductions is None:
+            reductions = [1 if i in (3, 7, 13) else 0 for i in range(n_blocks)]
+        self.input_dim, self.n_blocks, self.batch, self.output = input_dim, n_blocks, batch, output
+        self.reductions = list(reductions)
+        self._red = (C.c_int * n_blocks)(*self.reductions)
+        final_depth = 4 * init_filters * (2 ** sum(self.reductions))
+        self.final_depth = final_depth
+        # reference: resnet.cu:3245-3296
+        self.dims = lib.init_dimensions(input_dim, 7, init_filters, 2, 3, 2, n_blocks, self._red, final_depth, output)
+        self.gen = lib.resnet_b200_rng_create(seed)
+        self.model = lib.init_resnet(self.dims, self.gen)
+        self.batch_struct = lib.init_general_batch(batch, input_dim * input_dim * 3, input_dim, batch)
+        self._dump_dir = b"resnet_b200"
+        self.t = lib.init_trainer(self.model, self.batch_struct, batch, lr, wd, b1, b2, eps, 1, self._dump_dir)
+        check()
+        P = self.model.contents.params.contents
+        self.n_locations = P.n_locations
+        self.sizes = [P.sizes[i] for i in range(P.n_locations)]
+
+    # ---- parameters / optimizer state, in locations[] order (reference: resnet.h:85-87)
+    def _tree(self, which):
+        bb = self.t.contents.backprop_buffer.contents
+        return [self.model.contents.params, bb.param_derivs, bb.prev_means, bb.prev_vars][which].contents
+
+    def get_params(self, which=0):
+        tr = self._tree(which)
+        return [d2h(tr.locations[i], self.sizes[i]) for i in range(self.n_locations)]
+
+    def set_params(self, arrays, which=0):
+        tr = self._tree(which)
+        for i, a in enumerate(arrays):
+            a = np.ascontiguousarray(a, np.float32).reshape(-1)
+            assert a.size == self.sizes[i], (i, a.size, self.sizes[i])
+            h2d(tr.locations[i], a)
+
+    # ---- batch
+    def set_batch(self, images, labels):
+        """blocking copy into cur_batch->images / correct_classes (what load_new_batch does, reference: resnet.cu:1315-1316)"""
+        b = self.batch_struct.contents
+        h2d(b.images, np.ascontiguousarray(images, np.float32))
+        h2d(b.correct_classes, np.ascontiguousarray(labels, np.int32))
+        C.memmove(b.correct_classes_cpu, np.ascontiguousarray(labels, np.int32).ctypes.data, 4 * self.batch)
+
+    # ---- the reference's step
+    def forward(self):
+        L().forward_pass(self.t)
+        check()
+        return np.ctypeslib.as_array(self.t.contents.forward_buffer.contents.pred_cpu, shape=(self.batch, self.output)).copy()
+
+    def backward(self):
+        L().backwards_pass(self.t)
+        check()
+
+    def update(self):
+        L().update_parameters(self.t)
+        check()
+
+    def sync(self):
+        L().resnet_b200_trainer_sync(self.t)
+        check()
+
+    def loss_accuracy(self):
+        ls, nw = C.c_float(), C.c_int()
+        L().resnet_b200_loss_accuracy(self.t, C.byref(ls), C.byref(nw))
+        return ls.value, nw.value
+
+    def uses_tensor_cores(self):
+        return bool(L().resnet_b200_uses_tensor_cores(self.t))
+
+    # ---- named activations (same names as oracle.OracleNet.act / reference struct fields)
+    def activation(self, name, deriv=False, dtype=np.float32):
+        t = self.t.contents
+        A = (t.backprop_buffer.contents.activation_derivs if deriv else t.forward_buffer.contents.activations).contents
+        N, d = self.batch, self.dims.contents
+        S1 = d.input // d.init_conv_stride
+        S2 = S1 // d.init_maxpool_stride
+        F = d.init_conv_filters
+        top = {"init_conv_applied": (A.init_conv_applied, N * S1 * S1 * F), "init_conv_activated": (A.init_conv_activated, N * S1 * S1 * F),
+               "init_convblock_input": (A.init_convblock_input, N * S2 * S2 * F), "max_inds": (A.max_inds, N * S2 * S2 * F),
+               "final_conv_output_pooled": (A.final_conv_output_pooled, N * d.final_depth), "linear_output": (A.linear_output, N * d.output)}
+        if name in top:
+            ptr, n = top[name]
+        elif name.startswith("norm_init_conv."):
+            ptr, n = getattr(A.norm_init_conv.contents, name.split(".")[1]), F
+        else:
+            bi, field = name.split(".", 1)
+            b = A.activation_conv_blocks[int(bi[1:])].contents
+            s_in, s_out = b.incoming_spatial_dim, b.incoming_spatial_dim // b.stride
+            sizes = {"post_reduced": N * s_in * s_in * b.reduced_depth, "post_reduced_activated": N * s_in * s_in * b.reduced_depth,
+                     "post_spatial": N * s_out * s_out * b.reduced_depth, "post_spatial_activated": N * s_out * s_out * b.reduced_depth}
+            if "." in field:
+                cache, f2 = field.split(".")
+                cb = getattr(b, cache)
+                if not cb:
+                    return None
+                ptr, n = getattr(cb.contents, f2), cb.contents.feature_size if f2 in ("means", "vars") else cb.contents.input_size
+            else:
+                ptr, n = getattr(b, field), sizes.get(field, N * s_out * s_out * b.expanded_depth)
+        if not ptr:
+            return None
+        return d2h(ptr, n, dtype)
+
+    def close(self):
+        if self.t:
+            L().resnet_b200_destroy_trainer(self.t)
+            self.t = None
+
+
+# ------------------------------------------------------------------------------------------- single operators
+def conv_forward(x, w, stride, impl=0):
+    N, S, _, cin = x.shape
+    cout, _, k, _ = w.shape
+    dx, dw = DevBuf(x), DevBuf(w)
+    dy = DevBuf(nbytes=4 * N * (S // stride) ** 2 * cout, zero=True)
+    L().resnet_b200_conv_forward(S, k, cin, cout, stride, N, dx.ptr, dw.ptr, dy.ptr, impl)
+    check()
+    return dy.get((N, S // stride, S // stride, cout))
+
+
+def conv_backward(x, w, dy, stride, din_base=None, want_din=True, impl=0):
+    N, S, _, cin = x.shape
+    cout, _, k, _ = w.shape
+    bx, bw, bdy = DevBuf(x), DevBuf(w), DevBuf(dy)
+    bdw = DevBuf(nbytes=w.nbytes, zero=True)
+    bdin = None
+    if want_din:
+        bdin = DevBuf(din_base) if din_base is not None else DevBuf(nbytes=x.nbytes, zero=True)
+    L().resnet_b200_conv_backward(S, k, cin, cout, stride, N, int(din_base is not None), bx.ptr, bw.ptr, bdy.ptr,
+                                  bdin.ptr if bdin else None, bdw.ptr, impl)
+    check()
+    return (bdin.get(x.shape) if bdin else None), bdw.get(w.shape)
+
+
+def batchnorm_forward(x, gamma, beta, eps, relu, residual=None, round_tf32=False):
+    N, S, _, Cc = x.shape
+    bx, bg, bb = DevBuf(x), DevBuf(gamma), DevBuf(beta)
+    bm, bv, by = DevBuf(nbytes=4 * Cc), DevBuf(nbytes=4 * Cc), DevBuf(nbytes=x.nbytes)
+    br = DevBuf(residual) if residual is not None else None
+    L().resnet_b200_batchnorm_forward(S, Cc, N, eps, bx.ptr, bg.ptr, bb.ptr, bm.ptr, bv.ptr, by.ptr, int(relu), br.ptr if br else None,
+                                      int(round_tf32))
+    check()
+    return bm.get((Cc,)), bv.get((Cc,)), by.get(x.shape)
+
+
+def batchnorm_backward(x, gamma, eps, means, vars_, activated, dy, relu):
+    N, S, _, Cc = x.shape
+    bx, bg, bm, bv, ba, bdy = DevBuf(x), DevBuf(gamma), DevBuf(means), DevBuf(vars_), DevBuf(activated), DevBuf(dy)
+    bdg, bdb, bdx = DevBuf(nbytes=4 * Cc), DevBuf(nbytes=4 * Cc), DevBuf(nbytes=x.nbytes)
+    L().resnet_b200_batchnorm_backward(S, Cc, N, eps, bx.ptr, bg.ptr, bm.ptr, bv.ptr, ba.ptr, bdy.ptr, bdg.ptr, bdb.ptr, bdx.ptr, int(relu))
+    check()
+    return bdg.get((Cc,)), bdb.get((Cc,)), bdx.get(x.shape)
+
+
+def maxpool_forward(x, k, stride):
+    N, S, _, Cc = x.shape
+    So = S // stride
+    bx, bi, bo = DevBuf(x), DevBuf(nbytes=4 * N * So * So * Cc), DevBuf(nbytes=4 * N * So * So * Cc)
+    L().resnet_b200_maxpool_forward(bx.ptr, k, stride, S, Cc, N, bi.ptr, bo.ptr)
+    check()
+    return bo.get((N, So, So, Cc)), bi.get((N, So, So, Cc), np.int32)
+
+
+def maxpool_backward(inds, dout, in_shape, k, stride):
+    N, S, _, Cc = in_shape
+    bi, bd = DevBuf(inds), DevBuf(dout)
+    bo = DevBuf(nbytes=4 * int(np.prod(in_shape)))
+    L().resnet_b200_maxpool_backward(bi.ptr, bd.ptr, k, S, stride, Cc, N, bo.ptr)
+    check()
+    return bo.get(in_shape)
+
+
+def avgpool_forward(x):
+    N, S, _, Cc = x.shape
+    bx, bo = DevBuf(x), DevBuf(nbytes=4 * N * Cc)
+    L().resnet_b200_avgpool_forward(bx.ptr, S, Cc, N, bo.ptr)
+    check()
+    return bo.get((N, Cc))
+
+
+def avgpool_backward(dp, S):
+    N, Cc = dp.shape
+    bd, bo = DevBuf(dp), DevBuf(nbytes=4 * N * S * S * Cc)
+    L().resnet_b200_avgpool_backward(bd.ptr, Cc, N, S, bo.ptr)
+    check()
+    return bo.get((N, S, S, Cc))
+
+
+def matmul(A, B, ta=False, tb=False):
+    m, k = (A.shape[1], A.shape[0]) if ta else A.shape
+    n = B.shape[0] if tb else B.shape[1]
+    ba, bb, bo = DevBuf(A), DevBuf(B), DevBuf(nbytes=4 * m * n)
+    L().resnet_b200_matmul(ba.ptr, bb.ptr, m, k, n, int(ta), int(tb), bo.ptr)
+    check()
+    return bo.get((m, n))
+
+
+def softmax_ce(logits, labels):
+    N, Lc = logits.shape
+    bl, bi = DevBuf(logits), DevBuf(np.ascontiguousarray(labels, np.int32))
+    bp, bd = DevBuf(nbytes=logits.nbytes), DevBuf(nbytes=logits.nbytes)
+    L().resnet_b200_softmax_ce(bl.ptr, bi.ptr, N, Lc, bp.ptr, bd.ptr)
+    check()
+    return bp.get(logits.shape), bd.get(logits.shape)
+
+
+def adam(p, g, m, v, lr, wd, b1, b2, cur_b1, cur_b2, eps):
+    n = p.size
+    pad = (-n) % 4
+    bufs = [DevBuf(np.concatenate([a.reshape(-1), np.zeros(pad, np.float32)])) for a in (p, g, m, v)]
+    L().resnet_b200_adam(bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, n + pad, lr, wd, b1, b2, cur_b1, cur_b2, eps)
+    check()
+    return [b.get((n + pad,))[:n].reshape(p.shape) for b in bufs]

@@ -1,0 +1,612 @@
+// bw_kernels.cu -- HBM-bound kernels of the training step: BatchNorm statistics / apply / backward, ReLU,
+// residual join, max / average pooling, softmax cross-entropy, fused Adam, weight re-layout.
+//
+// Roofline: HBM bandwidth (MEASURED_PEAKS.json hbm_gbs).  Every tensor pass is a flat, fully coalesced
+// 128-bit grid-stride stream; per-channel quantities ride in registers because the grid stride is a multiple
+// of C/4, so a thread always sees the same four channels (NHWC: C is the contiguous axis).
+// Reference semantics: resnet.cu:289-342 (BN fwd), 350-426 (BN bwd), 433-494 (max pool), 500-542 (avg pool),
+// 545-602 (ReLU, softmax, CE), 605-662 (Adam).
+#include "common.cuh"
+#include <stdarg.h>
+#include <math.h>
+
+namespace rb {
+
+// ------------------------------------------------------------------------------------------- errors
+long long g_launches = 0;
+static char g_err[512];
+static bool g_has_err = false;
+void set_error(const char *fmt, ...) {
+	if (g_has_err) return;
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	g_has_err = true;
+	fprintf(stderr, "[resnet_b200] error: %s\n", g_err);
+}
+const char *last_error() { return g_has_err ? g_err : ""; }
+void clear_error() { g_has_err = false; g_err[0] = 0; }
+bool has_error() { return g_has_err; }
+
+// ------------------------------------------------------------------------------------------- helpers
+constexpr int kThreads = 256;
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<1> { using T = float; };
+
+template <int VEC> __device__ __forceinline__ void ldv(const float *p, long long i, float (&v)[VEC]) {
+	if constexpr (VEC == 4) {
+		float4 t = reinterpret_cast<const float4 *>(p)[i];
+		v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+	} else v[0] = p[i];
+}
+template <int VEC> __device__ __forceinline__ void stv(float *p, long long i, const float (&v)[VEC]) {
+	if constexpr (VEC == 4) reinterpret_cast<float4 *>(p)[i] = make_float4(v[0], v[1], v[2], v[3]);
+	else p[i] = v[0];
+}
+__device__ __forceinline__ float round_tf32(float x) {
+	uint32_t r;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+	return __uint_as_float(r);
+}
+
+// Launch shape for a flat stream of nvec vectors with V vectors per row: total threads is a multiple of V when
+// possible ("fixed column" mode), capped at max_blocks.
+static int flat_grid(long long nvec, int V, int max_blocks, bool *fixed) {
+	long long want = (nvec + (long long)kThreads * 4 - 1) / ((long long)kThreads * 4);
+	int grid = (int)(want < 1 ? 1 : (want > max_blocks ? max_blocks : want));
+	*fixed = false;
+	if (kThreads % V == 0) *fixed = true;
+	else if (V % kThreads == 0) {
+		int m = V / kThreads;
+		grid = (grid + m - 1) / m * m;
+		if (grid > max_blocks) grid = max_blocks / m * m;
+		*fixed = grid > 0;
+		if (!*fixed) grid = 1;
+	}
+	return grid;
+}
+constexpr int kMaxFlatBlocks = kNumSMs * 8;
+
+// ------------------------------------------------------------------------------------------- BN statistics
+// partials[blk][0][c] = sum x, partials[blk][1][c] = sum x^2 over the rows this block streamed.
+template <int VEC, bool FIXED, bool BWD>
+__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                            const float *__restrict__ mask, const float *__restrict__ means,
+                                                            long long nvec, int V, float *__restrict__ partials) {
+	extern __shared__ float sm[];  // [2][C]
+	const int Cc = V * VEC;
+	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) sm[i] = 0.f;
+	__syncthreads();
+	const long long T = (long long)gridDim.x * kThreads;
+	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+	float s[VEC], q[VEC], mu[VEC];
+#pragma unroll
+	for (int j = 0; j < VEC; j++) s[j] = q[j] = mu[j] = 0.f;
+	const int col0 = (int)(g % V) * VEC;
+	if (FIXED && BWD) {
+#pragma unroll
+		for (int j = 0; j < VEC; j++) mu[j] = means[col0 + j];
+	}
+	for (long long i = g; i < nvec; i += T) {
+		float a[VEC];
+		ldv<VEC>(x, i, a);
+		if constexpr (!BWD) {
+			if constexpr (FIXED) {
+#pragma unroll
+				for (int j = 0; j < VEC; j++) { s[j] += a[j]; q[j] += a[j] * a[j]; }
+			} else {
+				const int c = (int)(i % V) * VEC;
+#pragma unroll
+				for (int j = 0; j < VEC; j++) { atomicAdd(&sm[c + j], a[j]); atomicAdd(&sm[Cc + c + j], a[j] * a[j]); }
+			}
+		} else {
+			float d[VEC];
+			ldv<VEC>(dy, i, d);
+			if (mask) {
+				float mk[VEC];
+				ldv<VEC>(mask, i, mk);
+#pragma unroll
+				for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
+			}
+			if constexpr (FIXED) {
+#pragma unroll
+				for (int j = 0; j < VEC; j++) { s[j] += d[j]; q[j] += d[j] * (a[j] - mu[j]); }
+			} else {
+				const int c = (int)(i % V) * VEC;
+#pragma unroll
+				for (int j = 0; j < VEC; j++) { atomicAdd(&sm[c + j], d[j]); atomicAdd(&sm[Cc + c + j], d[j] * (a[j] - means[c + j])); }
+			}
+		}
+	}
+	if constexpr (FIXED) {
+#pragma unroll
+		for (int j = 0; j < VEC; j++) { atomicAdd(&sm[col0 + j], s[j]); atomicAdd(&sm[Cc + col0 + j], q[j]); }
+	}
+	__syncthreads();
+	float *out = partials + (size_t)blockIdx.x * 2 * Cc;
+	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) out[i] = sm[i];
+}
+
+// one thread per channel: fold the per-block partials (fp64) into mean, biased variance, a = gamma*rstd, b = beta - mean*a
+__global__ void bn_finalize_kernel(const float *__restrict__ partials, int nblk, double inv_n, int Cc, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float eps, float *__restrict__ means, float *__restrict__ vars,
+                                   float *__restrict__ ab) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= Cc) return;
+	double s = 0, q = 0;
+	for (int b = 0; b < nblk; b++) {
+		s += (double)partials[(size_t)b * 2 * Cc + c];
+		q += (double)partials[(size_t)b * 2 * Cc + Cc + c];
+	}
+	const double mean = s * inv_n;
+	double var = q * inv_n - mean * mean;
+	if (var < 0) var = 0;
+	const float meanf = (float)mean, varf = (float)var;
+	means[c] = meanf;
+	vars[c] = varf;
+	const float a = gamma[c] / sqrtf(varf + eps);
+	ab[c] = a;
+	ab[Cc + c] = beta[c] - meanf * a;
+}
+
+static void launch_reduce(bool bwd, const float *x, const float *dy, const float *mask, const float *means, long long rows, int C,
+                          float *partials, int max_blocks, int *grid_out, cudaStream_t st) {
+	const int VEC = (C % 4 == 0) ? 4 : 1;
+	const int V = C / VEC;
+	const long long nvec = rows * V;
+	bool fixed;
+	int cap = max_blocks < kMaxFlatBlocks ? max_blocks : kMaxFlatBlocks;
+	int grid = flat_grid(nvec, V, cap, &fixed);
+	if (VEC == 1) fixed = false;
+	const size_t smem = 2 * (size_t)C * sizeof(float);
+#define RB_RED(VEC_, FIX_, BWD_) bn_reduce_kernel<VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>(x, dy, mask, means, nvec, V, partials)
+	if (VEC == 4) {
+		if (fixed) { if (bwd) RB_RED(4, true, true); else RB_RED(4, true, false); }
+		else { if (bwd) RB_RED(4, false, true); else RB_RED(4, false, false); }
+	} else { if (bwd) RB_RED(1, false, true); else RB_RED(1, false, false); }
+#undef RB_RED
+	RB_LAUNCH_CHECK();
+	*grid_out = grid;
+}
+
+void bn_finalize(const float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
+                 float *means, float *vars, float *ab, cudaStream_t st) {
+	bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partials, nblk, 1.0 / (double)rows, C, gamma, beta, eps, means, vars, ab);
+	RB_LAUNCH_CHECK();
+}
+
+void bn_stats(const float *x, long long rows, int C, const float *gamma, const float *beta, float eps, float *means, float *vars,
+              float *ab, float *partials, int max_blocks, cudaStream_t st) {
+	int grid;
+	launch_reduce(false, x, nullptr, nullptr, nullptr, rows, C, partials, max_blocks, &grid, st);
+	bn_finalize(partials, grid, rows, C, gamma, beta, eps, means, vars, ab, st);
+}
+
+// ------------------------------------------------------------------------------------------- BN apply (+ residual + ReLU)
+template <int VEC, bool FIXED>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restrict__ x, const float *__restrict__ ab, long long nvec, int V,
+                                                           int relu, const float *__restrict__ res, const float *__restrict__ ab2,
+                                                           float *__restrict__ y, int rnd) {
+	const int Cc = V * VEC;
+	const long long T = (long long)gridDim.x * kThreads;
+	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+	float a[VEC], b[VEC], a2[VEC], b2[VEC];
+	if constexpr (FIXED) {
+		const int c0 = (int)(g % V) * VEC;
+#pragma unroll
+		for (int j = 0; j < VEC; j++) {
+			a[j] = ab[c0 + j]; b[j] = ab[Cc + c0 + j];
+			a2[j] = ab2 ? ab2[c0 + j] : 1.f; b2[j] = ab2 ? ab2[Cc + c0 + j] : 0.f;
+		}
+	}
+	for (long long i = g; i < nvec; i += T) {
+		if constexpr (!FIXED) {
+			const int c0 = (int)(i % V) * VEC;
+#pragma unroll
+			for (int j = 0; j < VEC; j++) {
+				a[j] = ab[c0 + j]; b[j] = ab[Cc + c0 + j];
+				a2[j] = ab2 ? ab2[c0 + j] : 1.f; b2[j] = ab2 ? ab2[Cc + c0 + j] : 0.f;
+			}
+		}
+		float v[VEC];
+		ldv<VEC>(x, i, v);
+#pragma unroll
+		for (int j = 0; j < VEC; j++) v[j] = fmaf(v[j], a[j], b[j]);
+		if (res) {
+			float r[VEC];
+			ldv<VEC>(res, i, r);
+#pragma unroll
+			for (int j = 0; j < VEC; j++) v[j] += fmaf(r[j], a2[j], b2[j]);
+		}
+#pragma unroll
+		for (int j = 0; j < VEC; j++) {
+			if (relu) v[j] = fmaxf(v[j], 0.f);
+			if (rnd) v[j] = round_tf32(v[j]);
+		}
+		stv<VEC>(y, i, v);
+	}
+}
+
+void bn_apply(const float *x, const float *ab, long long rows, int C, int relu, const float *res, const float *ab2, float *y,
+              int rnd, cudaStream_t st) {
+	const int VEC = (C % 4 == 0) ? 4 : 1;
+	const int V = C / VEC;
+	const long long nvec = rows * V;
+	bool fixed;
+	int grid = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
+	if (VEC == 4 && fixed) bn_apply_kernel<4, true><<<grid, kThreads, 0, st>>>(x, ab, nvec, V, relu, res, ab2, y, rnd);
+	else if (VEC == 4) bn_apply_kernel<4, false><<<grid, kThreads, 0, st>>>(x, ab, nvec, V, relu, res, ab2, y, rnd);
+	else bn_apply_kernel<1, false><<<grid, kThreads, 0, st>>>(x, ab, nvec, V, relu, res, ab2, y, rnd);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- BN backward
+// s1 = sum dy', s2 = sum dy' (x - mean);  dbeta = s1, dgamma = s2 * rstd,
+// dx = c1*dy' + c2 + c3*(x - mean) with c1 = gamma*rstd, c2 = -c1*s1/n, c3 = -c1*rstd^2*s2/n
+// (algebraically the reference's three-term form, resnet.cu:394-422).
+__global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int nblk, double inv_n, int Cc, const float *__restrict__ gamma,
+                                       const float *__restrict__ means, const float *__restrict__ vars, float eps,
+                                       float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= Cc) return;
+	double s1 = 0, s2 = 0;
+	for (int b = 0; b < nblk; b++) {
+		s1 += (double)partials[(size_t)b * 2 * Cc + c];
+		s2 += (double)partials[(size_t)b * 2 * Cc + Cc + c];
+	}
+	const float rstd = 1.0f / sqrtf(vars[c] + eps);
+	dbeta[c] = (float)s1;
+	dgamma[c] = (float)(s2 * (double)rstd);
+	const double c1 = (double)gamma[c] * (double)rstd;
+	coef[c] = (float)c1;
+	coef[Cc + c] = (float)(-c1 * s1 * inv_n);
+	coef[2 * Cc + c] = (float)(-c1 * (double)rstd * (double)rstd * s2 * inv_n);
+	coef[3 * Cc + c] = means[c];
+}
+
+template <int VEC, bool FIXED>
+__global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__restrict__ x, const float *dy, const float *__restrict__ mask,
+                                                            const float *__restrict__ coef, long long nvec, int V, float *dx, int rnd) {
+	const int Cc = V * VEC;
+	const long long T = (long long)gridDim.x * kThreads;
+	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+	float c1[VEC], c2[VEC], c3[VEC], mu[VEC];
+	if constexpr (FIXED) {
+		const int c0 = (int)(g % V) * VEC;
+#pragma unroll
+		for (int j = 0; j < VEC; j++) { c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j]; }
+	}
+	for (long long i = g; i < nvec; i += T) {
+		if constexpr (!FIXED) {
+			const int c0 = (int)(i % V) * VEC;
+#pragma unroll
+			for (int j = 0; j < VEC; j++) { c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j]; }
+		}
+		float a[VEC], d[VEC];
+		ldv<VEC>(x, i, a);
+		ldv<VEC>(dy, i, d);
+		if (mask) {
+			float mk[VEC];
+			ldv<VEC>(mask, i, mk);
+#pragma unroll
+			for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
+		}
+#pragma unroll
+		for (int j = 0; j < VEC; j++) {
+			float r = fmaf(c1[j], d[j], fmaf(c3[j], a[j] - mu[j], c2[j]));
+			d[j] = rnd ? round_tf32(r) : r;
+		}
+		stv<VEC>(dx, i, d);
+	}
+}
+
+void bn_bwd(const float *x, const float *dy, const float *mask_src, const float *gamma, const float *means, const float *vars, float eps,
+            long long rows, int C, float *dgamma, float *dbeta, float *dx, float *partials, int max_blocks, float *coef, int rnd,
+            cudaStream_t st) {
+	int grid;
+	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st);
+	bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
+	RB_LAUNCH_CHECK();
+	const int VEC = (C % 4 == 0) ? 4 : 1;
+	const int V = C / VEC;
+	const long long nvec = rows * V;
+	bool fixed;
+	int g2 = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
+	if (VEC == 4 && fixed) bn_bwd_dx_kernel<4, true><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd);
+	else if (VEC == 4) bn_bwd_dx_kernel<4, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd);
+	else bn_bwd_dx_kernel<1, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- ReLU backward (identity shortcut)
+__global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const float *__restrict__ y, const float *__restrict__ dy, long long n, float *__restrict__ dx) {
+	const long long T = (long long)gridDim.x * kThreads;
+	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
+	const long long n4 = n / 4;
+	for (long long i = g; i < n4; i += T) {
+		float4 a = reinterpret_cast<const float4 *>(y)[i], d = reinterpret_cast<const float4 *>(dy)[i];
+		reinterpret_cast<float4 *>(dx)[i] = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);
+	}
+	for (long long i = n4 * 4 + g; i < n; i += T) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+void relu_bwd(const float *y, const float *dy, long long n, float *dx, cudaStream_t st) {
+	int grid = (int)((n / 4 + kThreads * 4 - 1) / (kThreads * 4));
+	grid = grid < 1 ? 1 : (grid > kMaxFlatBlocks ? kMaxFlatBlocks : grid);
+	relu_bwd_kernel<<<grid, kThreads, 0, st>>>(y, dy, n, dx);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- max pool
+// reference resnet.cu:433-471: init -1024, strict '>', row-major window scan, flat input index.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float *__restrict__ x, int N, int S, int C, int k, int stride,
+                                                              int *__restrict__ inds, float *__restrict__ out) {
+	const int So = S / stride, half = k / 2, V = C / VEC;
+	const long long total = (long long)N * So * So * V;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+		const int cv = (int)(i % V);
+		long long p = i / V;
+		const int ow = (int)(p % So); p /= So;
+		const int oh = (int)(p % So);
+		const int n = (int)(p / So);
+		float mv[VEC]; int mi[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++) { mv[j] = -1024.f; mi[j] = -1024; }
+		for (int r = -half; r <= half; r++) {
+			const int h = stride * oh + r;
+			if (h < 0 || h >= S) continue;
+			for (int c = -half; c <= half; c++) {
+				const int w = stride * ow + c;
+				if (w < 0 || w >= S) continue;
+				const long long base = (((long long)n * S + h) * S + w) * C + (long long)cv * VEC;
+				float v[VEC];
+				ldv<VEC>(x, base / VEC, v);
+#pragma unroll
+				for (int j = 0; j < VEC; j++) if (v[j] > mv[j]) { mv[j] = v[j]; mi[j] = (int)(base + j); }
+			}
+		}
+		stv<VEC>(out, i, mv);
+		if constexpr (VEC == 4) reinterpret_cast<int4 *>(inds)[i] = make_int4(mi[0], mi[1], mi[2], mi[3]);
+		else inds[i] = mi[0];
+	}
+}
+void maxpool_fwd(const float *x, int N, int S, int C, int k, int stride, int *max_inds, float *out, cudaStream_t st) {
+	const int So = S / stride;
+	if (C % 4 == 0) {
+		long long total = (long long)N * So * So * (C / 4);
+		int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
+		maxpool_fwd_kernel<4><<<grid, kThreads, 0, st>>>(x, N, S, C, k, stride, max_inds, out);
+	} else {
+		long long total = (long long)N * So * So * C;
+		int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
+		maxpool_fwd_kernel<1><<<grid, kThreads, 0, st>>>(x, N, S, C, k, stride, max_inds, out);
+	}
+	RB_LAUNCH_CHECK();
+}
+
+// Gather form of the reference's scatter (resnet.cu:476-494): every input element sums the gradients of the
+// windows whose recorded argmax is that element.  Deterministic, and accumulates where the reference's
+// overlapping-window scatter races (its cuDNN variants accumulate too).
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const int *__restrict__ inds, const float *__restrict__ dout, int N, int S, int C,
+                                                              int k, int stride, float *__restrict__ din) {
+	const int So = S / stride, half = k / 2;
+	const long long total = (long long)N * S * S * C;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+		const int c = (int)(i % C);
+		long long p = i / C;
+		const int w = (int)(p % S); p /= S;
+		const int h = (int)(p % S);
+		const int n = (int)(p / S);
+		// windows oh with stride*oh - half <= h <= stride*oh + half
+		int oh_lo = (h - half + stride - 1); oh_lo = oh_lo < 0 ? 0 : oh_lo / stride;
+		int oh_hi = (h + half) / stride; oh_hi = oh_hi >= So ? So - 1 : oh_hi;
+		int ow_lo = (w - half + stride - 1); ow_lo = ow_lo < 0 ? 0 : ow_lo / stride;
+		int ow_hi = (w + half) / stride; ow_hi = ow_hi >= So ? So - 1 : ow_hi;
+		float acc = 0.f;
+		for (int oh = oh_lo; oh <= oh_hi; oh++)
+			for (int ow = ow_lo; ow <= ow_hi; ow++) {
+				const long long o = (((long long)n * So + oh) * So + ow) * C + c;
+				if (inds[o] == (int)i) acc += dout[o];
+			}
+		din[i] = acc;
+	}
+}
+void maxpool_bwd(const int *max_inds, const float *dout, int N, int S, int C, int k, int stride, float *din, cudaStream_t st) {
+	long long total = (long long)N * S * S * C;
+	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 8 ? kMaxFlatBlocks * 8 : grid;
+	maxpool_bwd_kernel<<<grid, kThreads, 0, st>>>(max_inds, dout, N, S, C, k, stride, din);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- average pool
+__global__ void avgpool_fwd_kernel(const float *__restrict__ x, int N, int SS, int C, float *__restrict__ out) {
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (n, c)
+	if (i >= (long long)N * C) return;
+	const int c = (int)(i % C), n = (int)(i / C);
+	float s = 0.f;
+	for (int p = 0; p < SS; p++) s += x[((long long)n * SS + p) * C + c];
+	out[i] = s / (float)SS;
+}
+void avgpool_fwd(const float *x, int N, int S, int C, float *out, cudaStream_t st) {
+	avgpool_fwd_kernel<<<ceil_div((long long)N * C, 256), 256, 0, st>>>(x, N, S * S, C, out);
+	RB_LAUNCH_CHECK();
+}
+__global__ void avgpool_bwd_kernel(const float *__restrict__ dp, int N, int SS, int C, float *__restrict__ din) {
+	const long long total = (long long)N * SS * C;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const int c = (int)(i % C);
+		const int n = (int)(i / ((long long)SS * C));
+		din[i] = dp[(long long)n * C + c] / (float)SS;
+	}
+}
+void avgpool_bwd(const float *dpooled, int N, int S, int C, float *din, cudaStream_t st) {
+	long long total = (long long)N * S * S * C;
+	int grid = (int)((total + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
+	avgpool_bwd_kernel<<<grid, 256, 0, st>>>(dpooled, N, S * S, C, din);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- softmax + cross entropy
+// one warp per row; max-subtracted (reference resnet_cudnn.cu:568-587), dlogits = pred - onehot with no 1/N.
+__global__ void softmax_ce_kernel(const float *__restrict__ logits, const int *__restrict__ labels, int N, int L, float *__restrict__ pred,
+                                  float *__restrict__ dlogits, float *__restrict__ row_loss, int *__restrict__ row_wrong) {
+	const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (row >= N) return;
+	const float *x = logits + (size_t)row * L;
+	float mx = -INFINITY;
+	for (int j = lane; j < L; j += 32) mx = fmaxf(mx, x[j]);
+	for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	float sum = 0.f;
+	for (int j = lane; j < L; j += 32) sum += expf(x[j] - mx);
+	for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+	const int lab = labels[row];
+	const float pl = expf(x[lab] - mx) / sum;
+	int wrong = 0;
+	for (int j = lane; j < L; j += 32) {
+		const float p = expf(x[j] - mx) / sum;
+		pred[(size_t)row * L + j] = p;
+		if (dlogits) dlogits[(size_t)row * L + j] = (j == lab) ? p - 1.f : p;
+		if (j != lab && p >= pl) wrong = 1;
+	}
+	wrong = __any_sync(0xffffffffu, wrong);
+	if (lane == 0) {
+		if (row_loss) row_loss[row] = -logf(pl);
+		if (row_wrong) row_wrong[row] = wrong;
+	}
+}
+void softmax_ce(const float *logits, const int *labels, int N, int L, float *pred, float *dlogits, float *row_loss, int *row_wrong,
+                cudaStream_t st) {
+	softmax_ce_kernel<<<ceil_div((long long)N * 32, 128), 128, 0, st>>>(logits, labels, N, L, pred, dlogits, row_loss, row_wrong);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- Adam
+// reference resnet.cu:605-662 fused: one pass reads p,g,m,v and writes p,m,v and g=0 (the reference memsets the
+// gradients afterwards, resnet.cu:2972-2975).  Non-finite gradient: moments kept; non-finite result: param kept.
+__global__ void __launch_bounds__(kThreads) adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                                                       long long n4, float lr, float wd, float b1, float b2, float cb1, float cb2, float eps,
+                                                       int *__restrict__ bad) {
+	const long long T = (long long)gridDim.x * kThreads;
+	int nbad = 0;
+	const float ib1 = 1.f - cb1, ib2 = 1.f - cb2;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += T) {
+		float4 P = reinterpret_cast<float4 *>(p)[i], G = reinterpret_cast<float4 *>(g)[i];
+		float4 M = reinterpret_cast<float4 *>(m)[i], Vv = reinterpret_cast<float4 *>(v)[i];
+		float pp[4] = {P.x, P.y, P.z, P.w}, gg[4] = {G.x, G.y, G.z, G.w}, mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {Vv.x, Vv.y, Vv.z, Vv.w};
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			if (isfinite(gg[j])) {
+				const float gd = gg[j] + wd * pp[j];
+				mm[j] = b1 * mm[j] + (1.f - b1) * gd;
+				vv[j] = b2 * vv[j] + (1.f - b2) * gd * gd;
+			} else nbad++;
+			const float ma = mm[j] / ib1, va = vv[j] / ib2;
+			const float np_ = pp[j] - (lr * (ma / (sqrtf(va) + eps)) + wd * pp[j]);
+			if (isfinite(np_)) pp[j] = np_; else nbad++;
+		}
+		reinterpret_cast<float4 *>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+		reinterpret_cast<float4 *>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+		reinterpret_cast<float4 *>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+		reinterpret_cast<float4 *>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	if (nbad && bad) atomicAdd(bad, nbad);
+}
+void adam_step(float *p, float *g, float *m, float *v, long long n, float lr, float wd, float b1, float b2, float cur_b1, float cur_b2,
+               float eps, int *bad, cudaStream_t st) {
+	if (n % 4) { set_error("adam_step: arena length %lld not a multiple of 4", n); return; }
+	long long n4 = n / 4;
+	int grid = (int)((n4 + kThreads * 2 - 1) / (kThreads * 2)); grid = grid < 1 ? 1 : (grid > kMaxFlatBlocks ? kMaxFlatBlocks : grid);
+	adam_kernel<<<grid, kThreads, 0, st>>>(p, g, m, v, n4, lr, wd, b1, b2, cur_b1, cur_b2, eps, bad);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- fp32 SGEMM (FC head)
+// 64x64 tile, BK 16, 4x4 per thread.  Used for the 2048x1000 fully-connected layer (0.03% of step FLOPs).
+__global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ Cm, int M, int N, int K,
+                                                   int ta, int tb) {
+	__shared__ float As[16][65], Bs[16][65];
+	const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+	const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+	float acc[4][4] = {};
+	for (int k0 = 0; k0 < K; k0 += 16) {
+		for (int e = threadIdx.x; e < 1024; e += 256) {
+			int kk, mm;
+			if (ta) { mm = e % 64; kk = e / 64; } else { kk = e % 16; mm = e / 16; }
+			const int gm = m0 + mm, gk = k0 + kk;
+			As[kk][mm] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f;
+			int kb, nn;
+			if (tb) { kb = e % 16; nn = e / 16; } else { nn = e % 64; kb = e / 64; }
+			const int gn = n0 + nn, gkb = k0 + kb;
+			Bs[kb][nn] = (gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int kk = 0; kk < 16; kk++) {
+			float a[4], b[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+			if (gm < M && gn < N) Cm[(size_t)gm * N + gn] = acc[i][j];
+		}
+}
+void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int ta, int tb, cudaStream_t st) {
+	dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+	sgemm_kernel<<<grid, 256, 0, st>>>(A, B, Cm, M, N, K, ta, tb);
+	RB_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------- weight re-layout
+__global__ void pack_weights_kernel(const PackJob *__restrict__ jobs, int rnd) {
+	const PackJob jb = jobs[blockIdx.y];
+	const long long total = (long long)jb.cout * jb.cin * jb.taps;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		// i indexes the source [co][ci][tap]
+		const int tap = (int)(i % jb.taps);
+		const int ci = (int)((i / jb.taps) % jb.cin);
+		const int co = (int)(i / ((long long)jb.taps * jb.cin));
+		float w = jb.src[i];
+		if (rnd) w = round_tf32(w);
+		jb.wf[((long long)co * jb.taps + tap) * jb.cin + ci] = w;
+		if (jb.wd) jb.wd[((long long)ci * jb.taps + tap) * jb.cout + co] = w;
+	}
+}
+void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int rnd, cudaStream_t st) {
+	int gx = ceil_div(max_elems, 256 * 8); gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+	pack_weights_kernel<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
+	RB_LAUNCH_CHECK();
+}
+
+__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, int cin, int taps, float *__restrict__ dw) {
+	const long long per = (long long)taps * cout * cin;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+		// i indexes partial [tap][co][ci]
+		const int ci = (int)(i % cin);
+		const int co = (int)((i / cin) % cout);
+		const int tap = (int)(i / ((long long)cin * cout));
+		float s = 0.f;
+		for (int sp = 0; sp < splits; sp++) s += partial[(long long)sp * per + i];
+		dw[((long long)co * cin + ci) * taps + tap] = s;
+	}
+}
+void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps, float *dw, cudaStream_t st) {
+	long long per = (long long)taps * cout * cin;
+	int grid = (int)((per + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
+	wgrad_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, cout, cin, taps, dw);
+	RB_LAUNCH_CHECK();
+}
+
+}  // namespace rb

@@ -1,0 +1,237 @@
+// capi.cu -- C-ABI services and single-operator entry points declared in include/resnet_b200.h.
+#include "engine.h"
+#include "../../include/resnet_b200.h"
+#include <curand.h>
+
+using namespace rb;
+
+namespace {
+struct Tmp {
+	std::vector<void *> ptrs;
+	template <typename T> T *get(long long n) {
+		void *p = nullptr;
+		RB_CUDA(cudaMalloc(&p, (size_t)(n > 0 ? n : 1) * sizeof(T)));
+		ptrs.push_back(p);
+		return (T *)p;
+	}
+	~Tmp() { for (void *p : ptrs) cudaFree(p); }
+};
+int status() { return has_error() ? 1 : 0; }
+
+// packs [Cout][Cin][k][k] into Wf / Wd on the default stream
+void pack_one(const float *w, float *wf, float *wd, int cout, int cin, int taps, int rnd, Tmp &tmp) {
+	PackJob job{w, wf, wd, cout, cin, taps};
+	PackJob *jd = tmp.get<PackJob>(1);
+	RB_CUDA(cudaMemcpy(jd, &job, sizeof(job), cudaMemcpyHostToDevice));
+	pack_weights(jd, 1, cout * cin * taps, rnd, 0);
+}
+}  // namespace
+
+extern "C" {
+
+const char *resnet_b200_last_error(void) { return last_error(); }
+void resnet_b200_clear_error(void) { clear_error(); }
+int resnet_b200_set_device(int device) { RB_CUDA(cudaSetDevice(device)); return status(); }
+void *resnet_b200_malloc(size_t bytes) { void *p = nullptr; RB_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
+void resnet_b200_free(void *p) { if (p) RB_CUDA(cudaFree(p)); }
+void *resnet_b200_malloc_host(size_t bytes) { void *p = nullptr; RB_CUDA(cudaMallocHost(&p, bytes ? bytes : 1)); return p; }
+void resnet_b200_free_host(void *p) { if (p) RB_CUDA(cudaFreeHost(p)); }
+int resnet_b200_memcpy_h2d(void *d, const void *h, size_t n) { RB_CUDA(cudaMemcpy(d, h, n, cudaMemcpyHostToDevice)); return status(); }
+int resnet_b200_memcpy_d2h(void *h, const void *d, size_t n) { RB_CUDA(cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost)); return status(); }
+int resnet_b200_memcpy_d2d(void *d, const void *s, size_t n) { RB_CUDA(cudaMemcpy(d, s, n, cudaMemcpyDeviceToDevice)); return status(); }
+int resnet_b200_memset(void *d, int v, size_t n) { RB_CUDA(cudaMemset(d, v, n)); return status(); }
+int resnet_b200_sync(void) { RB_CUDA(cudaDeviceSynchronize()); return status(); }
+
+void *resnet_b200_rng_create(unsigned long long seed) {
+	curandGenerator_t *g = (curandGenerator_t *)malloc(sizeof(curandGenerator_t));
+	if (curandCreateGenerator(g, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS) { set_error("curandCreateGenerator failed"); free(g); return NULL; }
+	curandSetPseudoRandomGeneratorSeed(*g, seed);
+	return g;
+}
+void resnet_b200_rng_destroy(void *gen) {
+	if (!gen) return;
+	curandDestroyGenerator(*(curandGenerator_t *)gen);
+	free(gen);
+}
+
+int resnet_b200_stage_batch(Train_ResNet *t, const float *images_host, const int *labels_host) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("stage_batch: unknown trainer"); return 1; }
+	Batch *b = t->cur_batch;
+	RB_CUDA(cudaMemcpyAsync(b->images, images_host, (size_t)t->batch_size * b->image_size * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+	RB_CUDA(cudaMemcpyAsync(b->correct_classes, labels_host, (size_t)t->batch_size * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	return status();
+}
+int resnet_b200_stage_batch_device(Train_ResNet *t, const float *images_dev, const int *labels_dev) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("stage_batch_device: unknown trainer"); return 1; }
+	Batch *b = t->cur_batch;
+	RB_CUDA(cudaMemcpyAsync(b->images, images_dev, (size_t)t->batch_size * b->image_size * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+	RB_CUDA(cudaMemcpyAsync(b->correct_classes, labels_dev, (size_t)t->batch_size * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+	return status();
+}
+int resnet_b200_trainer_sync(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("trainer_sync: unknown trainer"); return 1; }
+	RB_CUDA(cudaStreamSynchronize(e->stream));
+	return status();
+}
+int resnet_b200_timer_begin(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) return 1;
+	RB_CUDA(cudaEventRecord(e->ev0, e->stream));
+	return status();
+}
+float resnet_b200_timer_end_ms(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) return -1.f;
+	float ms = -1.f;
+	RB_CUDA(cudaEventRecord(e->ev1, e->stream));
+	RB_CUDA(cudaEventSynchronize(e->ev1));
+	RB_CUDA(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+	return ms;
+}
+int resnet_b200_loss_accuracy(Train_ResNet *t, float *loss_sum, int *n_wrong) {
+	Engine *e = engine_of(t);
+	if (!e) return 1;
+	std::vector<float> l(e->N);
+	std::vector<int> w(e->N);
+	RB_CUDA(cudaMemcpyAsync(l.data(), e->row_loss, e->N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	RB_CUDA(cudaMemcpyAsync(w.data(), e->row_wrong, e->N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+	RB_CUDA(cudaStreamSynchronize(e->stream));
+	float ls = 0.f;
+	int nw = 0;
+	for (int i = 0; i < e->N; i++) { ls += l[i]; nw += w[i]; }
+	*loss_sum = ls;
+	*n_wrong = nw;
+	return status();
+}
+long long resnet_b200_launch_count(void) { return g_launches; }
+int resnet_b200_uses_tensor_cores(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) return 0;
+	int n = 0;
+	for (auto &b : e->blocks) n += b.reduce.use_tc + b.spatial.use_tc + b.expand.use_tc;
+	return n > 0;
+}
+void resnet_b200_destroy_trainer(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) return;
+	cudaStreamSynchronize(e->stream);
+	for (auto &b : e->blocks)
+		for (ConvRef *c : {&b.reduce, &b.spatial, &b.expand, &b.proj}) {
+			if (c->fprop) tc_free(c->fprop);
+			if (c->dgrad) tc_free(c->dgrad);
+			if (c->wgrad) tc_free(c->wgrad);
+		}
+	for (void *p : e->allocs) cudaFree(p);
+	for (Params *P : {t->backprop_buffer->param_derivs, t->backprop_buffer->prev_means, t->backprop_buffer->prev_vars}) {
+		ParamStore *ps = param_store_of(P);
+		if (ps) cudaFree(ps->base);
+	}
+	cudaFreeHost(e->pred_host);
+	cudaFreeHost(e->bad_host);
+	cudaStreamDestroy(e->stream);
+}
+
+// ---------------------------------------------------------------------------------------------- single operators
+int resnet_b200_conv_forward(int S, int k, int cin, int cout, int stride, int N, const float *input, const float *weights, float *output, int impl) {
+	Tmp tmp;
+	ConvGeom g{N, S, cin, cout, k, stride};
+	float *wf = tmp.get<float>(g.w_elems());
+	pack_one(weights, wf, nullptr, cout, cin, k * k, 0, tmp);
+	if (impl == 0) {
+		TcPlan *pl = tc_make_fprop(g, input, wf, output);
+		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
+	} else {
+		simt_conv_fprop(g, input, wf, output, 0);
+	}
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+
+int resnet_b200_conv_backward(int S, int k, int cin, int cout, int stride, int N, int to_add, const float *input, const float *weights,
+                              const float *out_deriv, float *input_deriv, float *weight_deriv, int impl) {
+	Tmp tmp;
+	ConvGeom g{N, S, cin, cout, k, stride};
+	float *wf = tmp.get<float>(g.w_elems()), *wd = tmp.get<float>(g.w_elems());
+	pack_one(weights, wf, wd, cout, cin, k * k, 0, tmp);
+	if (impl == 0) {
+		if (input_deriv) {
+			TcPlan *pl = tc_make_dgrad(g, out_deriv, wd, input_deriv, to_add);
+			if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
+		}
+		size_t ws = tc_wgrad_workspace_bytes(g);
+		float *wsp = (float *)tmp.get<char>((long long)ws);
+		TcPlan *pl = tc_make_wgrad(g, input, out_deriv, weight_deriv, wsp, ws);
+		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
+	} else {
+		if (input_deriv) simt_conv_dgrad(g, out_deriv, wd, input_deriv, to_add, 0);
+		simt_conv_wgrad(g, input, out_deriv, weight_deriv, 0);
+	}
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+
+int resnet_b200_batchnorm_forward(int S, int C, int N, float eps, const float *input, const float *gamma, const float *beta, float *means,
+                                  float *vars, float *activated, int to_activate, const float *residual, int rnd) {
+	Tmp tmp;
+	const long long rows = (long long)N * S * S;
+	const int maxb = kNumSMs * 8;
+	float *partials = tmp.get<float>((long long)maxb * 2 * C), *ab = tmp.get<float>(2LL * C);
+	bn_stats(input, rows, C, gamma, beta, eps, means, vars, ab, partials, maxb, 0);
+	bn_apply(input, ab, rows, C, to_activate, residual, nullptr, activated, rnd, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+
+int resnet_b200_batchnorm_backward(int S, int C, int N, float eps, const float *input, const float *gamma, const float *means, const float *vars,
+                                   const float *activated, const float *out_layer_deriv, float *gamma_deriv, float *beta_deriv,
+                                   float *input_deriv, int to_activate_deriv) {
+	Tmp tmp;
+	const long long rows = (long long)N * S * S;
+	const int maxb = kNumSMs * 8;
+	float *partials = tmp.get<float>((long long)maxb * 2 * C), *coef = tmp.get<float>(4LL * C);
+	bn_bwd(input, out_layer_deriv, to_activate_deriv ? activated : nullptr, gamma, means, vars, eps, rows, C, gamma_deriv, beta_deriv, input_deriv,
+	       partials, maxb, coef, 0, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+
+int resnet_b200_maxpool_forward(const float *input, int k, int stride, int S, int C, int N, int *max_inds, float *out) {
+	maxpool_fwd(input, N, S, C, k, stride, max_inds, out, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+int resnet_b200_maxpool_backward(const int *max_inds, const float *out_deriv, int k, int S, int stride, int C, int N, float *input_deriv) {
+	maxpool_bwd(max_inds, out_deriv, N, S, C, k, stride, input_deriv, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+int resnet_b200_avgpool_forward(const float *input, int S, int C, int N, float *out) {
+	avgpool_fwd(input, N, S, C, out, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+int resnet_b200_avgpool_backward(const float *pooled_deriv, int C, int N, int S, float *out) {
+	avgpool_bwd(pooled_deriv, N, S, C, out, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+int resnet_b200_matmul(const float *A, const float *B, int m, int k, int n, int ta, int tb, float *out) {
+	sgemm(A, B, out, m, n, k, ta, tb, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+int resnet_b200_softmax_ce(const float *logits, const int *labels, int N, int L, float *pred, float *output_deriv) {
+	softmax_ce(logits, labels, N, L, pred, output_deriv, nullptr, nullptr, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+int resnet_b200_adam(float *p, float *g, float *m, float *v, long long n, float lr, float wd, float b1, float b2, float cb1, float cb2, float eps) {
+	adam_step(p, g, m, v, n, lr, wd, b1, b2, cb1, cb2, eps, nullptr, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
+
+}  // extern "C"

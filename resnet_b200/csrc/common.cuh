@@ -1,0 +1,96 @@
+// common.cuh -- shared declarations of libresnet_b200.so (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace rb {
+
+// First error wins; readable through resnet_b200_last_error().  The reference ignores every CUDA status
+// (SURVEY.md 8b "error conventions"); we keep the void signatures but record the failure.
+void set_error(const char *fmt, ...);
+const char *last_error();
+bool has_error();
+void clear_error();
+
+#define RB_CUDA(call)                                                                              \
+	do {                                                                                           \
+		cudaError_t _e = (call);                                                                   \
+		if (_e != cudaSuccess) rb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+	} while (0)
+
+extern long long g_launches;  // kernels launched by this library (bench.py gpu_launches)
+#define RB_LAUNCH_CHECK()          \
+	do {                           \
+		rb::g_launches++;          \
+		RB_CUDA(cudaGetLastError()); \
+	} while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// conv geometry shared by the SIMT and tcgen05 paths
+struct ConvGeom {
+	int N, S, cin, cout, k, stride;  // input spatial S x S, zero pad k/2, output So = S / stride
+	__host__ __device__ int So() const { return S / stride; }
+	__host__ __device__ int taps() const { return k * k; }
+	__host__ __device__ long long in_elems() const { return (long long)N * S * S * cin; }
+	__host__ __device__ long long out_elems() const { return (long long)N * So() * So() * cout; }
+	__host__ __device__ long long w_elems() const { return (long long)cout * cin * k * k; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// bandwidth-bound kernels (bw_kernels.cu).  All take a stream; all tensors fp32, NHWC, C % 4 == 0.
+struct BnScratch {       // per-call scratch carved from the engine workspace
+	float *partials;     // [grid][2][C]
+	int max_blocks;
+};
+
+// statistics of x[rows][C]: means, biased vars, and the folded scale/shift a = gamma*rstd, b = beta - mean*a
+void bn_stats(const float *x, long long rows, int C, const float *gamma, const float *beta, float eps, float *means,
+              float *vars, float *ab /* [2][C] */, float *partials, int max_blocks, cudaStream_t st);
+// finalize only (statistics partials already produced, e.g. by a conv epilogue): partials [nblk][2][C]
+void bn_finalize(const float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
+                 float *means, float *vars, float *ab, cudaStream_t st);
+// y = act(x*a + b [+ residual]);  residual: res (identity) or res*a2 + b2 (projected, ab2 != NULL)
+void bn_apply(const float *x, const float *ab, long long rows, int C, int relu, const float *res, const float *ab2, float *y,
+              int round_tf32, cudaStream_t st);
+// BatchNorm backward.  mask_src != NULL: dy is masked where mask_src <= 0 (ReLU).  Produces dgamma, dbeta and
+// dx (may alias dy).  coef scratch [4][C].
+void bn_bwd(const float *x, const float *dy, const float *mask_src, const float *gamma, const float *means, const float *vars,
+            float eps, long long rows, int C, float *dgamma, float *dbeta, float *dx, float *partials, int max_blocks,
+            float *coef, int round_tf32, cudaStream_t st);
+void relu_bwd(const float *y, const float *dy, long long n, float *dx, cudaStream_t st);
+void maxpool_fwd(const float *x, int N, int S, int C, int k, int stride, int *max_inds, float *out, cudaStream_t st);
+void maxpool_bwd(const int *max_inds, const float *dout, int N, int S, int C, int k, int stride, float *din, cudaStream_t st);
+void avgpool_fwd(const float *x, int N, int S, int C, float *out, cudaStream_t st);
+void avgpool_bwd(const float *dpooled, int N, int S, int C, float *din, cudaStream_t st);
+// pred = softmax(logits); dlogits = pred - onehot(labels) (no 1/N, reference resnet.cu:1806-1811);
+// per-row loss = -log pred[label] and wrong flag (ties wrong, reference resnet.cu:3376)
+void softmax_ce(const float *logits, const int *labels, int N, int L, float *pred, float *dlogits, float *row_loss,
+                int *row_wrong, cudaStream_t st);
+// fused Adam over a flat arena (reference resnet.cu:605-662); zeroes g; counts non-finite hits in *bad
+void adam_step(float *p, float *g, float *m, float *v, long long n, float lr, float wd, float b1, float b2, float cur_b1,
+               float cur_b2, float eps, int *bad, cudaStream_t st);
+// C[M][N] = op(A) * op(B), fp32 FMA; ta: A stored [K][M]; tb: B stored [N][K]
+void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int ta, int tb, cudaStream_t st);
+
+// weight re-layout [Cout][Cin][k][k] -> Wf [Cout][k*k][Cin] and Wd [Cin][k*k][Cout] (optionally tf32-rounded)
+struct PackJob { const float *src; float *wf; float *wd; int cout, cin, taps; };
+void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int round_tf32, cudaStream_t st);
+// dW [Cout][Cin][k][k] = sum_s partial[s][tap][Cout][Cin]  (deterministic split-K reduce + re-layout)
+void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps, float *dw, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
+// SIMT fp32 implicit-GEMM convolution (simt_conv.cu): exact-fp32 device-side checker and the C1 stem path.
+void simt_conv_fprop(const ConvGeom &g, const float *x, const float *wf, float *y, cudaStream_t st);
+void simt_conv_dgrad(const ConvGeom &g, const float *dy, const float *wd, float *dx, int accumulate, cudaStream_t st);
+// writes dW in the public [Cout][Cin][k][k] layout (zeroes it first, split-K atomics)
+void simt_conv_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, cudaStream_t st);
+
+}  // namespace rb

@@ -1,0 +1,90 @@
+// engine.h -- private state behind the public resnet.h structs (side tables keyed by the public pointers, so
+// the public struct prefix stays byte-identical to the reference's).
+#pragma once
+#include "common.cuh"
+#include "igemm.h"
+#include "../../include/resnet.h"
+#include <vector>
+
+namespace rb {
+
+// One contiguous fp32 arena per Params tree; locations[i] are 256-byte aligned views in the reference's order
+// (reference: resnet.cu:839-943), so Adam / zeroing / allreduce are single passes over [base, base + total).
+struct ParamStore {
+	Params *tree;
+	float *base;
+	long long total;              // floats, including alignment padding (padding stays zero)
+	std::vector<long long> offs;  // per location
+};
+ParamStore *param_store_of(const Params *p);
+
+struct BnRef {
+	int C;
+	long long rows;
+	float *gamma, *beta, *dgamma, *dbeta;
+	float *means, *vars;
+	float *ab;  // [2][C] folded scale / shift of the current batch
+	Cache_BatchNorm *cache;
+};
+
+struct ConvRef {
+	ConvGeom g;
+	int loc;
+	float *w, *dw;    // public [Cout][Cin][k][k]
+	float *wf, *wd;   // packed
+	bool use_tc;
+	TcPlan *fprop, *dgrad, *wgrad;
+};
+
+struct BlockRef {
+	bool has_proj;
+	ConvRef reduce, spatial, expand, proj;
+	BnRef bn_r, bn_s, bn_e, bn_p;
+	const float *x_in;  // block input (previous block's output_activated / init_convblock_input)
+	float *Xr, *Yr, *Xs, *Ys, *Xe, *Xp, *OA;
+	// gradient buffers for this block (may alias scratch)
+	float *dOA, *dBI, *dXe, *dXp, *dYs, *dXs, *dYr, *dXr;
+	long long n_in, n_red_in, n_red_out, n_exp_out;
+};
+
+struct Engine {
+	Train_ResNet *trainer;
+	cudaStream_t stream;
+	int conv_mode;    // 0 = tcgen05 (default), 1 = simt fp32
+	int round_tf32;   // producers round conv inputs to tf32 (tensor-core mode only)
+	int keep_all;     // materialise every reference buffer (debug / parity)
+	int N;
+	// stem
+	ConvRef stem;
+	BnRef bn0;
+	float *X0, *Y0, *P0;  // init_conv_applied, init_conv_activated, init_convblock_input
+	int *max_inds;
+	float *dP0, *dY0, *dX0;
+	std::vector<BlockRef> blocks;
+	// head
+	float *pooled, *logits, *pred, *dlogits, *dpooled, *row_loss;
+	int *row_wrong;
+	float *pred_host;  // pinned
+	// workspaces
+	float *bn_partials;
+	int bn_max_blocks;
+	float *bn_coef;
+	float *wgrad_ws;
+	size_t wgrad_ws_bytes;
+	PackJob *pack_jobs_dev;
+	int n_pack_jobs, pack_max_elems;
+	float *ones, *zeros, *tmp_ab, *tmp_mv;  // keep-all helpers
+	int *bad_dev, *bad_host;
+	std::vector<void *> allocs;
+	// data-parallel hook (dp.cu)
+	void *dp;
+	// step timing
+	cudaEvent_t ev0, ev1;
+};
+Engine *engine_of(const Train_ResNet *t);
+
+// dp.cu
+void dp_block_done(Engine *e, int block);  // block's gradients are enqueued: issue the buckets that became complete
+void dp_allreduce_grads(Engine *e);       // end of backward: flush remaining buckets, compute stream waits
+
+}  // namespace rb

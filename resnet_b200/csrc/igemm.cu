@@ -1,0 +1,671 @@
+// igemm.cu -- tcgen05 / TMA implicit-GEMM convolution for sm_100a: fprop, dgrad (K-major operands) and wgrad
+// (MN-major operands), TF32 inputs with fp32 accumulation in TMEM.
+//
+// Replaces the reference's doConvolution / convolutionDerivInput / convolutionDerivWeights
+// (reference: resnet.cu:109-156, 166-219, 227-281 and their launchers 1386-1429).
+//
+// Data layout (DESIGN.md "HBM layout"): activations NHWC fp32; packed weights Wf[Cout][tap][Cin] (fprop) and
+// Wd[Cin][tap][Cout] (dgrad), both K-major for the GEMM that reads them.
+//
+// fprop / dgrad kernel (igemm_kmajor_kernel): D[128 pixels x BN] += A[128 x 32] * B[BN x 32]^T per pipeline stage.
+//   * A tile = a (bw x bh x bn) box of output pixels; for filter tap (kh, kw) the SAME box shifted by the tap
+//     offset is fetched by ONE 4-D TMA tiled load {32 ch, bw, bh, bn}; out-of-bounds coordinates are zero-filled
+//     by the TMA unit, which is exactly the convolution's zero padding (im2col never exists in memory).
+//     Stride-2 layers read through four "parity" tensor maps (even/odd rows x even/odd cols of the input), so
+//     every tap is again a dense shifted box.  Stride-2 dgrad is decomposed into the four output parities
+//     (1 + 2 + 2 + 4 taps): no multiply by structural zeros.
+//   * B tile = BN weight rows x 32 k via a 2-D TMA load.  Both tiles land in 128-byte-swizzled K-major layout,
+//     the canonical operand layout of tcgen05.mma (UMMA) descriptors.
+//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (4 x K=8 MMAs per stage);
+//     warps 2-5: epilogue (tcgen05.ld TMEM -> registers -> global), overlapped with the next tile's mainloop
+//     through a double-buffered TMEM accumulator (2 x BN <= 512 columns).  Persistent: one CTA per SM.
+//
+// wgrad kernel (igemm_mnmajor_kernel): dW[tap][128 co x BN ci] += dY[32 px x 128 co]^T * X_tap[32 px x BN ci].
+//   The reduction (GEMM K) runs over pixels, so both operands are MN-major straight out of NHWC memory:
+//   a TMA box of 32 pixels x 32 channels is one 128B-swizzled MN-major atom column.  Split-K over pixel ranges
+//   into a workspace, reduced deterministically (and re-laid to [Cout][Cin][kh][kw]) by wgrad_reduce.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "igemm.h"
+#include <algorithm>
+#include <vector>
+
+namespace rb {
+using namespace ptx;
+
+// ------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+	static EncodeTiledFn fn = nullptr;
+	if (!fn) {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+		if (e != cudaSuccess || !p) { set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e)); return nullptr; }
+		fn = (EncodeTiledFn)p;
+	}
+	return fn;
+}
+
+// rank-4 fp32 map, dims[0] innermost (channels), 128B swizzle, zero OOB fill. strides in ELEMENTS for dims 1..3.
+static bool make_map4(CUtensorMap *m, const float *base, const long long dims[4], const long long strides_elems[3], const int box[4]) {
+	EncodeTiledFn enc = get_encode();
+	if (!enc) return false;
+	cuuint64_t gd[4], gs[3];
+	cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+	for (int i = 0; i < 4; i++) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
+	for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides_elems[i] * sizeof(float);
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		set_error("cuTensorMapEncodeTiled(4d) failed: %d dims=(%lld,%lld,%lld,%lld) box=(%d,%d,%d,%d)", (int)r, dims[0], dims[1], dims[2],
+		          dims[3], box[0], box[1], box[2], box[3]);
+		return false;
+	}
+	return true;
+}
+static bool make_map2(CUtensorMap *m, const float *base, long long cols, long long rows, long long row_stride_elems, int box_cols, int box_rows) {
+	EncodeTiledFn enc = get_encode();
+	if (!enc) return false;
+	cuuint64_t gd[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)row_stride_elems * sizeof(float)};
+	cuuint32_t bx[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, es[2] = {1, 1};
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d cols=%lld rows=%lld box=(%d,%d)", (int)r, cols, rows, box_cols, box_rows); return false; }
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------ kernel parameters
+struct TapDesc { int dx, dy, amap, bcol; };
+struct GroupDesc { int ntaps, oh_off, ow_off, pad; TapDesc taps[9]; };
+
+struct alignas(64) IgemmParams {
+	CUtensorMap amap[4];
+	CUtensorMap bmap;
+	GroupDesc groups[4];
+	int ngroups;
+	int bw, bh, bn, tiles_w, tiles_h, tiles_b, m_tiles;
+	int Wm, Hm, Nn;
+	int kchunks;
+	int BN, n_tiles, Ncol;
+	int stages;
+	uint32_t a_bytes, b_bytes;
+	float *out;
+	int OH, OW, os, accumulate;
+};
+
+struct alignas(64) WgradParams {
+	CUtensorMap amap;
+	CUtensorMap bmap[4];
+	TapDesc taps[9];
+	int ntaps;
+	int bw, bh, bn, tiles_w, tiles_h, tiles_b, k_boxes;
+	int splits, boxes_per_split;
+	int co_tiles, ci_tiles, BN, cin, cout;
+	int stages;
+	uint32_t a_bytes, b_bytes, lbo, sbo;
+	float *partial;
+};
+
+constexpr int kIgemmThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kABytes = 128 * 32 * 4;  // 128 rows x 32 tf32 = 16 KB
+
+__device__ __forceinline__ uint8_t *align1024(uint8_t *p) {
+	return reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad
+__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t *base = align1024(smem_raw);
+	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+	uint64_t *full = reinterpret_cast<uint64_t *>(base + (size_t)p.stages * stage_bytes);
+	uint64_t *empty = full + p.stages;
+	uint64_t *tfull = empty + p.stages;
+	uint64_t *tempty = tfull + 2;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (warp == 0 && lane == 0) {
+		for (int i = 0; i < 4; i++) prefetch_tmap(&p.amap[i]);
+		prefetch_tmap(&p.bmap);
+	}
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+			fence_barrier_init();
+		}
+		__syncwarp();
+		tmem_alloc(tmem_slot, kTmemCols);
+		tmem_relinquish();
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			int stage = 0;
+			uint32_t phase = 0;
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				const int nt = tile % p.n_tiles;
+				int r = tile / p.n_tiles;
+				const int mt = r % p.m_tiles;
+				const GroupDesc &g = p.groups[r / p.m_tiles];
+				const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+				for (int t = 0; t < g.ntaps; t++) {
+					const TapDesc tp = g.taps[t];
+					for (int kc = 0; kc < p.kchunks; kc++) {
+						mbar_wait(&empty[stage], phase ^ 1);
+						uint8_t *sa = base + (size_t)stage * stage_bytes;
+						mbar_expect_tx(&full[stage], stage_bytes);
+						tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * 32, ow0 + tp.dx, oh0 + tp.dy, n0);
+						tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * 32, nt * p.BN);
+						if (++stage == p.stages) { stage = 0; phase ^= 1; }
+					}
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == 1) {
+		if (lane == 0) {
+			const uint32_t idesc = make_idesc_tf32(128, p.BN, 0, 0);
+			int stage = 0, acc = 0;
+			uint32_t phase = 0, accphase = 0;
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				const GroupDesc &g = p.groups[(tile / p.n_tiles) / p.m_tiles];
+				const int iters = g.ntaps * p.kchunks;
+				mbar_wait(&tempty[acc], accphase ^ 1);
+				tc_fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+				for (int it = 0; it < iters; it++) {
+					mbar_wait(&full[stage], phase);
+					tc_fence_after();
+					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
+					const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+					const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, 16, 1024);
+#pragma unroll
+					for (int k = 0; k < 4; k++) mma_tf32_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+					mma_commit(&empty[stage]);
+					if (++stage == p.stages) { stage = 0; phase ^= 1; }
+				}
+				mma_commit(&tfull[acc]);
+				acc ^= 1;
+				if (acc == 0) accphase ^= 1;
+			}
+		}
+		__syncwarp();
+	} else {
+		const int q = warp & 3;
+		const int row = q * 32 + lane;
+		const int wq = row % p.bw, hq = (row / p.bw) % p.bh, nq = row / (p.bw * p.bh);
+		int acc = 0;
+		uint32_t accphase = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			const int nt = tile % p.n_tiles;
+			int r = tile / p.n_tiles;
+			const int mt = r % p.m_tiles;
+			const GroupDesc &g = p.groups[r / p.m_tiles];
+			const int ow = (mt % p.tiles_w) * p.bw + wq, oh = ((mt / p.tiles_w) % p.tiles_h) * p.bh + hq, n = (mt / (p.tiles_w * p.tiles_h)) * p.bn + nq;
+			const bool valid = (nq < p.bn) && (ow < p.Wm) && (oh < p.Hm) && (n < p.Nn);
+			float *dst = p.out + (((size_t)n * p.OH + (size_t)(oh * p.os + g.oh_off)) * p.OW + (size_t)(ow * p.os + g.ow_off)) * p.Ncol + (size_t)nt * p.BN;
+			mbar_wait(&tfull[acc], accphase);
+			tc_fence_after();
+			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+			for (int c = 0; c < p.BN / 32; c++) {
+				float v[32];
+				tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+				if (valid) {
+					float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
+					if (p.accumulate) {
+#pragma unroll
+						for (int j = 0; j < 8; j++) {
+							float4 o = d4[j];
+							d4[j] = make_float4(o.x + v[4 * j], o.y + v[4 * j + 1], o.z + v[4 * j + 2], o.w + v[4 * j + 3]);
+						}
+					} else {
+#pragma unroll
+						for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					}
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&tempty[acc]);
+			acc ^= 1;
+			if (acc == 0) accphase ^= 1;
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tc_fence_after();
+		tmem_dealloc(tmem_base, kTmemCols);
+	}
+}
+
+// ------------------------------------------------------------------------------------------ wgrad
+__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const __grid_constant__ WgradParams p) {
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t *base = align1024(smem_raw);
+	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+	uint64_t *full = reinterpret_cast<uint64_t *>(base + (size_t)p.stages * stage_bytes);
+	uint64_t *empty = full + p.stages;
+	uint64_t *tfull = empty + p.stages;
+	uint64_t *tempty = tfull + 2;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (warp == 0 && lane == 0) {
+		prefetch_tmap(&p.amap);
+		for (int i = 0; i < 4; i++) prefetch_tmap(&p.bmap[i]);
+	}
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+			fence_barrier_init();
+		}
+		__syncwarp();
+		tmem_alloc(tmem_slot, kTmemCols);
+		tmem_relinquish();
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	// tile = ((tap * co_tiles + cot) * ci_tiles + cit) * splits + split
+	const int total_tiles = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
+	const int nb_boxes = p.BN / 32;
+	const uint32_t box_bytes = 32 * 128;  // 32 pixels x 32 channels x 4 B
+
+	if (warp == 0) {
+		if (lane == 0) {
+			int stage = 0;
+			uint32_t phase = 0;
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				const int split = tile % p.splits;
+				int r = tile / p.splits;
+				const int cit = r % p.ci_tiles; r /= p.ci_tiles;
+				const int cot = r % p.co_tiles;
+				const TapDesc tp = p.taps[r / p.co_tiles];
+				const int kb0 = split * p.boxes_per_split;
+				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
+				for (int kb = kb0; kb < kb1; kb++) {
+					const int ow0 = (kb % p.tiles_w) * p.bw, oh0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh, n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bn;
+					mbar_wait(&empty[stage], phase ^ 1);
+					uint8_t *sa = base + (size_t)stage * stage_bytes;
+					mbar_expect_tx(&full[stage], stage_bytes);
+					for (int j = 0; j < 4; j++) tma_load_4d(sa + j * box_bytes, &p.amap, &full[stage], cot * 128 + j * 32, ow0, oh0, n0);
+					for (int j = 0; j < nb_boxes; j++)
+						tma_load_4d(sa + p.a_bytes + j * box_bytes, &p.bmap[tp.amap], &full[stage], cit * p.BN + j * 32, ow0 + tp.dx, oh0 + tp.dy, n0);
+					if (++stage == p.stages) { stage = 0; phase ^= 1; }
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == 1) {
+		if (lane == 0) {
+			const uint32_t idesc = make_idesc_tf32(128, p.BN, 1, 1);
+			int stage = 0, acc = 0;
+			uint32_t phase = 0, accphase = 0;
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				const int split = tile % p.splits;
+				const int kb0 = split * p.boxes_per_split;
+				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
+				mbar_wait(&tempty[acc], accphase ^ 1);
+				tc_fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+				for (int kb = kb0; kb < kb1; kb++) {
+					mbar_wait(&full[stage], phase);
+					tc_fence_after();
+					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
+					const uint64_t adesc = make_smem_desc(a_addr, p.lbo, p.sbo);
+					const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo);
+#pragma unroll
+					for (int k = 0; k < 4; k++)  // 8 pixel rows (1024 B) per K=8 MMA
+						mma_tf32_ss(d_tmem, adesc + (uint64_t)(k * 64), bdesc + (uint64_t)(k * 64), idesc, (uint32_t)((kb > kb0) || (k != 0)));
+					mma_commit(&empty[stage]);
+					if (++stage == p.stages) { stage = 0; phase ^= 1; }
+				}
+				mma_commit(&tfull[acc]);
+				acc ^= 1;
+				if (acc == 0) accphase ^= 1;
+			}
+		}
+		__syncwarp();
+	} else {
+		const int q = warp & 3;
+		const int row = q * 32 + lane;
+		int acc = 0;
+		uint32_t accphase = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			const int split = tile % p.splits;
+			int r = tile / p.splits;
+			const int cit = r % p.ci_tiles; r /= p.ci_tiles;
+			const int cot = r % p.co_tiles;
+			const int tap = r / p.co_tiles;
+			const int co = cot * 128 + row;
+			const bool valid = co < p.cout;
+			float *dst = p.partial + (((size_t)split * p.ntaps + tap) * p.cout + co) * p.cin + (size_t)cit * p.BN;
+			mbar_wait(&tfull[acc], accphase);
+			tc_fence_after();
+			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+			for (int c = 0; c < p.BN / 32; c++) {
+				float v[32];
+				tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+				if (valid) {
+					float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
+#pragma unroll
+					for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&tempty[acc]);
+			acc ^= 1;
+			if (acc == 0) accphase ^= 1;
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tc_fence_after();
+		tmem_dealloc(tmem_base, kTmemCols);
+	}
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct TcPlan {
+	int kind;  // 0 = kmajor (fprop / dgrad), 1 = wgrad
+	IgemmParams ip;
+	WgradParams wp;
+	int grid;
+	size_t smem;
+	// wgrad epilogue
+	float *dw;
+	int cout, cin, taps;
+};
+
+static const size_t kMaxDynSmem = 227 * 1024;
+
+// choose a pixel box (bw, bh, bn) with product <= cap (exact == cap if exact) maximising coverage of (W, H, N)
+static void choose_box(int W, int H, int N, int cap, bool exact, int *bw, int *bh, int *bn) {
+	double best = -1;
+	*bw = 1; *bh = 1; *bn = cap;
+	for (int w = 1; w <= cap; w++) {
+		for (int h = 1; w * h <= cap; h++) {
+			int n = cap / (w * h);
+			if (exact && w * h * n != cap) continue;
+			if (n < 1) continue;
+			// boxes may overhang (TMA zero-fills), but avoid boxes larger than the tensor when another choice exists
+			double over = (w > W ? 0.5 : 1.0) * (h > H ? 0.5 : 1.0) * (n > N ? 0.75 : 1.0);
+			long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(N, n);
+			double util = (double)W * H * N / ((double)tiles * cap) * over;
+			util += 1e-6 * (w * h) + 1e-8 * w;  // tie-break: larger spatial patch (tap halo reuse), then wider rows
+			if (util > best) { best = util; *bw = w; *bh = h; *bn = n; }
+		}
+	}
+}
+
+static int pick_bn(int ncol) {
+	for (int bn : {256, 128, 64, 32})
+		if (ncol % bn == 0) return bn;
+	return 0;
+}
+
+bool tc_supported(const ConvGeom &g) {
+	if (g.cin % 32 || g.cout % 32) return false;
+	if (!(g.k == 1 || g.k == 3)) return false;
+	if (g.stride == 2 && (g.k != 3 || (g.S % 2))) return false;
+	if (g.stride != 1 && g.stride != 2) return false;
+	return true;
+}
+
+// parity decomposition of "stride*o + k - pad" for stride 2, k 3, pad 1:  k=0 -> (odd, o-1), k=1 -> (even, o), k=2 -> (odd, o)
+static void s2_tap(int kk, int *parity, int *d) {
+	if (kk == 0) { *parity = 1; *d = -1; }
+	else if (kk == 1) { *parity = 0; *d = 0; }
+	else { *parity = 1; *d = 0; }
+}
+
+// maps over an NHWC tensor [N][S][S][C] as seen by a conv of stride `stride`: 1 map (stride 1) or 4 parity maps
+static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int C, int stride, const int box[4], bool flat) {
+	if (flat) {  // 1x1: pixels are a flat list
+		long long P = (long long)N * S * S;
+		long long dims[4] = {C, P, 1, 1}, str[3] = {C, P * C, P * C};
+		return make_map4(&maps[0], x, dims, str, box);
+	}
+	if (stride == 1) {
+		long long dims[4] = {C, S, S, N}, str[3] = {C, (long long)S * C, (long long)S * S * C};
+		return make_map4(&maps[0], x, dims, str, box);
+	}
+	for (int ph = 0; ph < 2; ph++)
+		for (int pw = 0; pw < 2; pw++) {
+			long long dims[4] = {C, S / 2, S / 2, N}, str[3] = {2LL * C, 2LL * S * C, (long long)S * S * C};
+			if (!make_map4(&maps[ph * 2 + pw], x + ((long long)ph * S + pw) * C, dims, str, box)) return false;
+		}
+	return true;
+}
+
+static void finish_kmajor(TcPlan *pl) {
+	IgemmParams &p = pl->ip;
+	p.a_bytes = kABytes;
+	p.b_bytes = (uint32_t)p.BN * 128;
+	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
+	p.stages = stages > 8 ? 8 : stages;
+	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+	const int total = p.ngroups * p.m_tiles * p.n_tiles;
+	pl->grid = total < kNumSMs ? total : kNumSMs;
+	pl->kind = 0;
+}
+
+TcPlan *tc_make_fprop(const ConvGeom &g, const float *x, const float *wf, float *y) {
+	if (!tc_supported(g)) { set_error("tc_make_fprop: unsupported geometry"); return nullptr; }
+	TcPlan *pl = new TcPlan();
+	memset(pl, 0, sizeof(*pl));
+	IgemmParams &p = pl->ip;
+	const int So = g.So();
+	const bool flat = (g.k == 1);
+	if (flat) { p.Wm = (int)((long long)g.N * So * So); p.Hm = 1; p.Nn = 1; p.bw = 128; p.bh = 1; p.bn = 1; }
+	else { p.Wm = So; p.Hm = So; p.Nn = g.N; choose_box(So, So, g.N, 128, false, &p.bw, &p.bh, &p.bn); }
+	p.tiles_w = ceil_div(p.Wm, p.bw); p.tiles_h = ceil_div(p.Hm, p.bh); p.tiles_b = ceil_div(p.Nn, p.bn);
+	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+	p.Ncol = g.cout; p.BN = pick_bn(g.cout); p.n_tiles = g.cout / p.BN;
+	p.kchunks = g.cin / 32;
+	const int box[4] = {32, p.bw, p.bh, p.bn};
+	bool ok = make_input_maps(p.amap, x, g.N, g.S, g.cin, g.stride, box, flat);
+	for (int i = 1; i < 4; i++) if (g.stride == 1) p.amap[i] = p.amap[0];
+	ok = ok && make_map2(&p.bmap, wf, (long long)g.taps() * g.cin, g.cout, (long long)g.taps() * g.cin, 32, p.BN);
+	p.ngroups = 1;
+	GroupDesc &gr = p.groups[0];
+	gr.oh_off = gr.ow_off = 0;
+	gr.ntaps = g.taps();
+	for (int kh = 0; kh < g.k; kh++)
+		for (int kw = 0; kw < g.k; kw++) {
+			TapDesc &t = gr.taps[kh * g.k + kw];
+			t.bcol = (kh * g.k + kw) * g.cin;
+			if (g.k == 1) { t.dx = t.dy = 0; t.amap = 0; }
+			else if (g.stride == 1) { t.dx = kw - 1; t.dy = kh - 1; t.amap = 0; }
+			else { int ph, pw; s2_tap(kh, &ph, &t.dy); s2_tap(kw, &pw, &t.dx); t.amap = ph * 2 + pw; }
+		}
+	p.out = y;
+	if (flat) { p.OH = 1; p.OW = p.Wm; } else { p.OH = So; p.OW = So; }
+	p.os = 1; p.accumulate = 0;
+	finish_kmajor(pl);
+	if (!ok) { delete pl; return nullptr; }
+	return pl;
+}
+
+TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float *dx, int accumulate) {
+	if (!tc_supported(g)) { set_error("tc_make_dgrad: unsupported geometry"); return nullptr; }
+	TcPlan *pl = new TcPlan();
+	memset(pl, 0, sizeof(*pl));
+	IgemmParams &p = pl->ip;
+	const int So = g.So();
+	const bool flat = (g.k == 1);
+	// GEMM-M space: input pixels (stride 1) or one output-parity class of them (stride 2) == the dy grid
+	if (flat) { p.Wm = (int)((long long)g.N * So * So); p.Hm = 1; p.Nn = 1; p.bw = 128; p.bh = 1; p.bn = 1; }
+	else { p.Wm = So; p.Hm = So; p.Nn = g.N; choose_box(So, So, g.N, 128, false, &p.bw, &p.bh, &p.bn); }
+	p.tiles_w = ceil_div(p.Wm, p.bw); p.tiles_h = ceil_div(p.Hm, p.bh); p.tiles_b = ceil_div(p.Nn, p.bn);
+	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+	p.Ncol = g.cin; p.BN = pick_bn(g.cin); p.n_tiles = g.cin / p.BN;
+	p.kchunks = g.cout / 32;
+	const int box[4] = {32, p.bw, p.bh, p.bn};
+	bool ok = make_input_maps(p.amap, dy, g.N, So, g.cout, 1, box, flat);
+	for (int i = 1; i < 4; i++) p.amap[i] = p.amap[0];
+	ok = ok && make_map2(&p.bmap, wd, (long long)g.taps() * g.cout, g.cin, (long long)g.taps() * g.cout, 32, p.BN);
+	p.out = dx;
+	p.accumulate = accumulate;
+	if (g.k == 1) {
+		p.ngroups = 1;
+		p.groups[0].ntaps = 1; p.groups[0].oh_off = p.groups[0].ow_off = 0;
+		p.groups[0].taps[0] = TapDesc{0, 0, 0, 0};
+		p.OH = 1; p.OW = p.Wm; p.os = 1;
+	} else if (g.stride == 1) {
+		p.ngroups = 1;
+		GroupDesc &gr = p.groups[0];
+		gr.ntaps = 9; gr.oh_off = gr.ow_off = 0;
+		for (int kh = 0; kh < 3; kh++)
+			for (int kw = 0; kw < 3; kw++) gr.taps[kh * 3 + kw] = TapDesc{1 - kw, 1 - kh, 0, (kh * 3 + kw) * g.cout};
+		p.OH = g.S; p.OW = g.S; p.os = 1;
+	} else {
+		// dx[2h'+ph] gathers dy[h' + d] * W[kh]:  ph = 0 -> (kh 1, d 0);  ph = 1 -> (kh 0, d +1), (kh 2, d 0)
+		p.ngroups = 4;
+		const int order[4][2] = {{1, 1}, {1, 0}, {0, 1}, {0, 0}};  // heaviest first
+		for (int gi = 0; gi < 4; gi++) {
+			const int ph = order[gi][0], pw = order[gi][1];
+			GroupDesc &gr = p.groups[gi];
+			gr.oh_off = ph; gr.ow_off = pw; gr.ntaps = 0;
+			int khs[2], dhs[2], nh, kws[2], dws[2], nw;
+			if (ph == 0) { nh = 1; khs[0] = 1; dhs[0] = 0; } else { nh = 2; khs[0] = 0; dhs[0] = 1; khs[1] = 2; dhs[1] = 0; }
+			if (pw == 0) { nw = 1; kws[0] = 1; dws[0] = 0; } else { nw = 2; kws[0] = 0; dws[0] = 1; kws[1] = 2; dws[1] = 0; }
+			for (int a = 0; a < nh; a++)
+				for (int b = 0; b < nw; b++) gr.taps[gr.ntaps++] = TapDesc{dws[b], dhs[a], 0, (khs[a] * 3 + kws[b]) * g.cout};
+		}
+		p.OH = g.S; p.OW = g.S; p.os = 2;
+	}
+	finish_kmajor(pl);
+	if (!ok) { delete pl; return nullptr; }
+	return pl;
+}
+
+size_t tc_wgrad_workspace_bytes(const ConvGeom &g) {
+	// mirrors the split choice in tc_make_wgrad
+	const int So = g.So();
+	int bw, bh, bn;
+	const bool flat = (g.k == 1);
+	long long k_boxes;
+	if (flat) k_boxes = ceil_div((long long)g.N * So * So, 32);
+	else { choose_box(So, So, g.N, 32, true, &bw, &bh, &bn); k_boxes = (long long)ceil_div(So, bw) * ceil_div(So, bh) * ceil_div(g.N, bn); }
+	const int BN = pick_bn(g.cin);
+	const int tiles = g.taps() * ceil_div(g.cout, 128) * (g.cin / BN);
+	long long splits = ceil_div(2 * kNumSMs, tiles);
+	if (splits > k_boxes) splits = k_boxes;
+	if (splits < 1) splits = 1;
+	const long long bps = ceil_div(k_boxes, splits);
+	splits = ceil_div(k_boxes, bps);
+	return (size_t)splits * g.taps() * g.cout * g.cin * sizeof(float);
+}
+
+TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *workspace, size_t ws_bytes) {
+	if (!tc_supported(g)) { set_error("tc_make_wgrad: unsupported geometry"); return nullptr; }
+	TcPlan *pl = new TcPlan();
+	memset(pl, 0, sizeof(*pl));
+	WgradParams &p = pl->wp;
+	const int So = g.So();
+	const bool flat = (g.k == 1);
+	int Wm, Hm, Nn;
+	if (flat) { Wm = (int)((long long)g.N * So * So); Hm = 1; Nn = 1; p.bw = 32; p.bh = 1; p.bn = 1; }
+	else { Wm = So; Hm = So; Nn = g.N; choose_box(So, So, g.N, 32, true, &p.bw, &p.bh, &p.bn); }
+	p.tiles_w = ceil_div(Wm, p.bw); p.tiles_h = ceil_div(Hm, p.bh); p.tiles_b = ceil_div(Nn, p.bn);
+	p.k_boxes = p.tiles_w * p.tiles_h * p.tiles_b;
+	p.cin = g.cin; p.cout = g.cout;
+	p.BN = pick_bn(g.cin);
+	p.ci_tiles = g.cin / p.BN;
+	p.co_tiles = ceil_div(g.cout, 128);
+	p.ntaps = g.taps();
+	const int tiles = p.ntaps * p.co_tiles * p.ci_tiles;
+	int splits = ceil_div(2 * kNumSMs, tiles);
+	if (splits > p.k_boxes) splits = p.k_boxes;
+	if (splits < 1) splits = 1;
+	p.boxes_per_split = ceil_div(p.k_boxes, splits);
+	p.splits = ceil_div(p.k_boxes, p.boxes_per_split);
+	if ((size_t)p.splits * p.ntaps * g.cout * g.cin * sizeof(float) > ws_bytes) { set_error("tc_make_wgrad: workspace too small"); delete pl; return nullptr; }
+	const int box[4] = {32, p.bw, p.bh, p.bn};
+	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat);
+	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat);
+	if (g.stride == 1) for (int i = 1; i < 4; i++) p.bmap[i] = p.bmap[0];
+	for (int kh = 0; kh < g.k; kh++)
+		for (int kw = 0; kw < g.k; kw++) {
+			TapDesc &t = p.taps[kh * g.k + kw];
+			t.bcol = 0;
+			if (g.k == 1) { t.dx = t.dy = 0; t.amap = 0; }
+			else if (g.stride == 1) { t.dx = kw - 1; t.dy = kh - 1; t.amap = 0; }
+			else { int ph, pw; s2_tap(kh, &ph, &t.dy); s2_tap(kw, &pw, &t.dx); t.amap = ph * 2 + pw; }
+		}
+	p.a_bytes = 4 * 32 * 128;
+	p.b_bytes = (uint32_t)(p.BN / 32) * 32 * 128;
+	// MN-major, 128B swizzle: LBO = distance between 32-channel column blocks (one TMA box), SBO = 8-row group pitch
+	p.lbo = 32 * 128;
+	p.sbo = 1024;
+	if (const char *e = getenv("RESNET_B200_WGRAD_DESC")) {  // bring-up aid: "lbo,sbo"
+		unsigned a, b;
+		if (sscanf(e, "%u,%u", &a, &b) == 2) { p.lbo = a; p.sbo = b; }
+	}
+	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
+	p.stages = stages > 8 ? 8 : stages;
+	p.partial = workspace;
+	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+	const int total = tiles * p.splits;
+	pl->grid = total < kNumSMs ? total : kNumSMs;
+	pl->kind = 1;
+	pl->dw = dw; pl->cout = g.cout; pl->cin = g.cin; pl->taps = g.taps();
+	if (!ok) { delete pl; return nullptr; }
+	return pl;
+}
+
+void tc_run(TcPlan *pl, cudaStream_t st) {
+	if (!pl) { set_error("tc_run: null plan"); return; }
+	static bool attr_set = false;
+	if (!attr_set) {
+		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		attr_set = true;
+	}
+	if (pl->kind == 0) {
+		igemm_kmajor_kernel<<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->ip);
+		RB_LAUNCH_CHECK();
+	} else {
+		igemm_mnmajor_kernel<<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
+		RB_LAUNCH_CHECK();
+		wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
+	}
+}
+
+void tc_free(TcPlan *pl) { delete pl; }
+
+void tc_describe(const TcPlan *pl, char *buf, size_t n) {
+	if (!pl) { snprintf(buf, n, "null"); return; }
+	if (pl->kind == 0) {
+		const IgemmParams &p = pl->ip;
+		snprintf(buf, n, "kmajor box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu", p.bw, p.bh, p.bn,
+		         p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem);
+	} else {
+		const WgradParams &p = pl->wp;
+		snprintf(buf, n, "wgrad box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d stages=%d grid=%d smem=%zu", p.bw, p.bh,
+		         p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.stages, pl->grid, pl->smem);
+	}
+}
+
+}  // namespace rb

@@ -1,0 +1,653 @@
+// model.cu -- the reference's entry points (resnet.h) on the B200 path: allocation (init_*), forward_pass,
+// backwards_pass, update_parameters, load_new_batch.
+//
+// reference: resnet.cu:666-1231 (init_*), 1235-1381 (loader, class metadata), 1526-1775 (forward_pass),
+// 1777-2248 (backwards_pass; block wiring per resnet_clean.cu:2459-2958), 2910-2987 (update_parameters).
+//
+// Differences that are deliberate: arena allocation instead of ~1400 cudaMallocs; nothing is
+// allocated inside the step; fused kernels (BN apply + residual + ReLU; Adam m/v/p + grad zeroing); recomputable
+// buffers (x-hat, pre-ReLU sums) exist only in keep-all mode; one stream instead of the legacy default stream.
+#include "engine.h"
+#include <curand.h>
+#include <map>
+#include <mutex>
+
+namespace rb {
+
+static std::map<const Params *, ParamStore *> g_param_stores;
+static std::map<const Train_ResNet *, Engine *> g_engines;
+static std::mutex g_mu;
+
+ParamStore *param_store_of(const Params *p) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	auto it = g_param_stores.find(p);
+	return it == g_param_stores.end() ? nullptr : it->second;
+}
+Engine *engine_of(const Train_ResNet *t) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	auto it = g_engines.find(t);
+	return it == g_engines.end() ? nullptr : it->second;
+}
+
+static int env_int(const char *name, int dflt) {
+	const char *v = getenv(name);
+	return v ? atoi(v) : dflt;
+}
+
+static long long align_up(long long n, long long a) { return (n + a - 1) / a * a; }
+
+__global__ void fill_kernel(float *p, long long n, float v) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+static void fill(float *p, long long n, float v, cudaStream_t st) {
+	if (n <= 0) return;
+	int grid = (int)((n + 255) / 256);
+	fill_kernel<<<grid > 2048 ? 2048 : grid, 256, 0, st>>>(p, n, v);
+	RB_LAUNCH_CHECK();
+}
+
+// d = pred - onehot (reference: resnet.cu:1800-1804 memcpy + crossEntropyDeriv; no 1/N, 1806-1811)
+__global__ void ce_deriv_kernel(const float *__restrict__ pred, const int *__restrict__ labels, int N, int L, float *__restrict__ d) {
+	const long long total = (long long)N * L;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const int row = (int)(i / L), col = (int)(i % L);
+		d[i] = pred[i] - (labels[row] == col ? 1.f : 0.f);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ parameters
+// Builds a Params tree over one arena.  gen != NULL: weights ~ N(0, 2/(fan_in+fan_out)), FC ~ N(0, 1e-4), gamma 1,
+// beta 0, drawn with curandGenerateNormal in the reference's order (reference: resnet.cu:730,741,754,790,835,938)
+// so the same generator seed reproduces the reference's initial bytes.  gen == NULL: all zeros (is_zero).
+static Params *make_params(Dims *d, curandGenerator_t *gen) {
+	const int nb = d->n_conv_blocks;
+	Params *P = (Params *)calloc(1, sizeof(Params));
+	P->n_locations = 16 + 9 * nb;  // reference: resnet.cu:819 (upper bound; trailing entries unused)
+	P->locations = (float **)calloc(P->n_locations, sizeof(float *));
+	P->sizes = (int *)calloc(P->n_locations, sizeof(int));
+	P->conv_blocks = (ConvBlock **)calloc(nb, sizeof(ConvBlock *));
+
+	struct Spec { long long size; int kind; float var; };  // kind 0 weight, 1 gamma, 2 beta
+	std::vector<Spec> specs;
+	auto add_conv = [&](int cout, int cin, int k) {
+		specs.push_back({(long long)cout * cin * k * k, 0, 2.0f / (float)(k * k * (cin + cout))});
+		specs.push_back({cout, 1, 0.f});
+		specs.push_back({cout, 2, 0.f});
+	};
+	add_conv(d->init_conv_filters, 3, d->init_kernel_dim);
+	int incoming = d->init_conv_filters, spatial = d->input / 4, reduced = d->init_conv_filters, expanded = 4 * d->init_conv_filters;
+	struct BlkDims { int incoming, spatial, reduced, expanded, stride; bool proj; };
+	std::vector<BlkDims> bd;
+	for (int i = 0; i < nb; i++) {
+		int stride = 1;
+		if (d->is_block_spatial_reduction[i] == 1) { stride = 2; reduced *= 2; expanded *= 2; }
+		const bool proj = incoming != expanded;
+		bd.push_back({incoming, spatial, reduced, expanded, stride, proj});
+		add_conv(reduced, incoming, 1);
+		add_conv(reduced, reduced, 3);
+		add_conv(expanded, reduced, 1);
+		if (proj) add_conv(expanded, incoming, stride == 2 ? 3 : 1);
+		if (stride == 2) spatial /= 2;
+		incoming = expanded;
+	}
+	specs.push_back({(long long)expanded * d->output, 0, 0.0001f});
+	const int nloc = (int)specs.size();
+	if (nloc > P->n_locations) { set_error("make_params: location overflow"); return nullptr; }
+	P->n_locations = nloc;  // equals 16 + 9*nb for ResNet-50's four projections (reference: resnet.cu:819)
+
+	ParamStore *ps = new ParamStore();
+	ps->tree = P;
+	long long off = 0;
+	for (auto &s : specs) { ps->offs.push_back(off); off += align_up(s.size, 64); }
+	ps->total = off;
+	RB_CUDA(cudaMalloc(&ps->base, ps->total * sizeof(float)));
+	RB_CUDA(cudaMemset(ps->base, 0, ps->total * sizeof(float)));
+	for (int i = 0; i < nloc; i++) {
+		P->locations[i] = ps->base + ps->offs[i];
+		P->sizes[i] = (int)specs[i].size;
+		if (gen) {
+			if (specs[i].kind == 0) {
+				curandStatus_t cs = curandGenerateNormal(*gen, P->locations[i], (size_t)specs[i].size, 0.f, sqrtf(specs[i].var));
+				if (cs != CURAND_STATUS_SUCCESS) set_error("curandGenerateNormal failed (%d) at location %d", (int)cs, i);
+			} else if (specs[i].kind == 1) fill(P->locations[i], specs[i].size, 1.0f, 0);
+		}
+	}
+	RB_CUDA(cudaDeviceSynchronize());
+
+	auto mk_bn = [&](int loc, int sp, int depth) {
+		BatchNorm *b = (BatchNorm *)calloc(1, sizeof(BatchNorm));
+		b->spatial_dim = sp; b->depth = depth; b->gamma = P->locations[loc + 1]; b->beta = P->locations[loc + 2];
+		return b;
+	};
+	int li = 0;
+	P->init_conv_layer = P->locations[0];
+	P->norm_init_conv = mk_bn(0, d->input / d->init_conv_stride, d->init_conv_filters);
+	li = 3;
+	for (int i = 0; i < nb; i++) {
+		const BlkDims &b = bd[i];
+		ConvBlock *cb = (ConvBlock *)calloc(1, sizeof(ConvBlock));
+		cb->incoming_filters = b.incoming; cb->incoming_spatial_dim = b.spatial; cb->reduced_depth = b.reduced;
+		cb->expanded_depth = b.expanded; cb->stride = b.stride;
+		const int sp_out = b.spatial / b.stride;
+		cb->depth_reduction = P->locations[li]; cb->norm_depth_reduction = mk_bn(li, b.spatial, b.reduced);
+		cb->spatial = P->locations[li + 3]; cb->norm_spatial = mk_bn(li + 3, sp_out, b.reduced);
+		cb->depth_expansion = P->locations[li + 6]; cb->norm_expansion = mk_bn(li + 6, sp_out, b.expanded);
+		if (b.proj) { cb->projection = P->locations[li + 9]; cb->norm_projection = mk_bn(li + 9, sp_out, b.expanded); li += 12; }
+		else { cb->projection = NULL; cb->norm_projection = NULL; li += 9; }
+		P->conv_blocks[i] = cb;
+	}
+	P->fully_connected = P->locations[li];
+	{
+		std::lock_guard<std::mutex> lk(g_mu);
+		g_param_stores[P] = ps;
+	}
+	return P;
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct Bump {
+	Engine *e;
+	template <typename T> T *get(long long n) {
+		if (n <= 0) n = 1;
+		void *p = nullptr;
+		RB_CUDA(cudaMalloc(&p, (size_t)align_up(n * (long long)sizeof(T), 256)));
+		e->allocs.push_back(p);
+		return (T *)p;
+	}
+};
+
+static Cache_BatchNorm *mk_cache(Bump &B, long long input_size, int C, bool keep_all, bool with_stats) {
+	Cache_BatchNorm *c = (Cache_BatchNorm *)calloc(1, sizeof(Cache_BatchNorm));
+	c->input_size = (int)input_size; c->feature_size = C;
+	if (with_stats) { c->means = B.get<float>(C); c->vars = B.get<float>(C); }
+	if (keep_all) { c->normalized_temp = B.get<float>(input_size); c->normalized = B.get<float>(input_size); }
+	return c;
+}
+
+static void setup_conv(Engine *e, Bump &B, ConvRef &c, int N, int S, int cin, int cout, int k, int stride, int loc, Params *P, Params *G,
+                       std::vector<PackJob> &jobs) {
+	c.g = ConvGeom{N, S, cin, cout, k, stride};
+	c.loc = loc;
+	c.w = P->locations[loc];
+	c.dw = G->locations[loc];
+	c.wf = B.get<float>(c.g.w_elems());
+	c.wd = B.get<float>(c.g.w_elems());
+	c.use_tc = (e->conv_mode == 0) && tc_supported(c.g);
+	c.fprop = c.dgrad = c.wgrad = nullptr;
+	jobs.push_back(PackJob{c.w, c.wf, c.wd, cout, cin, k * k});
+	if (c.use_tc) {
+		size_t ws = tc_wgrad_workspace_bytes(c.g);
+		if (ws > e->wgrad_ws_bytes) e->wgrad_ws_bytes = ws;
+	}
+}
+
+static BnRef mk_bnref(Bump &B, BatchNorm *p, BatchNorm *gp, Cache_BatchNorm *cache, long long rows) {
+	BnRef r;
+	r.C = p->depth; r.rows = rows; r.gamma = p->gamma; r.beta = p->beta; r.dgamma = gp->gamma; r.dbeta = gp->beta;
+	r.means = cache->means; r.vars = cache->vars; r.cache = cache;
+	r.ab = B.get<float>(2 * (long long)p->depth);
+	return r;
+}
+
+static Engine *build_engine(Train_ResNet *t) {
+	Engine *e = new Engine();
+	e->trainer = t;
+	e->N = t->batch_size;
+	const char *cm = getenv("RESNET_B200_CONV");
+	e->conv_mode = (cm && !strcmp(cm, "simt")) ? 1 : 0;
+	e->round_tf32 = (e->conv_mode == 0) ? env_int("RESNET_B200_TF32_ROUND", 1) : 0;
+	e->keep_all = env_int("RESNET_B200_KEEP_ALL", 0);
+	e->dp = nullptr;
+	e->wgrad_ws_bytes = 0;
+	RB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	RB_CUDA(cudaEventCreate(&e->ev0));
+	RB_CUDA(cudaEventCreate(&e->ev1));
+	Bump B{e};
+	Dims *d = t->model->dims;
+	Params *P = t->model->params;
+	const int N = e->N, nb = d->n_conv_blocks;
+	const bool ka = e->keep_all != 0;
+
+	// ---- public structs: forward buffer
+	Forward_Buffer *fb = (Forward_Buffer *)calloc(1, sizeof(Forward_Buffer));
+	Backprop_Buffer *bb = (Backprop_Buffer *)calloc(1, sizeof(Backprop_Buffer));
+	t->forward_buffer = fb;
+	t->backprop_buffer = bb;
+	bb->param_derivs = make_params(d, nullptr);
+	bb->prev_means = make_params(d, nullptr);
+	bb->prev_vars = make_params(d, nullptr);
+	Params *G = bb->param_derivs;
+	Activations *A = (Activations *)calloc(1, sizeof(Activations));
+	Activations *DA = (Activations *)calloc(1, sizeof(Activations));
+	fb->activations = A;
+	bb->activation_derivs = DA;
+	A->n_conv_blocks = DA->n_conv_blocks = nb;
+	A->activation_conv_blocks = (Activation_ConvBlock **)calloc(nb, sizeof(Activation_ConvBlock *));
+	DA->activation_conv_blocks = (Activation_ConvBlock **)calloc(nb, sizeof(Activation_ConvBlock *));
+
+	std::vector<PackJob> jobs;
+	const int S0 = d->input, S1 = d->input / d->init_conv_stride, S2 = S1 / d->init_maxpool_stride, F = d->init_conv_filters;
+	const long long n_x0 = (long long)N * S1 * S1 * F, n_p0 = (long long)N * S2 * S2 * F;
+	setup_conv(e, B, e->stem, N, S0, 3, F, d->init_kernel_dim, d->init_conv_stride, 0, P, G, jobs);
+	e->X0 = A->init_conv_applied = B.get<float>(n_x0);
+	A->norm_init_conv = mk_cache(B, n_x0, F, ka, true);
+	e->Y0 = A->init_conv_activated = B.get<float>(n_x0);
+	e->max_inds = A->max_inds = B.get<int>(n_p0);
+	e->P0 = A->init_convblock_input = B.get<float>(n_p0);
+	e->bn0 = mk_bnref(B, P->norm_init_conv, G->norm_init_conv, A->norm_init_conv, (long long)N * S1 * S1);
+
+	// ---- blocks
+	e->blocks.resize(nb);
+	long long max_exp_out = n_p0, max_red_in = 1, max_red_out = 1;
+	const float *x_in = e->P0;
+	for (int i = 0; i < nb; i++) {
+		ConvBlock *cb = P->conv_blocks[i], *gcb = G->conv_blocks[i];
+		BlockRef &b = e->blocks[i];
+		Activation_ConvBlock *ab = (Activation_ConvBlock *)calloc(1, sizeof(Activation_ConvBlock));
+		A->activation_conv_blocks[i] = ab;
+		ab->incoming_filters = cb->incoming_filters; ab->incoming_spatial_dim = cb->incoming_spatial_dim;
+		ab->reduced_depth = cb->reduced_depth; ab->expanded_depth = cb->expanded_depth; ab->stride = cb->stride;
+		const int Sin = cb->incoming_spatial_dim, Sout = Sin / cb->stride;
+		b.has_proj = cb->projection != NULL;
+		b.n_in = (long long)N * Sin * Sin * cb->incoming_filters;
+		b.n_red_in = (long long)N * Sin * Sin * cb->reduced_depth;
+		b.n_red_out = (long long)N * Sout * Sout * cb->reduced_depth;
+		b.n_exp_out = (long long)N * Sout * Sout * cb->expanded_depth;
+		max_exp_out = std::max(max_exp_out, std::max(b.n_exp_out, b.n_in));
+		max_red_in = std::max(max_red_in, b.n_red_in);
+		max_red_out = std::max(max_red_out, b.n_red_out);
+		int li = 0;
+		for (int l = 0; l < P->n_locations; l++) if (P->locations[l] == cb->depth_reduction) { li = l; break; }
+		setup_conv(e, B, b.reduce, N, Sin, cb->incoming_filters, cb->reduced_depth, 1, 1, li, P, G, jobs);
+		setup_conv(e, B, b.spatial, N, Sin, cb->reduced_depth, cb->reduced_depth, 3, cb->stride, li + 3, P, G, jobs);
+		setup_conv(e, B, b.expand, N, Sout, cb->reduced_depth, cb->expanded_depth, 1, 1, li + 6, P, G, jobs);
+		if (b.has_proj) setup_conv(e, B, b.proj, N, Sin, cb->incoming_filters, cb->expanded_depth, cb->stride == 2 ? 3 : 1, cb->stride, li + 9, P, G, jobs);
+		b.x_in = x_in;
+		b.Xr = ab->post_reduced = B.get<float>(b.n_red_in);
+		ab->norm_post_reduced = mk_cache(B, b.n_red_in, cb->reduced_depth, ka, true);
+		b.Yr = ab->post_reduced_activated = B.get<float>(b.n_red_in);
+		b.Xs = ab->post_spatial = B.get<float>(b.n_red_out);
+		ab->norm_post_spatial = mk_cache(B, b.n_red_out, cb->reduced_depth, ka, true);
+		b.Ys = ab->post_spatial_activated = B.get<float>(b.n_red_out);
+		b.Xe = ab->post_expanded = B.get<float>(b.n_exp_out);
+		ab->norm_post_expanded = mk_cache(B, b.n_exp_out, cb->expanded_depth, ka, true);
+		ab->post_expanded_norm_vals = ka ? B.get<float>(b.n_exp_out) : NULL;
+		if (b.has_proj) {
+			b.Xp = ab->transformed_residual = B.get<float>(b.n_exp_out);
+			ab->norm_post_projection = mk_cache(B, b.n_exp_out, cb->expanded_depth, ka, true);
+			ab->post_projection_norm_vals = ka ? B.get<float>(b.n_exp_out) : NULL;
+		} else { b.Xp = NULL; }
+		ab->output = ka ? B.get<float>(b.n_exp_out) : NULL;
+		b.OA = ab->output_activated = B.get<float>(b.n_exp_out);
+		b.bn_r = mk_bnref(B, cb->norm_depth_reduction, gcb->norm_depth_reduction, ab->norm_post_reduced, (long long)N * Sin * Sin);
+		b.bn_s = mk_bnref(B, cb->norm_spatial, gcb->norm_spatial, ab->norm_post_spatial, (long long)N * Sout * Sout);
+		b.bn_e = mk_bnref(B, cb->norm_expansion, gcb->norm_expansion, ab->norm_post_expanded, (long long)N * Sout * Sout);
+		if (b.has_proj) b.bn_p = mk_bnref(B, cb->norm_projection, gcb->norm_projection, ab->norm_post_projection, (long long)N * Sout * Sout);
+		x_in = b.OA;
+	}
+	// ---- head
+	e->pooled = A->final_conv_output_pooled = B.get<float>((long long)N * d->final_depth);
+	e->logits = A->linear_output = B.get<float>((long long)N * d->output);
+	e->pred = fb->pred = B.get<float>((long long)N * d->output);
+	RB_CUDA(cudaMallocHost(&e->pred_host, (size_t)N * d->output * sizeof(float)));
+	fb->pred_cpu = e->pred_host;
+	e->dlogits = bb->output_layer_deriv = B.get<float>((long long)N * d->output);
+	e->dpooled = DA->final_conv_output_pooled = B.get<float>((long long)N * d->final_depth);
+	DA->linear_output = e->dlogits;
+	e->row_loss = B.get<float>(N);
+	e->row_wrong = B.get<int>(N);
+
+	// ---- gradient buffers: per-role scratch (default) or a full mirror (keep-all)
+	float *pp[2] = {nullptr, nullptr}, *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;
+	if (!ka) {
+		pp[0] = B.get<float>(max_exp_out); pp[1] = B.get<float>(max_exp_out);
+		T1 = B.get<float>(max_exp_out); T2 = B.get<float>(max_red_out); T3 = B.get<float>(max_red_in);
+	}
+	e->dP0 = DA->init_convblock_input = ka ? B.get<float>(n_p0) : pp[1];  // block 0 writes its input gradient into pp[(0+1)&1]
+	e->dY0 = DA->init_conv_activated = B.get<float>(n_x0);
+	e->dX0 = DA->init_conv_applied = ka ? B.get<float>(n_x0) : e->dY0;
+	DA->norm_init_conv = mk_cache(B, n_x0, F, false, false);
+	DA->max_inds = NULL;
+	for (int i = 0; i < nb; i++) {
+		BlockRef &b = e->blocks[i];
+		Activation_ConvBlock *ab = A->activation_conv_blocks[i];
+		Activation_ConvBlock *db = (Activation_ConvBlock *)calloc(1, sizeof(Activation_ConvBlock));
+		*db = *ab;
+		DA->activation_conv_blocks[i] = db;
+		db->norm_post_reduced = db->norm_post_spatial = db->norm_post_expanded = db->norm_post_projection = NULL;
+		db->post_expanded_norm_vals = db->post_projection_norm_vals = db->output = NULL;
+		if (ka) {
+			b.dOA = B.get<float>(b.n_exp_out);
+			b.dXe = B.get<float>(b.n_exp_out);
+			b.dXp = b.has_proj ? B.get<float>(b.n_exp_out) : NULL;
+			b.dYs = B.get<float>(b.n_red_out); b.dXs = B.get<float>(b.n_red_out);
+			b.dYr = B.get<float>(b.n_red_in); b.dXr = B.get<float>(b.n_red_in);
+			db->output = B.get<float>(b.n_exp_out);
+		} else {
+			b.dOA = pp[i & 1];
+			b.dXe = T1; b.dXp = b.has_proj ? T1 : NULL;
+			b.dYs = b.dXs = T2;
+			b.dYr = b.dXr = T3;
+		}
+		db->output_activated = b.dOA;
+		db->post_expanded = b.dXe; db->transformed_residual = b.dXp;
+		db->post_spatial_activated = b.dYs; db->post_spatial = b.dXs;
+		db->post_reduced_activated = b.dYr; db->post_reduced = b.dXr;
+	}
+	for (int i = 0; i < nb; i++) e->blocks[i].dBI = (i == 0) ? e->dP0 : e->blocks[i - 1].dOA;
+
+	// ---- workspaces
+	e->bn_max_blocks = kNumSMs * 8;
+	int maxC = d->final_depth > F ? d->final_depth : F;
+	e->bn_partials = B.get<float>((long long)e->bn_max_blocks * 2 * maxC);
+	e->bn_coef = B.get<float>(4LL * maxC);
+	e->ones = B.get<float>(maxC); e->zeros = B.get<float>(maxC); e->tmp_ab = B.get<float>(2LL * maxC); e->tmp_mv = B.get<float>(2LL * maxC);
+	fill(e->ones, maxC, 1.f, e->stream);
+	fill(e->zeros, maxC, 0.f, e->stream);
+	e->wgrad_ws = e->wgrad_ws_bytes ? (float *)B.get<char>((long long)e->wgrad_ws_bytes) : nullptr;
+	e->bad_dev = B.get<int>(1);
+	RB_CUDA(cudaMemsetAsync(e->bad_dev, 0, sizeof(int), e->stream));
+	RB_CUDA(cudaMallocHost(&e->bad_host, sizeof(int)));
+	*e->bad_host = 0;
+	e->n_pack_jobs = (int)jobs.size();
+	e->pack_max_elems = 0;
+	for (auto &j : jobs) e->pack_max_elems = std::max(e->pack_max_elems, j.cout * j.cin * j.taps);
+	e->pack_jobs_dev = (PackJob *)B.get<char>((long long)(jobs.size() * sizeof(PackJob)));
+	RB_CUDA(cudaMemcpyAsync(e->pack_jobs_dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, e->stream));
+	RB_CUDA(cudaStreamSynchronize(e->stream));
+
+	// ---- tensor-core plans (tensor maps bind the arena addresses, so they are built once)
+	auto plan = [&](ConvRef &c, const float *in, float *out, const float *dout, float *din, int din_accumulate) {
+		if (!c.use_tc) return;
+		c.fprop = tc_make_fprop(c.g, in, c.wf, out);
+		if (din) c.dgrad = tc_make_dgrad(c.g, dout, c.wd, din, din_accumulate);
+		c.wgrad = tc_make_wgrad(c.g, in, dout, c.dw, e->wgrad_ws, e->wgrad_ws_bytes);
+	};
+	for (int i = 0; i < nb; i++) {
+		BlockRef &b = e->blocks[i];
+		plan(b.reduce, b.x_in, b.Xr, b.dXr, b.dBI, 1);  // joins the shortcut gradient (reference: resnet.cu:2157 toAdd=true)
+		plan(b.spatial, b.Yr, b.Xs, b.dXs, b.dYr, 0);
+		plan(b.expand, b.Ys, b.Xe, b.dXe, b.dYs, 0);
+		if (b.has_proj) plan(b.proj, b.x_in, b.Xp, b.dXp, b.dBI, 0);
+	}
+	{
+		std::lock_guard<std::mutex> lk(g_mu);
+		g_engines[t] = e;
+	}
+	return e;
+}
+
+// ------------------------------------------------------------------------------------------------ layer helpers
+static void conv_fwd(Engine *e, ConvRef &c, const float *in, float *out) {
+	if (c.use_tc) tc_run(c.fprop, e->stream);
+	else simt_conv_fprop(c.g, in, c.wf, out, e->stream);
+}
+static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, float *din, int accumulate) {
+	if (c.use_tc) {
+		if (din) tc_run(c.dgrad, e->stream);
+		tc_run(c.wgrad, e->stream);
+	} else {
+		if (din) simt_conv_dgrad(c.g, dout, c.wd, din, accumulate, e->stream);
+		simt_conv_wgrad(c.g, in, dout, c.dw, e->stream);
+	}
+}
+static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps) {
+	bn_stats(x, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->bn_partials, e->bn_max_blocks, e->stream);
+	if (e->keep_all && bn.cache->normalized) {
+		bn_apply(x, bn.ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized, 0, e->stream);
+		bn_stats(x, bn.rows, bn.C, e->ones, e->zeros, eps, e->tmp_mv, e->tmp_mv + bn.C, e->tmp_ab, e->bn_partials, e->bn_max_blocks, e->stream);
+		bn_apply(x, e->tmp_ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized_temp, 0, e->stream);
+	}
+}
+static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps) {
+	bn_bwd(x, dy, mask, bn.gamma, bn.means, bn.vars, eps, bn.rows, bn.C, bn.dgamma, bn.dbeta, dx, e->bn_partials, e->bn_max_blocks, e->bn_coef,
+	       e->round_tf32, e->stream);
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+// ================================================================================================ C ABI
+extern "C" {
+
+Dims *init_dimensions(int input, int init_kernel_dim, int init_conv_filters, int init_conv_stride, int init_maxpool_dim, int init_maxpool_stride,
+                      int n_conv_blocks, int *is_block_spatial_reduction, int final_depth, int output) {
+	Dims *d = (Dims *)malloc(sizeof(Dims));
+	d->input = input; d->init_kernel_dim = init_kernel_dim; d->init_conv_filters = init_conv_filters; d->init_conv_stride = init_conv_stride;
+	d->init_maxpool_dim = init_maxpool_dim; d->init_maxpool_stride = init_maxpool_stride; d->n_conv_blocks = n_conv_blocks;
+	d->is_block_spatial_reduction = is_block_spatial_reduction; d->final_depth = final_depth; d->output = output;
+	return d;
+}
+
+ResNet *init_resnet(Dims *dims, void *gen) {
+	ResNet *m = (ResNet *)malloc(sizeof(ResNet));
+	m->dims = dims;
+	m->params = make_params(dims, (curandGenerator_t *)gen);
+	return m;
+}
+
+Batch *init_general_batch(int n_images, int image_size, int image_dim, int shard_n_images) {
+	Batch *b = (Batch *)calloc(1, sizeof(Batch));
+	b->n_images = n_images; b->image_size = image_size; b->image_dim = image_dim;
+	RB_CUDA(cudaMallocHost(&b->images_float_cpu, (size_t)n_images * image_size * sizeof(float)));
+	RB_CUDA(cudaMalloc(&b->images, (size_t)n_images * image_size * sizeof(float)));
+	RB_CUDA(cudaMallocHost(&b->correct_classes_cpu, n_images * sizeof(int)));
+	RB_CUDA(cudaMalloc(&b->correct_classes, n_images * sizeof(int)));
+	b->cur_shard_id = -1; b->cur_batch_in_shard = -1; b->shard_n_images = shard_n_images;
+	// host staging of one shard (reference: resnet.cu:1227-1228); allocated lazily by load_new_batch
+	b->full_shard_images = NULL; b->full_shard_correct_classes = NULL;
+	return b;
+}
+
+Train_ResNet *init_trainer(ResNet *model, Batch *cur_batch, int batch_size, float learning_rate, float weight_decay, float mean_decay,
+                           float var_decay, float eps, int n_epochs, const char *dump_dir) {
+	Train_ResNet *t = (Train_ResNet *)calloc(1, sizeof(Train_ResNet));
+	t->model = model; t->cur_batch = cur_batch; t->batch_size = batch_size;
+	t->learning_rate = learning_rate; t->weight_decay = weight_decay; t->base_mean_decay = mean_decay; t->base_var_decay = var_decay;
+	t->cur_mean_decay = 1; t->cur_var_decay = 1; t->eps = eps; t->n_epochs = n_epochs; t->cur_dump_id = -1; t->cur_epoch = 0;
+	t->loss_per_epoch = (float *)calloc(n_epochs > 0 ? n_epochs : 1, sizeof(float));
+	t->accuracy_per_epoch = (float *)calloc(n_epochs > 0 ? n_epochs : 1, sizeof(float));
+	t->init_loaded = 0; t->dump_dir = dump_dir;
+	build_engine(t);
+	return t;
+}
+
+// ---- forward (reference: resnet.cu:1526-1775)
+void forward_pass(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("forward_pass: unknown trainer"); return; }
+	cudaStream_t st = e->stream;
+	Dims *d = t->model->dims;
+	const float eps = t->eps;
+	const int rnd = e->round_tf32;
+	// weights may have been written through locations[] since the last step (update, checkpoint restore): re-pack
+	pack_weights(e->pack_jobs_dev, e->n_pack_jobs, e->pack_max_elems, rnd, st);
+
+	conv_fwd(e, e->stem, t->cur_batch->images, e->X0);
+	bn_forward(e, e->bn0, e->X0, eps);
+	bn_apply(e->X0, e->bn0.ab, e->bn0.rows, e->bn0.C, 1, nullptr, nullptr, e->Y0, rnd, st);
+	const int S1 = d->input / d->init_conv_stride;
+	maxpool_fwd(e->Y0, e->N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->max_inds, e->P0, st);
+
+	for (size_t i = 0; i < e->blocks.size(); i++) {
+		BlockRef &b = e->blocks[i];
+		Activation_ConvBlock *ab = t->forward_buffer->activations->activation_conv_blocks[i];
+		conv_fwd(e, b.reduce, b.x_in, b.Xr);
+		bn_forward(e, b.bn_r, b.Xr, eps);
+		bn_apply(b.Xr, b.bn_r.ab, b.bn_r.rows, b.bn_r.C, 1, nullptr, nullptr, b.Yr, rnd, st);
+		conv_fwd(e, b.spatial, b.Yr, b.Xs);
+		bn_forward(e, b.bn_s, b.Xs, eps);
+		bn_apply(b.Xs, b.bn_s.ab, b.bn_s.rows, b.bn_s.C, 1, nullptr, nullptr, b.Ys, rnd, st);
+		conv_fwd(e, b.expand, b.Ys, b.Xe);
+		bn_forward(e, b.bn_e, b.Xe, eps);
+		if (b.has_proj) {
+			conv_fwd(e, b.proj, b.x_in, b.Xp);
+			bn_forward(e, b.bn_p, b.Xp, eps);
+		}
+		if (e->keep_all) {
+			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, nullptr, nullptr, ab->post_expanded_norm_vals, 0, st);
+			if (b.has_proj) bn_apply(b.Xp, b.bn_p.ab, b.bn_p.rows, b.bn_p.C, 0, nullptr, nullptr, ab->post_projection_norm_vals, 0, st);
+			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, ab->output, 0, st);
+		}
+		// output_activated = relu(bn(expanded) + shortcut)   (reference: resnet.cu:1670-1723, four kernels there)
+		bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 1, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, b.OA, rnd, st);
+	}
+	BlockRef &last = e->blocks.back();
+	const int Sl = last.expand.g.S;
+	avgpool_fwd(last.OA, e->N, Sl, d->final_depth, e->pooled, st);
+	sgemm(e->pooled, t->model->params->fully_connected, e->logits, e->N, d->output, d->final_depth, 0, 0, st);
+	softmax_ce(e->logits, t->cur_batch->correct_classes, e->N, d->output, e->pred, nullptr, e->row_loss, e->row_wrong, st);
+	RB_CUDA(cudaMemcpyAsync(e->pred_host, e->pred, (size_t)e->N * d->output * sizeof(float), cudaMemcpyDeviceToHost, st));
+	RB_CUDA(cudaStreamSynchronize(st));  // pred_cpu is valid on return, as in the reference (resnet.cu:1774)
+}
+
+// ---- backward (reference: resnet.cu:1777-2248; spatial-BN call per resnet_clean.cu:2778)
+void backwards_pass(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("backwards_pass: unknown trainer"); return; }
+	cudaStream_t st = e->stream;
+	Dims *d = t->model->dims;
+	const float eps = t->eps;
+	Params *G = t->backprop_buffer->param_derivs;
+	const int N = e->N;
+	{
+		long long total = (long long)N * d->output;
+		int grid = (int)((total + 255) / 256);
+		ce_deriv_kernel<<<grid, 256, 0, st>>>(e->pred, t->cur_batch->correct_classes, N, d->output, e->dlogits);
+		RB_LAUNCH_CHECK();
+	}
+	// dW_fc = pooled^T . dlogits ; dpooled = dlogits . W_fc^T   (reference: resnet.cu:1823, 1830)
+	sgemm(e->pooled, e->dlogits, G->fully_connected, d->final_depth, d->output, N, 1, 0, st);
+	sgemm(e->dlogits, t->model->params->fully_connected, e->dpooled, N, d->final_depth, d->output, 0, 1, st);
+	BlockRef &last = e->blocks.back();
+	avgpool_bwd(e->dpooled, N, last.expand.g.S, d->final_depth, last.dOA, st);
+
+	for (int i = (int)e->blocks.size() - 1; i >= 0; i--) {
+		BlockRef &b = e->blocks[i];
+		if (e->keep_all) {
+			Activation_ConvBlock *db = t->backprop_buffer->activation_derivs->activation_conv_blocks[i];
+			relu_bwd(b.OA, b.dOA, b.n_exp_out, db->output, st);  // d(output), reference: resnet.cu:1934
+		}
+		// shortcut branch first (its scratch is reused by the expanded branch)
+		if (b.has_proj) {
+			bn_backward(e, b.bn_p, b.Xp, b.dOA, b.OA, b.dXp, eps);
+			conv_bwd(e, b.proj, b.x_in, b.dXp, b.dBI, 0);
+		} else {
+			relu_bwd(b.OA, b.dOA, b.n_exp_out, b.dBI, st);
+		}
+		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps);
+		conv_bwd(e, b.expand, b.Ys, b.dXe, b.dYs, 0);
+		bn_backward(e, b.bn_s, b.Xs, b.dYs, b.Ys, b.dXs, eps);
+		conv_bwd(e, b.spatial, b.Yr, b.dXs, b.dYr, 0);
+		bn_backward(e, b.bn_r, b.Xr, b.dYr, b.Yr, b.dXr, eps);
+		conv_bwd(e, b.reduce, b.x_in, b.dXr, b.dBI, 1);
+		dp_block_done(e, i);
+	}
+	const int S1 = d->input / d->init_conv_stride;
+	maxpool_bwd(e->max_inds, e->dP0, N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->dY0, st);
+	bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
+	       e->bn_partials, e->bn_max_blocks, e->bn_coef, 0, st);
+	conv_bwd(e, e->stem, t->cur_batch->images, e->dX0, nullptr, 0);  // no input gradient (reference: resnet.cu:2243-2245)
+	dp_allreduce_grads(e);
+}
+
+// ---- Adam (reference: resnet.cu:2910-2987)
+void update_parameters(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("update_parameters: unknown trainer"); return; }
+	cudaStream_t st = e->stream;
+	const float cur_mean_decay = t->cur_mean_decay * t->base_mean_decay;
+	const float cur_var_decay = t->cur_var_decay * t->base_var_decay;
+	ParamStore *p = param_store_of(t->model->params), *g = param_store_of(t->backprop_buffer->param_derivs);
+	ParamStore *m = param_store_of(t->backprop_buffer->prev_means), *v = param_store_of(t->backprop_buffer->prev_vars);
+	if (*e->bad_host) {
+		// the reference dumps and exit(1)s on the first NaN/Inf it finds (resnet.cu:2893-2900)
+		fprintf(stderr, "ERROR: nan or inf found in %d parameter/gradient entries during the previous update\n", *e->bad_host);
+		set_error("non-finite values in update_parameters (%d entries)", *e->bad_host);
+		if (env_int("RESNET_B200_EXIT_ON_NAN", 0)) exit(1);
+	}
+	adam_step(p->base, g->base, m->base, v->base, p->total, t->learning_rate, t->weight_decay, t->base_mean_decay, t->base_var_decay,
+	          cur_mean_decay, cur_var_decay, t->eps, e->bad_dev, st);
+	RB_CUDA(cudaMemcpyAsync(e->bad_host, e->bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+	// reference resets the batch buffers before the next load (resnet.cu:2981-2982)
+	Batch *b = t->cur_batch;
+	RB_CUDA(cudaMemsetAsync(b->images, 0, (size_t)t->batch_size * b->image_size * sizeof(float), st));
+	RB_CUDA(cudaMemsetAsync(b->correct_classes, 0, (size_t)t->batch_size * sizeof(int), st));
+	t->cur_mean_decay = cur_mean_decay;
+	t->cur_var_decay = cur_var_decay;
+}
+
+// ---- shard loader (reference: resnet.cu:1235-1325).  Same file format and traversal; the shard directory is
+// RESNET_B200_SHARD_DIR (default: the reference's hard-coded path).
+void load_new_batch(Train_ResNet *trainer, Class_Metadata *class_metadata, Batch *bb) {
+	(void)class_metadata;
+	Engine *e = engine_of(trainer);
+	cudaStream_t st = e ? e->stream : 0;
+	const int batch_size = bb->n_images, image_size = bb->image_size;
+	const size_t total_pixels = (size_t)batch_size * image_size;
+	if (!bb->full_shard_images) {
+		bb->full_shard_images = (float *)malloc((size_t)bb->shard_n_images * image_size * sizeof(float));
+		bb->full_shard_correct_classes = (int *)malloc((size_t)bb->shard_n_images * sizeof(int));
+	}
+	int cur_batch_in_shard = bb->cur_batch_in_shard;
+	const int start_img = cur_batch_in_shard * batch_size;
+	if (trainer->init_loaded || bb->cur_shard_id == -1 || start_img >= bb->shard_n_images) {
+		if (!trainer->init_loaded) bb->cur_shard_id += 1;
+		const char *dir = getenv("RESNET_B200_SHARD_DIR");
+		if (!dir) dir = "/mnt/storage/data/vision/imagenet/2012/train_data_shards";
+		char path[1024];
+		snprintf(path, sizeof(path), "%s/%03d.images", dir, bb->cur_shard_id);
+		FILE *f = fopen(path, "rb");
+		if (!f) { set_error("load_new_batch: cannot open %s", path); return; }
+		size_t nr = fread(bb->full_shard_images, sizeof(float), (size_t)bb->shard_n_images * image_size, f);
+		fclose(f);
+		if (nr != (size_t)bb->shard_n_images * image_size) set_error("load_new_batch: short read on %s", path);
+		snprintf(path, sizeof(path), "%s/%03d.labels", dir, bb->cur_shard_id);
+		f = fopen(path, "rb");
+		if (!f) { set_error("load_new_batch: cannot open %s", path); return; }
+		nr = fread(bb->full_shard_correct_classes, sizeof(int), bb->shard_n_images, f);
+		fclose(f);
+		if (!trainer->init_loaded) { cur_batch_in_shard = 0; bb->cur_batch_in_shard = 0; }
+		trainer->init_loaded = 0;
+	}
+	memcpy(bb->images_float_cpu, bb->full_shard_images + (size_t)cur_batch_in_shard * total_pixels, total_pixels * sizeof(float));
+	memcpy(bb->correct_classes_cpu, bb->full_shard_correct_classes + (size_t)cur_batch_in_shard * batch_size, batch_size * sizeof(int));
+	RB_CUDA(cudaMemcpyAsync(bb->images, bb->images_float_cpu, total_pixels * sizeof(float), cudaMemcpyHostToDevice, st));
+	RB_CUDA(cudaMemcpyAsync(bb->correct_classes, bb->correct_classes_cpu, batch_size * sizeof(int), cudaMemcpyHostToDevice, st));
+	RB_CUDA(cudaStreamSynchronize(st));
+	bb->cur_batch_in_shard = cur_batch_in_shard + 1;
+	trainer->cur_dump_id += 1;
+}
+
+// ---- class metadata (reference: resnet.cu:1331-1381)
+static int read_lines(const char *filename, char **text, int *ints, int n) {
+	FILE *fp = fopen(filename, "r");
+	if (!fp) return -1;
+	char *line = NULL;
+	size_t len = 0;
+	int cnt = 0;
+	while (cnt < n && getline(&line, &len, fp) != -1) {
+		if (text) text[cnt] = strdup(line);
+		if (ints) ints[cnt] = atoi(line);
+		cnt++;
+	}
+	free(line);
+	fclose(fp);
+	return cnt;
+}
+Class_Metadata *populate_class_info(char *label_filename, char *synset_filename, char *class_size_filename, int n_classes) {
+	Class_Metadata *c = (Class_Metadata *)malloc(sizeof(Class_Metadata));
+	c->labels = (char **)calloc(n_classes, sizeof(char *));
+	c->synsets = (char **)calloc(n_classes, sizeof(char *));
+	c->counts = (int *)calloc(n_classes, sizeof(int));
+	c->n_classes = n_classes;
+	if (read_lines(label_filename, c->labels, NULL, n_classes) < 0 || read_lines(synset_filename, c->synsets, NULL, n_classes) < 0 ||
+	    read_lines(class_size_filename, NULL, c->counts, n_classes) < 0) {
+		fprintf(stderr, "populate_class_info: cannot open metadata file\n");
+		exit(EXIT_FAILURE);  // reference: resnet.cu:1341-1342
+	}
+	return c;
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+"""GPU parity tests of the whole step through the reference's entry points (include/resnet.h):
+forward_pass / backwards_pass / update_parameters vs the host oracle, per layer and per step.
+
+Bars: fp32 mode (RESNET_B200_CONV=simt): activations 1e-4 rel-to-max, gradients 1e-3 rel-L2, parameters after Adam
+1e-5 abs; TF32 tensor-core mode: activations 1e-2 rel-to-max, gradients 3e-2 rel-L2; argmax and labels bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import golden_cases as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_max(a, b):
+    return float(np.abs(a - b).max() / max(1e-9, np.abs(b).max()))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.reshape(-1) - b.reshape(-1)) / max(1e-9, np.linalg.norm(b)))
+
+
+def make_pair(cfg, mode, keep_all=True):
+    from resnet_b200 import api
+    os.environ["RESNET_B200_CONV"] = mode
+    os.environ["RESNET_B200_KEEP_ALL"] = "1" if keep_all else "0"
+    try:
+        t = api.Trainer(input_dim=cfg["input_dim"], n_blocks=cfg["n_blocks"], reductions=cfg["reductions"], batch=cfg["batch"],
+                        output=cfg["output"], lr=cfg["lr"], wd=cfg["wd"], b1=cfg["b1"], b2=cfg["b2"], eps=cfg["eps"])
+    finally:
+        os.environ.pop("RESNET_B200_CONV", None)
+        os.environ.pop("RESNET_B200_KEEP_ALL", None)
+    net = O.OracleNet(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], cfg["batch"], output=cfg["output"], lr=cfg["lr"],
+                      wd=cfg["wd"], b1=cfg["b1"], b2=cfg["b2"], eps=cfg["eps"])
+    shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
+    W = G.mini_weights(shapes)
+    t.set_params(W)
+    net.set_params([w.copy() for w in W])
+    return t, net
+
+
+@pytest.mark.parametrize("mode,cfg_name", [("simt", "MINI4"), ("tc", "MINI4"), ("tc", "MINI")])
+def test_step_vs_oracle_per_layer(mode, cfg_name):
+    cfg = getattr(G, cfg_name)
+    t, net = make_pair(cfg, mode)
+    assert t.uses_tensor_cores() == (mode == "tc")
+    act_tol, grad_tol = (1e-4, 1e-3) if mode == "simt" else (1e-2, 3e-2)
+    img, lab = G.mini_batch(cfg)
+    t.set_batch(img, lab)
+    pred = t.forward()
+    opred = net.forward(img, lab)
+    # ---- forward, layer by layer
+    names = ["init_conv_applied", "init_conv_activated", "init_convblock_input", "final_conv_output_pooled", "linear_output"]
+    for bi in range(cfg["n_blocks"]):
+        names += ["b%d.%s" % (bi, f) for f in ("post_reduced", "post_reduced_activated", "post_spatial", "post_spatial_activated",
+                                                "post_expanded", "post_expanded_norm_vals", "output", "output_activated",
+                                                "norm_post_reduced.means", "norm_post_reduced.vars", "norm_post_expanded.vars")]
+        if net.plan[bi]["proj"]:
+            names += ["b%d.transformed_residual" % bi, "b%d.post_projection_norm_vals" % bi]
+    for nm in names:
+        got = t.activation(nm)
+        assert got is not None, nm
+        assert rel_max(got, net.act[nm].reshape(-1)) < act_tol, nm
+    np.testing.assert_array_equal(t.activation("max_inds", dtype=np.int32), net.act["max_inds"].reshape(-1)) if mode == "simt" else None
+    assert (pred.argmax(1) == opred.argmax(1)).all()
+    assert rel_max(pred, opred) < act_tol * 5
+    loss, nwrong = t.loss_accuracy()
+    oloss, onwrong = net.loss_acc()
+    assert abs(loss - oloss) < 1e-3 * abs(oloss) + 1e-4 and nwrong == onwrong
+    # ---- backward: every parameter gradient + the activation gradients the trainer keeps
+    t.backward()
+    og = net.backward()
+    for i, (g, r) in enumerate(zip(t.get_params(1), og)):
+        assert rel_l2(g, r) < grad_tol, ("grad", i, net.shapes[i])
+    for nm in ["init_convblock_input", "init_conv_applied", "b0.post_reduced", "b1.post_expanded", "b1.transformed_residual",
+               "b1.post_spatial", "b0.output_activated", "b1.post_reduced_activated", "b1.output"]:
+        got = t.activation(nm, deriv=True)
+        assert got is not None, nm
+        assert rel_l2(got, net.dact[nm]) < grad_tol, ("dact", nm)
+    # ---- Adam, two steps
+    t.update()
+    net.update()
+    for i, (p, r) in enumerate(zip(t.get_params(0), net.params)):
+        tol = 1e-5 if mode == "simt" else 2.5 * cfg["lr"]     # TF32 noise can flip the sign of a near-zero first-step gradient
+        assert np.abs(p - r.reshape(-1)).max() <= tol, ("param", i)
+    assert all((g == 0).all() for g in t.get_params(1))      # gradients zeroed (reference: resnet.cu:2972-2975)
+    b = t.batch_struct.contents
+    from resnet_b200 import api
+    assert (api.d2h(b.images, 64) == 0).all()                # batch reset (reference: resnet.cu:2981-2982)
+    tr = t.t.contents
+    assert abs(tr.cur_mean_decay - cfg["b1"]) < 1e-7 and abs(tr.cur_var_decay - cfg["b2"]) < 1e-7
+    t.set_batch(img, lab)
+    pred2 = t.forward()
+    opred2 = net.forward(img, lab)
+    assert rel_max(pred2, opred2) < (1e-3 if mode == "simt" else 0.2)
+    t.close()
+
+
+def test_default_mode_aliases_unkept_buffers():
+    """Without keep-all the recomputable buffers are NULL (as in the reference's resnet_clean.h) and results are the same."""
+    cfg = G.MINI
+    t, net = make_pair(cfg, "tc", keep_all=False)
+    img, lab = G.mini_batch(cfg)
+    t.set_batch(img, lab)
+    pred = t.forward()
+    assert t.activation("b0.output") is None and t.activation("b0.post_expanded_norm_vals") is None
+    assert t.activation("b0.norm_post_reduced.normalized") is None
+    opred = net.forward(img, lab)
+    assert (pred.argmax(1) == opred.argmax(1)).all() and rel_max(pred, opred) < 5e-2
+    t.backward()
+    og = net.backward()
+    for i, (g, r) in enumerate(zip(t.get_params(1), og)):
+        assert rel_l2(g, r) < 3e-2, ("grad", i)
+    t.close()
+
+
+def test_curand_init_matches_reference_bytes():
+    """init_resnet draws weights with cuRAND in the reference's order: seed 1234 reproduces the reference's initial
+    parameters (fingerprints recorded from the reference's own init_resnet, tests/golden)."""
+    gold_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_b200.npz")
+    if not os.path.exists(gold_path):
+        pytest.skip("golden fixture not generated yet")
+    gold = np.load(gold_path)
+    from resnet_b200 import api
+    cfg = G.MINI
+    t = api.Trainer(input_dim=cfg["input_dim"], n_blocks=cfg["n_blocks"], reductions=cfg["reductions"], batch=cfg["batch"],
+                    output=cfg["output"], seed=1234)
+    ours = np.stack([G.summary(a) for a in t.get_params(0)])
+    np.testing.assert_array_equal(ours, gold["mini.curand_init"])
+    t.close()
+
+
+def test_full_size_stem_config1():
+    """BASELINE config 1: ResNet-50 stem (conv1 7x7/2 + BN + ReLU + maxpool) forward + backward, batch 8, fp32, 224x224,
+    vs the host oracle (1e-4 abs / rel; argmax indices exact)."""
+    from resnet_b200 import api
+    rng = np.random.default_rng(1234)
+    img, _ = O.synthetic_batch(8, 224, seed=1234)
+    w = rng.normal(0, np.sqrt(2.0 / (49 * 67)), (64, 3, 7, 7)).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(64)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(64)).astype(np.float32)
+    x0 = api.conv_forward(img, w, 2, impl=1)
+    ox0 = O.conv_fwd(img, w, 2)
+    np.testing.assert_allclose(x0, ox0, rtol=1e-4, atol=1e-3)   # |x0| ~ 20: 1e-4 relative
+    mu, var, y0 = api.batchnorm_forward(ox0, g, b, 1e-7, True)
+    omu, ovar, oy0, _, _ = O.bn_fwd(ox0, g, b, 1e-7, True)
+    np.testing.assert_allclose(y0, oy0, rtol=1e-4, atol=1e-4)
+    p0, inds = api.maxpool_forward(oy0, 3, 2)
+    op0, oinds = O.maxpool_fwd(oy0, 3, 2)
+    np.testing.assert_array_equal(inds, oinds)
+    np.testing.assert_array_equal(p0, op0)
+    dp0 = np.random.default_rng(99).standard_normal(p0.shape).astype(np.float32)
+    dy0 = api.maxpool_backward(oinds, dp0, oy0.shape, 3, 2)
+    ody0 = O.maxpool_bwd(oinds, dp0, oy0.shape)
+    np.testing.assert_allclose(dy0, ody0, rtol=1e-6, atol=1e-6)
+    dg, db, dx0 = api.batchnorm_backward(ox0, g, 1e-7, omu, ovar, oy0, ody0, True)
+    odg, odb, odx0 = O.bn_bwd(ox0, g, 1e-7, omu, ovar, oy0, ody0, True)
+    np.testing.assert_allclose(dg, odg, rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(db, odb, rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(dx0, odx0, rtol=1e-3, atol=1e-5)
+    _, dw = api.conv_backward(img, w, odx0, 2, want_din=False, impl=1)
+    odw = O.conv_wgrad(img, odx0, 7, 2)
+    assert np.linalg.norm(dw - odw) / np.linalg.norm(odw) < 1e-4
