@@ -8,8 +8,10 @@ import numpy as np
 CONV_CASES = [(16, 7, 3, 8, 2, 2), (8, 1, 16, 32, 1, 4), (8, 3, 16, 16, 1, 2), (8, 3, 16, 24, 2, 2), (14, 3, 8, 16, 2, 1),
               (7, 3, 8, 8, 1, 2)]
 BN_CASES = [(4, 6, 10, 0), (4, 6, 10, 1), (2, 4, 64, 1)]  # (N, S, C, relu)
-MINI = dict(input_dim=32, n_blocks=2, reductions=[0, 1], batch=4, output=10, lr=1e-3, wd=0.0, b1=0.9, b2=0.999, eps=1e-7)
-MINI4 = dict(input_dim=32, n_blocks=4, reductions=[0, 1, 0, 1], batch=2, output=10, lr=1e-3, wd=0.0, b1=0.9, b2=0.999, eps=1e-7)
+# NB: the last block of every network config is non-strided: the reference pools the final activation over the LAST
+# BLOCK'S *incoming* spatial dim (reference: resnet.cu:1732), which equals the output dim only then (true for ResNet-50).
+MINI = dict(input_dim=32, n_blocks=3, reductions=[0, 1, 0], batch=4, output=10, lr=1e-3, wd=0.0, b1=0.9, b2=0.999, eps=1e-7)
+MINI4 = dict(input_dim=32, n_blocks=4, reductions=[0, 1, 0, 0], batch=2, output=10, lr=1e-3, wd=0.0, b1=0.9, b2=0.999, eps=1e-7)
 
 
 def conv_inputs(idx):

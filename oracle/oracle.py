@@ -220,6 +220,8 @@ class OracleNet:
         self.pool_k, self.pool_stride, self.init_k, self.init_stride = pool_k, pool_stride, init_k, init_stride
         self.cur_b1 = self.cur_b2 = 1.0
         self.plan = block_plan(input_dim, n_blocks, reductions, init_filters)
+        # reference: resnet.cu:1732 pools over the last block's INCOMING spatial dim; only a non-strided last block is well-defined
+        assert self.plan[-1]["stride"] == 1, "last block must not be a spatial-reduction block"
         self.shapes = param_shapes(input_dim, n_blocks, reductions, init_filters, init_k, output)
         self.params = [np.zeros(s, np.float32) for s in self.shapes]
         self.m = [np.zeros(s, np.float32) for s in self.shapes]

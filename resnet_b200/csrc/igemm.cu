@@ -50,15 +50,16 @@ static EncodeTiledFn get_encode() {
 }
 
 // rank-4 fp32 map, dims[0] innermost (channels), 128B swizzle, zero OOB fill. strides in ELEMENTS for dims 1..3.
-static bool make_map4(CUtensorMap *m, const float *base, const long long dims[4], const long long strides_elems[3], const int box[4]) {
+static bool make_map4(CUtensorMap *m, const float *base, const long long dims[4], const long long strides_elems[3], const int box[4],
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
 	EncodeTiledFn enc = get_encode();
 	if (!enc) return false;
 	cuuint64_t gd[4], gs[3];
 	cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
 	for (int i = 0; i < 4; i++) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
 	for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides_elems[i] * sizeof(float);
-	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+	                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled(4d) failed: %d dims=(%lld,%lld,%lld,%lld) box=(%d,%d,%d,%d)", (int)r, dims[0], dims[1], dims[2],
 		          dims[3], box[0], box[1], box[2], box[3]);
@@ -91,7 +92,7 @@ struct alignas(64) IgemmParams {
 	int kchunks;
 	int BN, n_tiles, Ncol;
 	int stages;
-	uint32_t a_bytes, b_bytes;
+	uint32_t a_bytes, b_bytes, a_tx_bytes;  // smem slot sizes; bytes one A box actually transfers (bw*bh*bn rows)
 	float *out;
 	int OH, OW, os, accumulate;
 };
@@ -105,7 +106,7 @@ struct alignas(64) WgradParams {
 	int splits, boxes_per_split;
 	int co_tiles, ci_tiles, BN, cin, cout;
 	int stages;
-	uint32_t a_bytes, b_bytes, lbo, sbo;
+	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
 	float *partial;
 };
 
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 					for (int kc = 0; kc < p.kchunks; kc++) {
 						mbar_wait(&empty[stage], phase ^ 1);
 						uint8_t *sa = base + (size_t)stage * stage_bytes;
-						mbar_expect_tx(&full[stage], stage_bytes);
+						mbar_expect_tx(&full[stage], p.a_tx_bytes + p.b_bytes);
 						tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * 32, ow0 + tp.dx, oh0 + tp.dy, n0);
 						tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * 32, nt * p.BN);
 						if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -328,8 +329,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 					mbar_wait(&full[stage], phase);
 					tc_fence_after();
 					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
-					const uint64_t adesc = make_smem_desc(a_addr, p.lbo, p.sbo);
-					const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo);
+					const uint64_t adesc = make_smem_desc(a_addr, p.lbo, p.sbo, p.layout_type);
+					const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
 					for (int k = 0; k < 4; k++)  // 8 pixel rows (1024 B) per K=8 MMA
 						mma_tf32_ss(d_tmem, adesc + (uint64_t)(k * 64), bdesc + (uint64_t)(k * 64), idesc, (uint32_t)((kb > kb0) || (k != 0)));
@@ -438,20 +439,21 @@ static void s2_tap(int kk, int *parity, int *d) {
 }
 
 // maps over an NHWC tensor [N][S][S][C] as seen by a conv of stride `stride`: 1 map (stride 1) or 4 parity maps
-static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int C, int stride, const int box[4], bool flat) {
+static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int C, int stride, const int box[4], bool flat,
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
 	if (flat) {  // 1x1: pixels are a flat list
 		long long P = (long long)N * S * S;
 		long long dims[4] = {C, P, 1, 1}, str[3] = {C, P * C, P * C};
-		return make_map4(&maps[0], x, dims, str, box);
+		return make_map4(&maps[0], x, dims, str, box, swz);
 	}
 	if (stride == 1) {
 		long long dims[4] = {C, S, S, N}, str[3] = {C, (long long)S * C, (long long)S * S * C};
-		return make_map4(&maps[0], x, dims, str, box);
+		return make_map4(&maps[0], x, dims, str, box, swz);
 	}
 	for (int ph = 0; ph < 2; ph++)
 		for (int pw = 0; pw < 2; pw++) {
 			long long dims[4] = {C, S / 2, S / 2, N}, str[3] = {2LL * C, 2LL * S * C, (long long)S * S * C};
-			if (!make_map4(&maps[ph * 2 + pw], x + ((long long)ph * S + pw) * C, dims, str, box)) return false;
+			if (!make_map4(&maps[ph * 2 + pw], x + ((long long)ph * S + pw) * C, dims, str, box, swz)) return false;
 		}
 	return true;
 }
@@ -459,6 +461,7 @@ static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int
 static void finish_kmajor(TcPlan *pl) {
 	IgemmParams &p = pl->ip;
 	p.a_bytes = kABytes;
+	p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128;
 	p.b_bytes = (uint32_t)p.BN * 128;
 	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
@@ -602,8 +605,17 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 	p.splits = ceil_div(p.k_boxes, p.boxes_per_split);
 	if ((size_t)p.splits * p.ntaps * g.cout * g.cin * sizeof(float) > ws_bytes) { set_error("tc_make_wgrad: workspace too small"); delete pl; return nullptr; }
 	const int box[4] = {32, p.bw, p.bh, p.bn};
-	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat);
-	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat);
+	// MN-major tf32 operands exist only in the "128B swizzle, 32B atom" shared-memory layout (4-row atoms)
+	CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+	p.layout_type = 1;
+	p.lbo = 32 * 128;  // distance between 32-channel column blocks (one TMA box of 32 pixel rows)
+	p.sbo = 512;       // pitch of the 4-row swizzle atoms along the pixel (K) axis
+	if (const char *e = getenv("RESNET_B200_WGRAD_DESC")) {  // bring-up aid: "lbo,sbo,layout_type,tma_swizzle_enum"
+		unsigned a, b, c, d;
+		if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { p.lbo = a; p.sbo = b; p.layout_type = c; swz = (CUtensorMapSwizzle)d; }
+	}
+	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat, swz);
+	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat, swz);
 	if (g.stride == 1) for (int i = 1; i < 4; i++) p.bmap[i] = p.bmap[0];
 	for (int kh = 0; kh < g.k; kh++)
 		for (int kw = 0; kw < g.k; kw++) {
@@ -615,13 +627,6 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 		}
 	p.a_bytes = 4 * 32 * 128;
 	p.b_bytes = (uint32_t)(p.BN / 32) * 32 * 128;
-	// MN-major, 128B swizzle: LBO = distance between 32-channel column blocks (one TMA box), SBO = 8-row group pitch
-	p.lbo = 32 * 128;
-	p.sbo = 1024;
-	if (const char *e = getenv("RESNET_B200_WGRAD_DESC")) {  // bring-up aid: "lbo,sbo"
-		unsigned a, b;
-		if (sscanf(e, "%u,%u", &a, &b) == 2) { p.lbo = a; p.sbo = b; }
-	}
 	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;

@@ -105,14 +105,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-// layout type [61,64) (2 = 128-byte swizzle).
-__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout type [61,64) (2 = 128-byte swizzle, 1 = 128-byte swizzle with 32-byte atoms).
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
 	uint64_t d = 0;
 	d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
 	d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
 	d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
 	d |= (uint64_t)1 << 46;
-	d |= (uint64_t)2 << 61;
+	d |= (uint64_t)(layout_type & 7) << 61;
 	return d;
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate: c_format=F32 [4,6), a/b_format=TF32 [7,10)/[10,13),

@@ -157,7 +157,7 @@ def _torch_net(net, images, labels):
 
 def test_full_network_vs_autograd():
     """Forward, backward and one Adam step of a 4-block miniature (both shortcut kinds, both strides)."""
-    net = O.OracleNet(32, 4, [0, 1, 0, 1], batch=4, output=10, lr=1e-3)
+    net = O.OracleNet(32, 5, [0, 1, 0, 1, 0], batch=4, output=10, lr=1e-3)
     net.init_like_reference(seed=5)
     # break the gamma=1/beta=0 symmetry so BN parameter gradients are exercised
     rng = np.random.default_rng(6)
