@@ -1,0 +1,332 @@
+"""bench.py -- ResNet-50 training throughput of the B200-native hot path (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): the reference's ResNet-50 variant (3x3/2 projection shortcuts, 47.6 M parameters,
+39.09 GFLOP / image / training step), full training step = batch in -> forward_pass -> backwards_pass ->
+update_parameters (Adam), batch 256 per GPU, 224x224 synthetic images, fp32 storage, TF32 tensor-core convolutions
+with fp32 accumulation.  N > 1: batch-sharded data parallel, one process per GPU, NCCL gradient allreduce (weak scaling).
+
+  value    images/s with the batch already resident in HBM (device->device restore of cur_batch each step, because the
+           reference's update_parameters zeroes it); CUDA events on the trainer's stream; max over ranks.
+  e2e      the same step through the public C API with HOST buffers: pinned host -> device copy of images + labels
+           and the device -> host read of pred_cpu inside the timed region.
+  roofline dominant kernel family, timed per launch with CUDA events on the launching stream in an instrumented pass
+           of the same step right after the timed region (the event pairs would perturb the headline number).
+  cpu_baseline  the host-core C oracle (port of the reference's kernels; the reference has no CPU path) on a bounded
+           sample of the same workload.
+  --impl reference  the reference's own resnet_cudnn_fast.cu (oracle/_ref/libref_fast.so, unmodified sources, its own
+           forward_pass/backwards_pass/update_parameters) on the same config on this GPU; falls back to the oracle port
+           on host cores when that library cannot run.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R50_REDUCTIONS = [1 if i in (3, 7, 13) else 0 for i in range(16)]
+FLOP_PER_IMAGE_STEP = 39.09e9  # fprop + dgrad + wgrad, no stem dgrad
+METRIC = "ResNet-50 train img/s"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        try:
+            p.update(json.load(open(f)))
+            p["src"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init_dist(world):
+    if world <= 1:
+        return None
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dist.init_process_group(backend="gloo")  # plumbing only: rendezvous, barrier, max-reduce of timings, NCCL id broadcast
+    return dist
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def reduce_max(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_baseline(batch=4):
+    from oracle import oracle as O
+    net = O.OracleNet(224, 16, R50_REDUCTIONS, batch=batch)
+    net.init_like_reference(0)
+    img, lab = O.synthetic_batch(batch, 224, seed=1234)
+    t0 = time.time()
+    net.forward(img, lab)
+    net.backward()
+    net.update()
+    dt = time.time() - t0
+    return {"value": batch / dt, "unit": "img/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "1 full training step (forward, backward, Adam) of the same ResNet-50 at batch %d, oracle/ops.c with OpenMP, %.1f s" % (batch, dt)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    out = {"impl": "reference", "metric": METRIC, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
+    from oracle import oracle as O
+    from oracle import ref as R
+    img, lab = O.synthetic_batch(args.batch, 224, seed=1234)
+    done = False
+    if R.available("fast"):
+        try:
+            # the reference's cuDNN build, unmodified: its own init_*, forward_pass, backwards_pass, update_parameters
+            r = R.Ref("fast").create(224, 16, R50_REDUCTIONS, args.batch, output=1000, lr=1e-3, seed=1234)
+            r.set_batch(img, lab)
+            ms = r.time_steps(args.warmup, args.steps, e2e=False)
+            ms_e2e = r.time_steps(1, max(2, args.steps // 2), e2e=True)
+            v = args.batch / (ms / 1e3)
+            out.update({"value": v, "ms_per_step": ms, "dtype": "tf32", "gpu_launches": None,
+                        "config": {"workload": "ResNet-50 (reference variant) full training step, batch %d, 224x224, the reference's resnet_cudnn_fast.cu "
+                                               "(cuDNN 9.10, fp32 NCHW, TENSOR_OP_MATH_ALLOW_CONVERSION) on 1 B200, compiled -O3 --use_fast_math sm_100a" % args.batch,
+                                   "global_batch": args.batch, "inputs": "larger than L2", "note": "reference is single-GPU; runs on GPU 0 for every --gpus"},
+                        "cpu_baseline": {"value": v, "unit": "img/s", "cores": 0, "kind": "reference",
+                                         "sample": "GPU run of oracle/_ref/libref_fast.so (the reference has no CPU path); cuda error: " + r.cuda_error()},
+                        "e2e": {"value": args.batch / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": int(img.nbytes + lab.nbytes),
+                                "d2h_bytes_per_step": int(args.batch * 1000 * 4)}})
+            done = np.isfinite(v) and v > 0
+        except Exception as e:  # noqa: BLE001
+            out["reference_gpu_error"] = repr(e)
+    if not done:
+        cb = cpu_baseline(batch=4)
+        out.update({"value": cb["value"], "ms_per_step": 1e3 * 4 / cb["value"], "dtype": "f32", "gpu_launches": 0, "cpu_baseline": cb,
+                    "config": {"workload": "ResNet-50 (reference variant) full training step, host-core port of the reference's kernels", "global_batch": 4},
+                    "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = init_dist(world)
+    from resnet_b200 import api
+    L = api.L()
+    L.resnet_b200_set_device(local_rank)
+    pk = peaks()
+    N = args.batch
+    t = api.Trainer(input_dim=224, n_blocks=16, reductions=R50_REDUCTIONS, batch=N, output=1000, lr=1e-4, seed=1234, device=local_rank)
+    assert t.uses_tensor_cores(), "bench must run the tcgen05 path"
+    if world > 1:
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            L.resnet_b200_dp_unique_id(idbuf)
+        import torch
+        tid = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8)
+        dist.broadcast(tid, src=0)
+        idbuf = (C.c_char * 128)(*bytes(tid.tolist()))
+        L.resnet_b200_dp_init(t.t, idbuf, rank, world, 0)
+        api.check()
+
+    from oracle import oracle as O  # synthetic batch generator only (shared with the tests)
+    img, lab = O.synthetic_batch(N, 224, seed=1234 + 1000 * rank)
+    npix = img.size
+    host_img = L.resnet_b200_malloc_host(img.nbytes)
+    host_lab = L.resnet_b200_malloc_host(lab.nbytes)
+    C.memmove(host_img, img.ctypes.data, img.nbytes)
+    C.memmove(host_lab, lab.ctypes.data, lab.nbytes)
+    dev_img = api.DevBuf(img)
+    dev_lab = api.DevBuf(lab)
+
+    def step(e2e):
+        if e2e:
+            L.resnet_b200_stage_batch(t.t, host_img, host_lab)
+        else:
+            L.resnet_b200_stage_batch_device(t.t, dev_img.ptr, dev_lab.ptr)
+        L.forward_pass(t.t)                                   # returns with pred_cpu valid (D2H inside)
+        _ = t.t.contents.forward_buffer.contents.pred_cpu[0]  # the host reads the prediction, as the reference's loop does
+        L.backwards_pass(t.t)
+        L.update_parameters(t.t)
+
+    for _ in range(max(3, args.warmup)):
+        step(False)
+    t.sync()
+    api.check()
+
+    # ---- timed region: value (batch resident in HBM)
+    barrier(dist)
+    t.sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = L.resnet_b200_launch_count()
+    L.resnet_b200_timer_begin(t.t)
+    for _ in range(args.steps):
+        step(False)
+    ms = L.resnet_b200_timer_end_ms(t.t)
+    t.sync()
+    launches = L.resnet_b200_launch_count() - launches0
+    barrier(dist)
+    clocks = sampler.stop() if sampler else None
+    ms_max = reduce_max(dist, ms)
+    api.check()
+
+    # ---- timed region: e2e (host buffers, copies inside)
+    barrier(dist)
+    t.sync()
+    L.resnet_b200_timer_begin(t.t)
+    for _ in range(args.steps):
+        step(True)
+    ms_e2e = L.resnet_b200_timer_end_ms(t.t)
+    t.sync()
+    ms_e2e_max = reduce_max(dist, ms_e2e)
+    loss, nwrong = t.loss_accuracy()
+
+    # ---- instrumented pass: per-family CUDA-event timing
+    L.resnet_b200_profile(1)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step(False)
+    t.sync()
+    fam = {}
+    for f, name in ((0, "igemm_kmajor_kernel (tcgen05 fprop+dgrad)"), (1, "igemm_mnmajor_kernel (tcgen05 wgrad + split-K reduce)"),
+                    (2, "BatchNorm/elementwise"), (3, "simt_conv_kernel (stem 7x7, fp32)")):
+        tms, n, w = C.c_double(), C.c_longlong(), C.c_double()
+        L.resnet_b200_profile_read(f, C.byref(tms), C.byref(n), C.byref(w))
+        fam[f] = {"name": name, "ms": tms.value, "launches": n.value, "work": w.value}
+    L.resnet_b200_profile(0)
+    api.check()
+
+    if rank == 0:
+        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+        rl_all = []
+        for f in (0, 1, 3):
+            if fam[f]["launches"]:
+                ach = fam[f]["work"] / (fam[f]["ms"] * 1e-3) / 1e12
+                peak = tf32_peak if f != 3 else 75.0
+                rl_all.append({"kernel": fam[f]["name"], "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                               "ms_per_step": fam[f]["ms"] / prof_steps, "launches_per_step": fam[f]["launches"] / prof_steps,
+                               "flops_per_launch": fam[f]["work"] / fam[f]["launches"]})
+        if fam[2]["launches"]:
+            ach = fam[2]["work"] / (fam[2]["ms"] * 1e-3) / 1e9
+            rl_all.append({"kernel": fam[2]["name"], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                           "ms_per_step": fam[2]["ms"] / prof_steps, "launches_per_step": fam[2]["launches"] / prof_steps,
+                           "bytes_per_launch": fam[2]["work"] / fam[2]["launches"]})
+        dom = max(rl_all, key=lambda r: r["ms_per_step"])
+        roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
+                    "traffic": None, "kernel": dom["kernel"],
+                    "peak_source": ("MEASURED_PEAKS.json (%s): " % pk["src"]) + ("bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate; kernel timed inside a long step)"
+                                                                                 if dom["bound"] == "tensor" else "hbm_gbs copy bandwidth"),
+                    "how": "CUDA events around every launch of the family on the launching stream, %d instrumented steps after the timed region" % prof_steps}
+        total_img = N * world * args.steps
+        value = total_img / (ms_max * 1e-3)
+        out = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+               "config": {"workload": "ResNet-50 (reference variant: 3x3/2 projection shortcuts, 47.58 M params, 39.09 GFLOP/img/step) full training step "
+                                      "(forward_pass + backwards_pass + Adam update_parameters), batch %d per GPU, 224x224, fp32 storage NHWC, TF32 tcgen05 convs" % N,
+                          "global_batch": N * world, "per_gpu_batch": N, "parallelism": "dp%d" % world,
+                          "l2": "inputs larger than L2 (tens of GB touched per step), no flush needed",
+                          "step_flops": FLOP_PER_IMAGE_STEP * N, "achieved_step_tflops_per_gpu": FLOP_PER_IMAGE_STEP * N / (ms_max / args.steps * 1e-3) / 1e12},
+               "e2e": {"value": total_img / (ms_e2e_max * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(img.nbytes + lab.nbytes),
+                       "d2h_bytes_per_step": int(N * 1000 * 4), "ms_per_step": ms_e2e_max / args.steps},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_all": rl_all,
+               "last_step": {"loss_per_image": loss / N, "n_wrong": nwrong}}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(batch=4)
+        print(json.dumps(out), flush=True)
+    barrier(dist)
+    t.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,11 @@ float resnet_b200_timer_end_ms(Train_ResNet * trainer);
 int resnet_b200_loss_accuracy(Train_ResNet * trainer, float * loss_sum, int * n_wrong);
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 long long resnet_b200_launch_count(void);
+/* per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline leg): enable (resets the
+ * records), run steps, then read family f: 0 = tcgen05 fprop+dgrad, 1 = tcgen05 wgrad (+ split-K reduce),
+ * 2 = BatchNorm / elementwise, 3 = SIMT conv (stem).  work = algorithmic FLOPs (0, 1, 3) or HBM bytes (2). */
+void resnet_b200_profile(int enable);
+int resnet_b200_profile_read(int family, double * ms, long long * launches, double * work);
 /* 1 when conv layers of this trainer run on the tcgen05 path, 0 when on the fp32 SIMT path */
 int resnet_b200_uses_tensor_cores(Train_ResNet * trainer);
 void resnet_b200_destroy_trainer(Train_ResNet * trainer);

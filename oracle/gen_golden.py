@@ -51,11 +51,13 @@ def stage_ops(out):
 
 
 def stage_net(out, tag, variant):
-    cfg = G.MINI if tag == "mini" else G.MINI4
+    cfg = {"mini": G.MINI, "mini4": G.MINI4, "mini5": G.MINI5}[tag]
     shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
     W = G.mini_weights(shapes)
     img, lab = G.mini_batch(cfg)
     r = Ref(variant).create(seed=1234, **cfg)
+    r.n_locations = len(shapes)  # the reference over-counts locations unless there are exactly 4 projections (resnet.cu:819)
+    r.sizes = r.sizes[:len(shapes)]
     if tag == "mini" and variant == "naive":
         out["mini.curand_init"] = np.stack([G.summary(a) for a in r.get_params()])  # the reference's own cuRAND init
     r.set_params(W)
@@ -107,7 +109,7 @@ def run_stage(stage, part_path):
 
 def main(out_path):
     os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
-    stages = ["ops"] + ["net:%s:%s" % (t, v) for t in ("mini", "mini4") for v in ("naive", "clean", "cudnn") if available(v)]
+    stages = ["ops", "net:mini:naive", "net:mini4:naive"] + ["net:mini5:%s" % v for v in ("naive", "clean", "cudnn") if available(v)]
     merged, notes = {}, []
     for st in stages:
         part = out_path + "." + st.replace(":", "_") + ".part.npz"

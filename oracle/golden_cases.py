@@ -11,6 +11,9 @@ BN_CASES = [(4, 6, 10, 0), (4, 6, 10, 1), (2, 4, 64, 1)]  # (N, S, C, relu)
 # NB: the last block of every network config is non-strided: the reference pools the final activation over the LAST
 # BLOCK'S *incoming* spatial dim (reference: resnet.cu:1732), which equals the output dim only then (true for ResNet-50).
 MINI = dict(input_dim=32, n_blocks=3, reductions=[0, 1, 0], batch=4, output=10, lr=1e-3, wd=0.0, b1=0.9, b2=0.999, eps=1e-7)
+# MINI5 has exactly four projection blocks, so the reference's n_locations = 16 + 9*n_blocks (reference: resnet.cu:819) is exact
+# and its update_parameters / check_errors loops (resnet.cu:2952) do not run off the end of locations[].
+MINI5 = dict(input_dim=32, n_blocks=5, reductions=[0, 1, 1, 1, 0], batch=4, output=10, lr=1e-3, wd=0.0, b1=0.9, b2=0.999, eps=1e-7)
 MINI4 = dict(input_dim=32, n_blocks=4, reductions=[0, 1, 0, 0], batch=2, output=10, lr=1e-3, wd=0.0, b1=0.9, b2=0.999, eps=1e-7)
 
 

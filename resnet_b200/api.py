@@ -100,10 +100,12 @@ class Trainer:
         return [self.model.contents.params, bb.param_derivs, bb.prev_means, bb.prev_vars][which].contents
 
     def get_params(self, which=0):
+        self.sync()
         tr = self._tree(which)
         return [d2h(tr.locations[i], self.sizes[i]) for i in range(self.n_locations)]
 
     def set_params(self, arrays, which=0):
+        self.sync()
         tr = self._tree(which)
         for i, a in enumerate(arrays):
             a = np.ascontiguousarray(a, np.float32).reshape(-1)
@@ -113,6 +115,7 @@ class Trainer:
     # ---- batch
     def set_batch(self, images, labels):
         """blocking copy into cur_batch->images / correct_classes (what load_new_batch does, reference: resnet.cu:1315-1316)"""
+        self.sync()
         b = self.batch_struct.contents
         h2d(b.images, np.ascontiguousarray(images, np.float32))
         h2d(b.correct_classes, np.ascontiguousarray(labels, np.int32))
@@ -146,6 +149,7 @@ class Trainer:
 
     # ---- named activations (same names as oracle.OracleNet.act / reference struct fields)
     def activation(self, name, deriv=False, dtype=np.float32):
+        self.sync()
         t = self.t.contents
         A = (t.backprop_buffer.contents.activation_derivs if deriv else t.forward_buffer.contents.activations).contents
         N, d = self.batch, self.dims.contents

@@ -1,5 +1,6 @@
 // capi.cu -- C-ABI services and single-operator entry points declared in include/resnet_b200.h.
 #include "engine.h"
+#include "prof.h"
 #include "../../include/resnet_b200.h"
 #include <curand.h>
 
@@ -107,6 +108,8 @@ int resnet_b200_loss_accuracy(Train_ResNet *t, float *loss_sum, int *n_wrong) {
 	return status();
 }
 long long resnet_b200_launch_count(void) { return g_launches; }
+void resnet_b200_profile(int enable) { prof_reset(); prof_enable(enable != 0); }
+int resnet_b200_profile_read(int family, double *ms, long long *launches, double *work) { return prof_read(family, ms, launches, work); }
 int resnet_b200_uses_tensor_cores(Train_ResNet *t) {
 	Engine *e = engine_of(t);
 	if (!e) return 0;

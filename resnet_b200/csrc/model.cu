@@ -8,6 +8,7 @@
 // allocated inside the step; fused kernels (BN apply + residual + ReLU; Adam m/v/p + grad zeroing); recomputable
 // buffers (x-hat, pre-ReLU sums) exist only in keep-all mode; one stream instead of the legacy default stream.
 #include "engine.h"
+#include "prof.h"
 #include <curand.h>
 #include <map>
 #include <mutex>
@@ -199,7 +200,9 @@ static Engine *build_engine(Train_ResNet *t) {
 	e->keep_all = env_int("RESNET_B200_KEEP_ALL", 0);
 	e->dp = nullptr;
 	e->wgrad_ws_bytes = 0;
-	RB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	// a BLOCKING stream: it synchronises with the legacy default stream, so a host driver's plain cudaMemcpy / kernels on
+	// stream 0 (how the reference's own code touches these buffers) stay ordered with our launches
+	RB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamDefault));
 	RB_CUDA(cudaEventCreate(&e->ev0));
 	RB_CUDA(cudaEventCreate(&e->ev1));
 	Bump B{e};
@@ -378,20 +381,31 @@ static Engine *build_engine(Train_ResNet *t) {
 }
 
 // ------------------------------------------------------------------------------------------------ layer helpers
+// algorithmic FLOPs of one conv pass: 2 * N * Ho * Wo * Cout * Cin * k^2
+static double conv_flops(const ConvGeom &g) { return 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k; }
+
 static void conv_fwd(Engine *e, ConvRef &c, const float *in, float *out) {
+	ProfScope ps(e->stream, c.use_tc ? PROF_IGEMM_KMAJOR : PROF_STEM_SIMT, conv_flops(c.g));
 	if (c.use_tc) tc_run(c.fprop, e->stream);
 	else simt_conv_fprop(c.g, in, c.wf, out, e->stream);
 }
 static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, float *din, int accumulate) {
 	if (c.use_tc) {
-		if (din) tc_run(c.dgrad, e->stream);
+		if (din) { ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, conv_flops(c.g)); tc_run(c.dgrad, e->stream); }
+		ProfScope ps(e->stream, PROF_IGEMM_WGRAD, conv_flops(c.g));
 		tc_run(c.wgrad, e->stream);
 	} else {
+		ProfScope ps(e->stream, PROF_STEM_SIMT, conv_flops(c.g) * (din ? 2 : 1));
 		if (din) simt_conv_dgrad(c.g, dout, c.wd, din, accumulate, e->stream);
 		simt_conv_wgrad(c.g, in, dout, c.dw, e->stream);
 	}
 }
+// algorithmic HBM bytes of the BatchNorm / elementwise kernels, E = rows * C elements of 4 bytes:
+// statistics 1E; apply 2E (+1E residual); backward reduce 2E (+1E mask) and dx 3E (+1E mask)
+static double bn_bytes(const BnRef &bn, double passes) { return passes * 4.0 * (double)bn.rows * bn.C; }
+
 static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps) {
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, 1));
 	bn_stats(x, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->bn_partials, e->bn_max_blocks, e->stream);
 	if (e->keep_all && bn.cache->normalized) {
 		bn_apply(x, bn.ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized, 0, e->stream);
@@ -399,7 +413,16 @@ static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps) {
 		bn_apply(x, e->tmp_ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized_temp, 0, e->stream);
 	}
 }
+static void bn_act(Engine *e, BnRef &bn, const float *x, int relu, const float *res, const float *ab2, float *y, int rnd) {
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, res ? 3 : 2));
+	bn_apply(x, bn.ab, bn.rows, bn.C, relu, res, ab2, y, rnd, e->stream);
+}
+static void relu_backward(Engine *e, const float *y, const float *dy, long long n, float *dx) {
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, 12.0 * (double)n);
+	relu_bwd(y, dy, n, dx, e->stream);
+}
 static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps) {
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, mask ? 7 : 5));
 	bn_bwd(x, dy, mask, bn.gamma, bn.means, bn.vars, eps, bn.rows, bn.C, bn.dgamma, bn.dbeta, dx, e->bn_partials, e->bn_max_blocks, e->bn_coef,
 	       e->round_tf32, e->stream);
 }
@@ -466,7 +489,7 @@ void forward_pass(Train_ResNet *t) {
 
 	conv_fwd(e, e->stem, t->cur_batch->images, e->X0);
 	bn_forward(e, e->bn0, e->X0, eps);
-	bn_apply(e->X0, e->bn0.ab, e->bn0.rows, e->bn0.C, 1, nullptr, nullptr, e->Y0, rnd, st);
+	bn_act(e, e->bn0, e->X0, 1, nullptr, nullptr, e->Y0, rnd);
 	const int S1 = d->input / d->init_conv_stride;
 	maxpool_fwd(e->Y0, e->N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->max_inds, e->P0, st);
 
@@ -475,10 +498,10 @@ void forward_pass(Train_ResNet *t) {
 		Activation_ConvBlock *ab = t->forward_buffer->activations->activation_conv_blocks[i];
 		conv_fwd(e, b.reduce, b.x_in, b.Xr);
 		bn_forward(e, b.bn_r, b.Xr, eps);
-		bn_apply(b.Xr, b.bn_r.ab, b.bn_r.rows, b.bn_r.C, 1, nullptr, nullptr, b.Yr, rnd, st);
+		bn_act(e, b.bn_r, b.Xr, 1, nullptr, nullptr, b.Yr, rnd);
 		conv_fwd(e, b.spatial, b.Yr, b.Xs);
 		bn_forward(e, b.bn_s, b.Xs, eps);
-		bn_apply(b.Xs, b.bn_s.ab, b.bn_s.rows, b.bn_s.C, 1, nullptr, nullptr, b.Ys, rnd, st);
+		bn_act(e, b.bn_s, b.Xs, 1, nullptr, nullptr, b.Ys, rnd);
 		conv_fwd(e, b.expand, b.Ys, b.Xe);
 		bn_forward(e, b.bn_e, b.Xe, eps);
 		if (b.has_proj) {
@@ -491,7 +514,7 @@ void forward_pass(Train_ResNet *t) {
 			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, ab->output, 0, st);
 		}
 		// output_activated = relu(bn(expanded) + shortcut)   (reference: resnet.cu:1670-1723, four kernels there)
-		bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 1, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, b.OA, rnd, st);
+		bn_act(e, b.bn_e, b.Xe, 1, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, b.OA, rnd);
 	}
 	BlockRef &last = e->blocks.back();
 	const int Sl = last.expand.g.S;
@@ -534,7 +557,7 @@ void backwards_pass(Train_ResNet *t) {
 			bn_backward(e, b.bn_p, b.Xp, b.dOA, b.OA, b.dXp, eps);
 			conv_bwd(e, b.proj, b.x_in, b.dXp, b.dBI, 0);
 		} else {
-			relu_bwd(b.OA, b.dOA, b.n_exp_out, b.dBI, st);
+			relu_backward(e, b.OA, b.dOA, b.n_exp_out, b.dBI);
 		}
 		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps);
 		conv_bwd(e, b.expand, b.Ys, b.dXe, b.dYs, 0);
@@ -546,8 +569,11 @@ void backwards_pass(Train_ResNet *t) {
 	}
 	const int S1 = d->input / d->init_conv_stride;
 	maxpool_bwd(e->max_inds, e->dP0, N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->dY0, st);
-	bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
-	       e->bn_partials, e->bn_max_blocks, e->bn_coef, 0, st);
+	{
+		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e->bn0, 7));
+		bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
+		       e->bn_partials, e->bn_max_blocks, e->bn_coef, 0, st);
+	}
 	conv_bwd(e, e->stem, t->cur_batch->images, e->dX0, nullptr, 0);  // no input gradient (reference: resnet.cu:2243-2245)
 	dp_allreduce_grads(e);
 }

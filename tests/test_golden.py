@@ -61,10 +61,10 @@ def test_maxpool_and_adam_kernels(gold):
     np.testing.assert_allclose(v, gold["adam.v2"], rtol=1e-6, atol=1e-8)
 
 
-@pytest.mark.parametrize("tag", ["mini", "mini4"])
+@pytest.mark.parametrize("tag", ["mini", "mini4", "mini5"])
 def test_network_forward_vs_resnet_cu(gold, tag):
     """forward_pass of the reference's resnet.cu, layer by layer (fingerprints) and pred (full)."""
-    cfg = G.MINI if tag == "mini" else G.MINI4
+    cfg = {"mini": G.MINI, "mini4": G.MINI4, "mini5": G.MINI5}[tag]
     net = O.OracleNet(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], cfg["batch"], output=cfg["output"], lr=cfg["lr"])
     shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
     net.set_params(G.mini_weights(shapes))
@@ -85,14 +85,14 @@ def test_network_forward_vs_resnet_cu(gold, tag):
     assert checked > 20
 
 
-@pytest.mark.parametrize("tag,variant", [("mini", "clean"), ("mini4", "clean"), ("mini", "cudnn"), ("mini4", "cudnn")])
+@pytest.mark.parametrize("tag,variant", [("mini5", "clean"), ("mini5", "cudnn")])
 def test_network_step_vs_complete_variants(gold, tag, variant):
     """full step (forward, backward, Adam x2) of resnet_clean.cu / resnet_cudnn.cu: pred, every parameter gradient,
     parameters after one and two updates."""
     key = "%s.%s" % (tag, variant)
     if key + ".grads" not in gold.files:
         pytest.skip("variant did not run on the generating box")
-    cfg = G.MINI if tag == "mini" else G.MINI4
+    cfg = G.MINI5
     net = O.OracleNet(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], cfg["batch"], output=cfg["output"], lr=cfg["lr"])
     shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
     net.set_params(G.mini_weights(shapes))
