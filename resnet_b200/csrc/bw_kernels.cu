@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 #pragma unroll
 		for (int j = 0; j < VEC; j++) mu[j] = means[col0 + j];
 	}
+#pragma unroll 4
 	for (long long i = g; i < nvec; i += T) {
 		float a[VEC];
 		ldv<VEC>(x, i, a);
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
 			a2[j] = ab2 ? ab2[c0 + j] : 1.f; b2[j] = ab2 ? ab2[Cc + c0 + j] : 0.f;
 		}
 	}
+#pragma unroll 4
 	for (long long i = g; i < nvec; i += T) {
 		if constexpr (!FIXED) {
 			const int c0 = (int)(i % V) * VEC;
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__rest
 #pragma unroll
 		for (int j = 0; j < VEC; j++) { c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j]; }
 	}
+#pragma unroll 4
 	for (long long i = g; i < nvec; i += T) {
 		if constexpr (!FIXED) {
 			const int c0 = (int)(i % V) * VEC;
@@ -326,6 +329,7 @@ __global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const float *__restr
 	const long long T = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	const long long n4 = n / 4;
+#pragma unroll 4
 	for (long long i = g; i < n4; i += T) {
 		float4 a = reinterpret_cast<const float4 *>(y)[i], d = reinterpret_cast<const float4 *>(dy)[i];
 		reinterpret_cast<float4 *>(dx)[i] = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);

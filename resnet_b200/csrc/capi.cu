@@ -143,7 +143,13 @@ int resnet_b200_conv_forward(int S, int k, int cin, int cout, int stride, int N,
 	ConvGeom g{N, S, cin, cout, k, stride};
 	float *wf = tmp.get<float>(g.w_elems());
 	pack_one(weights, wf, nullptr, cout, cin, k * k, 0, tmp);
-	if (impl == 0) {
+	if (impl == 0 && tc_stem_supported(S, k, cin, cout, stride)) {
+		float *xp = tmp.get<float>((long long)stem_xp_elems(N, S)), *wfs = tmp.get<float>((long long)cout * 7 * 32);
+		stem_pad_input(input, N, S, xp, 0, 0);
+		stem_pack_weights(weights, cout, wfs, 0, 0);
+		TcPlan *pl = tc_make_stem_fprop(N, S, cout, xp, wfs, output);
+		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
+	} else if (impl == 0) {
 		TcPlan *pl = tc_make_fprop(g, input, wf, output);
 		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 	} else {
@@ -159,7 +165,16 @@ int resnet_b200_conv_backward(int S, int k, int cin, int cout, int stride, int N
 	ConvGeom g{N, S, cin, cout, k, stride};
 	float *wf = tmp.get<float>(g.w_elems()), *wd = tmp.get<float>(g.w_elems());
 	pack_one(weights, wf, wd, cout, cin, k * k, 0, tmp);
-	if (impl == 0) {
+	if (impl == 0 && tc_stem_supported(S, k, cin, cout, stride)) {
+		// stem: weight gradient on the tensor cores; the (never needed, reference: resnet.cu:2243-2245) input gradient stays SIMT
+		if (input_deriv) simt_conv_dgrad(g, out_deriv, wd, input_deriv, to_add, 0);
+		float *xp = tmp.get<float>((long long)stem_xp_elems(N, S));
+		stem_pad_input(input, N, S, xp, 0, 0);
+		size_t ws = tc_stem_wgrad_workspace_bytes(N, S, cout);
+		float *wsp = (float *)tmp.get<char>((long long)ws);
+		TcPlan *pl = tc_make_stem_wgrad(N, S, cout, xp, out_deriv, weight_deriv, wsp, ws);
+		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
+	} else if (impl == 0) {
 		if (input_deriv) {
 			TcPlan *pl = tc_make_dgrad(g, out_deriv, wd, input_deriv, to_add);
 			if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }

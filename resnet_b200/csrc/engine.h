@@ -60,6 +60,10 @@ struct Engine {
 	float *X0, *Y0, *P0;  // init_conv_applied, init_conv_activated, init_convblock_input
 	int *max_inds;
 	float *dP0, *dY0, *dX0;
+	// stem on the tensor cores: zero-bordered NHWC4 copy of the batch, packed [Cout][7][8][4] weights, plans
+	bool stem_tc;
+	float *stem_xp, *stem_wfs;
+	TcPlan *stem_fprop, *stem_wgrad;
 	std::vector<BlockRef> blocks;
 	// head
 	float *pooled, *logits, *pred, *dlogits, *dpooled, *row_loss;

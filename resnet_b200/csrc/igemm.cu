@@ -104,6 +104,7 @@ struct alignas(64) WgradParams {
 	int ntaps;
 	int bw, bh, bn, tiles_w, tiles_h, tiles_b, k_boxes;
 	int splits, boxes_per_split;
+	int tpt;  // filter taps per tile (they share the dY tile of each stage); tpt * BN <= 256 TMEM columns
 	int co_tiles, ci_tiles, BN, cin, cout;
 	int stages;
 	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const __grid_constant__ WgradParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
-	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	uint64_t *full = reinterpret_cast<uint64_t *>(base + (size_t)p.stages * stage_bytes);
 	uint64_t *empty = full + p.stages;
 	uint64_t *tfull = empty + p.stages;
@@ -283,10 +284,13 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
 
-	// tile = ((tap * co_tiles + cot) * ci_tiles + cit) * splits + split
-	const int total_tiles = p.ntaps * p.co_tiles * p.ci_tiles * p.splits;
+	// tile = ((tap_group * co_tiles + cot) * ci_tiles + cit) * splits + split; a tap group shares one dY (A) tile per
+	// stage between up to `tpt` filter taps, each with its own BN-column accumulator (tpt * BN <= 256 TMEM columns)
+	const int n_groups = (p.ntaps + p.tpt - 1) / p.tpt;
+	const int total_tiles = n_groups * p.co_tiles * p.ci_tiles * p.splits;
 	const int nb_boxes = p.BN / 32;
 	const uint32_t box_bytes = 32 * 128;  // 32 pixels x 32 channels x 4 B
+	const uint32_t acc_cols = (uint32_t)(p.tpt * p.BN);
 
 	if (warp == 0) {
 		if (lane == 0) {
@@ -297,17 +301,22 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 				int r = tile / p.splits;
 				const int cit = r % p.ci_tiles; r /= p.ci_tiles;
 				const int cot = r % p.co_tiles;
-				const TapDesc tp = p.taps[r / p.co_tiles];
+				const int tap0 = (r / p.co_tiles) * p.tpt;
+				const int ntg = min(p.tpt, p.ntaps - tap0);
 				const int kb0 = split * p.boxes_per_split;
 				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
 				for (int kb = kb0; kb < kb1; kb++) {
 					const int ow0 = (kb % p.tiles_w) * p.bw, oh0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh, n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bn;
 					mbar_wait(&empty[stage], phase ^ 1);
 					uint8_t *sa = base + (size_t)stage * stage_bytes;
-					mbar_expect_tx(&full[stage], stage_bytes);
+					mbar_expect_tx(&full[stage], p.a_bytes + (uint32_t)ntg * p.b_bytes);
 					for (int j = 0; j < 4; j++) tma_load_4d(sa + j * box_bytes, &p.amap, &full[stage], cot * 128 + j * 32, ow0, oh0, n0);
-					for (int j = 0; j < nb_boxes; j++)
-						tma_load_4d(sa + p.a_bytes + j * box_bytes, &p.bmap[tp.amap], &full[stage], cit * p.BN + j * 32, ow0 + tp.dx, oh0 + tp.dy, n0);
+					for (int t = 0; t < ntg; t++) {
+						const TapDesc tp = p.taps[tap0 + t];
+						uint8_t *sb = sa + p.a_bytes + (size_t)t * p.b_bytes;
+						for (int j = 0; j < nb_boxes; j++)
+							tma_load_4d(sb + j * box_bytes, &p.bmap[tp.amap], &full[stage], cit * p.BN + j * 32, ow0 + tp.dx, oh0 + tp.dy, n0);
+					}
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
 			}
@@ -320,20 +329,25 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			uint32_t phase = 0, accphase = 0;
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 				const int split = tile % p.splits;
+				const int tap0 = ((tile / p.splits) / p.ci_tiles / p.co_tiles) * p.tpt;
+				const int ntg = min(p.tpt, p.ntaps - tap0);
 				const int kb0 = split * p.boxes_per_split;
 				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
 				mbar_wait(&tempty[acc], accphase ^ 1);
 				tc_fence_after();
-				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+				const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
 				for (int kb = kb0; kb < kb1; kb++) {
 					mbar_wait(&full[stage], phase);
 					tc_fence_after();
 					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
 					const uint64_t adesc = make_smem_desc(a_addr, p.lbo, p.sbo, p.layout_type);
-					const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
+					for (int t = 0; t < ntg; t++) {
+						const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-					for (int k = 0; k < 4; k++)  // 8 pixel rows (1024 B) per K=8 MMA
-						mma_tf32_ss(d_tmem, adesc + (uint64_t)(k * 64), bdesc + (uint64_t)(k * 64), idesc, (uint32_t)((kb > kb0) || (k != 0)));
+						for (int k = 0; k < 4; k++)  // 8 pixel rows (1024 B) per K=8 MMA
+							mma_tf32_ss(d_tmem + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 64), bdesc + (uint64_t)(k * 64), idesc,
+							            (uint32_t)((kb > kb0) || (k != 0)));
+					}
 					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
@@ -353,20 +367,23 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			int r = tile / p.splits;
 			const int cit = r % p.ci_tiles; r /= p.ci_tiles;
 			const int cot = r % p.co_tiles;
-			const int tap = r / p.co_tiles;
+			const int tap0 = (r / p.co_tiles) * p.tpt;
+			const int ntg = min(p.tpt, p.ntaps - tap0);
 			const int co = cot * 128 + row;
 			const bool valid = co < p.cout;
-			float *dst = p.partial + (((size_t)split * p.ntaps + tap) * p.cout + co) * p.cin + (size_t)cit * p.BN;
 			mbar_wait(&tfull[acc], accphase);
 			tc_fence_after();
-			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-			for (int c = 0; c < p.BN / 32; c++) {
-				float v[32];
-				tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-				if (valid) {
-					float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
+			for (int t = 0; t < ntg; t++) {
+				float *dst = p.partial + (((size_t)split * p.ntaps + tap0 + t) * p.cout + co) * p.cin + (size_t)cit * p.BN;
+				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.BN);
+				for (int c = 0; c < p.BN / 32; c++) {
+					float v[32];
+					tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+					if (valid) {
+						float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
 #pragma unroll
-					for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+						for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					}
 				}
 			}
 			tc_fence_before();
@@ -562,22 +579,35 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float
 	return pl;
 }
 
-size_t tc_wgrad_workspace_bytes(const ConvGeom &g) {
-	// mirrors the split choice in tc_make_wgrad
-	const int So = g.So();
-	int bw, bh, bn;
-	const bool flat = (g.k == 1);
-	long long k_boxes;
-	if (flat) k_boxes = ceil_div((long long)g.N * So * So, 32);
-	else { choose_box(So, So, g.N, 32, true, &bw, &bh, &bn); k_boxes = (long long)ceil_div(So, bw) * ceil_div(So, bh) * ceil_div(g.N, bn); }
-	const int BN = pick_bn(g.cin);
-	const int tiles = g.taps() * ceil_div(g.cout, 128) * (g.cin / BN);
-	long long splits = ceil_div(2 * kNumSMs, tiles);
-	if (splits > k_boxes) splits = k_boxes;
+// shape decisions of a wgrad launch, shared by the workspace query and the plan builder
+struct WgradShape { int bw, bh, bn, tiles_w, tiles_h, tiles_b, k_boxes, BN, ci_tiles, co_tiles, ntaps, tpt, splits, boxes_per_split; };
+static WgradShape wgrad_shape(int Wm, int Hm, int Nn, bool flat, int cin_cols, int cout, int ntaps) {
+	WgradShape w;
+	if (flat) { w.bw = 32; w.bh = 1; w.bn = 1; }
+	else choose_box(Wm, Hm, Nn, 32, true, &w.bw, &w.bh, &w.bn);
+	w.tiles_w = ceil_div(Wm, w.bw); w.tiles_h = ceil_div(Hm, w.bh); w.tiles_b = ceil_div(Nn, w.bn);
+	w.k_boxes = w.tiles_w * w.tiles_h * w.tiles_b;
+	w.BN = pick_bn(cin_cols);
+	w.ci_tiles = cin_cols / w.BN;
+	w.co_tiles = ceil_div(cout, 128);
+	w.ntaps = ntaps;
+	w.tpt = 256 / w.BN;  // double-buffered accumulators: 2 * tpt * BN <= 512 TMEM columns
+	if (w.tpt > ntaps) w.tpt = ntaps;
+	if (w.tpt < 1) w.tpt = 1;
+	const int tiles = ceil_div(ntaps, w.tpt) * w.co_tiles * w.ci_tiles;
+	int splits = ceil_div(2 * kNumSMs, tiles);
+	if (splits > w.k_boxes) splits = w.k_boxes;
 	if (splits < 1) splits = 1;
-	const long long bps = ceil_div(k_boxes, splits);
-	splits = ceil_div(k_boxes, bps);
-	return (size_t)splits * g.taps() * g.cout * g.cin * sizeof(float);
+	w.boxes_per_split = ceil_div(w.k_boxes, splits);
+	w.splits = ceil_div(w.k_boxes, w.boxes_per_split);
+	return w;
+}
+
+size_t tc_wgrad_workspace_bytes(const ConvGeom &g) {
+	const int So = g.So();
+	const bool flat = (g.k == 1);
+	WgradShape w = flat ? wgrad_shape((int)((long long)g.N * So * So), 1, 1, true, g.cin, g.cout, 1) : wgrad_shape(So, So, g.N, false, g.cin, g.cout, g.taps());
+	return (size_t)w.splits * g.taps() * g.cout * g.cin * sizeof(float);
 }
 
 TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *workspace, size_t ws_bytes) {
@@ -587,22 +617,11 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 	WgradParams &p = pl->wp;
 	const int So = g.So();
 	const bool flat = (g.k == 1);
-	int Wm, Hm, Nn;
-	if (flat) { Wm = (int)((long long)g.N * So * So); Hm = 1; Nn = 1; p.bw = 32; p.bh = 1; p.bn = 1; }
-	else { Wm = So; Hm = So; Nn = g.N; choose_box(So, So, g.N, 32, true, &p.bw, &p.bh, &p.bn); }
-	p.tiles_w = ceil_div(Wm, p.bw); p.tiles_h = ceil_div(Hm, p.bh); p.tiles_b = ceil_div(Nn, p.bn);
-	p.k_boxes = p.tiles_w * p.tiles_h * p.tiles_b;
-	p.cin = g.cin; p.cout = g.cout;
-	p.BN = pick_bn(g.cin);
-	p.ci_tiles = g.cin / p.BN;
-	p.co_tiles = ceil_div(g.cout, 128);
-	p.ntaps = g.taps();
-	const int tiles = p.ntaps * p.co_tiles * p.ci_tiles;
-	int splits = ceil_div(2 * kNumSMs, tiles);
-	if (splits > p.k_boxes) splits = p.k_boxes;
-	if (splits < 1) splits = 1;
-	p.boxes_per_split = ceil_div(p.k_boxes, splits);
-	p.splits = ceil_div(p.k_boxes, p.boxes_per_split);
+	WgradShape w = flat ? wgrad_shape((int)((long long)g.N * So * So), 1, 1, true, g.cin, g.cout, 1) : wgrad_shape(So, So, g.N, false, g.cin, g.cout, g.taps());
+	p.bw = w.bw; p.bh = w.bh; p.bn = w.bn; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_b = w.tiles_b; p.k_boxes = w.k_boxes;
+	p.cin = g.cin; p.cout = g.cout; p.BN = w.BN; p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles; p.ntaps = w.ntaps; p.tpt = w.tpt;
+	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split;
+	const int tiles = ceil_div(p.ntaps, p.tpt) * p.co_tiles * p.ci_tiles;
 	if ((size_t)p.splits * p.ntaps * g.cout * g.cin * sizeof(float) > ws_bytes) { set_error("tc_make_wgrad: workspace too small"); delete pl; return nullptr; }
 	const int box[4] = {32, p.bw, p.bh, p.bn};
 	// MN-major tf32 operands exist only in the "128B swizzle, 32B atom" shared-memory layout (4-row atoms)
@@ -627,7 +646,7 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 		}
 	p.a_bytes = 4 * 32 * 128;
 	p.b_bytes = (uint32_t)(p.BN / 32) * 32 * 128;
-	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
 	p.partial = workspace;
@@ -636,6 +655,156 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 	pl->grid = total < kNumSMs ? total : kNumSMs;
 	pl->kind = 1;
 	pl->dw = dw; pl->cout = g.cout; pl->cin = g.cin; pl->taps = g.taps();
+	if (!ok) { delete pl; return nullptr; }
+	return pl;
+}
+
+// ------------------------------------------------------------------------------------------ stem (7x7 / 2, Cin = 3)
+// reference: resnet.cu:1547 (fprop) and 2243 (wgrad only).  TMA needs 16-byte pixel strides, so the batch is first copied
+// into a zero-bordered NHWC4 buffer xp[N][S][S+8][4] (3 pixels of left border = the convolution's padding).  One filter ROW
+// (kh) of one output pixel is then 32 CONTIGUOUS floats (8 taps x 4 channels, the 8th tap and 4th channel meet zero weights)
+// starting 8 floats after the previous output pixel's: an overlapping tensor map {32 floats, ow (stride 32 B), row, n}
+// turns every filter row into one K = 32 chunk of the same implicit GEMM (K = 7 x 32), on the same kernels as every other
+// layer.  Input rows 2*oh + kh - 3 are reached through even / odd row maps (dy below), out-of-range rows are zero-filled.
+constexpr int kStemK = 7, kStemPadL = 3, kStemPadW = 8;
+
+__global__ void stem_pad_input_kernel(const float *__restrict__ x, int N, int S, float *__restrict__ xp, int rnd) {
+	const int Wp = S + kStemPadW;
+	const long long total = (long long)N * S * Wp;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const int wp = (int)(i % Wp);
+		const long long row = i / Wp;  // n * S + h
+		const int w = wp - kStemPadL;
+		float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (w >= 0 && w < S) {
+			const float *s = x + (row * S + w) * 3;
+			v.x = s[0]; v.y = s[1]; v.z = s[2];
+			if (rnd) {
+				uint32_t r;
+				asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.x)); v.x = __uint_as_float(r);
+				asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.y)); v.y = __uint_as_float(r);
+				asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.z)); v.z = __uint_as_float(r);
+			}
+		}
+		reinterpret_cast<float4 *>(xp)[i] = v;
+	}
+}
+// w [Cout][3][7][7] -> wfs [Cout][7][8][4] (zero for kw = 7 and c = 3)
+__global__ void stem_pack_weights_kernel(const float *__restrict__ w, int cout, float *__restrict__ wfs, int rnd) {
+	const int total = cout * kStemK * 32;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		const int c = i % 4, kw = (i / 4) % 8, kh = (i / 32) % kStemK, co = i / (32 * kStemK);
+		float v = 0.f;
+		if (c < 3 && kw < kStemK) v = w[((co * 3 + c) * kStemK + kh) * kStemK + kw];
+		if (rnd) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
+		wfs[i] = v;
+	}
+}
+// dw [Cout][3][7][7] = sum_s partial[s][kh][Cout][kw*4 + c]
+__global__ void stem_wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, float *__restrict__ dw) {
+	const int total = cout * 3 * kStemK * kStemK;
+	const long long per = (long long)kStemK * cout * 32;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		const int kw = i % kStemK, kh = (i / kStemK) % kStemK, c = (i / (kStemK * kStemK)) % 3, co = i / (3 * kStemK * kStemK);
+		const long long src = ((long long)kh * cout + co) * 32 + kw * 4 + c;
+		float s = 0.f;
+		for (int sp = 0; sp < splits; sp++) s += partial[sp * per + src];
+		dw[i] = s;
+	}
+}
+
+void stem_pad_input(const float *x, int N, int S, float *xp, int rnd, cudaStream_t st) {
+	long long total = (long long)N * S * (S + kStemPadW);
+	int grid = (int)((total + 255) / 256);
+	stem_pad_input_kernel<<<grid > kNumSMs * 16 ? kNumSMs * 16 : grid, 256, 0, st>>>(x, N, S, xp, rnd);
+	RB_LAUNCH_CHECK();
+}
+void stem_pack_weights(const float *w, int cout, float *wfs, int rnd, cudaStream_t st) {
+	stem_pack_weights_kernel<<<ceil_div(cout * kStemK * 32, 256), 256, 0, st>>>(w, cout, wfs, rnd);
+	RB_LAUNCH_CHECK();
+}
+size_t stem_xp_elems(int N, int S) { return (size_t)N * S * (S + kStemPadW) * 4; }
+
+// row parity / offset of input row 2*oh + kh - 3 in the even/odd row maps
+static void stem_row(int kh, int *parity, int *dy) {
+	static const int par[7] = {1, 0, 1, 0, 1, 0, 1}, off[7] = {-2, -1, -1, 0, 0, 1, 1};
+	*parity = par[kh]; *dy = off[kh];
+}
+static bool make_stem_maps(CUtensorMap *maps, const float *xp, int N, int S, const int box[4], CUtensorMapSwizzle swz) {
+	const int So = S / 2, Wp = S + kStemPadW;
+	for (int ph = 0; ph < 2; ph++) {
+		long long dims[4] = {32, So, So, N}, str[3] = {8, 2LL * Wp * 4, (long long)S * Wp * 4};
+		if (!make_map4(&maps[ph], xp + (long long)ph * Wp * 4, dims, str, box, swz)) return false;
+	}
+	return true;
+}
+bool tc_stem_supported(int S, int k, int cin, int cout, int stride) { return k == kStemK && cin == 3 && stride == 2 && S % 2 == 0 && cout % 32 == 0 && cout <= 128; }
+
+TcPlan *tc_make_stem_fprop(int N, int S, int cout, const float *xp, const float *wfs, float *y) {
+	TcPlan *pl = new TcPlan();
+	memset(pl, 0, sizeof(*pl));
+	IgemmParams &p = pl->ip;
+	const int So = S / 2;
+	p.Wm = So; p.Hm = So; p.Nn = N;
+	choose_box(So, So, N, 128, false, &p.bw, &p.bh, &p.bn);
+	p.tiles_w = ceil_div(p.Wm, p.bw); p.tiles_h = ceil_div(p.Hm, p.bh); p.tiles_b = ceil_div(p.Nn, p.bn);
+	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+	p.Ncol = cout; p.BN = pick_bn(cout); p.n_tiles = cout / p.BN;
+	p.kchunks = 1;
+	const int box[4] = {32, p.bw, p.bh, p.bn};
+	bool ok = make_stem_maps(p.amap, xp, N, S, box, CU_TENSOR_MAP_SWIZZLE_128B);
+	p.amap[2] = p.amap[0]; p.amap[3] = p.amap[1];
+	ok = ok && make_map2(&p.bmap, wfs, kStemK * 32, cout, kStemK * 32, 32, p.BN);
+	p.ngroups = 1;
+	GroupDesc &gr = p.groups[0];
+	gr.ntaps = kStemK; gr.oh_off = gr.ow_off = 0;
+	for (int kh = 0; kh < kStemK; kh++) {
+		int par, dy;
+		stem_row(kh, &par, &dy);
+		gr.taps[kh] = TapDesc{0, dy, par, kh * 32};
+	}
+	p.out = y; p.OH = So; p.OW = So; p.os = 1; p.accumulate = 0;
+	finish_kmajor(pl);
+	if (!ok) { delete pl; return nullptr; }
+	return pl;
+}
+
+size_t tc_stem_wgrad_workspace_bytes(int N, int S, int cout) {
+	WgradShape w = wgrad_shape(S / 2, S / 2, N, false, 32, cout, kStemK);
+	return (size_t)w.splits * kStemK * cout * 32 * sizeof(float);
+}
+
+TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const float *xp, const float *dy, float *dw, float *workspace, size_t ws_bytes) {
+	TcPlan *pl = new TcPlan();
+	memset(pl, 0, sizeof(*pl));
+	WgradParams &p = pl->wp;
+	const int So = S / 2;
+	WgradShape w = wgrad_shape(So, So, N, false, 32, cout, kStemK);
+	p.bw = w.bw; p.bh = w.bh; p.bn = w.bn; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_b = w.tiles_b; p.k_boxes = w.k_boxes;
+	p.cin = 32; p.cout = cout; p.BN = w.BN; p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles; p.ntaps = w.ntaps; p.tpt = w.tpt;
+	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split;
+	if ((size_t)p.splits * kStemK * cout * 32 * sizeof(float) > ws_bytes) { set_error("tc_make_stem_wgrad: workspace too small"); delete pl; return nullptr; }
+	const int box[4] = {32, p.bw, p.bh, p.bn};
+	p.layout_type = 1; p.lbo = 32 * 128; p.sbo = 512;
+	bool ok = make_input_maps(&p.amap, dy, N, So, cout, 1, box, false, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+	ok = ok && make_stem_maps(p.bmap, xp, N, S, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+	p.bmap[2] = p.bmap[0]; p.bmap[3] = p.bmap[1];
+	for (int kh = 0; kh < kStemK; kh++) {
+		int par, dyy;
+		stem_row(kh, &par, &dyy);
+		p.taps[kh] = TapDesc{0, dyy, par, 0};
+	}
+	p.a_bytes = 4 * 32 * 128;
+	p.b_bytes = (uint32_t)(p.BN / 32) * 32 * 128;
+	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
+	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
+	p.stages = stages > 8 ? 8 : stages;
+	p.partial = workspace;
+	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+	const int total = ceil_div(p.ntaps, p.tpt) * p.co_tiles * p.ci_tiles * p.splits;
+	pl->grid = total < kNumSMs ? total : kNumSMs;
+	pl->kind = 2;
+	pl->dw = dw; pl->cout = cout; pl->cin = 3; pl->taps = kStemK * kStemK;
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
@@ -654,7 +823,11 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 	} else {
 		igemm_mnmajor_kernel<<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
 		RB_LAUNCH_CHECK();
-		wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
+		if (pl->kind == 1) wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
+		else {
+			stem_wgrad_reduce_kernel<<<ceil_div(pl->cout * 3 * kStemK * kStemK, 256), 256, 0, st>>>(pl->wp.partial, pl->wp.splits, pl->cout, pl->dw);
+			RB_LAUNCH_CHECK();
+		}
 	}
 }
 
@@ -668,8 +841,8 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 		         p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem);
 	} else {
 		const WgradParams &p = pl->wp;
-		snprintf(buf, n, "wgrad box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d stages=%d grid=%d smem=%zu", p.bw, p.bh,
-		         p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "wgrad box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu", p.bw, p.bh,
+		         p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
 	}
 }
 

@@ -232,6 +232,15 @@ static Engine *build_engine(Train_ResNet *t) {
 	const int S0 = d->input, S1 = d->input / d->init_conv_stride, S2 = S1 / d->init_maxpool_stride, F = d->init_conv_filters;
 	const long long n_x0 = (long long)N * S1 * S1 * F, n_p0 = (long long)N * S2 * S2 * F;
 	setup_conv(e, B, e->stem, N, S0, 3, F, d->init_kernel_dim, d->init_conv_stride, 0, P, G, jobs);
+	e->stem_tc = (e->conv_mode == 0) && env_int("RESNET_B200_STEM_TC", 1) && tc_stem_supported(S0, d->init_kernel_dim, 3, F, d->init_conv_stride);
+	e->stem_xp = e->stem_wfs = nullptr;
+	e->stem_fprop = e->stem_wgrad = nullptr;
+	if (e->stem_tc) {
+		e->stem_xp = B.get<float>((long long)stem_xp_elems(N, S0));
+		e->stem_wfs = B.get<float>((long long)F * 7 * 32);
+		size_t ws = tc_stem_wgrad_workspace_bytes(N, S0, F);
+		if (ws > e->wgrad_ws_bytes) e->wgrad_ws_bytes = ws;
+	}
 	e->X0 = A->init_conv_applied = B.get<float>(n_x0);
 	A->norm_init_conv = mk_cache(B, n_x0, F, ka, true);
 	e->Y0 = A->init_conv_activated = B.get<float>(n_x0);
@@ -373,11 +382,44 @@ static Engine *build_engine(Train_ResNet *t) {
 		plan(b.expand, b.Ys, b.Xe, b.dXe, b.dYs, 0);
 		if (b.has_proj) plan(b.proj, b.x_in, b.Xp, b.dXp, b.dBI, 0);
 	}
+	if (e->stem_tc) {
+		const bool had_error = has_error();
+		e->stem_fprop = tc_make_stem_fprop(N, S0, F, e->stem_xp, e->stem_wfs, e->X0);
+		e->stem_wgrad = tc_make_stem_wgrad(N, S0, F, e->stem_xp, e->dX0, e->stem.dw, e->wgrad_ws, e->wgrad_ws_bytes);
+		if (!e->stem_fprop || !e->stem_wgrad) {
+			// the overlapping-row tensor map was refused by the driver: keep the fp32 SIMT stem (slower, still correct)
+			fprintf(stderr, "[resnet_b200] stem tensor maps unavailable (%s); stem stays on the SIMT path\n", last_error());
+			if (!had_error) clear_error();
+			e->stem_tc = false;
+		}
+	}
 	{
 		std::lock_guard<std::mutex> lk(g_mu);
 		g_engines[t] = e;
 	}
 	return e;
+}
+
+static void conv_fwd(Engine *e, ConvRef &c, const float *in, float *out);
+
+static void stem_forward(Engine *e, const float *images) {
+	if (!e->stem_tc) { conv_fwd(e, e->stem, images, e->X0); return; }
+	const ConvGeom &g = e->stem.g;
+	stem_pack_weights(e->stem.w, g.cout, e->stem_wfs, e->round_tf32, e->stream);
+	stem_pad_input(images, g.N, g.S, e->stem_xp, e->round_tf32, e->stream);
+	ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
+	tc_run(e->stem_fprop, e->stream);
+}
+static void stem_backward(Engine *e, const float *images) {
+	if (!e->stem_tc) {  // no input gradient (reference: resnet.cu:2243-2245)
+		ConvRef &c = e->stem;
+		ProfScope ps(e->stream, PROF_STEM_SIMT, 2.0 * c.g.N * c.g.So() * c.g.So() * (double)c.g.cout * c.g.cin * c.g.k * c.g.k);
+		simt_conv_wgrad(c.g, images, e->dX0, c.dw, e->stream);
+		return;
+	}
+	const ConvGeom &g = e->stem.g;
+	ProfScope ps(e->stream, PROF_IGEMM_WGRAD, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
+	tc_run(e->stem_wgrad, e->stream);  // reads the padded copy made by this step's forward_pass
 }
 
 // ------------------------------------------------------------------------------------------------ layer helpers
@@ -487,7 +529,7 @@ void forward_pass(Train_ResNet *t) {
 	// weights may have been written through locations[] since the last step (update, checkpoint restore): re-pack
 	pack_weights(e->pack_jobs_dev, e->n_pack_jobs, e->pack_max_elems, rnd, st);
 
-	conv_fwd(e, e->stem, t->cur_batch->images, e->X0);
+	stem_forward(e, t->cur_batch->images);
 	bn_forward(e, e->bn0, e->X0, eps);
 	bn_act(e, e->bn0, e->X0, 1, nullptr, nullptr, e->Y0, rnd);
 	const int S1 = d->input / d->init_conv_stride;
@@ -572,9 +614,9 @@ void backwards_pass(Train_ResNet *t) {
 	{
 		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e->bn0, 7));
 		bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
-		       e->bn_partials, e->bn_max_blocks, e->bn_coef, 0, st);
+		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st);
 	}
-	conv_bwd(e, e->stem, t->cur_batch->images, e->dX0, nullptr, 0);  // no input gradient (reference: resnet.cu:2243-2245)
+	stem_backward(e, t->cur_batch->images);
 	dp_allreduce_grads(e);
 }
 

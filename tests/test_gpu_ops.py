@@ -89,6 +89,19 @@ def test_conv_tensor_core_linearity_full_size(api):
     assert rel_max(y1, api.conv_forward(x1, w, 1, impl=1)) < 3e-3
 
 
+@pytest.mark.parametrize("S,N", [(32, 4), (64, 3), (224, 2)])
+def test_stem_tensor_core_vs_oracle(api, S, N):
+    """7x7/2, Cin = 3 stem on the tcgen05 path (zero-bordered NHWC4 copy + overlapping-row tensor maps): fprop and wgrad."""
+    rng = np.random.default_rng(S + N)
+    x, _ = O.synthetic_batch(N, S, seed=S)
+    w = rng.normal(0, np.sqrt(2.0 / (49 * 67)), (64, 3, 7, 7)).astype(np.float32)
+    dy = rng.standard_normal((N, S // 2, S // 2, 64)).astype(np.float32)
+    y = api.conv_forward(x, w, 2, impl=0)
+    assert rel_max(y, O.conv_fwd(x, w, 2)) < 3e-3
+    _, dw = api.conv_backward(x, w, dy, 2, want_din=False, impl=0)
+    assert rel_max(dw, O.conv_wgrad(x, dy, 7, 2)) < 3e-3
+
+
 # ------------------------------------------------------------------------------ bandwidth-bound kernels
 @pytest.mark.parametrize("idx", range(len(G.BN_CASES)))
 def test_batchnorm_vs_oracle(api, idx):
