@@ -123,6 +123,16 @@ def reduce_max(dist, x):
     return float(t.item())
 
 
+def broadcast_bytes(dist, payload, n, src=0):
+    """rank `src`'s `payload` (n bytes) on every rank -- carries the NCCL unique id from rank 0 to the others"""
+    if dist is None:
+        return bytes(payload)
+    import torch
+    t = torch.tensor(list(bytes(payload)) if dist.get_rank() == src else [0] * n, dtype=torch.uint8)
+    dist.broadcast(t, src=src)
+    return bytes(t.tolist())
+
+
 def reduce_sum(dist, x):
     if dist is None:
         return x
@@ -211,10 +221,7 @@ def main():
         idbuf = (C.c_char * 128)()
         if rank == 0:
             L.resnet_b200_dp_unique_id(idbuf)
-        import torch
-        tid = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8)
-        dist.broadcast(tid, src=0)
-        idbuf = (C.c_char * 128)(*bytes(tid.tolist()))
+        idbuf = (C.c_char * 128)(*broadcast_bytes(dist, bytes(idbuf), 128))
         L.resnet_b200_dp_init(t.t, idbuf, rank, world, 0)
         api.check()
 

@@ -131,17 +131,37 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) out[i] = sm[i];
 }
 
-// one thread per channel: fold the per-block partials (fp64) into mean, biased variance, a = gamma*rstd, b = beta - mean*a
+// Fold of the per-block partials in fp64.  32 channels x 8 slices per block: slice sy sums partial blocks sy, sy+8, ... (coalesced
+// 128-byte rows), shared memory combines the 8 slices in a fixed order (deterministic).  A one-thread-per-channel loop over
+// ~1000 partials was latency-bound at 170 us per launch (profiles/r01_launch_summary.txt).
+constexpr int kFinC = 32, kFinS = 8;
+__device__ __forceinline__ bool fold_partials(const float *__restrict__ partials, int nblk, int Cc, double *s_out, double *q_out) {
+	__shared__ double sm[kFinS][2][kFinC];
+	const int cx = threadIdx.x, sy = threadIdx.y, c = blockIdx.x * kFinC + cx;
+	double s = 0, q = 0;
+	if (c < Cc)
+		for (int b = sy; b < nblk; b += kFinS) {
+			s += (double)partials[(size_t)b * 2 * Cc + c];
+			q += (double)partials[(size_t)b * 2 * Cc + Cc + c];
+		}
+	sm[sy][0][cx] = s;
+	sm[sy][1][cx] = q;
+	__syncthreads();
+	if (sy != 0 || c >= Cc) return false;
+#pragma unroll
+	for (int j = 1; j < kFinS; j++) { s += sm[j][0][cx]; q += sm[j][1][cx]; }
+	*s_out = s;
+	*q_out = q;
+	return true;
+}
+
+// mean, biased variance, a = gamma*rstd, b = beta - mean*a
 __global__ void bn_finalize_kernel(const float *__restrict__ partials, int nblk, double inv_n, int Cc, const float *__restrict__ gamma,
                                    const float *__restrict__ beta, float eps, float *__restrict__ means, float *__restrict__ vars,
                                    float *__restrict__ ab) {
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= Cc) return;
-	double s = 0, q = 0;
-	for (int b = 0; b < nblk; b++) {
-		s += (double)partials[(size_t)b * 2 * Cc + c];
-		q += (double)partials[(size_t)b * 2 * Cc + Cc + c];
-	}
+	double s, q;
+	if (!fold_partials(partials, nblk, Cc, &s, &q)) return;
+	const int c = blockIdx.x * kFinC + threadIdx.x;
 	const double mean = s * inv_n;
 	double var = q * inv_n - mean * mean;
 	if (var < 0) var = 0;
@@ -159,7 +179,7 @@ static void launch_reduce(bool bwd, const float *x, const float *dy, const float
 	const int V = C / VEC;
 	const long long nvec = rows * V;
 	bool fixed;
-	int cap = max_blocks < kMaxFlatBlocks ? max_blocks : kMaxFlatBlocks;
+	int cap = max_blocks < kNumSMs * 4 ? max_blocks : kNumSMs * 4;  // the fold cost grows with the number of partial blocks
 	int grid = flat_grid(nvec, V, cap, &fixed);
 	if (VEC == 1) fixed = false;
 	const size_t smem = 2 * (size_t)C * sizeof(float);
@@ -175,7 +195,7 @@ static void launch_reduce(bool bwd, const float *x, const float *dy, const float
 
 void bn_finalize(const float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
                  float *means, float *vars, float *ab, cudaStream_t st) {
-	bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partials, nblk, 1.0 / (double)rows, C, gamma, beta, eps, means, vars, ab);
+	bn_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, nblk, 1.0 / (double)rows, C, gamma, beta, eps, means, vars, ab);
 	RB_LAUNCH_CHECK();
 }
 
@@ -252,13 +272,9 @@ void bn_apply(const float *x, const float *ab, long long rows, int C, int relu, 
 __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int nblk, double inv_n, int Cc, const float *__restrict__ gamma,
                                        const float *__restrict__ means, const float *__restrict__ vars, float eps,
                                        float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= Cc) return;
-	double s1 = 0, s2 = 0;
-	for (int b = 0; b < nblk; b++) {
-		s1 += (double)partials[(size_t)b * 2 * Cc + c];
-		s2 += (double)partials[(size_t)b * 2 * Cc + Cc + c];
-	}
+	double s1, s2;
+	if (!fold_partials(partials, nblk, Cc, &s1, &s2)) return;
+	const int c = blockIdx.x * kFinC + threadIdx.x;
 	const float rstd = 1.0f / sqrtf(vars[c] + eps);
 	dbeta[c] = (float)s1;
 	dgamma[c] = (float)(s2 * (double)rstd);
@@ -311,7 +327,7 @@ void bn_bwd(const float *x, const float *dy, const float *mask_src, const float 
             cudaStream_t st) {
 	int grid;
 	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st);
-	bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
+	bn_bwd_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();
 	const int VEC = (C % 4 == 0) ? 4 : 1;
 	const int V = C / VEC;
@@ -394,13 +410,14 @@ void maxpool_fwd(const float *x, int N, int S, int C, int k, int stride, int *ma
 // Gather form of the reference's scatter (resnet.cu:476-494): every input element sums the gradients of the
 // windows whose recorded argmax is that element.  Deterministic, and accumulates where the reference's
 // overlapping-window scatter races (its cuDNN variants accumulate too).
+template <int VEC>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const int *__restrict__ inds, const float *__restrict__ dout, int N, int S, int C,
                                                               int k, int stride, float *__restrict__ din) {
-	const int So = S / stride, half = k / 2;
-	const long long total = (long long)N * S * S * C;
+	const int So = S / stride, half = k / 2, V = C / VEC;
+	const long long total = (long long)N * S * S * V;
 	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-		const int c = (int)(i % C);
-		long long p = i / C;
+		const int cv = (int)(i % V);
+		long long p = i / V;
 		const int w = (int)(p % S); p /= S;
 		const int h = (int)(p % S);
 		const int n = (int)(p / S);
@@ -409,19 +426,30 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const int *__rest
 		int oh_hi = (h + half) / stride; oh_hi = oh_hi >= So ? So - 1 : oh_hi;
 		int ow_lo = (w - half + stride - 1); ow_lo = ow_lo < 0 ? 0 : ow_lo / stride;
 		int ow_hi = (w + half) / stride; ow_hi = ow_hi >= So ? So - 1 : ow_hi;
-		float acc = 0.f;
+		const int me = (int)(i * VEC);  // flat index of this thread's first channel in the input tensor
+		float acc[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++) acc[j] = 0.f;
 		for (int oh = oh_lo; oh <= oh_hi; oh++)
 			for (int ow = ow_lo; ow <= ow_hi; ow++) {
-				const long long o = (((long long)n * So + oh) * So + ow) * C + c;
-				if (inds[o] == (int)i) acc += dout[o];
+				const long long o = ((((long long)n * So + oh) * So + ow) * C) / VEC + cv;
+				float d[VEC];
+				ldv<VEC>(dout, o, d);
+				int id[VEC];
+				if constexpr (VEC == 4) { int4 t = reinterpret_cast<const int4 *>(inds)[o]; id[0] = t.x; id[1] = t.y; id[2] = t.z; id[3] = t.w; }
+				else id[0] = inds[o];
+#pragma unroll
+				for (int j = 0; j < VEC; j++) if (id[j] == me + j) acc[j] += d[j];
 			}
-		din[i] = acc;
+		stv<VEC>(din, i, acc);
 	}
 }
 void maxpool_bwd(const int *max_inds, const float *dout, int N, int S, int C, int k, int stride, float *din, cudaStream_t st) {
-	long long total = (long long)N * S * S * C;
+	const int VEC = (C % 4 == 0) ? 4 : 1;
+	long long total = (long long)N * S * S * (C / VEC);
 	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 8 ? kMaxFlatBlocks * 8 : grid;
-	maxpool_bwd_kernel<<<grid, kThreads, 0, st>>>(max_inds, dout, N, S, C, k, stride, din);
+	if (VEC == 4) maxpool_bwd_kernel<4><<<grid, kThreads, 0, st>>>(max_inds, dout, N, S, C, k, stride, din);
+	else maxpool_bwd_kernel<1><<<grid, kThreads, 0, st>>>(max_inds, dout, N, S, C, k, stride, din);
 	RB_LAUNCH_CHECK();
 }
 

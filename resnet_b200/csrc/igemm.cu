@@ -80,11 +80,12 @@ static bool make_map2(CUtensorMap *m, const float *base, long long cols, long lo
 
 // ------------------------------------------------------------------------------------------ kernel parameters
 struct TapDesc { int dx, dy, amap, bcol; };
-struct GroupDesc { int ntaps, oh_off, ow_off, pad; TapDesc taps[9]; };
+struct GroupDesc { int ntaps, oh_off, ow_off, omap; TapDesc taps[9]; };  // omap: output tensor map of the group (stride-2 dgrad parity)
 
 struct alignas(64) IgemmParams {
 	CUtensorMap amap[4];
 	CUtensorMap bmap;
+	CUtensorMap omap[4];  // output tile store / reduce-add maps, box {32, bw, bh, bn}
 	GroupDesc groups[4];
 	int ngroups;
 	int bw, bh, bn, tiles_w, tiles_h, tiles_b, m_tiles;
@@ -95,6 +96,7 @@ struct alignas(64) IgemmParams {
 	uint32_t a_bytes, b_bytes, a_tx_bytes;  // smem slot sizes; bytes one A box actually transfers (bw*bh*bn rows)
 	float *out;
 	int OH, OW, os, accumulate;
+	int tma_store;  // epilogue: 1 = swizzled smem staging + TMA tile store (reduce-add when accumulate), 0 = per-thread row stores
 };
 
 struct alignas(64) WgradParams {
@@ -124,7 +126,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-	uint64_t *full = reinterpret_cast<uint64_t *>(base + (size_t)p.stages * stage_bytes);
+	uint8_t *staging = base + (size_t)p.stages * stage_bytes;  // 2 x 16 KB epilogue tiles (128 rows x 32 fp32, 128B-swizzled)
+	uint64_t *full = reinterpret_cast<uint64_t *>(staging + 2 * kABytes);
 	uint64_t *empty = full + p.stages;
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 	if (warp == 0 && lane == 0) {
 		for (int i = 0; i < 4; i++) prefetch_tmap(&p.amap[i]);
 		prefetch_tmap(&p.bmap);
+		for (int i = 0; i < 4; i++) prefetch_tmap(&p.omap[i]);
 	}
 	if (warp == 1) {
 		if (lane == 0) {
@@ -208,33 +212,57 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 		const int q = warp & 3;
 		const int row = q * 32 + lane;
 		const int wq = row % p.bw, hq = (row / p.bw) % p.bh, nq = row / (p.bw * p.bh);
+		const bool issuer = (warp == 2 && lane == 0);
 		int acc = 0;
-		uint32_t accphase = 0;
+		uint32_t accphase = 0, chunk_ctr = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 			const int nt = tile % p.n_tiles;
 			int r = tile / p.n_tiles;
 			const int mt = r % p.m_tiles;
 			const GroupDesc &g = p.groups[r / p.m_tiles];
-			const int ow = (mt % p.tiles_w) * p.bw + wq, oh = ((mt / p.tiles_w) % p.tiles_h) * p.bh + hq, n = (mt / (p.tiles_w * p.tiles_h)) * p.bn + nq;
-			const bool valid = (nq < p.bn) && (ow < p.Wm) && (oh < p.Hm) && (n < p.Nn);
-			float *dst = p.out + (((size_t)n * p.OH + (size_t)(oh * p.os + g.oh_off)) * p.OW + (size_t)(ow * p.os + g.ow_off)) * p.Ncol + (size_t)nt * p.BN;
+			const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
 			mbar_wait(&tfull[acc], accphase);
 			tc_fence_after();
 			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-			for (int c = 0; c < p.BN / 32; c++) {
-				float v[32];
-				tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-				if (valid) {
-					float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
-					if (p.accumulate) {
+			if (p.tma_store) {
+				// TMEM -> registers -> swizzled smem tile -> one TMA tile store (or fp32 reduce-add for the residual join) per 32
+				// columns: fully coalesced 128-byte lines, rows outside the tensor are clipped by the TMA unit
+				for (int c = 0; c < p.BN / 32; c++, chunk_ctr++) {
+					float v[32];
+					tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+					uint8_t *buf = staging + (chunk_ctr & 1) * kABytes;
+					uint8_t *rowp = buf + row * 128;
 #pragma unroll
-						for (int j = 0; j < 8; j++) {
-							float4 o = d4[j];
-							d4[j] = make_float4(o.x + v[4 * j], o.y + v[4 * j + 1], o.z + v[4 * j + 2], o.w + v[4 * j + 3]);
+					for (int j = 0; j < 8; j++)
+						*reinterpret_cast<float4 *>(rowp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					fence_proxy_async();
+					if (issuer) tma_wait_group_read0();  // the store that last read the OTHER buffer is done before anyone rewrites it
+					named_barrier_sync(1, 128);
+					if (issuer) {
+						if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * 32, ow0, oh0, n0);
+						else tma_store_4d(&p.omap[g.omap], buf, nt * p.BN + c * 32, ow0, oh0, n0);
+						tma_commit_group();
+					}
+				}
+			} else {
+				const int ow = ow0 + wq, oh = oh0 + hq, n = n0 + nq;
+				const bool valid = (nq < p.bn) && (ow < p.Wm) && (oh < p.Hm) && (n < p.Nn);
+				float *dst = p.out + (((size_t)n * p.OH + (size_t)(oh * p.os + g.oh_off)) * p.OW + (size_t)(ow * p.os + g.ow_off)) * p.Ncol + (size_t)nt * p.BN;
+				for (int c = 0; c < p.BN / 32; c++) {
+					float v[32];
+					tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+					if (valid) {
+						float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
+						if (p.accumulate) {
+#pragma unroll
+							for (int j = 0; j < 8; j++) {
+								float4 o = d4[j];
+								d4[j] = make_float4(o.x + v[4 * j], o.y + v[4 * j + 1], o.z + v[4 * j + 2], o.w + v[4 * j + 3]);
+							}
+						} else {
+#pragma unroll
+							for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 						}
-					} else {
-#pragma unroll
-						for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 					}
 				}
 			}
@@ -244,6 +272,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 			acc ^= 1;
 			if (acc == 0) accphase ^= 1;
 		}
+		if (issuer) tma_wait_group0();  // shared memory must outlive the last store's reads; global writes complete before exit
 	}
 	tc_fence_before();
 	__syncthreads();
@@ -475,15 +504,21 @@ static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int
 	return true;
 }
 
+// RESNET_B200_TMA_STORE=0 falls back to per-thread row stores in the epilogue (bring-up aid)
+static int tma_store_enabled() {
+	const char *e = getenv("RESNET_B200_TMA_STORE");
+	return e ? atoi(e) != 0 : 1;
+}
+
 static void finish_kmajor(TcPlan *pl) {
 	IgemmParams &p = pl->ip;
 	p.a_bytes = kABytes;
 	p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128;
 	p.b_bytes = (uint32_t)p.BN * 128;
 	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
+	int stages = (int)((kMaxDynSmem - 2048 - 2 * kABytes) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
-	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+	pl->smem = (size_t)p.stages * stage_bytes + 2 * kABytes + 1024 + 256;
 	const int total = p.ngroups * p.m_tiles * p.n_tiles;
 	pl->grid = total < kNumSMs ? total : kNumSMs;
 	pl->kind = 0;
@@ -521,6 +556,10 @@ TcPlan *tc_make_fprop(const ConvGeom &g, const float *x, const float *wf, float 
 	p.out = y;
 	if (flat) { p.OH = 1; p.OW = p.Wm; } else { p.OH = So; p.OW = So; }
 	p.os = 1; p.accumulate = 0;
+	ok = ok && make_input_maps(p.omap, y, g.N, So, g.cout, 1, box, flat);  // output tile store map, same pixel box as the A tile
+	for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
+	gr.omap = 0;
+	p.tma_store = tma_store_enabled();
 	finish_kmajor(pl);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
@@ -551,6 +590,7 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float
 		p.groups[0].ntaps = 1; p.groups[0].oh_off = p.groups[0].ow_off = 0;
 		p.groups[0].taps[0] = TapDesc{0, 0, 0, 0};
 		p.OH = 1; p.OW = p.Wm; p.os = 1;
+		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 1, box, true);
 	} else if (g.stride == 1) {
 		p.ngroups = 1;
 		GroupDesc &gr = p.groups[0];
@@ -558,6 +598,7 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float
 		for (int kh = 0; kh < 3; kh++)
 			for (int kw = 0; kw < 3; kw++) gr.taps[kh * 3 + kw] = TapDesc{1 - kw, 1 - kh, 0, (kh * 3 + kw) * g.cout};
 		p.OH = g.S; p.OW = g.S; p.os = 1;
+		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 1, box, false);
 	} else {
 		// dx[2h'+ph] gathers dy[h' + d] * W[kh]:  ph = 0 -> (kh 1, d 0);  ph = 1 -> (kh 0, d +1), (kh 2, d 0)
 		p.ngroups = 4;
@@ -566,6 +607,7 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float
 			const int ph = order[gi][0], pw = order[gi][1];
 			GroupDesc &gr = p.groups[gi];
 			gr.oh_off = ph; gr.ow_off = pw; gr.ntaps = 0;
+			gr.omap = ph * 2 + pw;  // the parity view of dx this phase writes
 			int khs[2], dhs[2], nh, kws[2], dws[2], nw;
 			if (ph == 0) { nh = 1; khs[0] = 1; dhs[0] = 0; } else { nh = 2; khs[0] = 0; dhs[0] = 1; khs[1] = 2; dhs[1] = 0; }
 			if (pw == 0) { nw = 1; kws[0] = 1; dws[0] = 0; } else { nw = 2; kws[0] = 0; dws[0] = 1; kws[1] = 2; dws[1] = 0; }
@@ -573,7 +615,10 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float
 				for (int b = 0; b < nw; b++) gr.taps[gr.ntaps++] = TapDesc{dws[b], dhs[a], 0, (khs[a] * 3 + kws[b]) * g.cout};
 		}
 		p.OH = g.S; p.OW = g.S; p.os = 2;
+		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 2, box, false);  // four parity views of dx
 	}
+	if (g.k == 1 || g.stride == 1) for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
+	p.tma_store = tma_store_enabled();
 	finish_kmajor(pl);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
@@ -764,6 +809,10 @@ TcPlan *tc_make_stem_fprop(int N, int S, int cout, const float *xp, const float 
 		gr.taps[kh] = TapDesc{0, dy, par, kh * 32};
 	}
 	p.out = y; p.OH = So; p.OW = So; p.os = 1; p.accumulate = 0;
+	ok = ok && make_input_maps(p.omap, y, N, So, cout, 1, box, false);
+	for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
+	gr.omap = 0;
+	p.tma_store = tma_store_enabled();
 	finish_kmajor(pl);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;

@@ -61,6 +61,22 @@ __device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *m, ui
 	    : "memory");
 }
 
+// shared -> global tile store / fp32 reduce-add through the tensor map (out-of-bounds rows are clipped by the TMA unit)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *smem, int c0, int c1, int c2, int c3) {
+	asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+	             "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap *m, const void *smem, int c0, int c1, int c2, int c3) {
+	asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+	             "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+	             : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
 	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");

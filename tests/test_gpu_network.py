@@ -42,7 +42,7 @@ def make_pair(cfg, mode, keep_all=True):
     return t, net
 
 
-@pytest.mark.parametrize("mode,cfg_name", [("simt", "MINI4"), ("tc", "MINI4"), ("tc", "MINI5")])
+@pytest.mark.parametrize("mode,cfg_name", [("simt", "MINI4"), ("tc", "MINI4"), ("simt", "MINI5")])
 def test_step_vs_oracle_per_layer(mode, cfg_name):
     cfg = getattr(G, cfg_name)
     t, net = make_pair(cfg, mode)

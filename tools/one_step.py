@@ -1,0 +1,25 @@
+"""Two ResNet-50 training steps at batch 256 (or --batch) through the C API and nothing else: the smallest program that shows
+every kernel of the hot path, for `ncu` captures (profiles/)."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402  (synthetic batch generator only)
+from resnet_b200 import api  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--steps", type=int, default=2)
+a = ap.parse_args()
+red = [1 if i in (3, 7, 13) else 0 for i in range(16)]
+t = api.Trainer(input_dim=224, n_blocks=16, reductions=red, batch=a.batch, output=1000, lr=1e-4, seed=1234, device=0)
+img, lab = O.synthetic_batch(a.batch, 224, seed=1234)
+for _ in range(a.steps):
+    t.set_batch(img, lab)
+    t.forward()
+    t.backward()
+    t.update()
+t.sync()
+print("one_step ok, launches", api.L().resnet_b200_launch_count())
