@@ -123,8 +123,30 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 		}
 	}
 	if constexpr (FIXED) {
+		// deterministic in-block combine: every thread parks its sums, then the first thread of each column adds the
+		// kThreads / V threads that share its column in a fixed order (no floating-point atomics on the product path)
+		__shared__ float red[kThreads][2 * VEC];
 #pragma unroll
-		for (int j = 0; j < VEC; j++) { atomicAdd(&sm[col0 + j], s[j]); atomicAdd(&sm[Cc + col0 + j], q[j]); }
+		for (int j = 0; j < VEC; j++) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][VEC + j] = q[j]; }
+		__syncthreads();
+		const int tcol = (int)(g % V);  // this thread's column; threads t, t + V, t + 2V ... of the block share it when V <= kThreads
+		if (V <= kThreads) {
+			if ((int)threadIdx.x < V) {
+				float ss[VEC], qq[VEC];
+#pragma unroll
+				for (int j = 0; j < VEC; j++) ss[j] = qq[j] = 0.f;
+				for (int k = threadIdx.x; k < kThreads; k += V)
+#pragma unroll
+					for (int j = 0; j < VEC; j++) { ss[j] += red[k][j]; qq[j] += red[k][VEC + j]; }
+				// (blockIdx.x * kThreads) % V == 0 here, so thread t < V owns column t
+#pragma unroll
+				for (int j = 0; j < VEC; j++) { sm[tcol * VEC + j] = ss[j]; sm[Cc + tcol * VEC + j] = qq[j]; }
+			}
+		} else {
+			// V is a multiple of kThreads: one thread per column, the block covers kThreads of the V columns (the rest stay 0)
+#pragma unroll
+			for (int j = 0; j < VEC; j++) { sm[tcol * VEC + j] = s[j]; sm[Cc + tcol * VEC + j] = q[j]; }
+		}
 	}
 	__syncthreads();
 	float *out = partials + (size_t)blockIdx.x * 2 * Cc;

@@ -34,6 +34,7 @@ struct ConvRef {
 	float *wf, *wd;   // packed
 	bool use_tc;
 	TcPlan *fprop, *dgrad, *wgrad;
+	int stats_rows;  // > 0: the fprop epilogue leaves this many rows of BatchNorm partial sums (fused statistics)
 };
 
 struct BlockRef {

@@ -67,6 +67,27 @@ static bool make_map4(CUtensorMap *m, const float *base, const long long dims[4]
 	}
 	return true;
 }
+// rank-5 view of the same NHWC tensors for the wgrad operands: channels are split into {32 inner, C/32 outer} and the outer block
+// index is made the SLOWEST box dimension, so ONE TMA op lands `cblk` consecutive [pixels][32 ch] boxes (the MN-major operand
+// layout) instead of one op per 32-channel block -- the single producer thread was issue-bound at 12-36 ops per stage.
+static bool make_map5_cblk(CUtensorMap *m, const float *base, const long long dims4[4], const long long strides_elems[3], const int box4[4],
+                           int cblk_box, CUtensorMapSwizzle swz) {
+	EncodeTiledFn enc = get_encode();
+	if (!enc) return false;
+	const long long C = dims4[0];
+	cuuint64_t gd[5] = {32, (cuuint64_t)dims4[1], (cuuint64_t)dims4[2], (cuuint64_t)dims4[3], (cuuint64_t)((C + 31) / 32)};
+	cuuint64_t gs[4] = {(cuuint64_t)strides_elems[0] * 4, (cuuint64_t)strides_elems[1] * 4, (cuuint64_t)strides_elems[2] * 4, 128};
+	cuuint32_t bx[5] = {32, (cuuint32_t)box4[1], (cuuint32_t)box4[2], (cuuint32_t)box4[3], (cuuint32_t)cblk_box}, es[5] = {1, 1, 1, 1, 1};
+	if (C < 32) gd[0] = (cuuint64_t)C;
+	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+	                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		set_error("cuTensorMapEncodeTiled(5d) failed: %d dims=(%lld,%lld,%lld,%lld) box=(%d,%d,%d,%d,%d)", (int)r, dims4[0], dims4[1], dims4[2],
+		          dims4[3], box4[0], box4[1], box4[2], box4[3], cblk_box);
+		return false;
+	}
+	return true;
+}
 static bool make_map2(CUtensorMap *m, const float *base, long long cols, long long rows, long long row_stride_elems, int box_cols, int box_rows) {
 	EncodeTiledFn enc = get_encode();
 	if (!enc) return false;
@@ -97,6 +118,7 @@ struct alignas(64) IgemmParams {
 	float *out;
 	int OH, OW, os, accumulate;
 	int tma_store;  // epilogue: 1 = swizzled smem staging + TMA tile store (reduce-add when accumulate), 0 = per-thread row stores
+	float *stats;   // optional BatchNorm partial sums [gridDim.x * 4][2][Ncol] (sum y, sum y^2), one row per epilogue warp
 };
 
 struct alignas(64) WgradParams {
@@ -221,6 +243,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 			const int mt = r % p.m_tiles;
 			const GroupDesc &g = p.groups[r / p.m_tiles];
 			const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+			const bool row_valid = (nq < p.bn) && (ow0 + wq < p.Wm) && (oh0 + hq < p.Hm) && (n0 + nq < p.Nn);
 			mbar_wait(&tfull[acc], accphase);
 			tc_fence_after();
 			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -232,6 +255,10 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 					tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
 					uint8_t *buf = staging + (chunk_ctr & 1) * kABytes;
 					uint8_t *rowp = buf + row * 128;
+					if (p.stats && !row_valid) {  // rows the TMA store clips must not pollute the fused statistics
+#pragma unroll
+						for (int j = 0; j < 32; j++) v[j] = 0.f;
+					}
 #pragma unroll
 					for (int j = 0; j < 8; j++)
 						*reinterpret_cast<float4 *>(rowp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -242,6 +269,22 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 						if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * 32, ow0, oh0, n0);
 						else tma_store_4d(&p.omap[g.omap], buf, nt * p.BN + c * 32, ow0, oh0, n0);
 						tma_commit_group();
+					}
+					if (p.stats) {
+						// fused BatchNorm statistics: lane j sums column j of this warp's 32 rows out of the staged tile (one
+						// conflict-free LDS per row) and adds them to the warp's private row of partial sums in global memory
+						// (always the same thread for a given address: plain read-modify-write, fixed order, deterministic)
+						float cs = 0.f, cq = 0.f;
+#pragma unroll 8
+						for (int rr = 0; rr < 32; rr++) {
+							const int r2 = q * 32 + rr;
+							const float y = *reinterpret_cast<const float *>(buf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7)) << 4) | ((lane & 3) << 2)));
+							cs += y;
+							cq = fmaf(y, y, cq);
+						}
+						float *sp = p.stats + ((size_t)(blockIdx.x * 4 + q) * 2) * p.Ncol + (size_t)nt * p.BN + c * 32 + lane;
+						sp[0] += cs;
+						sp[p.Ncol] += cq;
 					}
 				}
 			} else {
@@ -317,8 +360,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	// stage between up to `tpt` filter taps, each with its own BN-column accumulator (tpt * BN <= 256 TMEM columns)
 	const int n_groups = (p.ntaps + p.tpt - 1) / p.tpt;
 	const int total_tiles = n_groups * p.co_tiles * p.ci_tiles * p.splits;
-	const int nb_boxes = p.BN / 32;
-	const uint32_t box_bytes = 32 * 128;  // 32 pixels x 32 channels x 4 B
+	const int nb_boxes = p.BN / 32;  // [32 px][32 ch] boxes (4 KB each) per B tile
 	const uint32_t acc_cols = (uint32_t)(p.tpt * p.BN);
 
 	if (warp == 0) {
@@ -339,12 +381,10 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 					mbar_wait(&empty[stage], phase ^ 1);
 					uint8_t *sa = base + (size_t)stage * stage_bytes;
 					mbar_expect_tx(&full[stage], p.a_bytes + (uint32_t)ntg * p.b_bytes);
-					for (int j = 0; j < 4; j++) tma_load_4d(sa + j * box_bytes, &p.amap, &full[stage], cot * 128 + j * 32, ow0, oh0, n0);
+					tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * 4);  // 4 x [32 px][32 co] boxes in one op
 					for (int t = 0; t < ntg; t++) {
 						const TapDesc tp = p.taps[tap0 + t];
-						uint8_t *sb = sa + p.a_bytes + (size_t)t * p.b_bytes;
-						for (int j = 0; j < nb_boxes; j++)
-							tma_load_4d(sb + j * box_bytes, &p.bmap[tp.amap], &full[stage], cit * p.BN + j * 32, ow0 + tp.dx, oh0 + tp.dy, n0);
+						tma_load_5d(sa + p.a_bytes + (size_t)t * p.b_bytes, &p.bmap[tp.amap], &full[stage], 0, ow0 + tp.dx, oh0 + tp.dy, n0, cit * nb_boxes);
 					}
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
@@ -440,6 +480,9 @@ struct TcPlan {
 	// wgrad epilogue
 	float *dw;
 	int cout, cin, taps;
+	// fused BatchNorm statistics (fprop): rows of partial sums and their byte size
+	int stats_rows;
+	size_t stats_bytes;
 };
 
 static const size_t kMaxDynSmem = 227 * 1024;
@@ -486,20 +529,23 @@ static void s2_tap(int kk, int *parity, int *d) {
 
 // maps over an NHWC tensor [N][S][S][C] as seen by a conv of stride `stride`: 1 map (stride 1) or 4 parity maps
 static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int C, int stride, const int box[4], bool flat,
-                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int cblk = 0) {
+	auto mk = [&](CUtensorMap *m, const float *base, const long long dims[4], const long long str[3]) {
+		return cblk > 0 ? make_map5_cblk(m, base, dims, str, box, cblk, swz) : make_map4(m, base, dims, str, box, swz);
+	};
 	if (flat) {  // 1x1: pixels are a flat list
 		long long P = (long long)N * S * S;
 		long long dims[4] = {C, P, 1, 1}, str[3] = {C, P * C, P * C};
-		return make_map4(&maps[0], x, dims, str, box, swz);
+		return mk(&maps[0], x, dims, str);
 	}
 	if (stride == 1) {
 		long long dims[4] = {C, S, S, N}, str[3] = {C, (long long)S * C, (long long)S * S * C};
-		return make_map4(&maps[0], x, dims, str, box, swz);
+		return mk(&maps[0], x, dims, str);
 	}
 	for (int ph = 0; ph < 2; ph++)
 		for (int pw = 0; pw < 2; pw++) {
 			long long dims[4] = {C, S / 2, S / 2, N}, str[3] = {2LL * C, 2LL * S * C, (long long)S * S * C};
-			if (!make_map4(&maps[ph * 2 + pw], x + ((long long)ph * S + pw) * C, dims, str, box, swz)) return false;
+			if (!mk(&maps[ph * 2 + pw], x + ((long long)ph * S + pw) * C, dims, str)) return false;
 		}
 	return true;
 }
@@ -678,8 +724,8 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 		unsigned a, b, c, d;
 		if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { p.lbo = a; p.sbo = b; p.layout_type = c; swz = (CUtensorMapSwizzle)d; }
 	}
-	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat, swz);
-	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat, swz);
+	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat, swz, 4);
+	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat, swz, p.BN / 32);
 	if (g.stride == 1) for (int i = 1; i < 4; i++) p.bmap[i] = p.bmap[0];
 	for (int kh = 0; kh < g.k; kh++)
 		for (int kw = 0; kw < g.k; kw++) {
@@ -775,11 +821,12 @@ static void stem_row(int kh, int *parity, int *dy) {
 	static const int par[7] = {1, 0, 1, 0, 1, 0, 1}, off[7] = {-2, -1, -1, 0, 0, 1, 1};
 	*parity = par[kh]; *dy = off[kh];
 }
-static bool make_stem_maps(CUtensorMap *maps, const float *xp, int N, int S, const int box[4], CUtensorMapSwizzle swz) {
+static bool make_stem_maps(CUtensorMap *maps, const float *xp, int N, int S, const int box[4], CUtensorMapSwizzle swz, int cblk = 0) {
 	const int So = S / 2, Wp = S + kStemPadW;
 	for (int ph = 0; ph < 2; ph++) {
 		long long dims[4] = {32, So, So, N}, str[3] = {8, 2LL * Wp * 4, (long long)S * Wp * 4};
-		if (!make_map4(&maps[ph], xp + (long long)ph * Wp * 4, dims, str, box, swz)) return false;
+		const float *base = xp + (long long)ph * Wp * 4;
+		if (!(cblk > 0 ? make_map5_cblk(&maps[ph], base, dims, str, box, cblk, swz) : make_map4(&maps[ph], base, dims, str, box, swz))) return false;
 	}
 	return true;
 }
@@ -835,8 +882,8 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const float *xp, const float 
 	if ((size_t)p.splits * kStemK * cout * 32 * sizeof(float) > ws_bytes) { set_error("tc_make_stem_wgrad: workspace too small"); delete pl; return nullptr; }
 	const int box[4] = {32, p.bw, p.bh, p.bn};
 	p.layout_type = 1; p.lbo = 32 * 128; p.sbo = 512;
-	bool ok = make_input_maps(&p.amap, dy, N, So, cout, 1, box, false, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-	ok = ok && make_stem_maps(p.bmap, xp, N, S, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+	bool ok = make_input_maps(&p.amap, dy, N, So, cout, 1, box, false, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 4);
+	ok = ok && make_stem_maps(p.bmap, xp, N, S, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1);
 	p.bmap[2] = p.bmap[0]; p.bmap[3] = p.bmap[1];
 	for (int kh = 0; kh < kStemK; kh++) {
 		int par, dyy;
@@ -867,6 +914,7 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 		attr_set = true;
 	}
 	if (pl->kind == 0) {
+		if (pl->ip.stats) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
 		igemm_kmajor_kernel<<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->ip);
 		RB_LAUNCH_CHECK();
 	} else {
@@ -881,6 +929,17 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 }
 
 void tc_free(TcPlan *pl) { delete pl; }
+
+// Attach BatchNorm statistics to an fprop plan: the epilogue then also produces [rows][2][Cout] partial sums of the
+// conv output (sum, sum of squares) in `partials` (>= tc_stats_floats(cout) floats); returns the row count for bn_finalize.
+int tc_attach_stats(TcPlan *pl, float *partials) {
+	if (!pl || pl->kind != 0 || pl->ip.ngroups != 1 || !pl->ip.tma_store || pl->ip.accumulate) return 0;
+	pl->ip.stats = partials;
+	pl->stats_rows = pl->grid * 4;
+	pl->stats_bytes = (size_t)pl->stats_rows * 2 * pl->ip.Ncol * sizeof(float);
+	return pl->stats_rows;
+}
+size_t tc_stats_floats(int cout) { return (size_t)kNumSMs * 4 * 2 * cout; }
 
 void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }

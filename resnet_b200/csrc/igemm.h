@@ -22,6 +22,9 @@ void stem_pack_weights(const float *w, int cout, float *wfs, int round_tf32, cud
 TcPlan *tc_make_stem_fprop(int N, int S, int cout, const float *xp, const float *wfs, float *y);
 size_t tc_stem_wgrad_workspace_bytes(int N, int S, int cout);
 TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const float *xp, const float *dy, float *dw, float *workspace, size_t ws_bytes);
+// fused BatchNorm statistics in the fprop epilogue: returns the number of partial rows (0 = not available for this plan)
+int tc_attach_stats(TcPlan *pl, float *partials);
+size_t tc_stats_floats(int cout);
 void tc_run(TcPlan *pl, cudaStream_t st);
 void tc_free(TcPlan *pl);
 void tc_describe(const TcPlan *pl, char *buf, size_t n);

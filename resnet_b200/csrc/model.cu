@@ -175,6 +175,7 @@ static void setup_conv(Engine *e, Bump &B, ConvRef &c, int N, int S, int cin, in
 	c.wd = B.get<float>(c.g.w_elems());
 	c.use_tc = (e->conv_mode == 0) && tc_supported(c.g);
 	c.fprop = c.dgrad = c.wgrad = nullptr;
+	c.stats_rows = 0;
 	jobs.push_back(PackJob{c.w, c.wf, c.wd, cout, cin, k * k});
 	if (c.use_tc) {
 		size_t ws = tc_wgrad_workspace_bytes(c.g);
@@ -369,9 +370,11 @@ static Engine *build_engine(Train_ResNet *t) {
 	RB_CUDA(cudaStreamSynchronize(e->stream));
 
 	// ---- tensor-core plans (tensor maps bind the arena addresses, so they are built once)
+	const int fused_stats = env_int("RESNET_B200_FUSED_STATS", 1);
 	auto plan = [&](ConvRef &c, const float *in, float *out, const float *dout, float *din, int din_accumulate) {
 		if (!c.use_tc) return;
 		c.fprop = tc_make_fprop(c.g, in, c.wf, out);
+		c.stats_rows = fused_stats ? tc_attach_stats(c.fprop, e->bn_partials) : 0;
 		if (din) c.dgrad = tc_make_dgrad(c.g, dout, c.wd, din, din_accumulate);
 		c.wgrad = tc_make_wgrad(c.g, in, dout, c.dw, e->wgrad_ws, e->wgrad_ws_bytes);
 	};
@@ -385,12 +388,14 @@ static Engine *build_engine(Train_ResNet *t) {
 	if (e->stem_tc) {
 		const bool had_error = has_error();
 		e->stem_fprop = tc_make_stem_fprop(N, S0, F, e->stem_xp, e->stem_wfs, e->X0);
+		e->stem.stats_rows = fused_stats ? tc_attach_stats(e->stem_fprop, e->bn_partials) : 0;
 		e->stem_wgrad = tc_make_stem_wgrad(N, S0, F, e->stem_xp, e->dX0, e->stem.dw, e->wgrad_ws, e->wgrad_ws_bytes);
 		if (!e->stem_fprop || !e->stem_wgrad) {
 			// the overlapping-row tensor map was refused by the driver: keep the fp32 SIMT stem (slower, still correct)
 			fprintf(stderr, "[resnet_b200] stem tensor maps unavailable (%s); stem stays on the SIMT path\n", last_error());
 			if (!had_error) clear_error();
 			e->stem_tc = false;
+			e->stem.stats_rows = 0;
 		}
 	}
 	{
@@ -446,9 +451,11 @@ static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, 
 // statistics 1E; apply 2E (+1E residual); backward reduce 2E (+1E mask) and dx 3E (+1E mask)
 static double bn_bytes(const BnRef &bn, double passes) { return passes * 4.0 * (double)bn.rows * bn.C; }
 
-static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps) {
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, 1));
-	bn_stats(x, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->bn_partials, e->bn_max_blocks, e->stream);
+// stats_rows > 0: the producing conv's epilogue already left [stats_rows][2][C] partial sums in e->bn_partials (fused statistics)
+static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps, int stats_rows = 0) {
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, stats_rows ? 0.0 : bn_bytes(bn, 1));
+	if (stats_rows) bn_finalize(e->bn_partials, stats_rows, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->stream);
+	else bn_stats(x, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->bn_partials, e->bn_max_blocks, e->stream);
 	if (e->keep_all && bn.cache->normalized) {
 		bn_apply(x, bn.ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized, 0, e->stream);
 		bn_stats(x, bn.rows, bn.C, e->ones, e->zeros, eps, e->tmp_mv, e->tmp_mv + bn.C, e->tmp_ab, e->bn_partials, e->bn_max_blocks, e->stream);
@@ -530,7 +537,7 @@ void forward_pass(Train_ResNet *t) {
 	pack_weights(e->pack_jobs_dev, e->n_pack_jobs, e->pack_max_elems, rnd, st);
 
 	stem_forward(e, t->cur_batch->images);
-	bn_forward(e, e->bn0, e->X0, eps);
+	bn_forward(e, e->bn0, e->X0, eps, e->stem.stats_rows);
 	bn_act(e, e->bn0, e->X0, 1, nullptr, nullptr, e->Y0, rnd);
 	const int S1 = d->input / d->init_conv_stride;
 	maxpool_fwd(e->Y0, e->N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->max_inds, e->P0, st);
@@ -539,16 +546,16 @@ void forward_pass(Train_ResNet *t) {
 		BlockRef &b = e->blocks[i];
 		Activation_ConvBlock *ab = t->forward_buffer->activations->activation_conv_blocks[i];
 		conv_fwd(e, b.reduce, b.x_in, b.Xr);
-		bn_forward(e, b.bn_r, b.Xr, eps);
+		bn_forward(e, b.bn_r, b.Xr, eps, b.reduce.stats_rows);
 		bn_act(e, b.bn_r, b.Xr, 1, nullptr, nullptr, b.Yr, rnd);
 		conv_fwd(e, b.spatial, b.Yr, b.Xs);
-		bn_forward(e, b.bn_s, b.Xs, eps);
+		bn_forward(e, b.bn_s, b.Xs, eps, b.spatial.stats_rows);
 		bn_act(e, b.bn_s, b.Xs, 1, nullptr, nullptr, b.Ys, rnd);
 		conv_fwd(e, b.expand, b.Ys, b.Xe);
-		bn_forward(e, b.bn_e, b.Xe, eps);
+		bn_forward(e, b.bn_e, b.Xe, eps, b.expand.stats_rows);
 		if (b.has_proj) {
 			conv_fwd(e, b.proj, b.x_in, b.Xp);
-			bn_forward(e, b.bn_p, b.Xp, eps);
+			bn_forward(e, b.bn_p, b.Xp, eps, b.proj.stats_rows);
 		}
 		if (e->keep_all) {
 			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, nullptr, nullptr, ab->post_expanded_norm_vals, 0, st);

@@ -61,6 +61,14 @@ __device__ __forceinline__ void tma_load_4d(void *smem, const CUtensorMap *m, ui
 	    : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void *smem, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3, int c4) {
+	asm volatile(
+	    "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+	        smem_u32(smem)),
+	    "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+	    : "memory");
+}
+
 // shared -> global tile store / fp32 reduce-add through the tensor map (out-of-bounds rows are clipped by the TMA unit)
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *smem, int c0, int c1, int c2, int c3) {
 	asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),

@@ -207,6 +207,32 @@ def test_curand_init_matches_reference_bytes():
     t.close()
 
 
+def test_resnet152_geometry_runs():
+    """BASELINE config 5 geometry: 50 blocks, reductions at 3 / 11 / 47 (466 parameter tensors, 82.2 M parameters), a small batch:
+    every layer gets a tensor-core plan, one full step runs, results are finite and the loss is ln(1000) at init."""
+    from resnet_b200 import api
+    red = [1 if i in (3, 11, 47) else 0 for i in range(50)]
+    t = api.Trainer(input_dim=224, n_blocks=50, reductions=red, batch=4, output=1000, lr=1e-4, seed=1234)
+    assert t.n_locations == 16 + 9 * 50 and sum(t.sizes) == O_param_count(red)
+    assert t.uses_tensor_cores()
+    img, lab = O.synthetic_batch(4, 224, seed=5)
+    t.set_batch(img, lab)
+    pred = t.forward()
+    assert np.isfinite(pred).all() and abs(pred.sum(1) - 1).max() < 1e-4
+    loss, _ = t.loss_accuracy()
+    assert abs(loss / 4 - np.log(1000.0)) < 0.5
+    t.backward()
+    g = t.get_params(1)
+    assert all(np.isfinite(x).all() for x in g) and sum(float(np.abs(x).sum()) for x in g) > 0
+    t.update()
+    assert all(np.isfinite(x).all() for x in t.get_params(0))
+    t.close()
+
+
+def O_param_count(reductions):
+    return sum(int(np.prod(s)) for s in O.param_shapes(224, len(reductions), reductions))
+
+
 def test_full_size_stem_config1():
     """BASELINE config 1: ResNet-50 stem (conv1 7x7/2 + BN + ReLU + maxpool) forward + backward, batch 8, fp32, 224x224,
     vs the host oracle (1e-4 abs / rel; argmax indices exact)."""
