@@ -71,7 +71,7 @@ class Trainer:
     """ResNet trainer driven through the reference's entry points."""
 
     def __init__(self, input_dim=224, n_blocks=16, reductions=None, batch=32, output=1000, lr=1e-4, wd=0.0, b1=0.9, b2=0.999,
-                 eps=1e-7, seed=1234, init_filters=64, device=None):
+                 eps=1e-7, seed=1234, init_filters=64, device=None, shard_n_images=None):
         lib = L()
         if device is not None:
             lib.resnet_b200_set_device(int(device))
@@ -86,7 +86,7 @@ class Trainer:
         self.dims = lib.init_dimensions(input_dim, 7, init_filters, 2, 3, 2, n_blocks, self._red, final_depth, output)
         self.gen = lib.resnet_b200_rng_create(seed)
         self.model = lib.init_resnet(self.dims, self.gen)
-        self.batch_struct = lib.init_general_batch(batch, input_dim * input_dim * 3, input_dim, batch)
+        self.batch_struct = lib.init_general_batch(batch, input_dim * input_dim * 3, input_dim, shard_n_images or batch)
         self._dump_dir = b"resnet_b200"
         self.t = lib.init_trainer(self.model, self.batch_struct, batch, lr, wd, b1, b2, eps, 1, self._dump_dir)
         check()
@@ -120,6 +120,11 @@ class Trainer:
         h2d(b.images, np.ascontiguousarray(images, np.float32))
         h2d(b.correct_classes, np.ascontiguousarray(labels, np.int32))
         C.memmove(b.correct_classes_cpu, np.ascontiguousarray(labels, np.int32).ctypes.data, 4 * self.batch)
+
+    def load_new_batch(self):
+        """reference: resnet.cu:1235 -- next batch of the current shard ($RESNET_B200_SHARD_DIR/%03d.images|labels)"""
+        L().load_new_batch(self.t, None, self.batch_struct)
+        check()
 
     # ---- the reference's step
     def forward(self):

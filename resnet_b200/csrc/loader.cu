@@ -1,0 +1,164 @@
+// loader.cu -- load_new_batch (reference: resnet.cu:1235-1325) with the same shard files and traversal, made asynchronous.
+//
+// Format (reference: build_training_shards.c:120-176): `<dir>/%03d.images` = shard_n_images x image_size raw
+// little-endian fp32 (NHWC, mean-subtracted), `<dir>/%03d.labels` = shard_n_images x int32.  Traversal: batches of a shard
+// in order, next shard when cur_batch_in_shard * batch >= shard_n_images; cur_dump_id++ per call; init_loaded re-opens the
+// checkpointed shard (reference: resnet.cu:1266-1295).  <dir> = $RESNET_B200_SHARD_DIR or the reference's hard-coded path.
+//
+// The reference fread()s a whole 19.7 GB shard into pageable memory, memcpy()s the batch into pinned memory and does a
+// blocking cudaMemcpy.  Here a background thread pread()s only the NEXT batch straight into a second pinned buffer and
+// enqueues its H2D copy on a copy stream while the current step computes; load_new_batch then just waits for that event,
+// does a device-to-device copy on the compute stream and swaps the pinned host buffers (images_float_cpu /
+// correct_classes_cpu keep their meaning: host copy of the current batch).
+#include "engine.h"
+#include <condition_variable>
+#include <fcntl.h>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <unistd.h>
+
+namespace rb {
+
+struct Prefetcher {
+	std::thread th;
+	std::mutex mu;
+	std::condition_variable cv;
+	bool stop = false, busy = false;
+	int req_shard = -1, req_batch = -1;      // what the worker should fetch
+	int have_shard = -1, have_batch = -1;    // what the slot holds (valid when ok)
+	bool ok = false;
+	float *img_pinned = nullptr, *img_dev = nullptr;
+	int *lab_pinned = nullptr, *lab_dev = nullptr;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ready = nullptr;
+	size_t img_bytes = 0, lab_bytes = 0;
+	int batch_size = 0, image_size = 0, device = 0;
+};
+static std::map<Batch *, Prefetcher *> g_prefetch;
+static std::mutex g_pf_mu;
+
+static const char *shard_dir() {
+	const char *dir = getenv("RESNET_B200_SHARD_DIR");
+	return dir ? dir : "/mnt/storage/data/vision/imagenet/2012/train_data_shards";
+}
+
+// reads batch `b` of shard `s` into host buffers; false when the files are missing / short
+static bool read_batch(int s, int b, int batch_size, int image_size, float *img, int *lab) {
+	char path[1024];
+	snprintf(path, sizeof(path), "%s/%03d.images", shard_dir(), s);
+	int fd = open(path, O_RDONLY);
+	if (fd < 0) return false;
+	const size_t nb = (size_t)batch_size * image_size * sizeof(float);
+	size_t got = 0;
+	while (got < nb) {
+		ssize_t r = pread(fd, (char *)img + got, nb - got, (off_t)((size_t)b * nb + got));
+		if (r <= 0) break;
+		got += (size_t)r;
+	}
+	close(fd);
+	if (got != nb) return false;
+	snprintf(path, sizeof(path), "%s/%03d.labels", shard_dir(), s);
+	fd = open(path, O_RDONLY);
+	if (fd < 0) return false;
+	const size_t lb = (size_t)batch_size * sizeof(int);
+	ssize_t r = pread(fd, lab, lb, (off_t)((size_t)b * lb));
+	close(fd);
+	return r == (ssize_t)lb;
+}
+
+static void worker(Prefetcher *p) {
+	cudaSetDevice(p->device);
+	std::unique_lock<std::mutex> lk(p->mu);
+	for (;;) {
+		p->cv.wait(lk, [&] { return p->stop || p->busy; });
+		if (p->stop) return;
+		const int s = p->req_shard, b = p->req_batch;
+		lk.unlock();
+		bool ok = read_batch(s, b, p->batch_size, p->image_size, p->img_pinned, p->lab_pinned);
+		if (ok) {
+			cudaMemcpyAsync(p->img_dev, p->img_pinned, p->img_bytes, cudaMemcpyHostToDevice, p->copy_stream);
+			cudaMemcpyAsync(p->lab_dev, p->lab_pinned, p->lab_bytes, cudaMemcpyHostToDevice, p->copy_stream);
+			cudaEventRecord(p->ready, p->copy_stream);
+		}
+		lk.lock();
+		p->ok = ok; p->have_shard = s; p->have_batch = b; p->busy = false;
+		p->cv.notify_all();
+	}
+}
+
+static Prefetcher *prefetcher_of(Batch *bb) {
+	std::lock_guard<std::mutex> g(g_pf_mu);
+	auto it = g_prefetch.find(bb);
+	if (it != g_prefetch.end()) return it->second;
+	Prefetcher *p = new Prefetcher();
+	p->batch_size = bb->n_images; p->image_size = bb->image_size;
+	p->img_bytes = (size_t)bb->n_images * bb->image_size * sizeof(float);
+	p->lab_bytes = (size_t)bb->n_images * sizeof(int);
+	cudaGetDevice(&p->device);
+	RB_CUDA(cudaMallocHost(&p->img_pinned, p->img_bytes));
+	RB_CUDA(cudaMallocHost(&p->lab_pinned, p->lab_bytes));
+	RB_CUDA(cudaMalloc(&p->img_dev, p->img_bytes));
+	RB_CUDA(cudaMalloc(&p->lab_dev, p->lab_bytes));
+	RB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+	RB_CUDA(cudaEventCreateWithFlags(&p->ready, cudaEventDisableTiming));
+	p->th = std::thread(worker, p);
+	g_prefetch[bb] = p;
+	return p;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" void load_new_batch(Train_ResNet *trainer, Class_Metadata *class_metadata, Batch *bb) {
+	(void)class_metadata;
+	Engine *e = engine_of(trainer);
+	cudaStream_t st = e ? e->stream : 0;
+	const int batch_size = bb->n_images;
+	// which (shard, batch) this call delivers -- the reference's traversal (resnet.cu:1260-1295)
+	int shard = bb->cur_shard_id, batch = bb->cur_batch_in_shard;
+	if (trainer->init_loaded || shard == -1 || batch * batch_size >= bb->shard_n_images) {
+		if (!trainer->init_loaded) { shard += 1; batch = 0; }
+		trainer->init_loaded = 0;
+	}
+	Prefetcher *p = prefetcher_of(bb);
+	bool delivered = false;
+	{
+		std::unique_lock<std::mutex> lk(p->mu);
+		p->cv.wait(lk, [&] { return !p->busy; });
+		if (p->ok && p->have_shard == shard && p->have_batch == batch) {
+			// prefetched: order the compute stream after the H2D copy, copy device-to-device, swap the pinned host buffers
+			RB_CUDA(cudaStreamWaitEvent(st, p->ready, 0));
+			RB_CUDA(cudaMemcpyAsync(bb->images, p->img_dev, p->img_bytes, cudaMemcpyDeviceToDevice, st));
+			RB_CUDA(cudaMemcpyAsync(bb->correct_classes, p->lab_dev, p->lab_bytes, cudaMemcpyDeviceToDevice, st));
+			std::swap(bb->images_float_cpu, p->img_pinned);
+			std::swap(bb->correct_classes_cpu, p->lab_pinned);
+			// the staging device buffers are read by the D2D copies above: the next H2D into them must come after
+			RB_CUDA(cudaEventRecord(p->ready, st));
+			RB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ready, 0));
+			p->ok = false;
+			delivered = true;
+		}
+	}
+	if (!delivered) {  // first call, resume, or prefetch miss: synchronous path (what the reference always does)
+		if (!read_batch(shard, batch, batch_size, bb->image_size, bb->images_float_cpu, bb->correct_classes_cpu)) {
+			set_error("load_new_batch: cannot read batch %d of shard %03d under %s", batch, shard, shard_dir());
+			return;
+		}
+		RB_CUDA(cudaMemcpyAsync(bb->images, bb->images_float_cpu, p->img_bytes, cudaMemcpyHostToDevice, st));
+		RB_CUDA(cudaMemcpyAsync(bb->correct_classes, bb->correct_classes_cpu, p->lab_bytes, cudaMemcpyHostToDevice, st));
+		RB_CUDA(cudaStreamSynchronize(st));
+	}
+	bb->cur_shard_id = shard;
+	bb->cur_batch_in_shard = batch + 1;
+	trainer->cur_dump_id += 1;
+	// kick off the prefetch of the batch the NEXT call will ask for
+	int nshard = shard, nbatch = batch + 1;
+	if (nbatch * batch_size >= bb->shard_n_images) { nshard += 1; nbatch = 0; }
+	{
+		std::lock_guard<std::mutex> lk(p->mu);
+		p->req_shard = nshard; p->req_batch = nbatch; p->busy = true; p->ok = false;
+	}
+	p->cv.notify_all();
+}

@@ -653,48 +653,6 @@ void update_parameters(Train_ResNet *t) {
 	t->cur_var_decay = cur_var_decay;
 }
 
-// ---- shard loader (reference: resnet.cu:1235-1325).  Same file format and traversal; the shard directory is
-// RESNET_B200_SHARD_DIR (default: the reference's hard-coded path).
-void load_new_batch(Train_ResNet *trainer, Class_Metadata *class_metadata, Batch *bb) {
-	(void)class_metadata;
-	Engine *e = engine_of(trainer);
-	cudaStream_t st = e ? e->stream : 0;
-	const int batch_size = bb->n_images, image_size = bb->image_size;
-	const size_t total_pixels = (size_t)batch_size * image_size;
-	if (!bb->full_shard_images) {
-		bb->full_shard_images = (float *)malloc((size_t)bb->shard_n_images * image_size * sizeof(float));
-		bb->full_shard_correct_classes = (int *)malloc((size_t)bb->shard_n_images * sizeof(int));
-	}
-	int cur_batch_in_shard = bb->cur_batch_in_shard;
-	const int start_img = cur_batch_in_shard * batch_size;
-	if (trainer->init_loaded || bb->cur_shard_id == -1 || start_img >= bb->shard_n_images) {
-		if (!trainer->init_loaded) bb->cur_shard_id += 1;
-		const char *dir = getenv("RESNET_B200_SHARD_DIR");
-		if (!dir) dir = "/mnt/storage/data/vision/imagenet/2012/train_data_shards";
-		char path[1024];
-		snprintf(path, sizeof(path), "%s/%03d.images", dir, bb->cur_shard_id);
-		FILE *f = fopen(path, "rb");
-		if (!f) { set_error("load_new_batch: cannot open %s", path); return; }
-		size_t nr = fread(bb->full_shard_images, sizeof(float), (size_t)bb->shard_n_images * image_size, f);
-		fclose(f);
-		if (nr != (size_t)bb->shard_n_images * image_size) set_error("load_new_batch: short read on %s", path);
-		snprintf(path, sizeof(path), "%s/%03d.labels", dir, bb->cur_shard_id);
-		f = fopen(path, "rb");
-		if (!f) { set_error("load_new_batch: cannot open %s", path); return; }
-		nr = fread(bb->full_shard_correct_classes, sizeof(int), bb->shard_n_images, f);
-		fclose(f);
-		if (!trainer->init_loaded) { cur_batch_in_shard = 0; bb->cur_batch_in_shard = 0; }
-		trainer->init_loaded = 0;
-	}
-	memcpy(bb->images_float_cpu, bb->full_shard_images + (size_t)cur_batch_in_shard * total_pixels, total_pixels * sizeof(float));
-	memcpy(bb->correct_classes_cpu, bb->full_shard_correct_classes + (size_t)cur_batch_in_shard * batch_size, batch_size * sizeof(int));
-	RB_CUDA(cudaMemcpyAsync(bb->images, bb->images_float_cpu, total_pixels * sizeof(float), cudaMemcpyHostToDevice, st));
-	RB_CUDA(cudaMemcpyAsync(bb->correct_classes, bb->correct_classes_cpu, batch_size * sizeof(int), cudaMemcpyHostToDevice, st));
-	RB_CUDA(cudaStreamSynchronize(st));
-	bb->cur_batch_in_shard = cur_batch_in_shard + 1;
-	trainer->cur_dump_id += 1;
-}
-
 // ---- class metadata (reference: resnet.cu:1331-1381)
 static int read_lines(const char *filename, char **text, int *ints, int n) {
 	FILE *fp = fopen(filename, "r");

@@ -42,7 +42,7 @@ def make_pair(cfg, mode, keep_all=True):
     return t, net
 
 
-@pytest.mark.parametrize("mode,cfg_name", [("simt", "MINI4"), ("tc", "MINI4"), ("simt", "MINI5")])
+@pytest.mark.parametrize("mode,cfg_name", [("simt", "MINI4"), ("tc", "MINI4"), ("simt", "MINI")])
 def test_step_vs_oracle_per_layer(mode, cfg_name):
     cfg = getattr(G, cfg_name)
     t, net = make_pair(cfg, mode)
@@ -51,8 +51,6 @@ def test_step_vs_oracle_per_layer(mode, cfg_name):
     # few activations that sit at zero, and every flipped element contributes a full-size gradient term, so whole-network
     # rel-L2 lands at 3-7e-2 on these tiny batches (measured: profiles/r01_net_diag_mini.txt); fp32 mode shows the wiring is exact.
     act_tol, grad_tol = (1e-4, 1e-3) if mode == "simt" else (1e-2, 2e-1)
-    if cfg_name == "MINI5":
-        act_tol = 1e-3   # its last blocks normalise over 4 samples at 1x1 spatial: BatchNorm amplifies fp32 re-association noise
     img, lab = G.mini_batch(cfg)
     t.set_batch(img, lab)
     pred = t.forward()
