@@ -50,7 +50,10 @@ def test_step_vs_oracle_per_layer(mode, cfg_name):
     # TF32 gradients: each conv is within 1e-3 (tests/test_gpu_ops.py), but forward noise of ~2e-4 flips the ReLU mask of the
     # few activations that sit at zero, and every flipped element contributes a full-size gradient term, so whole-network
     # rel-L2 lands at 3-7e-2 on these tiny batches (measured: profiles/r01_net_diag_mini.txt); fp32 mode shows the wiring is exact.
-    act_tol, grad_tol = (1e-4, 1e-3) if mode == "simt" else (1e-2, 2e-1)
+    # fp32 mode: activations agree to ~1e-6, but a single ReLU-mask flip (|pre-activation| below that noise, ~0.3 expected per
+    # tensor here) already moves a gradient tensor's rel-L2 by ~5e-3, so the end-to-end gradient bar is 5e-2; the exact per-layer
+    # bars (1e-4 fp32, 3e-3 TF32) are held by test_step_layerwise_self_consistency, which feeds each layer the trainer's own masks.
+    act_tol, grad_tol = (1e-4, 5e-2) if mode == "simt" else (1e-2, 2e-1)
     img, lab = G.mini_batch(cfg)
     t.set_batch(img, lab)
     pred = t.forward()
@@ -107,19 +110,20 @@ def test_step_vs_oracle_per_layer(mode, cfg_name):
     t.close()
 
 
-def test_tensor_core_step_layerwise_self_consistency():
-    """TF32 mode, layer by layer on the trainer's OWN tensors: every conv / BatchNorm of the step is re-derived by the oracle
-    from the inputs the trainer actually used (its activations, masks and upstream gradients), so TF32 noise cannot compound
-    or flip ReLU masks between layers and each layer is held to the single-kernel bar (3e-3 of the tensor's max)."""
-    cfg = G.MINI4
-    t, net = make_pair(cfg, "tc")
+@pytest.mark.parametrize("mode,cfg_name,tol", [("tc", "MINI4", 3e-3), ("simt", "MINI4", 1e-4), ("simt", "MINI", 1e-4), ("tc", "MINI", 3e-3)])
+def test_step_layerwise_self_consistency(mode, cfg_name, tol):
+    """Layer by layer on the trainer's OWN tensors: every conv / BatchNorm of the step is re-derived by the oracle from the
+    inputs the trainer actually used (its activations, masks and upstream gradients), so rounding noise cannot compound or flip
+    ReLU masks between layers and each layer is held to the single-kernel bar (1e-4 fp32, 3e-3 TF32, of the tensor's max)."""
+    cfg = getattr(G, cfg_name)
+    t, net = make_pair(cfg, mode)
     img, lab = G.mini_batch(cfg)
     t.set_batch(img, lab)
     t.forward()
     t.backward()
     P = [p.reshape(s) for p, s in zip(t.get_params(0), net.shapes)]
     Gd = [g.reshape(s) for g, s in zip(t.get_params(1), net.shapes)]
-    N, eps, tol = cfg["batch"], cfg["eps"], 3e-3
+    N, eps = cfg["batch"], cfg["eps"]
     li = 3
     x_in_shape = (N, 8, 8, 64)
     x_in = t.activation("init_convblock_input").reshape(x_in_shape)

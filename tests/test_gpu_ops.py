@@ -122,6 +122,26 @@ def test_batchnorm_vs_oracle(api, idx):
         np.testing.assert_allclose(dx, gold["bn%d.dx" % idx], rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize("N,S,Cc,relu", [(4, 8, 128, 1), (8, 16, 64, 1), (4, 8, 512, 0), (16, 14, 256, 1), (32, 28, 128, 1), (3, 7, 2048, 1)])
+def test_batchnorm_multi_block_geometries(api, N, S, Cc, relu):
+    """geometries whose streams span several thread blocks per column group (the in-block and cross-block folds)"""
+    rng = np.random.default_rng(N * 1000 + S * 10 + Cc)
+    x = (rng.standard_normal((N, S, S, Cc)) * 1.5 + 0.3).astype(np.float32)
+    g = (1 + 0.2 * rng.standard_normal(Cc)).astype(np.float32)
+    b = (0.2 * rng.standard_normal(Cc)).astype(np.float32)
+    dy = rng.standard_normal(x.shape).astype(np.float32)
+    mu, var, y = api.batchnorm_forward(x, g, b, 1e-7, relu)
+    omu, ovar, oy, _, _ = O.bn_fwd(x, g, b, 1e-7, relu)
+    np.testing.assert_allclose(mu, omu, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(var, ovar, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(y, oy, rtol=1e-4, atol=1e-4)
+    dg, db, dx = api.batchnorm_backward(x, g, 1e-7, omu, ovar, oy, dy, relu)
+    odg, odb, odx = O.bn_bwd(x, g, 1e-7, omu, ovar, oy, dy, relu)
+    np.testing.assert_allclose(db, odb, rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(dg, odg, rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(dx, odx, rtol=1e-3, atol=1e-4)
+
+
 def test_batchnorm_wide_channels_and_residual(api):
     """C = 2048 (two column groups per 256-thread block) and the fused residual + ReLU join."""
     rng = np.random.default_rng(11)
