@@ -75,7 +75,7 @@ constexpr int kMaxFlatBlocks = kNumSMs * 8;
 template <int VEC, bool FIXED, bool BWD>
 __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy,
                                                             const float *__restrict__ mask, const float *__restrict__ means,
-                                                            long long nvec, int V, float *__restrict__ partials) {
+                                                            long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab) {
 	extern __shared__ float sm[];  // [2][C]
 	const int Cc = V * VEC;
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) sm[i] = 0.f;
@@ -86,9 +86,17 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 #pragma unroll
 	for (int j = 0; j < VEC; j++) s[j] = q[j] = mu[j] = 0.f;
 	const int col0 = (int)(g % V) * VEC;
+	// ReLU mask of a plain BN+ReLU layer, recomputed from x with the forward's own folded scale/shift (bit-identical sign to the
+	// stored activation, which then need not be read at all); layers with a residual join read the stored mask instead
+	const bool remask = FIXED && BWD && mab != nullptr;
+	float ma[VEC], mb[VEC];
 	if (FIXED && BWD) {
 #pragma unroll
-		for (int j = 0; j < VEC; j++) mu[j] = means[col0 + j];
+		for (int j = 0; j < VEC; j++) {
+			mu[j] = means[col0 + j];
+			ma[j] = remask ? mab[col0 + j] : 0.f;
+			mb[j] = remask ? mab[Cc + col0 + j] : 0.f;
+		}
 	}
 #pragma unroll 4
 	for (long long i = g; i < nvec; i += T) {
@@ -106,7 +114,10 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 		} else {
 			float d[VEC];
 			ldv<VEC>(dy, i, d);
-			if (mask) {
+			if (remask) {
+#pragma unroll
+				for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
+			} else if (mask) {
 				float mk[VEC];
 				ldv<VEC>(mask, i, mk);
 #pragma unroll
@@ -153,10 +164,10 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) out[i] = sm[i];
 }
 
-// Fold of the per-block partials in fp64.  32 channels x 8 slices per block: slice sy sums partial blocks sy, sy+8, ... (coalesced
-// 128-byte rows), shared memory combines the 8 slices in a fixed order (deterministic).  A one-thread-per-channel loop over
+// Fold of the per-block partials in fp64.  32 channels x 32 slices per block: slice sy sums partial blocks sy, sy+32, ... (coalesced
+// 128-byte rows), shared memory combines the slices in a fixed order (deterministic).  A one-thread-per-channel loop over
 // ~1000 partials was latency-bound at 170 us per launch (profiles/r01_launch_summary.txt).
-constexpr int kFinC = 32, kFinS = 8;
+constexpr int kFinC = 32, kFinS = 32;
 __device__ __forceinline__ bool fold_partials(const float *__restrict__ partials, int nblk, int Cc, double *s_out, double *q_out) {
 	__shared__ double sm[kFinS][2][kFinC];
 	const int cx = threadIdx.x, sy = threadIdx.y, c = blockIdx.x * kFinC + cx;
@@ -196,7 +207,7 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partials, int nblk,
 }
 
 static void launch_reduce(bool bwd, const float *x, const float *dy, const float *mask, const float *means, long long rows, int C,
-                          float *partials, int max_blocks, int *grid_out, cudaStream_t st) {
+                          float *partials, int max_blocks, int *grid_out, cudaStream_t st, const float *mab = nullptr) {
 	const int VEC = (C % 4 == 0) ? 4 : 1;
 	const int V = C / VEC;
 	const long long nvec = rows * V;
@@ -205,7 +216,7 @@ static void launch_reduce(bool bwd, const float *x, const float *dy, const float
 	int grid = flat_grid(nvec, V, cap, &fixed);
 	if (VEC == 1) fixed = false;
 	const size_t smem = 2 * (size_t)C * sizeof(float);
-#define RB_RED(VEC_, FIX_, BWD_) bn_reduce_kernel<VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>(x, dy, mask, means, nvec, V, partials)
+#define RB_RED(VEC_, FIX_, BWD_) bn_reduce_kernel<VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>(x, dy, mask, means, nvec, V, partials, mab)
 	if (VEC == 4) {
 		if (fixed) { if (bwd) RB_RED(4, true, true); else RB_RED(4, true, false); }
 		else { if (bwd) RB_RED(4, false, true); else RB_RED(4, false, false); }
@@ -309,15 +320,20 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
 
 template <int VEC, bool FIXED>
 __global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__restrict__ x, const float *dy, const float *__restrict__ mask,
-                                                            const float *__restrict__ coef, long long nvec, int V, float *dx, int rnd) {
+                                                            const float *__restrict__ coef, long long nvec, int V, float *dx, int rnd,
+                                                            const float *__restrict__ mab) {
 	const int Cc = V * VEC;
 	const long long T = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-	float c1[VEC], c2[VEC], c3[VEC], mu[VEC];
+	float c1[VEC], c2[VEC], c3[VEC], mu[VEC], ma[VEC], mb[VEC];
+	const bool remask = FIXED && mab != nullptr;
 	if constexpr (FIXED) {
 		const int c0 = (int)(g % V) * VEC;
 #pragma unroll
-		for (int j = 0; j < VEC; j++) { c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j]; }
+		for (int j = 0; j < VEC; j++) {
+			c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j];
+			ma[j] = remask ? mab[c0 + j] : 0.f; mb[j] = remask ? mab[Cc + c0 + j] : 0.f;
+		}
 	}
 #pragma unroll 4
 	for (long long i = g; i < nvec; i += T) {
@@ -329,7 +345,10 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__rest
 		float a[VEC], d[VEC];
 		ldv<VEC>(x, i, a);
 		ldv<VEC>(dy, i, d);
-		if (mask) {
+		if (remask) {
+#pragma unroll
+			for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
+		} else if (mask) {
 			float mk[VEC];
 			ldv<VEC>(mask, i, mk);
 #pragma unroll
@@ -346,9 +365,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__rest
 
 void bn_bwd(const float *x, const float *dy, const float *mask_src, const float *gamma, const float *means, const float *vars, float eps,
             long long rows, int C, float *dgamma, float *dbeta, float *dx, float *partials, int max_blocks, float *coef, int rnd,
-            cudaStream_t st) {
+            cudaStream_t st, const float *mab) {
 	int grid;
-	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st);
+	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab);
 	bn_bwd_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();
 	const int VEC = (C % 4 == 0) ? 4 : 1;
@@ -356,9 +375,9 @@ void bn_bwd(const float *x, const float *dy, const float *mask_src, const float 
 	const long long nvec = rows * V;
 	bool fixed;
 	int g2 = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
-	if (VEC == 4 && fixed) bn_bwd_dx_kernel<4, true><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd);
-	else if (VEC == 4) bn_bwd_dx_kernel<4, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd);
-	else bn_bwd_dx_kernel<1, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd);
+	if (VEC == 4 && fixed) bn_bwd_dx_kernel<4, true><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd, mab);
+	else if (VEC == 4) bn_bwd_dx_kernel<4, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd, mab);
+	else bn_bwd_dx_kernel<1, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd, mab);
 	RB_LAUNCH_CHECK();
 }
 

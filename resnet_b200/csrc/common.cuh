@@ -64,7 +64,8 @@ void bn_apply(const float *x, const float *ab, long long rows, int C, int relu, 
 // dx (may alias dy).  coef scratch [4][C].
 void bn_bwd(const float *x, const float *dy, const float *mask_src, const float *gamma, const float *means, const float *vars,
             float eps, long long rows, int C, float *dgamma, float *dbeta, float *dx, float *partials, int max_blocks,
-            float *coef, int round_tf32, cudaStream_t st);
+            float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr);
+// mask_ab != NULL ([2][C] folded scale/shift of the forward): the ReLU mask is recomputed as (x*a + b > 0) instead of read
 void relu_bwd(const float *y, const float *dy, long long n, float *dx, cudaStream_t st);
 void maxpool_fwd(const float *x, int N, int S, int C, int k, int stride, int *max_inds, float *out, cudaStream_t st);
 void maxpool_bwd(const int *max_inds, const float *dout, int N, int S, int C, int k, int stride, float *din, cudaStream_t st);

@@ -470,10 +470,13 @@ static void relu_backward(Engine *e, const float *y, const float *dy, long long 
 	ProfScope ps(e->stream, PROF_BN_ELTWISE, 12.0 * (double)n);
 	relu_bwd(y, dy, n, dx, e->stream);
 }
-static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps) {
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, mask ? 7 : 5));
+// remask: plain BN+ReLU layer, the mask is recomputed from x (the stored activation is not read); otherwise `mask` (the block's
+// output after the residual join) is read
+static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps, bool remask = false) {
+	const bool re = remask && (bn.C % 4 == 0) && env_int("RESNET_B200_REMASK", 1);
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, re ? 5 : (mask ? 7 : 5)));
 	bn_bwd(x, dy, mask, bn.gamma, bn.means, bn.vars, eps, bn.rows, bn.C, bn.dgamma, bn.dbeta, dx, e->bn_partials, e->bn_max_blocks, e->bn_coef,
-	       e->round_tf32, e->stream);
+	       e->round_tf32, e->stream, re ? bn.ab : nullptr);
 }
 
 }  // namespace rb
@@ -610,18 +613,18 @@ void backwards_pass(Train_ResNet *t) {
 		}
 		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps);
 		conv_bwd(e, b.expand, b.Ys, b.dXe, b.dYs, 0);
-		bn_backward(e, b.bn_s, b.Xs, b.dYs, b.Ys, b.dXs, eps);
+		bn_backward(e, b.bn_s, b.Xs, b.dYs, b.Ys, b.dXs, eps, true);
 		conv_bwd(e, b.spatial, b.Yr, b.dXs, b.dYr, 0);
-		bn_backward(e, b.bn_r, b.Xr, b.dYr, b.Yr, b.dXr, eps);
+		bn_backward(e, b.bn_r, b.Xr, b.dYr, b.Yr, b.dXr, eps, true);
 		conv_bwd(e, b.reduce, b.x_in, b.dXr, b.dBI, 1);
 		dp_block_done(e, i);
 	}
 	const int S1 = d->input / d->init_conv_stride;
 	maxpool_bwd(e->max_inds, e->dP0, N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->dY0, st);
 	{
-		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e->bn0, 7));
+		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e->bn0, 5));
 		bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
-		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st);
+		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bn0.ab);
 	}
 	stem_backward(e, t->cur_batch->images);
 	dp_allreduce_grads(e);

@@ -79,7 +79,8 @@ def test_step_vs_oracle_per_layer(mode, cfg_name):
     # ---- backward: every parameter gradient + the activation gradients the trainer keeps
     t.backward()
     og = [g.copy() for g in net.backward()]
-    for i, (g, r) in enumerate(zip(t.get_params(1), og)):
+    tgrads = t.get_params(1)
+    for i, (g, r) in enumerate(zip(tgrads, og)):
         assert rel_l2(g, r) < grad_tol, ("grad", i, net.shapes[i])
     for nm in ["init_convblock_input", "init_conv_applied", "b0.post_reduced", "b1.post_expanded", "b1.transformed_residual",
                "b1.post_spatial", "b0.output_activated", "b1.post_reduced_activated", "b1.output"]:
@@ -91,11 +92,12 @@ def test_step_vs_oracle_per_layer(mode, cfg_name):
     net.update()
     # Adam's first step is lr * g / (|g| + eps): exact to 1e-5 wherever |g| is well above eps = 1e-7, but an entry whose gradient is
     # itself ~eps (or, in TF32 mode, whose sign flips) may move by up to 2 * lr
-    for i, (p, r, g) in enumerate(zip(t.get_params(0), net.params, og)):
+    for i, (p, r, g, tg) in enumerate(zip(t.get_params(0), net.params, og, tgrads)):
         diff = np.abs(p - r.reshape(-1))
         assert diff.max() <= 2.5 * cfg["lr"], ("param", i)
-        if mode == "simt":
-            solid = np.abs(g.reshape(-1)) > 1e-3
+        if mode == "simt":   # wherever both sides saw the same (non-negligible) gradient, the update itself is exact
+            g = g.reshape(-1)
+            solid = (np.abs(g) > 1e-3) & (np.abs(tg - g) <= 1e-3 * np.abs(g))
             assert (diff[solid] <= 2e-5).all(), ("param", i)
     assert all((g == 0).all() for g in t.get_params(1))      # gradients zeroed (reference: resnet.cu:2972-2975)
     b = t.batch_struct.contents
