@@ -35,8 +35,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 R50_REDUCTIONS = [1 if i in (3, 7, 13) else 0 for i in range(16)]
+R152_REDUCTIONS = [1 if i in (3, 11, 47) else 0 for i in range(50)]
 FLOP_PER_IMAGE_STEP = 39.09e9  # fprop + dgrad + wgrad, no stem dgrad
 METRIC = "ResNet-50 train img/s"
+# BASELINE.json configs: c2 is the bench line (configs[1]); c3-c5 are the bf16 configurations, measured with --config
+CONFIGS = {
+    "c2": dict(name="ResNet-50", red=R50_REDUCTIONS, batch=256, dtype="tf32", fwd_only=False, gflop=39.09),
+    "c3": dict(name="ResNet-50", red=R50_REDUCTIONS, batch=1024, dtype="bf16", fwd_only=True, gflop=13.111),
+    "c4": dict(name="ResNet-50", red=R50_REDUCTIONS, batch=256, dtype="bf16", fwd_only=False, gflop=39.09),
+    "c5": dict(name="ResNet-152", red=R152_REDUCTIONS, batch=128, dtype="bf16", fwd_only=False, gflop=83.64),
+}
 
 
 def peaks():
@@ -200,10 +208,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default c2 = configs[1], the bench line)")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.batch is None:
+        args.batch = cfg["batch"]
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -215,8 +227,12 @@ def main():
     L.resnet_b200_set_device(local_rank)
     pk = peaks()
     N = args.batch
-    t = api.Trainer(input_dim=224, n_blocks=16, reductions=R50_REDUCTIONS, batch=N, output=1000, lr=1e-4, seed=1234, device=local_rank)
+    t = api.Trainer(input_dim=224, n_blocks=len(cfg["red"]), reductions=cfg["red"], batch=N, output=1000, lr=1e-4, seed=1234, device=local_rank,
+                    dtype=cfg["dtype"])
     assert t.uses_tensor_cores(), "bench must run the tcgen05 path"
+    assert t.bf16 == (cfg["dtype"] == "bf16")
+    fwd_only = cfg["fwd_only"]
+    flop_per_image = cfg["gflop"] * 1e9
     if world > 1:
         idbuf = (C.c_char * 128)()
         if rank == 0:
@@ -242,8 +258,9 @@ def main():
             L.resnet_b200_stage_batch_device(t.t, dev_img.ptr, dev_lab.ptr)
         L.forward_pass(t.t)                                   # returns with pred_cpu valid (D2H inside)
         _ = t.t.contents.forward_buffer.contents.pred_cpu[0]  # the host reads the prediction, as the reference's loop does
-        L.backwards_pass(t.t)
-        L.update_parameters(t.t)
+        if not fwd_only:
+            L.backwards_pass(t.t)
+            L.update_parameters(t.t)
 
     for _ in range(max(3, args.warmup)):
         step(False)
@@ -293,7 +310,7 @@ def main():
     api.check()
 
     if rank == 0:
-        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+        tf32_peak = pk["bf16_tflops_sustained"] / (1.0 if t.bf16 else 2.0)  # tensor peak of the MMA kind in use
         rl_all = []
         for f in (0, 1, 3):
             if fam[f]["launches"]:
@@ -310,18 +327,23 @@ def main():
         dom = max(rl_all, key=lambda r: r["ms_per_step"])
         roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
                     "traffic": None, "kernel": dom["kernel"],
-                    "peak_source": ("MEASURED_PEAKS.json (%s): " % pk["src"]) + ("bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate; kernel timed inside a long step)"
+                    "peak_source": ("MEASURED_PEAKS.json (%s): " % pk["src"]) + (("bf16_tflops_sustained (kernel timed inside a long step)" if t.bf16 else
+                                                                                  "bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate; kernel timed inside a long step)")
                                                                                  if dom["bound"] == "tensor" else "hbm_gbs copy bandwidth"),
                     "how": "CUDA events around every launch of the family on the launching stream, %d instrumented steps after the timed region" % prof_steps}
         total_img = N * world * args.steps
         value = total_img / (ms_max * 1e-3)
-        out = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-               "config": {"workload": "ResNet-50 (reference variant: 3x3/2 projection shortcuts, 47.58 M params, 39.09 GFLOP/img/step) full training step "
-                                      "(forward_pass + backwards_pass + Adam update_parameters), batch %d per GPU, 224x224, fp32 storage NHWC, TF32 tcgen05 convs" % N,
-                          "global_batch": N * world, "per_gpu_batch": N, "parallelism": "dp%d" % world,
+        out = {"metric": METRIC if args.config in ("c2", "c4") else ("ResNet-50 forward img/s" if fwd_only else "ResNet-152 train img/s"), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+               "config": {"workload": "%s (reference variant: 3x3/2 projection shortcuts, %.2f M params, %.2f GFLOP/img/step) %s, batch %d per GPU, 224x224, %s"
+                                      % (cfg["name"], sum(t.sizes) / 1e6, cfg["gflop"],
+                                         "forward_pass only (batch-statistics BatchNorm, as the reference has no inference mode)" if fwd_only else
+                                         "full training step (forward_pass + backwards_pass + Adam update_parameters)", N,
+                                         "bf16 storage NHWC, bf16 tcgen05 convs, fp32 master weights / gradients / Adam" if t.bf16 else
+                                         "fp32 storage NHWC, TF32 tcgen05 convs"),
+                          "baseline_config": args.config, "global_batch": N * world, "per_gpu_batch": N, "parallelism": "dp%d" % world,
                           "l2": "inputs larger than L2 (tens of GB touched per step), no flush needed",
-                          "step_flops": FLOP_PER_IMAGE_STEP * N, "achieved_step_tflops_per_gpu": FLOP_PER_IMAGE_STEP * N / (ms_max / args.steps * 1e-3) / 1e12},
+                          "step_flops": flop_per_image * N, "achieved_step_tflops_per_gpu": flop_per_image * N / (ms_max / args.steps * 1e-3) / 1e12},
                "e2e": {"value": total_img / (ms_e2e_max * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(img.nbytes + lab.nbytes),
                        "d2h_bytes_per_step": int(N * 1000 * 4), "ms_per_step": ms_e2e_max / args.steps},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_all": rl_all,

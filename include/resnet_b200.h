@@ -37,6 +37,20 @@ int resnet_b200_sync(void);                             /* cudaDeviceSynchronize
 void * resnet_b200_rng_create(unsigned long long seed);
 void resnet_b200_rng_destroy(void * gen);
 
+/* ---- storage / MMA type ------------------------------------------------------------------- */
+/* BASELINE config 2 keeps the reference's fp32 tensors (convolutions on kind::tf32 tensor-core MMAs); configs 3-5 store
+ * activations, activation gradients and packed weights as bf16 (kind::f16 MMAs, fp32 accumulation).  Master weights,
+ * gradients of parameters, Adam state, BatchNorm statistics, pooled features, logits and pred stay fp32 in both modes, so
+ * locations[] / param_derivs / pred_cpu keep the reference's types; the named activation buffers of resnet.h then hold
+ * bf16 bits behind their float* names (SURVEY.md 8b "in fast mode buffers may be bf16").
+ * set_dtype: storage of trainers created AFTER the call: -1 = follow $RESNET_B200_DTYPE ("bf16" or unset), 0 = fp32, 1 = bf16. */
+int resnet_b200_set_dtype(int bf16);
+int resnet_b200_trainer_dtype(Train_ResNet * trainer);  /* 0 = fp32/TF32, 1 = bf16, -1 = unknown trainer */
+/* element type of the ACTIVATION tensors the single-operator entry points below read and write (0 = fp32, 1 = bf16) */
+int resnet_b200_set_op_dtype(int bf16);
+/* device-side conversion of n elements: to_bf16 = 1: fp32 -> bf16 (round to nearest even), 0: bf16 -> fp32 */
+int resnet_b200_convert(const void * dev_src, void * dev_dst, long long n, int to_bf16);
+
 /* ---- trainer services ---------------------------------------------------------------------- */
 /* asynchronous copies on the trainer's stream: host (pinned) -> cur_batch->images / correct_classes */
 int resnet_b200_stage_batch(Train_ResNet * trainer, const float * images_host, const int * labels_host);

@@ -24,6 +24,45 @@ def check():
         raise RuntimeError("libresnet_b200: " + err)
 
 
+def to_bf16(a):
+    """float32 -> bf16 bits (uint16), round to nearest even: what cvt.rn.bf16.f32 does on the device"""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+def from_bf16(u):
+    return (np.ascontiguousarray(u, np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+def bf16_round(a):
+    """float32 values rounded to the nearest bf16 (still float32)"""
+    return from_bf16(to_bf16(a)).reshape(np.shape(a))
+
+
+class _OpDtype:
+    """single-operator calls inside this context read / write bf16 activation tensors"""
+
+    def __init__(self, bf16):
+        self.bf16 = bool(bf16)
+
+    def __enter__(self):
+        L().resnet_b200_set_op_dtype(int(self.bf16))
+        return self
+
+    def __exit__(self, *a):
+        L().resnet_b200_set_op_dtype(0)
+
+    def up(self, arr):
+        """host fp32 activation tensor -> device buffer in the op dtype"""
+        return DevBuf(to_bf16(arr) if self.bf16 else np.ascontiguousarray(arr, np.float32))
+
+    def out(self, n):
+        return DevBuf(nbytes=(2 if self.bf16 else 4) * int(n), zero=True)
+
+    def down(self, buf, shape):
+        return from_bf16(buf.get(shape, np.uint16)).reshape(shape) if self.bf16 else buf.get(shape)
+
+
 class DevBuf:
     """A device allocation owned by Python (single-operator tests)."""
 
@@ -71,7 +110,8 @@ class Trainer:
     """ResNet trainer driven through the reference's entry points."""
 
     def __init__(self, input_dim=224, n_blocks=16, reductions=None, batch=32, output=1000, lr=1e-4, wd=0.0, b1=0.9, b2=0.999,
-                 eps=1e-7, seed=1234, init_filters=64, device=None, shard_n_images=None):
+                 eps=1e-7, seed=1234, init_filters=64, device=None, shard_n_images=None, dtype=None):
+        """dtype: None = follow $RESNET_B200_DTYPE, "tf32" = fp32 tensors / TF32 MMAs, "bf16" = bf16 tensors (include/resnet_b200.h)"""
         lib = L()
         if device is not None:
             lib.resnet_b200_set_device(int(device))
@@ -88,8 +128,11 @@ class Trainer:
         self.model = lib.init_resnet(self.dims, self.gen)
         self.batch_struct = lib.init_general_batch(batch, input_dim * input_dim * 3, input_dim, shard_n_images or batch)
         self._dump_dir = b"resnet_b200"
+        lib.resnet_b200_set_dtype({None: -1, "tf32": 0, "fp32": 0, "bf16": 1}[dtype])
         self.t = lib.init_trainer(self.model, self.batch_struct, batch, lr, wd, b1, b2, eps, 1, self._dump_dir)
+        lib.resnet_b200_set_dtype(-1)
         check()
+        self.bf16 = lib.resnet_b200_trainer_dtype(self.t) == 1
         P = self.model.contents.params.contents
         self.n_locations = P.n_locations
         self.sizes = [P.sizes[i] for i in range(P.n_locations)]
@@ -184,6 +227,9 @@ class Trainer:
                 ptr, n = getattr(b, field), sizes.get(field, N * s_out * s_out * b.expanded_depth)
         if not ptr:
             return None
+        fp32_always = name in ("max_inds", "final_conv_output_pooled", "linear_output") or name.endswith((".means", ".vars"))
+        if self.bf16 and not fp32_always:
+            return from_bf16(d2h(ptr, n, np.uint16))
         return d2h(ptr, n, dtype)
 
     def close(self):
@@ -193,82 +239,92 @@ class Trainer:
 
 
 # ------------------------------------------------------------------------------------------- single operators
-def conv_forward(x, w, stride, impl=0):
+def conv_forward(x, w, stride, impl=0, dtype="f32"):
     N, S, _, cin = x.shape
     cout, _, k, _ = w.shape
-    dx, dw = DevBuf(x), DevBuf(w)
-    dy = DevBuf(nbytes=4 * N * (S // stride) ** 2 * cout, zero=True)
-    L().resnet_b200_conv_forward(S, k, cin, cout, stride, N, dx.ptr, dw.ptr, dy.ptr, impl)
-    check()
-    return dy.get((N, S // stride, S // stride, cout))
+    with _OpDtype(dtype == "bf16") as T:
+        dx = DevBuf(np.ascontiguousarray(x, np.float32)) if cin == 3 else T.up(x)  # the stem reads the fp32 batch in both modes
+        dw = DevBuf(w)
+        dy = T.out(N * (S // stride) ** 2 * cout)
+        L().resnet_b200_conv_forward(S, k, cin, cout, stride, N, dx.ptr, dw.ptr, dy.ptr, impl)
+        check()
+        return T.down(dy, (N, S // stride, S // stride, cout))
 
 
-def conv_backward(x, w, dy, stride, din_base=None, want_din=True, impl=0):
+def conv_backward(x, w, dy, stride, din_base=None, want_din=True, impl=0, dtype="f32"):
     N, S, _, cin = x.shape
     cout, _, k, _ = w.shape
-    bx, bw, bdy = DevBuf(x), DevBuf(w), DevBuf(dy)
-    bdw = DevBuf(nbytes=w.nbytes, zero=True)
-    bdin = None
-    if want_din:
-        bdin = DevBuf(din_base) if din_base is not None else DevBuf(nbytes=x.nbytes, zero=True)
-    L().resnet_b200_conv_backward(S, k, cin, cout, stride, N, int(din_base is not None), bx.ptr, bw.ptr, bdy.ptr,
-                                  bdin.ptr if bdin else None, bdw.ptr, impl)
-    check()
-    return (bdin.get(x.shape) if bdin else None), bdw.get(w.shape)
+    with _OpDtype(dtype == "bf16") as T:
+        bx = DevBuf(np.ascontiguousarray(x, np.float32)) if cin == 3 else T.up(x)
+        bw, bdy = DevBuf(w), T.up(dy)
+        bdw = DevBuf(nbytes=w.nbytes, zero=True)
+        bdin = None
+        if want_din:
+            bdin = T.up(din_base) if din_base is not None else T.out(x.size)
+        L().resnet_b200_conv_backward(S, k, cin, cout, stride, N, int(din_base is not None), bx.ptr, bw.ptr, bdy.ptr,
+                                      bdin.ptr if bdin else None, bdw.ptr, impl)
+        check()
+        return (T.down(bdin, x.shape) if bdin else None), bdw.get(w.shape)
 
 
-def batchnorm_forward(x, gamma, beta, eps, relu, residual=None, round_tf32=False):
+def batchnorm_forward(x, gamma, beta, eps, relu, residual=None, round_tf32=False, dtype="f32"):
     N, S, _, Cc = x.shape
-    bx, bg, bb = DevBuf(x), DevBuf(gamma), DevBuf(beta)
-    bm, bv, by = DevBuf(nbytes=4 * Cc), DevBuf(nbytes=4 * Cc), DevBuf(nbytes=x.nbytes)
-    br = DevBuf(residual) if residual is not None else None
-    L().resnet_b200_batchnorm_forward(S, Cc, N, eps, bx.ptr, bg.ptr, bb.ptr, bm.ptr, bv.ptr, by.ptr, int(relu), br.ptr if br else None,
-                                      int(round_tf32))
-    check()
-    return bm.get((Cc,)), bv.get((Cc,)), by.get(x.shape)
+    with _OpDtype(dtype == "bf16") as T:
+        bx, bg, bb = T.up(x), DevBuf(gamma), DevBuf(beta)
+        bm, bv, by = DevBuf(nbytes=4 * Cc), DevBuf(nbytes=4 * Cc), T.out(x.size)
+        br = T.up(residual) if residual is not None else None
+        L().resnet_b200_batchnorm_forward(S, Cc, N, eps, bx.ptr, bg.ptr, bb.ptr, bm.ptr, bv.ptr, by.ptr, int(relu), br.ptr if br else None,
+                                          int(round_tf32))
+        check()
+        return bm.get((Cc,)), bv.get((Cc,)), T.down(by, x.shape)
 
 
-def batchnorm_backward(x, gamma, eps, means, vars_, activated, dy, relu):
+def batchnorm_backward(x, gamma, eps, means, vars_, activated, dy, relu, dtype="f32"):
     N, S, _, Cc = x.shape
-    bx, bg, bm, bv, ba, bdy = DevBuf(x), DevBuf(gamma), DevBuf(means), DevBuf(vars_), DevBuf(activated), DevBuf(dy)
-    bdg, bdb, bdx = DevBuf(nbytes=4 * Cc), DevBuf(nbytes=4 * Cc), DevBuf(nbytes=x.nbytes)
-    L().resnet_b200_batchnorm_backward(S, Cc, N, eps, bx.ptr, bg.ptr, bm.ptr, bv.ptr, ba.ptr, bdy.ptr, bdg.ptr, bdb.ptr, bdx.ptr, int(relu))
-    check()
-    return bdg.get((Cc,)), bdb.get((Cc,)), bdx.get(x.shape)
+    with _OpDtype(dtype == "bf16") as T:
+        bx, bg, bm, bv, ba, bdy = T.up(x), DevBuf(gamma), DevBuf(means), DevBuf(vars_), T.up(activated), T.up(dy)
+        bdg, bdb, bdx = DevBuf(nbytes=4 * Cc), DevBuf(nbytes=4 * Cc), T.out(x.size)
+        L().resnet_b200_batchnorm_backward(S, Cc, N, eps, bx.ptr, bg.ptr, bm.ptr, bv.ptr, ba.ptr, bdy.ptr, bdg.ptr, bdb.ptr, bdx.ptr, int(relu))
+        check()
+        return bdg.get((Cc,)), bdb.get((Cc,)), T.down(bdx, x.shape)
 
 
-def maxpool_forward(x, k, stride):
+def maxpool_forward(x, k, stride, dtype="f32"):
     N, S, _, Cc = x.shape
     So = S // stride
-    bx, bi, bo = DevBuf(x), DevBuf(nbytes=4 * N * So * So * Cc), DevBuf(nbytes=4 * N * So * So * Cc)
-    L().resnet_b200_maxpool_forward(bx.ptr, k, stride, S, Cc, N, bi.ptr, bo.ptr)
-    check()
-    return bo.get((N, So, So, Cc)), bi.get((N, So, So, Cc), np.int32)
+    with _OpDtype(dtype == "bf16") as T:
+        bx, bi, bo = T.up(x), DevBuf(nbytes=4 * N * So * So * Cc), T.out(N * So * So * Cc)
+        L().resnet_b200_maxpool_forward(bx.ptr, k, stride, S, Cc, N, bi.ptr, bo.ptr)
+        check()
+        return T.down(bo, (N, So, So, Cc)), bi.get((N, So, So, Cc), np.int32)
 
 
-def maxpool_backward(inds, dout, in_shape, k, stride):
+def maxpool_backward(inds, dout, in_shape, k, stride, dtype="f32"):
     N, S, _, Cc = in_shape
-    bi, bd = DevBuf(inds), DevBuf(dout)
-    bo = DevBuf(nbytes=4 * int(np.prod(in_shape)))
-    L().resnet_b200_maxpool_backward(bi.ptr, bd.ptr, k, S, stride, Cc, N, bo.ptr)
-    check()
-    return bo.get(in_shape)
+    with _OpDtype(dtype == "bf16") as T:
+        bi, bd = DevBuf(inds), T.up(dout)
+        bo = T.out(int(np.prod(in_shape)))
+        L().resnet_b200_maxpool_backward(bi.ptr, bd.ptr, k, S, stride, Cc, N, bo.ptr)
+        check()
+        return T.down(bo, tuple(in_shape))
 
 
-def avgpool_forward(x):
+def avgpool_forward(x, dtype="f32"):
     N, S, _, Cc = x.shape
-    bx, bo = DevBuf(x), DevBuf(nbytes=4 * N * Cc)
-    L().resnet_b200_avgpool_forward(bx.ptr, S, Cc, N, bo.ptr)
-    check()
-    return bo.get((N, Cc))
+    with _OpDtype(dtype == "bf16") as T:
+        bx, bo = T.up(x), DevBuf(nbytes=4 * N * Cc)
+        L().resnet_b200_avgpool_forward(bx.ptr, S, Cc, N, bo.ptr)
+        check()
+        return bo.get((N, Cc))
 
 
-def avgpool_backward(dp, S):
+def avgpool_backward(dp, S, dtype="f32"):
     N, Cc = dp.shape
-    bd, bo = DevBuf(dp), DevBuf(nbytes=4 * N * S * S * Cc)
-    L().resnet_b200_avgpool_backward(bd.ptr, Cc, N, S, bo.ptr)
-    check()
-    return bo.get((N, S, S, Cc))
+    with _OpDtype(dtype == "bf16") as T:
+        bd, bo = DevBuf(dp), T.out(N * S * S * Cc)
+        L().resnet_b200_avgpool_backward(bd.ptr, Cc, N, S, bo.ptr)
+        check()
+        return T.down(bo, (N, S, S, Cc))
 
 
 def matmul(A, B, ta=False, tb=False):

@@ -32,19 +32,48 @@ bool has_error() { return g_has_err; }
 // ------------------------------------------------------------------------------------------- helpers
 constexpr int kThreads = 256;
 
-template <int VEC> struct Vec;
-template <> struct Vec<4> { using T = float4; };
-template <> struct Vec<1> { using T = float; };
+// Storage types: float (VEC = 4 or 1 elements per access) and bf16 (VEC = 8): one 128-bit access per thread either way; the
+// arithmetic is always fp32.  i indexes VECTORS.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+	uint32_t r;
+	asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+	return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <int VEC> __device__ __forceinline__ void ldv(const float *p, long long i, float (&v)[VEC]) {
-	if constexpr (VEC == 4) {
+template <typename T, int VEC> __device__ __forceinline__ void ldv(const T *p, long long i, float (&v)[VEC]) {
+	if constexpr (sizeof(T) == 2) {
+		static_assert(sizeof(T) != 2 || VEC == 8, "bf16 tensors are accessed 8 elements at a time");
+		const uint4 t = reinterpret_cast<const uint4 *>(p)[i];
+		v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+		v[4] = bf16_lo(t.z); v[5] = bf16_hi(t.z); v[6] = bf16_lo(t.w); v[7] = bf16_hi(t.w);
+	} else if constexpr (VEC == 4) {
 		float4 t = reinterpret_cast<const float4 *>(p)[i];
 		v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 	} else v[0] = p[i];
 }
-template <int VEC> __device__ __forceinline__ void stv(float *p, long long i, const float (&v)[VEC]) {
-	if constexpr (VEC == 4) reinterpret_cast<float4 *>(p)[i] = make_float4(v[0], v[1], v[2], v[3]);
+template <typename T, int VEC> __device__ __forceinline__ void stv(T *p, long long i, const float (&v)[VEC]) {
+	if constexpr (sizeof(T) == 2)
+		reinterpret_cast<uint4 *>(p)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+	else if constexpr (VEC == 4) reinterpret_cast<float4 *>(p)[i] = make_float4(v[0], v[1], v[2], v[3]);
 	else p[i] = v[0];
+}
+// scalar element access (small kernels)
+template <typename T> __device__ __forceinline__ float ld1(const T *p, long long i) {
+	if constexpr (sizeof(T) == 2) return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t *>(p)[i] << 16);
+	else return p[i];
+}
+template <typename T> __device__ __forceinline__ void st1(T *p, long long i, float v) {
+	if constexpr (sizeof(T) == 2) reinterpret_cast<uint16_t *>(p)[i] = (uint16_t)(pack_bf16x2(v, 0.f) & 0xffffu);
+	else p[i] = v;
+}
+typedef uint16_t bf16_t;  // raw bf16 bits; only sizeof(T) matters to the accessors above
+
+// vector width of a [rows][C] tensor of the given element type, 0 = unsupported
+static int vec_of(int C, int bf16) {
+	if (bf16) return (C % 8 == 0) ? 8 : 0;
+	return (C % 4 == 0) ? 4 : 1;
 }
 __device__ __forceinline__ float round_tf32(float x) {
 	uint32_t r;
@@ -72,15 +101,15 @@ constexpr int kMaxFlatBlocks = kNumSMs * 8;
 
 // ------------------------------------------------------------------------------------------- BN statistics
 // partials[blk][0][c] = sum x, partials[blk][1][c] = sum x^2 over the rows this block streamed.
-template <int VEC, bool FIXED, bool BWD>
-__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy,
-                                                            const float *__restrict__ mask, const float *__restrict__ means,
+template <typename T, int VEC, bool FIXED, bool BWD>
+__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+                                                            const T *__restrict__ mask, const float *__restrict__ means,
                                                             long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab) {
 	extern __shared__ float sm[];  // [2][C]
 	const int Cc = V * VEC;
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) sm[i] = 0.f;
 	__syncthreads();
-	const long long T = (long long)gridDim.x * kThreads;
+	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	float s[VEC], q[VEC], mu[VEC];
 #pragma unroll
@@ -99,9 +128,9 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 		}
 	}
 #pragma unroll 4
-	for (long long i = g; i < nvec; i += T) {
+	for (long long i = g; i < nvec; i += TS) {
 		float a[VEC];
-		ldv<VEC>(x, i, a);
+		ldv<T, VEC>(x, i, a);
 		if constexpr (!BWD) {
 			if constexpr (FIXED) {
 #pragma unroll
@@ -113,13 +142,13 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 			}
 		} else {
 			float d[VEC];
-			ldv<VEC>(dy, i, d);
+			ldv<T, VEC>(dy, i, d);
 			if (remask) {
 #pragma unroll
 				for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
 			} else if (mask) {
 				float mk[VEC];
-				ldv<VEC>(mask, i, mk);
+				ldv<T, VEC>(mask, i, mk);
 #pragma unroll
 				for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
 			}
@@ -164,25 +193,31 @@ __global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const float *__rest
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) out[i] = sm[i];
 }
 
-// Fold of the per-block partials in fp64.  32 channels x 32 slices per block: slice sy sums partial blocks sy, sy+32, ... (coalesced
-// 128-byte rows), shared memory combines the slices in a fixed order (deterministic).  A one-thread-per-channel loop over
-// ~1000 partials was latency-bound at 170 us per launch (profiles/r01_launch_summary.txt).
-constexpr int kFinC = 32, kFinS = 32;
+// Fold of the per-block partials in fp64.  8 channels x 128 slices per block: slice sy sums partial blocks sy, sy+128, ... (32-byte
+// sectors, ~5 independent loads per thread), then a fixed shuffle tree inside each warp and a fixed-order sum of the 32 warp
+// results (deterministic).  History: one thread per channel over ~1000 partials was latency-bound at 170 us per launch; 32
+// channels x 32 slices still spent 22 us in a 19-deep dependent L2 load chain (profiles/r01_ncu_all_kernels_one_step_summary.txt).
+constexpr int kFinC = 8, kFinS = 128;
 __device__ __forceinline__ bool fold_partials(const float *__restrict__ partials, int nblk, int Cc, double *s_out, double *q_out) {
-	__shared__ double sm[kFinS][2][kFinC];
+	__shared__ double sm[kFinS / 4][2][kFinC];
 	const int cx = threadIdx.x, sy = threadIdx.y, c = blockIdx.x * kFinC + cx;
 	double s = 0, q = 0;
-	if (c < Cc)
+	if (c < Cc) {
+#pragma unroll 4
 		for (int b = sy; b < nblk; b += kFinS) {
 			s += (double)partials[(size_t)b * 2 * Cc + c];
 			q += (double)partials[(size_t)b * 2 * Cc + Cc + c];
 		}
-	sm[sy][0][cx] = s;
-	sm[sy][1][cx] = q;
+	}
+	// a warp holds 4 consecutive slices x 8 channels: lanes l, l^8, l^16, l^24 share a channel
+	s += __shfl_xor_sync(0xffffffffu, s, 8);  q += __shfl_xor_sync(0xffffffffu, q, 8);
+	s += __shfl_xor_sync(0xffffffffu, s, 16); q += __shfl_xor_sync(0xffffffffu, q, 16);
+	if ((sy & 3) == 0) { sm[sy >> 2][0][cx] = s; sm[sy >> 2][1][cx] = q; }
 	__syncthreads();
 	if (sy != 0 || c >= Cc) return false;
+	s = 0; q = 0;
 #pragma unroll
-	for (int j = 1; j < kFinS; j++) { s += sm[j][0][cx]; q += sm[j][1][cx]; }
+	for (int j = 0; j < kFinS / 4; j++) { s += sm[j][0][cx]; q += sm[j][1][cx]; }
 	*s_out = s;
 	*q_out = q;
 	return true;
@@ -206,9 +241,11 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partials, int nblk,
 	ab[Cc + c] = beta[c] - meanf * a;
 }
 
-static void launch_reduce(bool bwd, const float *x, const float *dy, const float *mask, const float *means, long long rows, int C,
-                          float *partials, int max_blocks, int *grid_out, cudaStream_t st, const float *mab = nullptr) {
-	const int VEC = (C % 4 == 0) ? 4 : 1;
+static void launch_reduce(bool bwd, const void *x, const void *dy, const void *mask, const float *means, long long rows, int C,
+                          float *partials, int max_blocks, int *grid_out, cudaStream_t st, const float *mab, int bf16) {
+	const int VEC = vec_of(C, bf16);
+	*grid_out = 1;
+	if (!VEC) { set_error("BatchNorm over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
 	const int V = C / VEC;
 	const long long nvec = rows * V;
 	bool fixed;
@@ -216,11 +253,17 @@ static void launch_reduce(bool bwd, const float *x, const float *dy, const float
 	int grid = flat_grid(nvec, V, cap, &fixed);
 	if (VEC == 1) fixed = false;
 	const size_t smem = 2 * (size_t)C * sizeof(float);
-#define RB_RED(VEC_, FIX_, BWD_) bn_reduce_kernel<VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>(x, dy, mask, means, nvec, V, partials, mab)
-	if (VEC == 4) {
-		if (fixed) { if (bwd) RB_RED(4, true, true); else RB_RED(4, true, false); }
-		else { if (bwd) RB_RED(4, false, true); else RB_RED(4, false, false); }
-	} else { if (bwd) RB_RED(1, false, true); else RB_RED(1, false, false); }
+#define RB_RED(T_, VEC_, FIX_, BWD_) \
+	bn_reduce_kernel<T_, VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask, means, nvec, V, partials, mab)
+#define RB_RED2(T_, VEC_) \
+	do { \
+		if (fixed) { if (bwd) RB_RED(T_, VEC_, true, true); else RB_RED(T_, VEC_, true, false); } \
+		else { if (bwd) RB_RED(T_, VEC_, false, true); else RB_RED(T_, VEC_, false, false); } \
+	} while (0)
+	if (bf16) RB_RED2(bf16_t, 8);
+	else if (VEC == 4) RB_RED2(float, 4);
+	else { if (bwd) RB_RED(float, 1, false, true); else RB_RED(float, 1, false, false); }
+#undef RB_RED2
 #undef RB_RED
 	RB_LAUNCH_CHECK();
 	*grid_out = grid;
@@ -232,20 +275,20 @@ void bn_finalize(const float *partials, int nblk, long long rows, int C, const f
 	RB_LAUNCH_CHECK();
 }
 
-void bn_stats(const float *x, long long rows, int C, const float *gamma, const float *beta, float eps, float *means, float *vars,
-              float *ab, float *partials, int max_blocks, cudaStream_t st) {
+void bn_stats(const void *x, long long rows, int C, const float *gamma, const float *beta, float eps, float *means, float *vars,
+              float *ab, float *partials, int max_blocks, cudaStream_t st, int bf16) {
 	int grid;
-	launch_reduce(false, x, nullptr, nullptr, nullptr, rows, C, partials, max_blocks, &grid, st);
+	launch_reduce(false, x, nullptr, nullptr, nullptr, rows, C, partials, max_blocks, &grid, st, nullptr, bf16);
 	bn_finalize(partials, grid, rows, C, gamma, beta, eps, means, vars, ab, st);
 }
 
 // ------------------------------------------------------------------------------------------- BN apply (+ residual + ReLU)
-template <int VEC, bool FIXED>
-__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restrict__ x, const float *__restrict__ ab, long long nvec, int V,
-                                                           int relu, const float *__restrict__ res, const float *__restrict__ ab2,
-                                                           float *__restrict__ y, int rnd) {
+template <typename T, int VEC, bool FIXED>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T *__restrict__ x, const float *__restrict__ ab, long long nvec, int V,
+                                                           int relu, const T *__restrict__ res, const float *__restrict__ ab2,
+                                                           T *__restrict__ y, int rnd) {
 	const int Cc = V * VEC;
-	const long long T = (long long)gridDim.x * kThreads;
+	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	float a[VEC], b[VEC], a2[VEC], b2[VEC];
 	if constexpr (FIXED) {
@@ -257,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
 		}
 	}
 #pragma unroll 4
-	for (long long i = g; i < nvec; i += T) {
+	for (long long i = g; i < nvec; i += TS) {
 		if constexpr (!FIXED) {
 			const int c0 = (int)(i % V) * VEC;
 #pragma unroll
@@ -267,12 +310,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
 			}
 		}
 		float v[VEC];
-		ldv<VEC>(x, i, v);
+		ldv<T, VEC>(x, i, v);
 #pragma unroll
 		for (int j = 0; j < VEC; j++) v[j] = fmaf(v[j], a[j], b[j]);
 		if (res) {
 			float r[VEC];
-			ldv<VEC>(res, i, r);
+			ldv<T, VEC>(res, i, r);
 #pragma unroll
 			for (int j = 0; j < VEC; j++) v[j] += fmaf(r[j], a2[j], b2[j]);
 		}
@@ -281,20 +324,25 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
 			if (relu) v[j] = fmaxf(v[j], 0.f);
 			if (rnd) v[j] = round_tf32(v[j]);
 		}
-		stv<VEC>(y, i, v);
+		stv<T, VEC>(y, i, v);
 	}
 }
 
-void bn_apply(const float *x, const float *ab, long long rows, int C, int relu, const float *res, const float *ab2, float *y,
-              int rnd, cudaStream_t st) {
-	const int VEC = (C % 4 == 0) ? 4 : 1;
+void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, const void *res, const float *ab2, void *y,
+              int rnd, cudaStream_t st, int bf16) {
+	const int VEC = vec_of(C, bf16);
+	if (!VEC) { set_error("BatchNorm over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
 	const int V = C / VEC;
 	const long long nvec = rows * V;
 	bool fixed;
 	int grid = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
-	if (VEC == 4 && fixed) bn_apply_kernel<4, true><<<grid, kThreads, 0, st>>>(x, ab, nvec, V, relu, res, ab2, y, rnd);
-	else if (VEC == 4) bn_apply_kernel<4, false><<<grid, kThreads, 0, st>>>(x, ab, nvec, V, relu, res, ab2, y, rnd);
-	else bn_apply_kernel<1, false><<<grid, kThreads, 0, st>>>(x, ab, nvec, V, relu, res, ab2, y, rnd);
+#define RB_APPLY(T_, VEC_, FIX_) \
+	bn_apply_kernel<T_, VEC_, FIX_><<<grid, kThreads, 0, st>>>((const T_ *)x, ab, nvec, V, relu, (const T_ *)res, ab2, (T_ *)y, bf16 ? 0 : rnd)
+	if (bf16) { if (fixed) RB_APPLY(bf16_t, 8, true); else RB_APPLY(bf16_t, 8, false); }
+	else if (VEC == 4 && fixed) RB_APPLY(float, 4, true);
+	else if (VEC == 4) RB_APPLY(float, 4, false);
+	else RB_APPLY(float, 1, false);
+#undef RB_APPLY
 	RB_LAUNCH_CHECK();
 }
 
@@ -318,12 +366,12 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
 	coef[3 * Cc + c] = means[c];
 }
 
-template <int VEC, bool FIXED>
-__global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__restrict__ x, const float *dy, const float *__restrict__ mask,
-                                                            const float *__restrict__ coef, long long nvec, int V, float *dx, int rnd,
+template <typename T, int VEC, bool FIXED>
+__global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
+                                                            const float *__restrict__ coef, long long nvec, int V, T *dx, int rnd,
                                                             const float *__restrict__ mab) {
 	const int Cc = V * VEC;
-	const long long T = (long long)gridDim.x * kThreads;
+	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	float c1[VEC], c2[VEC], c3[VEC], mu[VEC], ma[VEC], mb[VEC];
 	const bool remask = FIXED && mab != nullptr;
@@ -336,21 +384,21 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__rest
 		}
 	}
 #pragma unroll 4
-	for (long long i = g; i < nvec; i += T) {
+	for (long long i = g; i < nvec; i += TS) {
 		if constexpr (!FIXED) {
 			const int c0 = (int)(i % V) * VEC;
 #pragma unroll
 			for (int j = 0; j < VEC; j++) { c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j]; }
 		}
 		float a[VEC], d[VEC];
-		ldv<VEC>(x, i, a);
-		ldv<VEC>(dy, i, d);
+		ldv<T, VEC>(x, i, a);
+		ldv<T, VEC>(dy, i, d);
 		if (remask) {
 #pragma unroll
 			for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
 		} else if (mask) {
 			float mk[VEC];
-			ldv<VEC>(mask, i, mk);
+			ldv<T, VEC>(mask, i, mk);
 #pragma unroll
 			for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
 		}
@@ -359,52 +407,64 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const float *__rest
 			float r = fmaf(c1[j], d[j], fmaf(c3[j], a[j] - mu[j], c2[j]));
 			d[j] = rnd ? round_tf32(r) : r;
 		}
-		stv<VEC>(dx, i, d);
+		stv<T, VEC>(dx, i, d);
 	}
 }
 
-void bn_bwd(const float *x, const float *dy, const float *mask_src, const float *gamma, const float *means, const float *vars, float eps,
-            long long rows, int C, float *dgamma, float *dbeta, float *dx, float *partials, int max_blocks, float *coef, int rnd,
-            cudaStream_t st, const float *mab) {
+void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars, float eps,
+            long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks, float *coef, int rnd,
+            cudaStream_t st, const float *mab, int bf16) {
 	int grid;
-	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab);
+	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab, bf16);
 	bn_bwd_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();
-	const int VEC = (C % 4 == 0) ? 4 : 1;
+	const int VEC = vec_of(C, bf16);
+	if (!VEC) return;
 	const int V = C / VEC;
 	const long long nvec = rows * V;
 	bool fixed;
 	int g2 = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
-	if (VEC == 4 && fixed) bn_bwd_dx_kernel<4, true><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd, mab);
-	else if (VEC == 4) bn_bwd_dx_kernel<4, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd, mab);
-	else bn_bwd_dx_kernel<1, false><<<g2, kThreads, 0, st>>>(x, dy, mask_src, coef, nvec, V, dx, rnd, mab);
+#define RB_DX(T_, VEC_, FIX_) \
+	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab)
+	if (bf16) { if (fixed) RB_DX(bf16_t, 8, true); else RB_DX(bf16_t, 8, false); }
+	else if (VEC == 4 && fixed) RB_DX(float, 4, true);
+	else if (VEC == 4) RB_DX(float, 4, false);
+	else RB_DX(float, 1, false);
+#undef RB_DX
 	RB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------- ReLU backward (identity shortcut)
-__global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const float *__restrict__ y, const float *__restrict__ dy, long long n, float *__restrict__ dx) {
-	const long long T = (long long)gridDim.x * kThreads;
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const T *__restrict__ y, const T *__restrict__ dy, long long n, T *__restrict__ dx) {
+	const long long T_ = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-	const long long n4 = n / 4;
+	const long long nv = n / VEC;
 #pragma unroll 4
-	for (long long i = g; i < n4; i += T) {
-		float4 a = reinterpret_cast<const float4 *>(y)[i], d = reinterpret_cast<const float4 *>(dy)[i];
-		reinterpret_cast<float4 *>(dx)[i] = make_float4(a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);
+	for (long long i = g; i < nv; i += T_) {
+		float a[VEC], d[VEC];
+		ldv<T, VEC>(y, i, a);
+		ldv<T, VEC>(dy, i, d);
+#pragma unroll
+		for (int j = 0; j < VEC; j++) d[j] = a[j] > 0.f ? d[j] : 0.f;
+		stv<T, VEC>(dx, i, d);
 	}
-	for (long long i = n4 * 4 + g; i < n; i += T) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+	for (long long i = nv * VEC + g; i < n; i += T_) st1<T>(dx, i, ld1<T>(y, i) > 0.f ? ld1<T>(dy, i) : 0.f);
 }
-void relu_bwd(const float *y, const float *dy, long long n, float *dx, cudaStream_t st) {
-	int grid = (int)((n / 4 + kThreads * 4 - 1) / (kThreads * 4));
+void relu_bwd(const void *y, const void *dy, long long n, void *dx, cudaStream_t st, int bf16) {
+	const int VEC = bf16 ? 8 : 4;
+	int grid = (int)((n / VEC + kThreads * 4 - 1) / (kThreads * 4));
 	grid = grid < 1 ? 1 : (grid > kMaxFlatBlocks ? kMaxFlatBlocks : grid);
-	relu_bwd_kernel<<<grid, kThreads, 0, st>>>(y, dy, n, dx);
+	if (bf16) relu_bwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>((const bf16_t *)y, (const bf16_t *)dy, n, (bf16_t *)dx);
+	else relu_bwd_kernel<float, 4><<<grid, kThreads, 0, st>>>((const float *)y, (const float *)dy, n, (float *)dx);
 	RB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------- max pool
 // reference resnet.cu:433-471: init -1024, strict '>', row-major window scan, flat input index.
-template <int VEC>
-__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float *__restrict__ x, int N, int S, int C, int k, int stride,
-                                                              int *__restrict__ inds, float *__restrict__ out) {
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T *__restrict__ x, int N, int S, int C, int k, int stride,
+                                                              int *__restrict__ inds, T *__restrict__ out) {
 	const int So = S / stride, half = k / 2, V = C / VEC;
 	const long long total = (long long)N * So * So * V;
 	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
@@ -424,36 +484,36 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float *__re
 				if (w < 0 || w >= S) continue;
 				const long long base = (((long long)n * S + h) * S + w) * C + (long long)cv * VEC;
 				float v[VEC];
-				ldv<VEC>(x, base / VEC, v);
+				ldv<T, VEC>(x, base / VEC, v);
 #pragma unroll
 				for (int j = 0; j < VEC; j++) if (v[j] > mv[j]) { mv[j] = v[j]; mi[j] = (int)(base + j); }
 			}
 		}
-		stv<VEC>(out, i, mv);
-		if constexpr (VEC == 4) reinterpret_cast<int4 *>(inds)[i] = make_int4(mi[0], mi[1], mi[2], mi[3]);
-		else inds[i] = mi[0];
+		stv<T, VEC>(out, i, mv);
+		if constexpr (VEC >= 4) {
+#pragma unroll
+			for (int h = 0; h < VEC / 4; h++) reinterpret_cast<int4 *>(inds)[i * (VEC / 4) + h] = make_int4(mi[4 * h], mi[4 * h + 1], mi[4 * h + 2], mi[4 * h + 3]);
+		} else inds[i] = mi[0];
 	}
 }
-void maxpool_fwd(const float *x, int N, int S, int C, int k, int stride, int *max_inds, float *out, cudaStream_t st) {
+void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16) {
 	const int So = S / stride;
-	if (C % 4 == 0) {
-		long long total = (long long)N * So * So * (C / 4);
-		int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
-		maxpool_fwd_kernel<4><<<grid, kThreads, 0, st>>>(x, N, S, C, k, stride, max_inds, out);
-	} else {
-		long long total = (long long)N * So * So * C;
-		int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
-		maxpool_fwd_kernel<1><<<grid, kThreads, 0, st>>>(x, N, S, C, k, stride, max_inds, out);
-	}
+	const int VEC = vec_of(C, bf16);
+	if (!VEC) { set_error("max pool over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
+	long long total = (long long)N * So * So * (C / VEC);
+	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
+	if (bf16) maxpool_fwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>((const bf16_t *)x, N, S, C, k, stride, max_inds, (bf16_t *)out);
+	else if (VEC == 4) maxpool_fwd_kernel<float, 4><<<grid, kThreads, 0, st>>>((const float *)x, N, S, C, k, stride, max_inds, (float *)out);
+	else maxpool_fwd_kernel<float, 1><<<grid, kThreads, 0, st>>>((const float *)x, N, S, C, k, stride, max_inds, (float *)out);
 	RB_LAUNCH_CHECK();
 }
 
 // Gather form of the reference's scatter (resnet.cu:476-494): every input element sums the gradients of the
 // windows whose recorded argmax is that element.  Deterministic, and accumulates where the reference's
 // overlapping-window scatter races (its cuDNN variants accumulate too).
-template <int VEC>
-__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const int *__restrict__ inds, const float *__restrict__ dout, int N, int S, int C,
-                                                              int k, int stride, float *__restrict__ din) {
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const int *__restrict__ inds, const T *__restrict__ dout, int N, int S, int C,
+                                                              int k, int stride, T *__restrict__ din) {
 	const int So = S / stride, half = k / 2, V = C / VEC;
 	const long long total = (long long)N * S * S * V;
 	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
@@ -475,50 +535,62 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const int *__rest
 			for (int ow = ow_lo; ow <= ow_hi; ow++) {
 				const long long o = ((((long long)n * So + oh) * So + ow) * C) / VEC + cv;
 				float d[VEC];
-				ldv<VEC>(dout, o, d);
+				ldv<T, VEC>(dout, o, d);
 				int id[VEC];
-				if constexpr (VEC == 4) { int4 t = reinterpret_cast<const int4 *>(inds)[o]; id[0] = t.x; id[1] = t.y; id[2] = t.z; id[3] = t.w; }
-				else id[0] = inds[o];
+				if constexpr (VEC >= 4) {
+#pragma unroll
+					for (int h = 0; h < VEC / 4; h++) {
+						int4 t = reinterpret_cast<const int4 *>(inds)[o * (VEC / 4) + h];
+						id[4 * h] = t.x; id[4 * h + 1] = t.y; id[4 * h + 2] = t.z; id[4 * h + 3] = t.w;
+					}
+				} else id[0] = inds[o];
 #pragma unroll
 				for (int j = 0; j < VEC; j++) if (id[j] == me + j) acc[j] += d[j];
 			}
-		stv<VEC>(din, i, acc);
+		stv<T, VEC>(din, i, acc);
 	}
 }
-void maxpool_bwd(const int *max_inds, const float *dout, int N, int S, int C, int k, int stride, float *din, cudaStream_t st) {
-	const int VEC = (C % 4 == 0) ? 4 : 1;
+void maxpool_bwd(const int *max_inds, const void *dout, int N, int S, int C, int k, int stride, void *din, cudaStream_t st, int bf16) {
+	const int VEC = vec_of(C, bf16);
+	if (!VEC) { set_error("max pool over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
 	long long total = (long long)N * S * S * (C / VEC);
 	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 8 ? kMaxFlatBlocks * 8 : grid;
-	if (VEC == 4) maxpool_bwd_kernel<4><<<grid, kThreads, 0, st>>>(max_inds, dout, N, S, C, k, stride, din);
-	else maxpool_bwd_kernel<1><<<grid, kThreads, 0, st>>>(max_inds, dout, N, S, C, k, stride, din);
+	if (bf16) maxpool_bwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>(max_inds, (const bf16_t *)dout, N, S, C, k, stride, (bf16_t *)din);
+	else if (VEC == 4) maxpool_bwd_kernel<float, 4><<<grid, kThreads, 0, st>>>(max_inds, (const float *)dout, N, S, C, k, stride, (float *)din);
+	else maxpool_bwd_kernel<float, 1><<<grid, kThreads, 0, st>>>(max_inds, (const float *)dout, N, S, C, k, stride, (float *)din);
 	RB_LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------- average pool
-__global__ void avgpool_fwd_kernel(const float *__restrict__ x, int N, int SS, int C, float *__restrict__ out) {
+// activations in T, pooled values and their gradient in fp32 (the FC head stays fp32)
+template <typename T>
+__global__ void avgpool_fwd_kernel(const T *__restrict__ x, int N, int SS, int C, float *__restrict__ out) {
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (n, c)
 	if (i >= (long long)N * C) return;
 	const int c = (int)(i % C), n = (int)(i / C);
 	float s = 0.f;
-	for (int p = 0; p < SS; p++) s += x[((long long)n * SS + p) * C + c];
+	for (int p = 0; p < SS; p++) s += ld1<T>(x, ((long long)n * SS + p) * C + c);
 	out[i] = s / (float)SS;
 }
-void avgpool_fwd(const float *x, int N, int S, int C, float *out, cudaStream_t st) {
-	avgpool_fwd_kernel<<<ceil_div((long long)N * C, 256), 256, 0, st>>>(x, N, S * S, C, out);
+void avgpool_fwd(const void *x, int N, int S, int C, float *out, cudaStream_t st, int bf16) {
+	if (bf16) avgpool_fwd_kernel<bf16_t><<<ceil_div((long long)N * C, 256), 256, 0, st>>>((const bf16_t *)x, N, S * S, C, out);
+	else avgpool_fwd_kernel<float><<<ceil_div((long long)N * C, 256), 256, 0, st>>>((const float *)x, N, S * S, C, out);
 	RB_LAUNCH_CHECK();
 }
-__global__ void avgpool_bwd_kernel(const float *__restrict__ dp, int N, int SS, int C, float *__restrict__ din) {
+template <typename T>
+__global__ void avgpool_bwd_kernel(const float *__restrict__ dp, int N, int SS, int C, T *__restrict__ din) {
 	const long long total = (long long)N * SS * C;
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
 		const int c = (int)(i % C);
 		const int n = (int)(i / ((long long)SS * C));
-		din[i] = dp[(long long)n * C + c] / (float)SS;
+		st1<T>(din, i, dp[(long long)n * C + c] / (float)SS);
 	}
 }
-void avgpool_bwd(const float *dpooled, int N, int S, int C, float *din, cudaStream_t st) {
+void avgpool_bwd(const float *dpooled, int N, int S, int C, void *din, cudaStream_t st, int bf16) {
 	long long total = (long long)N * S * S * C;
 	int grid = (int)((total + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
-	avgpool_bwd_kernel<<<grid, 256, 0, st>>>(dpooled, N, S * S, C, din);
+	if (bf16) avgpool_bwd_kernel<bf16_t><<<grid, 256, 0, st>>>(dpooled, N, S * S, C, (bf16_t *)din);
+	else avgpool_bwd_kernel<float><<<grid, 256, 0, st>>>(dpooled, N, S * S, C, (float *)din);
 	RB_LAUNCH_CHECK();
 }
 
@@ -643,6 +715,7 @@ void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int t
 }
 
 // ------------------------------------------------------------------------------------------- weight re-layout
+template <typename T>
 __global__ void pack_weights_kernel(const PackJob *__restrict__ jobs, int rnd) {
 	const PackJob jb = jobs[blockIdx.y];
 	const long long total = (long long)jb.cout * jb.cin * jb.taps;
@@ -652,14 +725,33 @@ __global__ void pack_weights_kernel(const PackJob *__restrict__ jobs, int rnd) {
 		const int ci = (int)((i / jb.taps) % jb.cin);
 		const int co = (int)(i / ((long long)jb.taps * jb.cin));
 		float w = jb.src[i];
-		if (rnd) w = round_tf32(w);
-		jb.wf[((long long)co * jb.taps + tap) * jb.cin + ci] = w;
-		if (jb.wd) jb.wd[((long long)ci * jb.taps + tap) * jb.cout + co] = w;
+		if (rnd && sizeof(T) == 4) w = round_tf32(w);
+		st1<T>((T *)jb.wf, ((long long)co * jb.taps + tap) * jb.cin + ci, w);
+		if (jb.wd) st1<T>((T *)jb.wd, ((long long)ci * jb.taps + tap) * jb.cout + co, w);
 	}
 }
-void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int rnd, cudaStream_t st) {
+void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int rnd, cudaStream_t st, int bf16) {
 	int gx = ceil_div(max_elems, 256 * 8); gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
-	pack_weights_kernel<<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
+	if (bf16) pack_weights_kernel<bf16_t><<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
+	else pack_weights_kernel<float><<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
+	RB_LAUNCH_CHECK();
+}
+
+// fp32 <-> bf16 conversion of a flat buffer (test entry points and the single-operator C API)
+__global__ void f32_to_bf16_kernel(const float *__restrict__ s, long long n, bf16_t *__restrict__ d) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) st1<bf16_t>(d, i, s[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16_t *__restrict__ s, long long n, float *__restrict__ d) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) d[i] = ld1<bf16_t>(s, i);
+}
+void convert_f32_to_bf16(const float *s, long long n, void *d, cudaStream_t st) {
+	int grid = (int)((n + 255) / 256); grid = grid < 1 ? 1 : (grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid);
+	f32_to_bf16_kernel<<<grid, 256, 0, st>>>(s, n, (bf16_t *)d);
+	RB_LAUNCH_CHECK();
+}
+void convert_bf16_to_f32(const void *s, long long n, float *d, cudaStream_t st) {
+	int grid = (int)((n + 255) / 256); grid = grid < 1 ? 1 : (grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid);
+	bf16_to_f32_kernel<<<grid, 256, 0, st>>>((const bf16_t *)s, n, d);
 	RB_LAUNCH_CHECK();
 }
 

@@ -18,13 +18,18 @@ struct Tmp {
 	~Tmp() { for (void *p : ptrs) cudaFree(p); }
 };
 int status() { return has_error() ? 1 : 0; }
+int g_op_bf16 = 0;  // element type of the activation tensors the single-operator entry points read and write
 
 // packs [Cout][Cin][k][k] into Wf / Wd on the default stream
-void pack_one(const float *w, float *wf, float *wd, int cout, int cin, int taps, int rnd, Tmp &tmp) {
+void pack_one(const float *w, void *wf, void *wd, int cout, int cin, int taps, int rnd, Tmp &tmp) {
 	PackJob job{w, wf, wd, cout, cin, taps};
 	PackJob *jd = tmp.get<PackJob>(1);
 	RB_CUDA(cudaMemcpy(jd, &job, sizeof(job), cudaMemcpyHostToDevice));
-	pack_weights(jd, 1, cout * cin * taps, rnd, 0);
+	pack_weights(jd, 1, cout * cin * taps, rnd, 0, g_op_bf16);
+}
+bool simt_in_bf16(int impl) {
+	if (impl != 0 && g_op_bf16) { set_error("the SIMT fp32 convolution has no bf16 variant (impl must be 0 when the op dtype is bf16)"); return true; }
+	return false;
 }
 }  // namespace
 
@@ -32,6 +37,21 @@ extern "C" {
 
 const char *resnet_b200_last_error(void) { return last_error(); }
 void resnet_b200_clear_error(void) { clear_error(); }
+// storage type of trainers created from now on: -1 = follow $RESNET_B200_DTYPE (default), 0 = fp32 tensors / TF32 MMAs, 1 = bf16
+int resnet_b200_set_dtype(int bf16) { g_default_bf16 = bf16 < 0 ? -1 : (bf16 ? 1 : 0); return 0; }
+int resnet_b200_trainer_dtype(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	return e ? e->bf16 : -1;
+}
+// element type of the ACTIVATION tensors passed to the single-operator entry points below (weights, statistics, pooled values,
+// logits and all gradients of parameters stay fp32): 0 = fp32, 1 = bf16
+int resnet_b200_set_op_dtype(int bf16) { g_op_bf16 = bf16 ? 1 : 0; return 0; }
+int resnet_b200_convert(const void *src, void *dst, long long n, int to_bf16) {
+	if (to_bf16) convert_f32_to_bf16((const float *)src, n, dst, 0);
+	else convert_bf16_to_f32(src, n, (float *)dst, 0);
+	RB_CUDA(cudaDeviceSynchronize());
+	return status();
+}
 int resnet_b200_set_device(int device) { RB_CUDA(cudaSetDevice(device)); return status(); }
 void *resnet_b200_malloc(size_t bytes) { void *p = nullptr; RB_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
 void resnet_b200_free(void *p) { if (p) RB_CUDA(cudaFree(p)); }
@@ -140,20 +160,22 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 // ---------------------------------------------------------------------------------------------- single operators
 int resnet_b200_conv_forward(int S, int k, int cin, int cout, int stride, int N, const float *input, const float *weights, float *output, int impl) {
 	Tmp tmp;
+	const int bf = g_op_bf16;
+	if (simt_in_bf16(impl)) return status();
 	ConvGeom g{N, S, cin, cout, k, stride};
-	float *wf = tmp.get<float>(g.w_elems());
+	void *wf = tmp.get<char>(g.w_elems() * 4);
 	pack_one(weights, wf, nullptr, cout, cin, k * k, 0, tmp);
-	if (impl == 0 && tc_stem_supported(S, k, cin, cout, stride)) {
-		float *xp = tmp.get<float>((long long)stem_xp_elems(N, S)), *wfs = tmp.get<float>((long long)cout * 7 * 32);
-		stem_pad_input(input, N, S, xp, 0, 0);
-		stem_pack_weights(weights, cout, wfs, 0, 0);
-		TcPlan *pl = tc_make_stem_fprop(N, S, cout, xp, wfs, output);
+	if (impl == 0 && tc_stem_supported(S, k, cin, cout, stride, bf)) {
+		void *xp = tmp.get<char>((long long)stem_xp_bytes(N, S, bf)), *wfs = tmp.get<char>((long long)stem_wfs_bytes(cout, bf));
+		stem_pad_input(input, N, S, xp, 0, bf, 0);  // the stem's input is the fp32 batch in both modes
+		stem_pack_weights(weights, cout, wfs, 0, bf, 0);
+		TcPlan *pl = tc_make_stem_fprop(N, S, cout, xp, wfs, output, bf);
 		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 	} else if (impl == 0) {
-		TcPlan *pl = tc_make_fprop(g, input, wf, output);
+		TcPlan *pl = tc_make_fprop(g, input, wf, output, bf);
 		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 	} else {
-		simt_conv_fprop(g, input, wf, output, 0);
+		simt_conv_fprop(g, input, (const float *)wf, output, 0);
 	}
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
@@ -162,29 +184,32 @@ int resnet_b200_conv_forward(int S, int k, int cin, int cout, int stride, int N,
 int resnet_b200_conv_backward(int S, int k, int cin, int cout, int stride, int N, int to_add, const float *input, const float *weights,
                               const float *out_deriv, float *input_deriv, float *weight_deriv, int impl) {
 	Tmp tmp;
+	const int bf = g_op_bf16;
+	if (simt_in_bf16(impl)) return status();
 	ConvGeom g{N, S, cin, cout, k, stride};
-	float *wf = tmp.get<float>(g.w_elems()), *wd = tmp.get<float>(g.w_elems());
+	void *wf = tmp.get<char>(g.w_elems() * 4), *wd = tmp.get<char>(g.w_elems() * 4);
 	pack_one(weights, wf, wd, cout, cin, k * k, 0, tmp);
-	if (impl == 0 && tc_stem_supported(S, k, cin, cout, stride)) {
+	if (impl == 0 && tc_stem_supported(S, k, cin, cout, stride, bf)) {
 		// stem: weight gradient on the tensor cores; the (never needed, reference: resnet.cu:2243-2245) input gradient stays SIMT
-		if (input_deriv) simt_conv_dgrad(g, out_deriv, wd, input_deriv, to_add, 0);
-		float *xp = tmp.get<float>((long long)stem_xp_elems(N, S));
-		stem_pad_input(input, N, S, xp, 0, 0);
-		size_t ws = tc_stem_wgrad_workspace_bytes(N, S, cout);
+		if (input_deriv && !bf) simt_conv_dgrad(g, out_deriv, (const float *)wd, input_deriv, to_add, 0);
+		if (input_deriv && bf) set_error("the stem has no input gradient in bf16 mode (reference: resnet.cu:2243-2245 never computes it)");
+		void *xp = tmp.get<char>((long long)stem_xp_bytes(N, S, bf));
+		stem_pad_input(input, N, S, xp, 0, bf, 0);
+		size_t ws = tc_stem_wgrad_workspace_bytes(N, S, cout, bf);
 		float *wsp = (float *)tmp.get<char>((long long)ws);
-		TcPlan *pl = tc_make_stem_wgrad(N, S, cout, xp, out_deriv, weight_deriv, wsp, ws);
+		TcPlan *pl = tc_make_stem_wgrad(N, S, cout, xp, out_deriv, weight_deriv, wsp, ws, bf);
 		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 	} else if (impl == 0) {
 		if (input_deriv) {
-			TcPlan *pl = tc_make_dgrad(g, out_deriv, wd, input_deriv, to_add);
+			TcPlan *pl = tc_make_dgrad(g, out_deriv, wd, input_deriv, to_add, bf);
 			if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 		}
-		size_t ws = tc_wgrad_workspace_bytes(g);
+		size_t ws = tc_wgrad_workspace_bytes(g, bf);
 		float *wsp = (float *)tmp.get<char>((long long)ws);
-		TcPlan *pl = tc_make_wgrad(g, input, out_deriv, weight_deriv, wsp, ws);
+		TcPlan *pl = tc_make_wgrad(g, input, out_deriv, weight_deriv, wsp, ws, bf);
 		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 	} else {
-		if (input_deriv) simt_conv_dgrad(g, out_deriv, wd, input_deriv, to_add, 0);
+		if (input_deriv) simt_conv_dgrad(g, out_deriv, (const float *)wd, input_deriv, to_add, 0);
 		simt_conv_wgrad(g, input, out_deriv, weight_deriv, 0);
 	}
 	RB_CUDA(cudaDeviceSynchronize());
@@ -197,8 +222,8 @@ int resnet_b200_batchnorm_forward(int S, int C, int N, float eps, const float *i
 	const long long rows = (long long)N * S * S;
 	const int maxb = kNumSMs * 8;
 	float *partials = tmp.get<float>((long long)maxb * 2 * C), *ab = tmp.get<float>(2LL * C);
-	bn_stats(input, rows, C, gamma, beta, eps, means, vars, ab, partials, maxb, 0);
-	bn_apply(input, ab, rows, C, to_activate, residual, nullptr, activated, rnd, 0);
+	bn_stats(input, rows, C, gamma, beta, eps, means, vars, ab, partials, maxb, 0, g_op_bf16);
+	bn_apply(input, ab, rows, C, to_activate, residual, nullptr, activated, rnd, 0, g_op_bf16);
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
 }
@@ -211,28 +236,28 @@ int resnet_b200_batchnorm_backward(int S, int C, int N, float eps, const float *
 	const int maxb = kNumSMs * 8;
 	float *partials = tmp.get<float>((long long)maxb * 2 * C), *coef = tmp.get<float>(4LL * C);
 	bn_bwd(input, out_layer_deriv, to_activate_deriv ? activated : nullptr, gamma, means, vars, eps, rows, C, gamma_deriv, beta_deriv, input_deriv,
-	       partials, maxb, coef, 0, 0);
+	       partials, maxb, coef, 0, 0, nullptr, g_op_bf16);
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
 }
 
 int resnet_b200_maxpool_forward(const float *input, int k, int stride, int S, int C, int N, int *max_inds, float *out) {
-	maxpool_fwd(input, N, S, C, k, stride, max_inds, out, 0);
+	maxpool_fwd(input, N, S, C, k, stride, max_inds, out, 0, g_op_bf16);
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
 }
 int resnet_b200_maxpool_backward(const int *max_inds, const float *out_deriv, int k, int S, int stride, int C, int N, float *input_deriv) {
-	maxpool_bwd(max_inds, out_deriv, N, S, C, k, stride, input_deriv, 0);
+	maxpool_bwd(max_inds, out_deriv, N, S, C, k, stride, input_deriv, 0, g_op_bf16);
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
 }
 int resnet_b200_avgpool_forward(const float *input, int S, int C, int N, float *out) {
-	avgpool_fwd(input, N, S, C, out, 0);
+	avgpool_fwd(input, N, S, C, out, 0, g_op_bf16);
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
 }
 int resnet_b200_avgpool_backward(const float *pooled_deriv, int C, int N, int S, float *out) {
-	avgpool_bwd(pooled_deriv, N, S, C, out, 0);
+	avgpool_bwd(pooled_deriv, N, S, C, out, 0, g_op_bf16);
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
 }

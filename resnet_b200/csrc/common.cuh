@@ -45,32 +45,31 @@ struct ConvGeom {
 };
 
 // ---------------------------------------------------------------------------------------------
-// bandwidth-bound kernels (bw_kernels.cu).  All take a stream; all tensors fp32, NHWC, C % 4 == 0.
-struct BnScratch {       // per-call scratch carved from the engine workspace
-	float *partials;     // [grid][2][C]
-	int max_blocks;
-};
+// bandwidth-bound kernels (bw_kernels.cu).  All take a stream.  Activation tensors are NHWC in one of two element types, chosen
+// by the trailing `bf16` flag: fp32 (C % 4 == 0 for the vector path) or bf16 (C % 8 == 0); the arithmetic, the per-channel
+// vectors (gamma, beta, means, vars, folded coefficients) and every partial sum are fp32 / fp64 in both modes.
 
 // statistics of x[rows][C]: means, biased vars, and the folded scale/shift a = gamma*rstd, b = beta - mean*a
-void bn_stats(const float *x, long long rows, int C, const float *gamma, const float *beta, float eps, float *means,
-              float *vars, float *ab /* [2][C] */, float *partials, int max_blocks, cudaStream_t st);
+void bn_stats(const void *x, long long rows, int C, const float *gamma, const float *beta, float eps, float *means,
+              float *vars, float *ab /* [2][C] */, float *partials, int max_blocks, cudaStream_t st, int bf16 = 0);
 // finalize only (statistics partials already produced, e.g. by a conv epilogue): partials [nblk][2][C]
 void bn_finalize(const float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
                  float *means, float *vars, float *ab, cudaStream_t st);
 // y = act(x*a + b [+ residual]);  residual: res (identity) or res*a2 + b2 (projected, ab2 != NULL)
-void bn_apply(const float *x, const float *ab, long long rows, int C, int relu, const float *res, const float *ab2, float *y,
-              int round_tf32, cudaStream_t st);
+void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, const void *res, const float *ab2, void *y,
+              int round_tf32, cudaStream_t st, int bf16 = 0);
 // BatchNorm backward.  mask_src != NULL: dy is masked where mask_src <= 0 (ReLU).  Produces dgamma, dbeta and
 // dx (may alias dy).  coef scratch [4][C].
-void bn_bwd(const float *x, const float *dy, const float *mask_src, const float *gamma, const float *means, const float *vars,
-            float eps, long long rows, int C, float *dgamma, float *dbeta, float *dx, float *partials, int max_blocks,
-            float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr);
 // mask_ab != NULL ([2][C] folded scale/shift of the forward): the ReLU mask is recomputed as (x*a + b > 0) instead of read
-void relu_bwd(const float *y, const float *dy, long long n, float *dx, cudaStream_t st);
-void maxpool_fwd(const float *x, int N, int S, int C, int k, int stride, int *max_inds, float *out, cudaStream_t st);
-void maxpool_bwd(const int *max_inds, const float *dout, int N, int S, int C, int k, int stride, float *din, cudaStream_t st);
-void avgpool_fwd(const float *x, int N, int S, int C, float *out, cudaStream_t st);
-void avgpool_bwd(const float *dpooled, int N, int S, int C, float *din, cudaStream_t st);
+void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars,
+            float eps, long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks,
+            float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr, int bf16 = 0);
+void relu_bwd(const void *y, const void *dy, long long n, void *dx, cudaStream_t st, int bf16 = 0);
+void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16 = 0);
+void maxpool_bwd(const int *max_inds, const void *dout, int N, int S, int C, int k, int stride, void *din, cudaStream_t st, int bf16 = 0);
+// pooled values and their gradient are fp32 in both modes (the FC head is fp32)
+void avgpool_fwd(const void *x, int N, int S, int C, float *out, cudaStream_t st, int bf16 = 0);
+void avgpool_bwd(const float *dpooled, int N, int S, int C, void *din, cudaStream_t st, int bf16 = 0);
 // pred = softmax(logits); dlogits = pred - onehot(labels) (no 1/N, reference resnet.cu:1806-1811);
 // per-row loss = -log pred[label] and wrong flag (ties wrong, reference resnet.cu:3376)
 void softmax_ce(const float *logits, const int *labels, int N, int L, float *pred, float *dlogits, float *row_loss,
@@ -81,11 +80,13 @@ void adam_step(float *p, float *g, float *m, float *v, long long n, float lr, fl
 // C[M][N] = op(A) * op(B), fp32 FMA; ta: A stored [K][M]; tb: B stored [N][K]
 void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int ta, int tb, cudaStream_t st);
 
-// weight re-layout [Cout][Cin][k][k] -> Wf [Cout][k*k][Cin] and Wd [Cin][k*k][Cout] (optionally tf32-rounded)
-struct PackJob { const float *src; float *wf; float *wd; int cout, cin, taps; };
-void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int round_tf32, cudaStream_t st);
+// weight re-layout [Cout][Cin][k][k] (fp32 master) -> Wf [Cout][k*k][Cin] and Wd [Cin][k*k][Cout], tf32-rounded fp32 or bf16
+struct PackJob { const float *src; void *wf; void *wd; int cout, cin, taps; };
+void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int round_tf32, cudaStream_t st, int bf16 = 0);
 // dW [Cout][Cin][k][k] = sum_s partial[s][tap][Cout][Cin]  (deterministic split-K reduce + re-layout)
 void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps, float *dw, cudaStream_t st);
+void convert_f32_to_bf16(const float *s, long long n, void *d, cudaStream_t st);
+void convert_bf16_to_f32(const void *s, long long n, float *d, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // SIMT fp32 implicit-GEMM convolution (simt_conv.cu): exact-fp32 device-side checker and the C1 stem path.

@@ -54,6 +54,7 @@ struct Engine {
 	int conv_mode;    // 0 = tcgen05 (default), 1 = simt fp32
 	int round_tf32;   // producers round conv inputs to tf32 (tensor-core mode only)
 	int keep_all;     // materialise every reference buffer (debug / parity)
+	int bf16, esz;    // activation / packed-weight storage: 0 = fp32 (tf32 MMAs), 1 = bf16; bytes per element
 	int N;
 	// stem
 	ConvRef stem;
@@ -87,6 +88,7 @@ struct Engine {
 	cudaEvent_t ev0, ev1;
 };
 Engine *engine_of(const Train_ResNet *t);
+extern int g_default_bf16;  // storage type of the next init_trainer (resnet_b200_set_dtype)
 
 // dp.cu
 void dp_block_done(Engine *e, int block);  // block's gradients are enqueued: issue the buckets that became complete

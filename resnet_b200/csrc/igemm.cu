@@ -49,16 +49,21 @@ static EncodeTiledFn get_encode() {
 	return fn;
 }
 
-// rank-4 fp32 map, dims[0] innermost (channels), 128B swizzle, zero OOB fill. strides in ELEMENTS for dims 1..3.
-static bool make_map4(CUtensorMap *m, const float *base, const long long dims[4], const long long strides_elems[3], const int box[4],
-                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+// element type of a tensor map: fp32 (tf32 MMAs) or bf16
+static inline CUtensorMapDataType map_dtype(int bf16) { return bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
+static inline size_t esize(int bf16) { return bf16 ? 2 : 4; }
+static inline const void *eptr(const void *base, long long elems, int bf16) { return (const char *)base + elems * (long long)esize(bf16); }
+
+// rank-4 map, dims[0] innermost (channels), 128B swizzle, zero OOB fill. strides in ELEMENTS for dims 1..3.
+static bool make_map4(CUtensorMap *m, const void *base, const long long dims[4], const long long strides_elems[3], const int box[4],
+                      int bf16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
 	EncodeTiledFn enc = get_encode();
 	if (!enc) return false;
 	cuuint64_t gd[4], gs[3];
 	cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
 	for (int i = 0; i < 4; i++) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
-	for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides_elems[i] * sizeof(float);
-	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+	for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides_elems[i] * esize(bf16);
+	CUresult r = enc(m, map_dtype(bf16), 4, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
 	                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled(4d) failed: %d dims=(%lld,%lld,%lld,%lld) box=(%d,%d,%d,%d)", (int)r, dims[0], dims[1], dims[2],
@@ -67,19 +72,20 @@ static bool make_map4(CUtensorMap *m, const float *base, const long long dims[4]
 	}
 	return true;
 }
-// rank-5 view of the same NHWC tensors for the wgrad operands: channels are split into {32 inner, C/32 outer} and the outer block
-// index is made the SLOWEST box dimension, so ONE TMA op lands `cblk` consecutive [pixels][32 ch] boxes (the MN-major operand
-// layout) instead of one op per 32-channel block -- the single producer thread was issue-bound at 12-36 ops per stage.
-static bool make_map5_cblk(CUtensorMap *m, const float *base, const long long dims4[4], const long long strides_elems[3], const int box4[4],
-                           int cblk_box, CUtensorMapSwizzle swz) {
+// rank-5 view of the same NHWC tensors for the wgrad operands: channels are split into {128 bytes inner (32 fp32 / 64 bf16), outer}
+// and the outer block index is made the SLOWEST box dimension, so ONE TMA op lands `cblk` consecutive [pixels][128 B] boxes (the
+// MN-major operand layout) instead of one op per channel block -- the single producer thread was issue-bound at 12-36 ops per stage.
+static bool make_map5_cblk(CUtensorMap *m, const void *base, const long long dims4[4], const long long strides_elems[3], const int box4[4],
+                           int cblk_box, int bf16, CUtensorMapSwizzle swz) {
 	EncodeTiledFn enc = get_encode();
 	if (!enc) return false;
 	const long long C = dims4[0];
-	cuuint64_t gd[5] = {32, (cuuint64_t)dims4[1], (cuuint64_t)dims4[2], (cuuint64_t)dims4[3], (cuuint64_t)((C + 31) / 32)};
-	cuuint64_t gs[4] = {(cuuint64_t)strides_elems[0] * 4, (cuuint64_t)strides_elems[1] * 4, (cuuint64_t)strides_elems[2] * 4, 128};
-	cuuint32_t bx[5] = {32, (cuuint32_t)box4[1], (cuuint32_t)box4[2], (cuuint32_t)box4[3], (cuuint32_t)cblk_box}, es[5] = {1, 1, 1, 1, 1};
-	if (C < 32) gd[0] = (cuuint64_t)C;
-	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+	const cuuint64_t es_ = esize(bf16), cb = 128 / es_;
+	cuuint64_t gd[5] = {cb, (cuuint64_t)dims4[1], (cuuint64_t)dims4[2], (cuuint64_t)dims4[3], (cuuint64_t)((C + cb - 1) / cb)};
+	cuuint64_t gs[4] = {(cuuint64_t)strides_elems[0] * es_, (cuuint64_t)strides_elems[1] * es_, (cuuint64_t)strides_elems[2] * es_, 128};
+	cuuint32_t bx[5] = {(cuuint32_t)cb, (cuuint32_t)box4[1], (cuuint32_t)box4[2], (cuuint32_t)box4[3], (cuuint32_t)cblk_box}, es[5] = {1, 1, 1, 1, 1};
+	if (C < (long long)cb) gd[0] = (cuuint64_t)C;
+	CUresult r = enc(m, map_dtype(bf16), 5, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
 	                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled(5d) failed: %d dims=(%lld,%lld,%lld,%lld) box=(%d,%d,%d,%d,%d)", (int)r, dims4[0], dims4[1], dims4[2],
@@ -88,12 +94,13 @@ static bool make_map5_cblk(CUtensorMap *m, const float *base, const long long di
 	}
 	return true;
 }
-static bool make_map2(CUtensorMap *m, const float *base, long long cols, long long rows, long long row_stride_elems, int box_cols, int box_rows) {
+static bool make_map2(CUtensorMap *m, const void *base, long long cols, long long rows, long long row_stride_elems, int box_cols, int box_rows,
+                      int bf16) {
 	EncodeTiledFn enc = get_encode();
 	if (!enc) return false;
-	cuuint64_t gd[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)row_stride_elems * sizeof(float)};
+	cuuint64_t gd[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)row_stride_elems * esize(bf16)};
 	cuuint32_t bx[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, es[2] = {1, 1};
-	CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	CUresult r = enc(m, map_dtype(bf16), 2, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
 	                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d cols=%lld rows=%lld box=(%d,%d)", (int)r, cols, rows, box_cols, box_rows); return false; }
 	return true;
@@ -111,7 +118,7 @@ struct alignas(64) IgemmParams {
 	int ngroups;
 	int bw, bh, bn, tiles_w, tiles_h, tiles_b, m_tiles;
 	int Wm, Hm, Nn;
-	int kchunks;
+	int kchunks, kelems;  // K chunks per tap and elements per chunk (one 128-byte swizzle row: 32 tf32 / 64 bf16)
 	int BN, n_tiles, Ncol;
 	int stages;
 	uint32_t a_bytes, b_bytes, a_tx_bytes;  // smem slot sizes; bytes one A box actually transfers (bw*bh*bn rows)
@@ -130,6 +137,8 @@ struct alignas(64) WgradParams {
 	int splits, boxes_per_split;
 	int tpt;  // filter taps per tile (they share the dY tile of each stage); tpt * BN <= 256 TMEM columns
 	int co_tiles, ci_tiles, BN, cin, cout;
+	int a_blocks, cb;  // 128-byte channel blocks per 128-channel A tile (4 tf32 / 2 bf16), channels per block (32 / 64)
+	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
 	int stages;
 	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
 	float *partial;
@@ -144,6 +153,16 @@ __device__ __forceinline__ uint8_t *align1024(uint8_t *p) {
 }
 
 // ------------------------------------------------------------------------------------------ fprop / dgrad
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+	uint32_t r;
+	asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+	return r;
+}
+
+// BF16 = false: fp32 tensors, kind::tf32 MMAs, 32 output columns per staged 128-byte row;
+// BF16 = true:  bf16 tensors, kind::f16 MMAs, 64 output columns per staged row.  The shared-memory tiles are byte-identical
+// in both modes (128 rows x 128 bytes, 4 MMAs per stage each advancing 32 bytes along K).
+template <bool BF16>
 __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
@@ -194,8 +213,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 						mbar_wait(&empty[stage], phase ^ 1);
 						uint8_t *sa = base + (size_t)stage * stage_bytes;
 						mbar_expect_tx(&full[stage], p.a_tx_bytes + p.b_bytes);
-						tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * 32, ow0 + tp.dx, oh0 + tp.dy, n0);
-						tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * 32, nt * p.BN);
+						tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * p.kelems, ow0 + tp.dx, oh0 + tp.dy, n0);
+						tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * p.kelems, nt * p.BN);
 						if (++stage == p.stages) { stage = 0; phase ^= 1; }
 					}
 				}
@@ -204,7 +223,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 		__syncwarp();
 	} else if (warp == 1) {
 		if (lane == 0) {
-			const uint32_t idesc = make_idesc_tf32(128, p.BN, 0, 0);
+			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -220,7 +239,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 					const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
 					const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, 16, 1024);
 #pragma unroll
-					for (int k = 0; k < 4; k++) mma_tf32_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+					for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
 					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
@@ -248,46 +267,66 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 			tc_fence_after();
 			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
 			if (p.tma_store) {
-				// TMEM -> registers -> swizzled smem tile -> one TMA tile store (or fp32 reduce-add for the residual join) per 32
-				// columns: fully coalesced 128-byte lines, rows outside the tensor are clipped by the TMA unit
-				for (int c = 0; c < p.BN / 32; c++, chunk_ctr++) {
-					float v[32];
-					tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+				// TMEM -> registers -> swizzled smem tile -> one TMA tile store (or reduce-add for the residual join) per 128-byte
+				// column chunk: fully coalesced lines, rows outside the tensor are clipped by the TMA unit
+				constexpr int CW = BF16 ? 64 : 32;  // output columns per staged 128-byte row
+				for (int c = 0; c < p.BN / CW; c++, chunk_ctr++) {
+					float v[CW];
+					if constexpr (BF16) tmem_ld_32x64(taddr + (uint32_t)(c * CW), v);
+					else tmem_ld_32x32(taddr + (uint32_t)(c * CW), v);
 					uint8_t *buf = staging + (chunk_ctr & 1) * kABytes;
 					uint8_t *rowp = buf + row * 128;
 					if (p.stats && !row_valid) {  // rows the TMA store clips must not pollute the fused statistics
 #pragma unroll
-						for (int j = 0; j < 32; j++) v[j] = 0.f;
+						for (int j = 0; j < CW; j++) v[j] = 0.f;
 					}
 #pragma unroll
-					for (int j = 0; j < 8; j++)
-						*reinterpret_cast<float4 *>(rowp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					for (int j = 0; j < 8; j++) {
+						if constexpr (BF16)
+							*reinterpret_cast<uint4 *>(rowp + ((j ^ (row & 7)) << 4)) =
+							    make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+							               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+						else
+							*reinterpret_cast<float4 *>(rowp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					}
 					fence_proxy_async();
 					if (issuer) tma_wait_group_read0();  // the store that last read the OTHER buffer is done before anyone rewrites it
 					named_barrier_sync(1, 128);
 					if (issuer) {
-						if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * 32, ow0, oh0, n0);
-						else tma_store_4d(&p.omap[g.omap], buf, nt * p.BN + c * 32, ow0, oh0, n0);
+						if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
+						else tma_store_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
 						tma_commit_group();
 					}
 					if (p.stats) {
-						// fused BatchNorm statistics: lane j sums column j of this warp's 32 rows out of the staged tile (one
-						// conflict-free LDS per row) and adds them to the warp's private row of partial sums in global memory
-						// (always the same thread for a given address: plain read-modify-write, fixed order, deterministic)
-						float cs = 0.f, cq = 0.f;
+						// fused BatchNorm statistics: lane j sums 32-bit word j (one fp32 column / two bf16 columns) of this warp's 32 rows
+						// out of the staged tile (one conflict-free LDS per row) and adds them to the warp's private row of partial sums
+						// in global memory with fire-and-forget reductions (always the same thread for a given address, in program
+						// order: deterministic; no load latency on the epilogue's critical path)
+						float cs = 0.f, cq = 0.f, cs1 = 0.f, cq1 = 0.f;
 #pragma unroll 8
 						for (int rr = 0; rr < 32; rr++) {
 							const int r2 = q * 32 + rr;
-							const float y = *reinterpret_cast<const float *>(buf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7)) << 4) | ((lane & 3) << 2)));
-							cs += y;
-							cq = fmaf(y, y, cq);
+							const uint32_t w = *reinterpret_cast<const uint32_t *>(buf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7)) << 4) | ((lane & 3) << 2)));
+							if constexpr (BF16) {
+								const float y0 = __uint_as_float(w << 16), y1 = __uint_as_float(w & 0xffff0000u);
+								cs += y0; cq = fmaf(y0, y0, cq);
+								cs1 += y1; cq1 = fmaf(y1, y1, cq1);
+							} else {
+								const float y = __uint_as_float(w);
+								cs += y;
+								cq = fmaf(y, y, cq);
+							}
 						}
-						float *sp = p.stats + ((size_t)(blockIdx.x * 4 + q) * 2) * p.Ncol + (size_t)nt * p.BN + c * 32 + lane;
-						sp[0] += cs;
-						sp[p.Ncol] += cq;
+						float *sp = p.stats + ((size_t)(blockIdx.x * 4 + q) * 2) * p.Ncol + (size_t)nt * p.BN + c * CW + (BF16 ? 2 * lane : lane);
+						atomicAdd(sp, cs);
+						atomicAdd(sp + p.Ncol, cq);
+						if constexpr (BF16) {
+							atomicAdd(sp + 1, cs1);
+							atomicAdd(sp + p.Ncol + 1, cq1);
+						}
 					}
 				}
-			} else {
+			} else if constexpr (!BF16) {
 				const int ow = ow0 + wq, oh = oh0 + hq, n = n0 + nq;
 				const bool valid = (nq < p.bn) && (ow < p.Wm) && (oh < p.Hm) && (n < p.Nn);
 				float *dst = p.out + (((size_t)n * p.OH + (size_t)(oh * p.os + g.oh_off)) * p.OW + (size_t)(ow * p.os + g.ow_off)) * p.Ncol + (size_t)nt * p.BN;
@@ -326,6 +365,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
+template <bool BF16>
 __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const __grid_constant__ WgradParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
@@ -360,7 +400,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	// stage between up to `tpt` filter taps, each with its own BN-column accumulator (tpt * BN <= 256 TMEM columns)
 	const int n_groups = (p.ntaps + p.tpt - 1) / p.tpt;
 	const int total_tiles = n_groups * p.co_tiles * p.ci_tiles * p.splits;
-	const int nb_boxes = p.BN / 32;  // [32 px][32 ch] boxes (4 KB each) per B tile
+	const int nb_boxes = p.BN / p.cb;  // [px][128 B of channels] boxes per B tile
 	const uint32_t acc_cols = (uint32_t)(p.tpt * p.BN);
 
 	if (warp == 0) {
@@ -381,7 +421,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 					mbar_wait(&empty[stage], phase ^ 1);
 					uint8_t *sa = base + (size_t)stage * stage_bytes;
 					mbar_expect_tx(&full[stage], p.a_bytes + (uint32_t)ntg * p.b_bytes);
-					tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * 4);  // 4 x [32 px][32 co] boxes in one op
+					tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * p.a_blocks);  // all [px][128 B of co] boxes in one op
 					for (int t = 0; t < ntg; t++) {
 						const TapDesc tp = p.taps[tap0 + t];
 						tma_load_5d(sa + p.a_bytes + (size_t)t * p.b_bytes, &p.bmap[tp.amap], &full[stage], 0, ow0 + tp.dx, oh0 + tp.dy, n0, cit * nb_boxes);
@@ -393,7 +433,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 		__syncwarp();
 	} else if (warp == 1) {
 		if (lane == 0) {
-			const uint32_t idesc = make_idesc_tf32(128, p.BN, 1, 1);
+			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 1, 1) : make_idesc_tf32(128, p.BN, 1, 1);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -413,9 +453,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 					for (int t = 0; t < ntg; t++) {
 						const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-						for (int k = 0; k < 4; k++)  // 8 pixel rows (1024 B) per K=8 MMA
-							mma_tf32_ss(d_tmem + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * 64), bdesc + (uint64_t)(k * 64), idesc,
-							            (uint32_t)((kb > kb0) || (k != 0)));
+						for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
+							mma_ss<BF16>(d_tmem + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
+							             (uint32_t)((kb > kb0) || (k != 0)));
 					}
 					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -472,7 +512,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 
 // ------------------------------------------------------------------------------------------ host side
 struct TcPlan {
-	int kind;  // 0 = kmajor (fprop / dgrad), 1 = wgrad
+	int kind;  // 0 = kmajor (fprop / dgrad), 1 = wgrad, 2 = stem wgrad
+	int bf16;  // element type of the activation / packed-weight tensors: 0 = fp32 (tf32 MMAs), 1 = bf16
 	IgemmParams ip;
 	WgradParams wp;
 	int grid;
@@ -486,6 +527,7 @@ struct TcPlan {
 };
 
 static const size_t kMaxDynSmem = 227 * 1024;
+static inline int kelems_of(int bf16) { return bf16 ? 64 : 32; }  // elements per 128-byte swizzle row
 
 // choose a pixel box (bw, bh, bn) with product <= cap (exact == cap if exact) maximising coverage of (W, H, N)
 static void choose_box(int W, int H, int N, int cap, bool exact, int *bw, int *bh, int *bn) {
@@ -506,14 +548,15 @@ static void choose_box(int W, int H, int N, int cap, bool exact, int *bw, int *b
 	}
 }
 
-static int pick_bn(int ncol) {
+static int pick_bn(int ncol, int bf16) {
 	for (int bn : {256, 128, 64, 32})
-		if (ncol % bn == 0) return bn;
+		if (ncol % bn == 0 && bn >= kelems_of(bf16)) return bn;
 	return 0;
 }
 
-bool tc_supported(const ConvGeom &g) {
-	if (g.cin % 32 || g.cout % 32) return false;
+bool tc_supported(const ConvGeom &g, int bf16) {
+	const int q = kelems_of(bf16);
+	if (g.cin % q || g.cout % q) return false;
 	if (!(g.k == 1 || g.k == 3)) return false;
 	if (g.stride == 2 && (g.k != 3 || (g.S % 2))) return false;
 	if (g.stride != 1 && g.stride != 2) return false;
@@ -528,10 +571,10 @@ static void s2_tap(int kk, int *parity, int *d) {
 }
 
 // maps over an NHWC tensor [N][S][S][C] as seen by a conv of stride `stride`: 1 map (stride 1) or 4 parity maps
-static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int C, int stride, const int box[4], bool flat,
+static bool make_input_maps(CUtensorMap *maps, const void *x, int N, int S, int C, int stride, const int box[4], bool flat, int bf16,
                             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int cblk = 0) {
-	auto mk = [&](CUtensorMap *m, const float *base, const long long dims[4], const long long str[3]) {
-		return cblk > 0 ? make_map5_cblk(m, base, dims, str, box, cblk, swz) : make_map4(m, base, dims, str, box, swz);
+	auto mk = [&](CUtensorMap *m, const void *base, const long long dims[4], const long long str[3]) {
+		return cblk > 0 ? make_map5_cblk(m, base, dims, str, box, cblk, bf16, swz) : make_map4(m, base, dims, str, box, bf16, swz);
 	};
 	if (flat) {  // 1x1: pixels are a flat list
 		long long P = (long long)N * S * S;
@@ -545,15 +588,15 @@ static bool make_input_maps(CUtensorMap *maps, const float *x, int N, int S, int
 	for (int ph = 0; ph < 2; ph++)
 		for (int pw = 0; pw < 2; pw++) {
 			long long dims[4] = {C, S / 2, S / 2, N}, str[3] = {2LL * C, 2LL * S * C, (long long)S * S * C};
-			if (!mk(&maps[ph * 2 + pw], x + ((long long)ph * S + pw) * C, dims, str)) return false;
+			if (!mk(&maps[ph * 2 + pw], eptr(x, ((long long)ph * S + pw) * C, bf16), dims, str)) return false;
 		}
 	return true;
 }
 
-// RESNET_B200_TMA_STORE=0 falls back to per-thread row stores in the epilogue (bring-up aid)
-static int tma_store_enabled() {
+// RESNET_B200_TMA_STORE=0 falls back to per-thread row stores in the epilogue (bring-up aid, fp32 only)
+static int tma_store_enabled(int bf16) {
 	const char *e = getenv("RESNET_B200_TMA_STORE");
-	return e ? atoi(e) != 0 : 1;
+	return (e && !bf16) ? atoi(e) != 0 : 1;
 }
 
 static void finish_kmajor(TcPlan *pl) {
@@ -570,23 +613,25 @@ static void finish_kmajor(TcPlan *pl) {
 	pl->kind = 0;
 }
 
-TcPlan *tc_make_fprop(const ConvGeom &g, const float *x, const float *wf, float *y) {
-	if (!tc_supported(g)) { set_error("tc_make_fprop: unsupported geometry"); return nullptr; }
+TcPlan *tc_make_fprop(const ConvGeom &g, const void *x, const void *wf, void *y, int bf16) {
+	if (!tc_supported(g, bf16)) { set_error("tc_make_fprop: unsupported geometry"); return nullptr; }
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
+	pl->bf16 = bf16;
 	IgemmParams &p = pl->ip;
-	const int So = g.So();
+	const int So = g.So(), ke = kelems_of(bf16);
 	const bool flat = (g.k == 1);
 	if (flat) { p.Wm = (int)((long long)g.N * So * So); p.Hm = 1; p.Nn = 1; p.bw = 128; p.bh = 1; p.bn = 1; }
 	else { p.Wm = So; p.Hm = So; p.Nn = g.N; choose_box(So, So, g.N, 128, false, &p.bw, &p.bh, &p.bn); }
 	p.tiles_w = ceil_div(p.Wm, p.bw); p.tiles_h = ceil_div(p.Hm, p.bh); p.tiles_b = ceil_div(p.Nn, p.bn);
 	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-	p.Ncol = g.cout; p.BN = pick_bn(g.cout); p.n_tiles = g.cout / p.BN;
-	p.kchunks = g.cin / 32;
-	const int box[4] = {32, p.bw, p.bh, p.bn};
-	bool ok = make_input_maps(p.amap, x, g.N, g.S, g.cin, g.stride, box, flat);
+	p.Ncol = g.cout; p.BN = pick_bn(g.cout, bf16); p.n_tiles = g.cout / p.BN;
+	p.kelems = ke;
+	p.kchunks = g.cin / ke;
+	const int box[4] = {ke, p.bw, p.bh, p.bn};
+	bool ok = make_input_maps(p.amap, x, g.N, g.S, g.cin, g.stride, box, flat, bf16);
 	for (int i = 1; i < 4; i++) if (g.stride == 1) p.amap[i] = p.amap[0];
-	ok = ok && make_map2(&p.bmap, wf, (long long)g.taps() * g.cin, g.cout, (long long)g.taps() * g.cin, 32, p.BN);
+	ok = ok && make_map2(&p.bmap, wf, (long long)g.taps() * g.cin, g.cout, (long long)g.taps() * g.cin, ke, p.BN, bf16);
 	p.ngroups = 1;
 	GroupDesc &gr = p.groups[0];
 	gr.oh_off = gr.ow_off = 0;
@@ -599,44 +644,46 @@ TcPlan *tc_make_fprop(const ConvGeom &g, const float *x, const float *wf, float 
 			else if (g.stride == 1) { t.dx = kw - 1; t.dy = kh - 1; t.amap = 0; }
 			else { int ph, pw; s2_tap(kh, &ph, &t.dy); s2_tap(kw, &pw, &t.dx); t.amap = ph * 2 + pw; }
 		}
-	p.out = y;
+	p.out = (float *)y;
 	if (flat) { p.OH = 1; p.OW = p.Wm; } else { p.OH = So; p.OW = So; }
 	p.os = 1; p.accumulate = 0;
-	ok = ok && make_input_maps(p.omap, y, g.N, So, g.cout, 1, box, flat);  // output tile store map, same pixel box as the A tile
+	ok = ok && make_input_maps(p.omap, y, g.N, So, g.cout, 1, box, flat, bf16);  // output tile store map, same pixel box as the A tile
 	for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
 	gr.omap = 0;
-	p.tma_store = tma_store_enabled();
+	p.tma_store = tma_store_enabled(bf16);
 	finish_kmajor(pl);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
 
-TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float *dx, int accumulate) {
-	if (!tc_supported(g)) { set_error("tc_make_dgrad: unsupported geometry"); return nullptr; }
+TcPlan *tc_make_dgrad(const ConvGeom &g, const void *dy, const void *wd, void *dx, int accumulate, int bf16) {
+	if (!tc_supported(g, bf16)) { set_error("tc_make_dgrad: unsupported geometry"); return nullptr; }
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
+	pl->bf16 = bf16;
 	IgemmParams &p = pl->ip;
-	const int So = g.So();
+	const int So = g.So(), ke = kelems_of(bf16);
 	const bool flat = (g.k == 1);
 	// GEMM-M space: input pixels (stride 1) or one output-parity class of them (stride 2) == the dy grid
 	if (flat) { p.Wm = (int)((long long)g.N * So * So); p.Hm = 1; p.Nn = 1; p.bw = 128; p.bh = 1; p.bn = 1; }
 	else { p.Wm = So; p.Hm = So; p.Nn = g.N; choose_box(So, So, g.N, 128, false, &p.bw, &p.bh, &p.bn); }
 	p.tiles_w = ceil_div(p.Wm, p.bw); p.tiles_h = ceil_div(p.Hm, p.bh); p.tiles_b = ceil_div(p.Nn, p.bn);
 	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-	p.Ncol = g.cin; p.BN = pick_bn(g.cin); p.n_tiles = g.cin / p.BN;
-	p.kchunks = g.cout / 32;
-	const int box[4] = {32, p.bw, p.bh, p.bn};
-	bool ok = make_input_maps(p.amap, dy, g.N, So, g.cout, 1, box, flat);
+	p.Ncol = g.cin; p.BN = pick_bn(g.cin, bf16); p.n_tiles = g.cin / p.BN;
+	p.kelems = ke;
+	p.kchunks = g.cout / ke;
+	const int box[4] = {ke, p.bw, p.bh, p.bn};
+	bool ok = make_input_maps(p.amap, dy, g.N, So, g.cout, 1, box, flat, bf16);
 	for (int i = 1; i < 4; i++) p.amap[i] = p.amap[0];
-	ok = ok && make_map2(&p.bmap, wd, (long long)g.taps() * g.cout, g.cin, (long long)g.taps() * g.cout, 32, p.BN);
-	p.out = dx;
+	ok = ok && make_map2(&p.bmap, wd, (long long)g.taps() * g.cout, g.cin, (long long)g.taps() * g.cout, ke, p.BN, bf16);
+	p.out = (float *)dx;
 	p.accumulate = accumulate;
 	if (g.k == 1) {
 		p.ngroups = 1;
 		p.groups[0].ntaps = 1; p.groups[0].oh_off = p.groups[0].ow_off = 0;
 		p.groups[0].taps[0] = TapDesc{0, 0, 0, 0};
 		p.OH = 1; p.OW = p.Wm; p.os = 1;
-		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 1, box, true);
+		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 1, box, true, bf16);
 	} else if (g.stride == 1) {
 		p.ngroups = 1;
 		GroupDesc &gr = p.groups[0];
@@ -644,7 +691,7 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float
 		for (int kh = 0; kh < 3; kh++)
 			for (int kw = 0; kw < 3; kw++) gr.taps[kh * 3 + kw] = TapDesc{1 - kw, 1 - kh, 0, (kh * 3 + kw) * g.cout};
 		p.OH = g.S; p.OW = g.S; p.os = 1;
-		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 1, box, false);
+		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 1, box, false, bf16);
 	} else {
 		// dx[2h'+ph] gathers dy[h' + d] * W[kh]:  ph = 0 -> (kh 1, d 0);  ph = 1 -> (kh 0, d +1), (kh 2, d 0)
 		p.ngroups = 4;
@@ -661,24 +708,26 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const float *dy, const float *wd, float
 				for (int b = 0; b < nw; b++) gr.taps[gr.ntaps++] = TapDesc{dws[b], dhs[a], 0, (khs[a] * 3 + kws[b]) * g.cout};
 		}
 		p.OH = g.S; p.OW = g.S; p.os = 2;
-		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 2, box, false);  // four parity views of dx
+		ok = ok && make_input_maps(p.omap, dx, g.N, g.S, g.cin, 2, box, false, bf16);  // four parity views of dx
 	}
 	if (g.k == 1 || g.stride == 1) for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
-	p.tma_store = tma_store_enabled();
+	p.tma_store = tma_store_enabled(bf16);
 	finish_kmajor(pl);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
 
-// shape decisions of a wgrad launch, shared by the workspace query and the plan builder
+// shape decisions of a wgrad launch, shared by the workspace query and the plan builder.  One pipeline stage reduces over a box
+// of `px` pixels = 4 MMAs: 32 pixels (tf32, K = 8) or 64 pixels (bf16, K = 16).
 struct WgradShape { int bw, bh, bn, tiles_w, tiles_h, tiles_b, k_boxes, BN, ci_tiles, co_tiles, ntaps, tpt, splits, boxes_per_split; };
-static WgradShape wgrad_shape(int Wm, int Hm, int Nn, bool flat, int cin_cols, int cout, int ntaps) {
+static WgradShape wgrad_shape(int Wm, int Hm, int Nn, bool flat, int cin_cols, int cout, int ntaps, int bf16) {
 	WgradShape w;
-	if (flat) { w.bw = 32; w.bh = 1; w.bn = 1; }
-	else choose_box(Wm, Hm, Nn, 32, true, &w.bw, &w.bh, &w.bn);
+	const int px = bf16 ? 64 : 32;
+	if (flat) { w.bw = px; w.bh = 1; w.bn = 1; }
+	else choose_box(Wm, Hm, Nn, px, true, &w.bw, &w.bh, &w.bn);
 	w.tiles_w = ceil_div(Wm, w.bw); w.tiles_h = ceil_div(Hm, w.bh); w.tiles_b = ceil_div(Nn, w.bn);
 	w.k_boxes = w.tiles_w * w.tiles_h * w.tiles_b;
-	w.BN = pick_bn(cin_cols);
+	w.BN = pick_bn(cin_cols, bf16);
 	w.ci_tiles = cin_cols / w.BN;
 	w.co_tiles = ceil_div(cout, 128);
 	w.ntaps = ntaps;
@@ -694,38 +743,52 @@ static WgradShape wgrad_shape(int Wm, int Hm, int Nn, bool flat, int cin_cols, i
 	return w;
 }
 
-size_t tc_wgrad_workspace_bytes(const ConvGeom &g) {
+// operand layout of the MN-major tiles: tf32 exists only as "128B swizzle, 32B atom" (4-row atoms, descriptor layout type 1);
+// bf16 uses the plain 128B swizzle (8-row atoms, layout type 2)
+static CUtensorMapSwizzle wgrad_layout(WgradParams &p, int bf16) {
+	const int px = bf16 ? 64 : 32;
+	p.cb = kelems_of(bf16);
+	p.a_blocks = 128 / p.cb;
+	p.lbo = (uint32_t)px * 128;      // distance between 128-byte channel blocks (one TMA box of px pixel rows)
+	p.sbo = bf16 ? 1024 : 512;        // pitch of the swizzle atoms along the pixel (K) axis
+	p.layout_type = bf16 ? 2 : 1;
+	p.kadv = bf16 ? 128 : 64;         // 16 / 8 pixel rows of 128 B per MMA, in 16-byte units
+	p.a_bytes = 128 * 128;            // 128 co x px pixels: 4 x [32 px][32 fp32] or 2 x [64 px][64 bf16]
+	p.b_bytes = (uint32_t)p.BN * 128;
+	return bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+}
+
+size_t tc_wgrad_workspace_bytes(const ConvGeom &g, int bf16) {
 	const int So = g.So();
 	const bool flat = (g.k == 1);
-	WgradShape w = flat ? wgrad_shape((int)((long long)g.N * So * So), 1, 1, true, g.cin, g.cout, 1) : wgrad_shape(So, So, g.N, false, g.cin, g.cout, g.taps());
+	WgradShape w = flat ? wgrad_shape((int)((long long)g.N * So * So), 1, 1, true, g.cin, g.cout, 1, bf16)
+	                    : wgrad_shape(So, So, g.N, false, g.cin, g.cout, g.taps(), bf16);
 	return (size_t)w.splits * g.taps() * g.cout * g.cin * sizeof(float);
 }
 
-TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *workspace, size_t ws_bytes) {
-	if (!tc_supported(g)) { set_error("tc_make_wgrad: unsupported geometry"); return nullptr; }
+TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *dw, float *workspace, size_t ws_bytes, int bf16) {
+	if (!tc_supported(g, bf16)) { set_error("tc_make_wgrad: unsupported geometry"); return nullptr; }
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
+	pl->bf16 = bf16;
 	WgradParams &p = pl->wp;
 	const int So = g.So();
 	const bool flat = (g.k == 1);
-	WgradShape w = flat ? wgrad_shape((int)((long long)g.N * So * So), 1, 1, true, g.cin, g.cout, 1) : wgrad_shape(So, So, g.N, false, g.cin, g.cout, g.taps());
+	WgradShape w = flat ? wgrad_shape((int)((long long)g.N * So * So), 1, 1, true, g.cin, g.cout, 1, bf16)
+	                    : wgrad_shape(So, So, g.N, false, g.cin, g.cout, g.taps(), bf16);
 	p.bw = w.bw; p.bh = w.bh; p.bn = w.bn; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_b = w.tiles_b; p.k_boxes = w.k_boxes;
 	p.cin = g.cin; p.cout = g.cout; p.BN = w.BN; p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles; p.ntaps = w.ntaps; p.tpt = w.tpt;
 	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split;
 	const int tiles = ceil_div(p.ntaps, p.tpt) * p.co_tiles * p.ci_tiles;
 	if ((size_t)p.splits * p.ntaps * g.cout * g.cin * sizeof(float) > ws_bytes) { set_error("tc_make_wgrad: workspace too small"); delete pl; return nullptr; }
-	const int box[4] = {32, p.bw, p.bh, p.bn};
-	// MN-major tf32 operands exist only in the "128B swizzle, 32B atom" shared-memory layout (4-row atoms)
-	CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-	p.layout_type = 1;
-	p.lbo = 32 * 128;  // distance between 32-channel column blocks (one TMA box of 32 pixel rows)
-	p.sbo = 512;       // pitch of the 4-row swizzle atoms along the pixel (K) axis
+	CUtensorMapSwizzle swz = wgrad_layout(p, bf16);
+	const int box[4] = {p.cb, p.bw, p.bh, p.bn};
 	if (const char *e = getenv("RESNET_B200_WGRAD_DESC")) {  // bring-up aid: "lbo,sbo,layout_type,tma_swizzle_enum"
 		unsigned a, b, c, d;
 		if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { p.lbo = a; p.sbo = b; p.layout_type = c; swz = (CUtensorMapSwizzle)d; }
 	}
-	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat, swz, 4);
-	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat, swz, p.BN / 32);
+	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat, bf16, swz, p.a_blocks);
+	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat, bf16, swz, p.BN / p.cb);
 	if (g.stride == 1) for (int i = 1; i < 4; i++) p.bmap[i] = p.bmap[0];
 	for (int kh = 0; kh < g.k; kh++)
 		for (int kw = 0; kw < g.k; kw++) {
@@ -735,8 +798,6 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 			else if (g.stride == 1) { t.dx = kw - 1; t.dy = kh - 1; t.amap = 0; }
 			else { int ph, pw; s2_tap(kh, &ph, &t.dy); s2_tap(kw, &pw, &t.dx); t.amap = ph * 2 + pw; }
 		}
-	p.a_bytes = 4 * 32 * 128;
-	p.b_bytes = (uint32_t)(p.BN / 32) * 32 * 128;
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
@@ -752,15 +813,18 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const float *x, const float *dy, float 
 
 // ------------------------------------------------------------------------------------------ stem (7x7 / 2, Cin = 3)
 // reference: resnet.cu:1547 (fprop) and 2243 (wgrad only).  TMA needs 16-byte pixel strides, so the batch is first copied
-// into a zero-bordered NHWC4 buffer xp[N][S][S+8][4] (3 pixels of left border = the convolution's padding).  One filter ROW
-// (kh) of one output pixel is then 32 CONTIGUOUS floats (8 taps x 4 channels, the 8th tap and 4th channel meet zero weights)
-// starting 8 floats after the previous output pixel's: an overlapping tensor map {32 floats, ow (stride 32 B), row, n}
-// turns every filter row into one K = 32 chunk of the same implicit GEMM (K = 7 x 32), on the same kernels as every other
-// layer.  Input rows 2*oh + kh - 3 are reached through even / odd row maps (dy below), out-of-range rows are zero-filled.
-constexpr int kStemK = 7, kStemPadL = 3, kStemPadW = 8;
+// into a zero-bordered NHWC4 buffer xp[N][S][S+PW][4] (3 pixels of left border = the convolution's padding).  One filter ROW
+// (kh) of one output pixel is then one contiguous 128-byte run -- 8 taps x 4 channels of fp32 or 16 taps x 4 channels of bf16;
+// the taps past the 7th and the 4th channel meet zero weights -- starting 2 pixels after the previous output pixel's: an
+// overlapping tensor map {128 B, ow (stride 2 pixels), row, n} turns every filter row into one K chunk of the same implicit GEMM
+// (7 chunks), on the same kernels as every other layer.  Input rows 2*oh + kh - 3 are reached through even / odd row maps
+// (dy below), out-of-range rows are zero-filled.
+constexpr int kStemK = 7, kStemPadL = 3;
+static inline int stem_padw(int bf16) { return bf16 ? 16 : 8; }     // extra (zero) pixels per padded row
+static inline int stem_row_elems(int bf16) { return bf16 ? 64 : 32; }  // elements of one filter row chunk: taps x 4 channels
 
-__global__ void stem_pad_input_kernel(const float *__restrict__ x, int N, int S, float *__restrict__ xp, int rnd) {
-	const int Wp = S + kStemPadW;
+template <bool BF16>
+__global__ void stem_pad_input_kernel(const float *__restrict__ x, int N, int S, void *__restrict__ xp, int Wp, int rnd) {
 	const long long total = (long long)N * S * Wp;
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
 		const int wp = (int)(i % Wp);
@@ -770,128 +834,142 @@ __global__ void stem_pad_input_kernel(const float *__restrict__ x, int N, int S,
 		if (w >= 0 && w < S) {
 			const float *s = x + (row * S + w) * 3;
 			v.x = s[0]; v.y = s[1]; v.z = s[2];
-			if (rnd) {
+			if (rnd && !BF16) {
 				uint32_t r;
 				asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.x)); v.x = __uint_as_float(r);
 				asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.y)); v.y = __uint_as_float(r);
 				asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v.z)); v.z = __uint_as_float(r);
 			}
 		}
-		reinterpret_cast<float4 *>(xp)[i] = v;
+		if constexpr (BF16) reinterpret_cast<uint2 *>(xp)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, 0.f));
+		else reinterpret_cast<float4 *>(xp)[i] = v;
 	}
 }
-// w [Cout][3][7][7] -> wfs [Cout][7][8][4] (zero for kw = 7 and c = 3)
-__global__ void stem_pack_weights_kernel(const float *__restrict__ w, int cout, float *__restrict__ wfs, int rnd) {
-	const int total = cout * kStemK * 32;
+// w [Cout][3][7][7] -> wfs [Cout][7][RE/4][4] (zero for kw >= 7 and c = 3); RE = elements of one filter-row chunk
+template <bool BF16>
+__global__ void stem_pack_weights_kernel(const float *__restrict__ w, int cout, void *__restrict__ wfs, int RE, int rnd) {
+	const int total = cout * kStemK * RE;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-		const int c = i % 4, kw = (i / 4) % 8, kh = (i / 32) % kStemK, co = i / (32 * kStemK);
+		const int c = i % 4, kw = (i / 4) % (RE / 4), kh = (i / RE) % kStemK, co = i / (RE * kStemK);
 		float v = 0.f;
 		if (c < 3 && kw < kStemK) v = w[((co * 3 + c) * kStemK + kh) * kStemK + kw];
-		if (rnd) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
-		wfs[i] = v;
+		if constexpr (BF16) reinterpret_cast<uint16_t *>(wfs)[i] = (uint16_t)(pack_bf16x2(v, 0.f) & 0xffffu);
+		else {
+			if (rnd) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); v = __uint_as_float(r); }
+			reinterpret_cast<float *>(wfs)[i] = v;
+		}
 	}
 }
 // dw [Cout][3][7][7] = sum_s partial[s][kh][Cout][kw*4 + c]
-__global__ void stem_wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, float *__restrict__ dw) {
+__global__ void stem_wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, int RE, float *__restrict__ dw) {
 	const int total = cout * 3 * kStemK * kStemK;
-	const long long per = (long long)kStemK * cout * 32;
+	const long long per = (long long)kStemK * cout * RE;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
 		const int kw = i % kStemK, kh = (i / kStemK) % kStemK, c = (i / (kStemK * kStemK)) % 3, co = i / (3 * kStemK * kStemK);
-		const long long src = ((long long)kh * cout + co) * 32 + kw * 4 + c;
+		const long long src = ((long long)kh * cout + co) * RE + kw * 4 + c;
 		float s = 0.f;
 		for (int sp = 0; sp < splits; sp++) s += partial[sp * per + src];
 		dw[i] = s;
 	}
 }
 
-void stem_pad_input(const float *x, int N, int S, float *xp, int rnd, cudaStream_t st) {
-	long long total = (long long)N * S * (S + kStemPadW);
+void stem_pad_input(const float *x, int N, int S, void *xp, int rnd, int bf16, cudaStream_t st) {
+	const int Wp = S + stem_padw(bf16);
+	long long total = (long long)N * S * Wp;
 	int grid = (int)((total + 255) / 256);
-	stem_pad_input_kernel<<<grid > kNumSMs * 16 ? kNumSMs * 16 : grid, 256, 0, st>>>(x, N, S, xp, rnd);
+	grid = grid > kNumSMs * 16 ? kNumSMs * 16 : grid;
+	if (bf16) stem_pad_input_kernel<true><<<grid, 256, 0, st>>>(x, N, S, xp, Wp, rnd);
+	else stem_pad_input_kernel<false><<<grid, 256, 0, st>>>(x, N, S, xp, Wp, rnd);
 	RB_LAUNCH_CHECK();
 }
-void stem_pack_weights(const float *w, int cout, float *wfs, int rnd, cudaStream_t st) {
-	stem_pack_weights_kernel<<<ceil_div(cout * kStemK * 32, 256), 256, 0, st>>>(w, cout, wfs, rnd);
+void stem_pack_weights(const float *w, int cout, void *wfs, int rnd, int bf16, cudaStream_t st) {
+	const int RE = stem_row_elems(bf16), grid = ceil_div(cout * kStemK * RE, 256);
+	if (bf16) stem_pack_weights_kernel<true><<<grid, 256, 0, st>>>(w, cout, wfs, RE, rnd);
+	else stem_pack_weights_kernel<false><<<grid, 256, 0, st>>>(w, cout, wfs, RE, rnd);
 	RB_LAUNCH_CHECK();
 }
-size_t stem_xp_elems(int N, int S) { return (size_t)N * S * (S + kStemPadW) * 4; }
+size_t stem_xp_bytes(int N, int S, int bf16) { return (size_t)N * S * (S + stem_padw(bf16)) * 4 * esize(bf16); }
+size_t stem_wfs_bytes(int cout, int bf16) { return (size_t)cout * kStemK * stem_row_elems(bf16) * esize(bf16); }
 
 // row parity / offset of input row 2*oh + kh - 3 in the even/odd row maps
 static void stem_row(int kh, int *parity, int *dy) {
 	static const int par[7] = {1, 0, 1, 0, 1, 0, 1}, off[7] = {-2, -1, -1, 0, 0, 1, 1};
 	*parity = par[kh]; *dy = off[kh];
 }
-static bool make_stem_maps(CUtensorMap *maps, const float *xp, int N, int S, const int box[4], CUtensorMapSwizzle swz, int cblk = 0) {
-	const int So = S / 2, Wp = S + kStemPadW;
+static bool make_stem_maps(CUtensorMap *maps, const void *xp, int N, int S, const int box[4], int bf16, CUtensorMapSwizzle swz, int cblk = 0) {
+	const int So = S / 2, Wp = S + stem_padw(bf16);
 	for (int ph = 0; ph < 2; ph++) {
-		long long dims[4] = {32, So, So, N}, str[3] = {8, 2LL * Wp * 4, (long long)S * Wp * 4};
-		const float *base = xp + (long long)ph * Wp * 4;
-		if (!(cblk > 0 ? make_map5_cblk(&maps[ph], base, dims, str, box, cblk, swz) : make_map4(&maps[ph], base, dims, str, box, swz))) return false;
+		long long dims[4] = {stem_row_elems(bf16), So, So, N}, str[3] = {8, 2LL * Wp * 4, (long long)S * Wp * 4};
+		const void *base = eptr(xp, (long long)ph * Wp * 4, bf16);
+		if (!(cblk > 0 ? make_map5_cblk(&maps[ph], base, dims, str, box, cblk, bf16, swz) : make_map4(&maps[ph], base, dims, str, box, bf16, swz))) return false;
 	}
 	return true;
 }
-bool tc_stem_supported(int S, int k, int cin, int cout, int stride) { return k == kStemK && cin == 3 && stride == 2 && S % 2 == 0 && cout % 32 == 0 && cout <= 128; }
+bool tc_stem_supported(int S, int k, int cin, int cout, int stride, int bf16) {
+	return k == kStemK && cin == 3 && stride == 2 && S % 2 == 0 && cout % kelems_of(bf16) == 0 && cout <= 128;
+}
 
-TcPlan *tc_make_stem_fprop(int N, int S, int cout, const float *xp, const float *wfs, float *y) {
+TcPlan *tc_make_stem_fprop(int N, int S, int cout, const void *xp, const void *wfs, void *y, int bf16) {
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
+	pl->bf16 = bf16;
 	IgemmParams &p = pl->ip;
-	const int So = S / 2;
+	const int So = S / 2, RE = stem_row_elems(bf16);
 	p.Wm = So; p.Hm = So; p.Nn = N;
 	choose_box(So, So, N, 128, false, &p.bw, &p.bh, &p.bn);
 	p.tiles_w = ceil_div(p.Wm, p.bw); p.tiles_h = ceil_div(p.Hm, p.bh); p.tiles_b = ceil_div(p.Nn, p.bn);
 	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-	p.Ncol = cout; p.BN = pick_bn(cout); p.n_tiles = cout / p.BN;
-	p.kchunks = 1;
-	const int box[4] = {32, p.bw, p.bh, p.bn};
-	bool ok = make_stem_maps(p.amap, xp, N, S, box, CU_TENSOR_MAP_SWIZZLE_128B);
+	p.Ncol = cout; p.BN = pick_bn(cout, bf16); p.n_tiles = cout / p.BN;
+	p.kchunks = 1; p.kelems = RE;
+	const int box[4] = {RE, p.bw, p.bh, p.bn};
+	bool ok = make_stem_maps(p.amap, xp, N, S, box, bf16, CU_TENSOR_MAP_SWIZZLE_128B);
 	p.amap[2] = p.amap[0]; p.amap[3] = p.amap[1];
-	ok = ok && make_map2(&p.bmap, wfs, kStemK * 32, cout, kStemK * 32, 32, p.BN);
+	ok = ok && make_map2(&p.bmap, wfs, kStemK * RE, cout, kStemK * RE, RE, p.BN, bf16);
 	p.ngroups = 1;
 	GroupDesc &gr = p.groups[0];
 	gr.ntaps = kStemK; gr.oh_off = gr.ow_off = 0;
 	for (int kh = 0; kh < kStemK; kh++) {
 		int par, dy;
 		stem_row(kh, &par, &dy);
-		gr.taps[kh] = TapDesc{0, dy, par, kh * 32};
+		gr.taps[kh] = TapDesc{0, dy, par, kh * RE};
 	}
-	p.out = y; p.OH = So; p.OW = So; p.os = 1; p.accumulate = 0;
-	ok = ok && make_input_maps(p.omap, y, N, So, cout, 1, box, false);
+	p.out = (float *)y; p.OH = So; p.OW = So; p.os = 1; p.accumulate = 0;
+	ok = ok && make_input_maps(p.omap, y, N, So, cout, 1, box, false, bf16);
 	for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
 	gr.omap = 0;
-	p.tma_store = tma_store_enabled();
+	p.tma_store = tma_store_enabled(bf16);
 	finish_kmajor(pl);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
 
-size_t tc_stem_wgrad_workspace_bytes(int N, int S, int cout) {
-	WgradShape w = wgrad_shape(S / 2, S / 2, N, false, 32, cout, kStemK);
-	return (size_t)w.splits * kStemK * cout * 32 * sizeof(float);
+size_t tc_stem_wgrad_workspace_bytes(int N, int S, int cout, int bf16) {
+	const int RE = stem_row_elems(bf16);
+	WgradShape w = wgrad_shape(S / 2, S / 2, N, false, RE, cout, kStemK, bf16);
+	return (size_t)w.splits * kStemK * cout * RE * sizeof(float);
 }
 
-TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const float *xp, const float *dy, float *dw, float *workspace, size_t ws_bytes) {
+TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *dy, float *dw, float *workspace, size_t ws_bytes, int bf16) {
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
+	pl->bf16 = bf16;
 	WgradParams &p = pl->wp;
-	const int So = S / 2;
-	WgradShape w = wgrad_shape(So, So, N, false, 32, cout, kStemK);
+	const int So = S / 2, RE = stem_row_elems(bf16);
+	WgradShape w = wgrad_shape(So, So, N, false, RE, cout, kStemK, bf16);
 	p.bw = w.bw; p.bh = w.bh; p.bn = w.bn; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_b = w.tiles_b; p.k_boxes = w.k_boxes;
-	p.cin = 32; p.cout = cout; p.BN = w.BN; p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles; p.ntaps = w.ntaps; p.tpt = w.tpt;
+	p.cin = RE; p.cout = cout; p.BN = w.BN; p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles; p.ntaps = w.ntaps; p.tpt = w.tpt;
 	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split;
-	if ((size_t)p.splits * kStemK * cout * 32 * sizeof(float) > ws_bytes) { set_error("tc_make_stem_wgrad: workspace too small"); delete pl; return nullptr; }
-	const int box[4] = {32, p.bw, p.bh, p.bn};
-	p.layout_type = 1; p.lbo = 32 * 128; p.sbo = 512;
-	bool ok = make_input_maps(&p.amap, dy, N, So, cout, 1, box, false, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 4);
-	ok = ok && make_stem_maps(p.bmap, xp, N, S, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 1);
+	if ((size_t)p.splits * kStemK * cout * RE * sizeof(float) > ws_bytes) { set_error("tc_make_stem_wgrad: workspace too small"); delete pl; return nullptr; }
+	const CUtensorMapSwizzle swz = wgrad_layout(p, bf16);
+	const int box[4] = {p.cb, p.bw, p.bh, p.bn};
+	bool ok = make_input_maps(&p.amap, dy, N, So, cout, 1, box, false, bf16, swz, p.a_blocks);
+	ok = ok && make_stem_maps(p.bmap, xp, N, S, box, bf16, swz, 1);
 	p.bmap[2] = p.bmap[0]; p.bmap[3] = p.bmap[1];
 	for (int kh = 0; kh < kStemK; kh++) {
 		int par, dyy;
 		stem_row(kh, &par, &dyy);
 		p.taps[kh] = TapDesc{0, dyy, par, 0};
 	}
-	p.a_bytes = 4 * 32 * 128;
-	p.b_bytes = (uint32_t)(p.BN / 32) * 32 * 128;
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
@@ -909,20 +987,24 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 	if (!pl) { set_error("tc_run: null plan"); return; }
 	static bool attr_set = false;
 	if (!attr_set) {
-		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		attr_set = true;
 	}
 	if (pl->kind == 0) {
 		if (pl->ip.stats) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
-		igemm_kmajor_kernel<<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->ip);
+		if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->ip);
+		else igemm_kmajor_kernel<false><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->ip);
 		RB_LAUNCH_CHECK();
 	} else {
-		igemm_mnmajor_kernel<<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
+		if (pl->bf16) igemm_mnmajor_kernel<true><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
+		else igemm_mnmajor_kernel<false><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
 		RB_LAUNCH_CHECK();
 		if (pl->kind == 1) wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
 		else {
-			stem_wgrad_reduce_kernel<<<ceil_div(pl->cout * 3 * kStemK * kStemK, 256), 256, 0, st>>>(pl->wp.partial, pl->wp.splits, pl->cout, pl->dw);
+			stem_wgrad_reduce_kernel<<<ceil_div(pl->cout * 3 * kStemK * kStemK, 256), 256, 0, st>>>(pl->wp.partial, pl->wp.splits, pl->cout, pl->wp.cin, pl->dw);
 			RB_LAUNCH_CHECK();
 		}
 	}
@@ -945,12 +1027,12 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
-		snprintf(buf, n, "kmajor box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu", p.bw, p.bh, p.bn,
-		         p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu", pl->bf16 ? "bf16" : "tf32",
+		         p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem);
 	} else {
 		const WgradParams &p = pl->wp;
-		snprintf(buf, n, "wgrad box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu", p.bw, p.bh,
-		         p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
+		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
 	}
 }
 

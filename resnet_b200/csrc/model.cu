@@ -30,6 +30,8 @@ Engine *engine_of(const Train_ResNet *t) {
 	return it == g_engines.end() ? nullptr : it->second;
 }
 
+int g_default_bf16 = -1;  // resnet_b200_set_dtype(): -1 = follow $RESNET_B200_DTYPE, 0 = fp32/tf32, 1 = bf16
+
 static int env_int(const char *name, int dflt) {
 	const char *v = getenv(name);
 	return v ? atoi(v) : dflt;
@@ -148,6 +150,8 @@ static Params *make_params(Dims *d, curandGenerator_t *gen) {
 // ------------------------------------------------------------------------------------------------ engine
 struct Bump {
 	Engine *e;
+	// activation tensor of n elements in the engine's storage type (fp32 or bf16); the public structs keep float* names
+	float *act(long long n) { return (float *)get<char>((n <= 0 ? 1 : n) * (long long)e->esz); }
 	template <typename T> T *get(long long n) {
 		if (n <= 0) n = 1;
 		void *p = nullptr;
@@ -161,7 +165,7 @@ static Cache_BatchNorm *mk_cache(Bump &B, long long input_size, int C, bool keep
 	Cache_BatchNorm *c = (Cache_BatchNorm *)calloc(1, sizeof(Cache_BatchNorm));
 	c->input_size = (int)input_size; c->feature_size = C;
 	if (with_stats) { c->means = B.get<float>(C); c->vars = B.get<float>(C); }
-	if (keep_all) { c->normalized_temp = B.get<float>(input_size); c->normalized = B.get<float>(input_size); }
+	if (keep_all) { c->normalized_temp = B.act(input_size); c->normalized = B.act(input_size); }
 	return c;
 }
 
@@ -171,14 +175,15 @@ static void setup_conv(Engine *e, Bump &B, ConvRef &c, int N, int S, int cin, in
 	c.loc = loc;
 	c.w = P->locations[loc];
 	c.dw = G->locations[loc];
-	c.wf = B.get<float>(c.g.w_elems());
-	c.wd = B.get<float>(c.g.w_elems());
-	c.use_tc = (e->conv_mode == 0) && tc_supported(c.g);
+	c.wf = B.act(c.g.w_elems());
+	c.wd = B.act(c.g.w_elems());
+	c.use_tc = (e->conv_mode == 0) && tc_supported(c.g, e->bf16);
+	if (e->bf16 && !c.use_tc && k != 7) set_error("bf16 mode: conv %dx%d/%d %d->%d has no tensor-core plan (channels must be multiples of 64)", k, k, stride, cin, cout);
 	c.fprop = c.dgrad = c.wgrad = nullptr;
 	c.stats_rows = 0;
 	jobs.push_back(PackJob{c.w, c.wf, c.wd, cout, cin, k * k});
 	if (c.use_tc) {
-		size_t ws = tc_wgrad_workspace_bytes(c.g);
+		size_t ws = tc_wgrad_workspace_bytes(c.g, e->bf16);
 		if (ws > e->wgrad_ws_bytes) e->wgrad_ws_bytes = ws;
 	}
 }
@@ -197,7 +202,15 @@ static Engine *build_engine(Train_ResNet *t) {
 	e->N = t->batch_size;
 	const char *cm = getenv("RESNET_B200_CONV");
 	e->conv_mode = (cm && !strcmp(cm, "simt")) ? 1 : 0;
-	e->round_tf32 = (e->conv_mode == 0) ? env_int("RESNET_B200_TF32_ROUND", 1) : 0;
+	// storage / MMA type: fp32 tensors + kind::tf32 (BASELINE config 2) or bf16 tensors + kind::f16 (configs 3-5); fp32 master
+	// weights, gradients, optimizer state, BatchNorm statistics and the FC head in both
+	{
+		const char *dt = getenv("RESNET_B200_DTYPE");
+		e->bf16 = g_default_bf16 >= 0 ? g_default_bf16 : ((dt && !strcmp(dt, "bf16")) ? 1 : 0);
+		if (e->bf16 && e->conv_mode != 0) { set_error("bf16 storage needs the tensor-core convolution path (RESNET_B200_CONV=simt is fp32 only)"); e->bf16 = 0; }
+		e->esz = e->bf16 ? 2 : 4;
+	}
+	e->round_tf32 = (e->conv_mode == 0 && !e->bf16) ? env_int("RESNET_B200_TF32_ROUND", 1) : 0;
 	e->keep_all = env_int("RESNET_B200_KEEP_ALL", 0);
 	e->dp = nullptr;
 	e->wgrad_ws_bytes = 0;
@@ -233,20 +246,21 @@ static Engine *build_engine(Train_ResNet *t) {
 	const int S0 = d->input, S1 = d->input / d->init_conv_stride, S2 = S1 / d->init_maxpool_stride, F = d->init_conv_filters;
 	const long long n_x0 = (long long)N * S1 * S1 * F, n_p0 = (long long)N * S2 * S2 * F;
 	setup_conv(e, B, e->stem, N, S0, 3, F, d->init_kernel_dim, d->init_conv_stride, 0, P, G, jobs);
-	e->stem_tc = (e->conv_mode == 0) && env_int("RESNET_B200_STEM_TC", 1) && tc_stem_supported(S0, d->init_kernel_dim, 3, F, d->init_conv_stride);
+	e->stem_tc = (e->conv_mode == 0) && (e->bf16 || env_int("RESNET_B200_STEM_TC", 1)) && tc_stem_supported(S0, d->init_kernel_dim, 3, F, d->init_conv_stride, e->bf16);
+	if (e->bf16 && !e->stem_tc) set_error("bf16 mode: the stem must be 7x7/2 with a multiple of 64 filters (<= 128)");
 	e->stem_xp = e->stem_wfs = nullptr;
 	e->stem_fprop = e->stem_wgrad = nullptr;
 	if (e->stem_tc) {
-		e->stem_xp = B.get<float>((long long)stem_xp_elems(N, S0));
-		e->stem_wfs = B.get<float>((long long)F * 7 * 32);
-		size_t ws = tc_stem_wgrad_workspace_bytes(N, S0, F);
+		e->stem_xp = (float *)B.get<char>((long long)stem_xp_bytes(N, S0, e->bf16));
+		e->stem_wfs = (float *)B.get<char>((long long)stem_wfs_bytes(F, e->bf16));
+		size_t ws = tc_stem_wgrad_workspace_bytes(N, S0, F, e->bf16);
 		if (ws > e->wgrad_ws_bytes) e->wgrad_ws_bytes = ws;
 	}
-	e->X0 = A->init_conv_applied = B.get<float>(n_x0);
+	e->X0 = A->init_conv_applied = B.act(n_x0);
 	A->norm_init_conv = mk_cache(B, n_x0, F, ka, true);
-	e->Y0 = A->init_conv_activated = B.get<float>(n_x0);
+	e->Y0 = A->init_conv_activated = B.act(n_x0);
 	e->max_inds = A->max_inds = B.get<int>(n_p0);
-	e->P0 = A->init_convblock_input = B.get<float>(n_p0);
+	e->P0 = A->init_convblock_input = B.act(n_p0);
 	e->bn0 = mk_bnref(B, P->norm_init_conv, G->norm_init_conv, A->norm_init_conv, (long long)N * S1 * S1);
 
 	// ---- blocks
@@ -276,22 +290,22 @@ static Engine *build_engine(Train_ResNet *t) {
 		setup_conv(e, B, b.expand, N, Sout, cb->reduced_depth, cb->expanded_depth, 1, 1, li + 6, P, G, jobs);
 		if (b.has_proj) setup_conv(e, B, b.proj, N, Sin, cb->incoming_filters, cb->expanded_depth, cb->stride == 2 ? 3 : 1, cb->stride, li + 9, P, G, jobs);
 		b.x_in = x_in;
-		b.Xr = ab->post_reduced = B.get<float>(b.n_red_in);
+		b.Xr = ab->post_reduced = B.act(b.n_red_in);
 		ab->norm_post_reduced = mk_cache(B, b.n_red_in, cb->reduced_depth, ka, true);
-		b.Yr = ab->post_reduced_activated = B.get<float>(b.n_red_in);
-		b.Xs = ab->post_spatial = B.get<float>(b.n_red_out);
+		b.Yr = ab->post_reduced_activated = B.act(b.n_red_in);
+		b.Xs = ab->post_spatial = B.act(b.n_red_out);
 		ab->norm_post_spatial = mk_cache(B, b.n_red_out, cb->reduced_depth, ka, true);
-		b.Ys = ab->post_spatial_activated = B.get<float>(b.n_red_out);
-		b.Xe = ab->post_expanded = B.get<float>(b.n_exp_out);
+		b.Ys = ab->post_spatial_activated = B.act(b.n_red_out);
+		b.Xe = ab->post_expanded = B.act(b.n_exp_out);
 		ab->norm_post_expanded = mk_cache(B, b.n_exp_out, cb->expanded_depth, ka, true);
-		ab->post_expanded_norm_vals = ka ? B.get<float>(b.n_exp_out) : NULL;
+		ab->post_expanded_norm_vals = ka ? B.act(b.n_exp_out) : NULL;
 		if (b.has_proj) {
-			b.Xp = ab->transformed_residual = B.get<float>(b.n_exp_out);
+			b.Xp = ab->transformed_residual = B.act(b.n_exp_out);
 			ab->norm_post_projection = mk_cache(B, b.n_exp_out, cb->expanded_depth, ka, true);
-			ab->post_projection_norm_vals = ka ? B.get<float>(b.n_exp_out) : NULL;
+			ab->post_projection_norm_vals = ka ? B.act(b.n_exp_out) : NULL;
 		} else { b.Xp = NULL; }
-		ab->output = ka ? B.get<float>(b.n_exp_out) : NULL;
-		b.OA = ab->output_activated = B.get<float>(b.n_exp_out);
+		ab->output = ka ? B.act(b.n_exp_out) : NULL;
+		b.OA = ab->output_activated = B.act(b.n_exp_out);
 		b.bn_r = mk_bnref(B, cb->norm_depth_reduction, gcb->norm_depth_reduction, ab->norm_post_reduced, (long long)N * Sin * Sin);
 		b.bn_s = mk_bnref(B, cb->norm_spatial, gcb->norm_spatial, ab->norm_post_spatial, (long long)N * Sout * Sout);
 		b.bn_e = mk_bnref(B, cb->norm_expansion, gcb->norm_expansion, ab->norm_post_expanded, (long long)N * Sout * Sout);
@@ -313,12 +327,12 @@ static Engine *build_engine(Train_ResNet *t) {
 	// ---- gradient buffers: per-role scratch (default) or a full mirror (keep-all)
 	float *pp[2] = {nullptr, nullptr}, *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;
 	if (!ka) {
-		pp[0] = B.get<float>(max_exp_out); pp[1] = B.get<float>(max_exp_out);
-		T1 = B.get<float>(max_exp_out); T2 = B.get<float>(max_red_out); T3 = B.get<float>(max_red_in);
+		pp[0] = B.act(max_exp_out); pp[1] = B.act(max_exp_out);
+		T1 = B.act(max_exp_out); T2 = B.act(max_red_out); T3 = B.act(max_red_in);
 	}
-	e->dP0 = DA->init_convblock_input = ka ? B.get<float>(n_p0) : pp[1];  // block 0 writes its input gradient into pp[(0+1)&1]
-	e->dY0 = DA->init_conv_activated = B.get<float>(n_x0);
-	e->dX0 = DA->init_conv_applied = ka ? B.get<float>(n_x0) : e->dY0;
+	e->dP0 = DA->init_convblock_input = ka ? B.act(n_p0) : pp[1];  // block 0 writes its input gradient into pp[(0+1)&1]
+	e->dY0 = DA->init_conv_activated = B.act(n_x0);
+	e->dX0 = DA->init_conv_applied = ka ? B.act(n_x0) : e->dY0;
 	DA->norm_init_conv = mk_cache(B, n_x0, F, false, false);
 	DA->max_inds = NULL;
 	for (int i = 0; i < nb; i++) {
@@ -330,12 +344,12 @@ static Engine *build_engine(Train_ResNet *t) {
 		db->norm_post_reduced = db->norm_post_spatial = db->norm_post_expanded = db->norm_post_projection = NULL;
 		db->post_expanded_norm_vals = db->post_projection_norm_vals = db->output = NULL;
 		if (ka) {
-			b.dOA = B.get<float>(b.n_exp_out);
-			b.dXe = B.get<float>(b.n_exp_out);
-			b.dXp = b.has_proj ? B.get<float>(b.n_exp_out) : NULL;
-			b.dYs = B.get<float>(b.n_red_out); b.dXs = B.get<float>(b.n_red_out);
-			b.dYr = B.get<float>(b.n_red_in); b.dXr = B.get<float>(b.n_red_in);
-			db->output = B.get<float>(b.n_exp_out);
+			b.dOA = B.act(b.n_exp_out);
+			b.dXe = B.act(b.n_exp_out);
+			b.dXp = b.has_proj ? B.act(b.n_exp_out) : NULL;
+			b.dYs = B.act(b.n_red_out); b.dXs = B.act(b.n_red_out);
+			b.dYr = B.act(b.n_red_in); b.dXr = B.act(b.n_red_in);
+			db->output = B.act(b.n_exp_out);
 		} else {
 			b.dOA = pp[i & 1];
 			b.dXe = T1; b.dXp = b.has_proj ? T1 : NULL;
@@ -373,10 +387,10 @@ static Engine *build_engine(Train_ResNet *t) {
 	const int fused_stats = env_int("RESNET_B200_FUSED_STATS", 1);
 	auto plan = [&](ConvRef &c, const float *in, float *out, const float *dout, float *din, int din_accumulate) {
 		if (!c.use_tc) return;
-		c.fprop = tc_make_fprop(c.g, in, c.wf, out);
+		c.fprop = tc_make_fprop(c.g, in, c.wf, out, e->bf16);
 		c.stats_rows = fused_stats ? tc_attach_stats(c.fprop, e->bn_partials) : 0;
-		if (din) c.dgrad = tc_make_dgrad(c.g, dout, c.wd, din, din_accumulate);
-		c.wgrad = tc_make_wgrad(c.g, in, dout, c.dw, e->wgrad_ws, e->wgrad_ws_bytes);
+		if (din) c.dgrad = tc_make_dgrad(c.g, dout, c.wd, din, din_accumulate, e->bf16);
+		c.wgrad = tc_make_wgrad(c.g, in, dout, c.dw, e->wgrad_ws, e->wgrad_ws_bytes, e->bf16);
 	};
 	for (int i = 0; i < nb; i++) {
 		BlockRef &b = e->blocks[i];
@@ -387,13 +401,13 @@ static Engine *build_engine(Train_ResNet *t) {
 	}
 	if (e->stem_tc) {
 		const bool had_error = has_error();
-		e->stem_fprop = tc_make_stem_fprop(N, S0, F, e->stem_xp, e->stem_wfs, e->X0);
+		e->stem_fprop = tc_make_stem_fprop(N, S0, F, e->stem_xp, e->stem_wfs, e->X0, e->bf16);
 		e->stem.stats_rows = fused_stats ? tc_attach_stats(e->stem_fprop, e->bn_partials) : 0;
-		e->stem_wgrad = tc_make_stem_wgrad(N, S0, F, e->stem_xp, e->dX0, e->stem.dw, e->wgrad_ws, e->wgrad_ws_bytes);
+		e->stem_wgrad = tc_make_stem_wgrad(N, S0, F, e->stem_xp, e->dX0, e->stem.dw, e->wgrad_ws, e->wgrad_ws_bytes, e->bf16);
 		if (!e->stem_fprop || !e->stem_wgrad) {
 			// the overlapping-row tensor map was refused by the driver: keep the fp32 SIMT stem (slower, still correct)
 			fprintf(stderr, "[resnet_b200] stem tensor maps unavailable (%s); stem stays on the SIMT path\n", last_error());
-			if (!had_error) clear_error();
+			if (!had_error && !e->bf16) clear_error();  // bf16 has no SIMT stem: the error stands
 			e->stem_tc = false;
 			e->stem.stats_rows = 0;
 		}
@@ -410,8 +424,8 @@ static void conv_fwd(Engine *e, ConvRef &c, const float *in, float *out);
 static void stem_forward(Engine *e, const float *images) {
 	if (!e->stem_tc) { conv_fwd(e, e->stem, images, e->X0); return; }
 	const ConvGeom &g = e->stem.g;
-	stem_pack_weights(e->stem.w, g.cout, e->stem_wfs, e->round_tf32, e->stream);
-	stem_pad_input(images, g.N, g.S, e->stem_xp, e->round_tf32, e->stream);
+	stem_pack_weights(e->stem.w, g.cout, e->stem_wfs, e->round_tf32, e->bf16, e->stream);
+	stem_pad_input(images, g.N, g.S, e->stem_xp, e->round_tf32, e->bf16, e->stream);
 	ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
 	tc_run(e->stem_fprop, e->stream);
 }
@@ -449,34 +463,34 @@ static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, 
 }
 // algorithmic HBM bytes of the BatchNorm / elementwise kernels, E = rows * C elements of 4 bytes:
 // statistics 1E; apply 2E (+1E residual); backward reduce 2E (+1E mask) and dx 3E (+1E mask)
-static double bn_bytes(const BnRef &bn, double passes) { return passes * 4.0 * (double)bn.rows * bn.C; }
+static double bn_bytes(const Engine *e, const BnRef &bn, double passes) { return passes * (double)e->esz * (double)bn.rows * bn.C; }
 
 // stats_rows > 0: the producing conv's epilogue already left [stats_rows][2][C] partial sums in e->bn_partials (fused statistics)
 static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps, int stats_rows = 0) {
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, stats_rows ? 0.0 : bn_bytes(bn, 1));
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, stats_rows ? 0.0 : bn_bytes(e, bn, 1));
 	if (stats_rows) bn_finalize(e->bn_partials, stats_rows, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->stream);
-	else bn_stats(x, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->bn_partials, e->bn_max_blocks, e->stream);
+	else bn_stats(x, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->bn_partials, e->bn_max_blocks, e->stream, e->bf16);
 	if (e->keep_all && bn.cache->normalized) {
-		bn_apply(x, bn.ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized, 0, e->stream);
-		bn_stats(x, bn.rows, bn.C, e->ones, e->zeros, eps, e->tmp_mv, e->tmp_mv + bn.C, e->tmp_ab, e->bn_partials, e->bn_max_blocks, e->stream);
-		bn_apply(x, e->tmp_ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized_temp, 0, e->stream);
+		bn_apply(x, bn.ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized, 0, e->stream, e->bf16);
+		bn_stats(x, bn.rows, bn.C, e->ones, e->zeros, eps, e->tmp_mv, e->tmp_mv + bn.C, e->tmp_ab, e->bn_partials, e->bn_max_blocks, e->stream, e->bf16);
+		bn_apply(x, e->tmp_ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized_temp, 0, e->stream, e->bf16);
 	}
 }
 static void bn_act(Engine *e, BnRef &bn, const float *x, int relu, const float *res, const float *ab2, float *y, int rnd) {
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, res ? 3 : 2));
-	bn_apply(x, bn.ab, bn.rows, bn.C, relu, res, ab2, y, rnd, e->stream);
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, res ? 3 : 2));
+	bn_apply(x, bn.ab, bn.rows, bn.C, relu, res, ab2, y, rnd, e->stream, e->bf16);
 }
 static void relu_backward(Engine *e, const float *y, const float *dy, long long n, float *dx) {
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, 12.0 * (double)n);
-	relu_bwd(y, dy, n, dx, e->stream);
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, 3.0 * e->esz * (double)n);
+	relu_bwd(y, dy, n, dx, e->stream, e->bf16);
 }
 // remask: plain BN+ReLU layer, the mask is recomputed from x (the stored activation is not read); otherwise `mask` (the block's
 // output after the residual join) is read
 static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps, bool remask = false) {
 	const bool re = remask && (bn.C % 4 == 0) && env_int("RESNET_B200_REMASK", 1);
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(bn, re ? 5 : (mask ? 7 : 5)));
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, re ? 5 : (mask ? 7 : 5)));
 	bn_bwd(x, dy, mask, bn.gamma, bn.means, bn.vars, eps, bn.rows, bn.C, bn.dgamma, bn.dbeta, dx, e->bn_partials, e->bn_max_blocks, e->bn_coef,
-	       e->round_tf32, e->stream, re ? bn.ab : nullptr);
+	       e->round_tf32, e->stream, re ? bn.ab : nullptr, e->bf16);
 }
 
 }  // namespace rb
@@ -537,13 +551,13 @@ void forward_pass(Train_ResNet *t) {
 	const float eps = t->eps;
 	const int rnd = e->round_tf32;
 	// weights may have been written through locations[] since the last step (update, checkpoint restore): re-pack
-	pack_weights(e->pack_jobs_dev, e->n_pack_jobs, e->pack_max_elems, rnd, st);
+	pack_weights(e->pack_jobs_dev, e->n_pack_jobs, e->pack_max_elems, rnd, st, e->bf16);
 
 	stem_forward(e, t->cur_batch->images);
 	bn_forward(e, e->bn0, e->X0, eps, e->stem.stats_rows);
 	bn_act(e, e->bn0, e->X0, 1, nullptr, nullptr, e->Y0, rnd);
 	const int S1 = d->input / d->init_conv_stride;
-	maxpool_fwd(e->Y0, e->N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->max_inds, e->P0, st);
+	maxpool_fwd(e->Y0, e->N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->max_inds, e->P0, st, e->bf16);
 
 	for (size_t i = 0; i < e->blocks.size(); i++) {
 		BlockRef &b = e->blocks[i];
@@ -561,16 +575,16 @@ void forward_pass(Train_ResNet *t) {
 			bn_forward(e, b.bn_p, b.Xp, eps, b.proj.stats_rows);
 		}
 		if (e->keep_all) {
-			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, nullptr, nullptr, ab->post_expanded_norm_vals, 0, st);
-			if (b.has_proj) bn_apply(b.Xp, b.bn_p.ab, b.bn_p.rows, b.bn_p.C, 0, nullptr, nullptr, ab->post_projection_norm_vals, 0, st);
-			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, ab->output, 0, st);
+			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, nullptr, nullptr, ab->post_expanded_norm_vals, 0, st, e->bf16);
+			if (b.has_proj) bn_apply(b.Xp, b.bn_p.ab, b.bn_p.rows, b.bn_p.C, 0, nullptr, nullptr, ab->post_projection_norm_vals, 0, st, e->bf16);
+			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, ab->output, 0, st, e->bf16);
 		}
 		// output_activated = relu(bn(expanded) + shortcut)   (reference: resnet.cu:1670-1723, four kernels there)
 		bn_act(e, b.bn_e, b.Xe, 1, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, b.OA, rnd);
 	}
 	BlockRef &last = e->blocks.back();
 	const int Sl = last.expand.g.S;
-	avgpool_fwd(last.OA, e->N, Sl, d->final_depth, e->pooled, st);
+	avgpool_fwd(last.OA, e->N, Sl, d->final_depth, e->pooled, st, e->bf16);
 	sgemm(e->pooled, t->model->params->fully_connected, e->logits, e->N, d->output, d->final_depth, 0, 0, st);
 	softmax_ce(e->logits, t->cur_batch->correct_classes, e->N, d->output, e->pred, nullptr, e->row_loss, e->row_wrong, st);
 	RB_CUDA(cudaMemcpyAsync(e->pred_host, e->pred, (size_t)e->N * d->output * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -596,13 +610,13 @@ void backwards_pass(Train_ResNet *t) {
 	sgemm(e->pooled, e->dlogits, G->fully_connected, d->final_depth, d->output, N, 1, 0, st);
 	sgemm(e->dlogits, t->model->params->fully_connected, e->dpooled, N, d->final_depth, d->output, 0, 1, st);
 	BlockRef &last = e->blocks.back();
-	avgpool_bwd(e->dpooled, N, last.expand.g.S, d->final_depth, last.dOA, st);
+	avgpool_bwd(e->dpooled, N, last.expand.g.S, d->final_depth, last.dOA, st, e->bf16);
 
 	for (int i = (int)e->blocks.size() - 1; i >= 0; i--) {
 		BlockRef &b = e->blocks[i];
 		if (e->keep_all) {
 			Activation_ConvBlock *db = t->backprop_buffer->activation_derivs->activation_conv_blocks[i];
-			relu_bwd(b.OA, b.dOA, b.n_exp_out, db->output, st);  // d(output), reference: resnet.cu:1934
+			relu_bwd(b.OA, b.dOA, b.n_exp_out, db->output, st, e->bf16);  // d(output), reference: resnet.cu:1934
 		}
 		// shortcut branch first (its scratch is reused by the expanded branch)
 		if (b.has_proj) {
@@ -620,11 +634,11 @@ void backwards_pass(Train_ResNet *t) {
 		dp_block_done(e, i);
 	}
 	const int S1 = d->input / d->init_conv_stride;
-	maxpool_bwd(e->max_inds, e->dP0, N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->dY0, st);
+	maxpool_bwd(e->max_inds, e->dP0, N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->dY0, st, e->bf16);
 	{
-		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e->bn0, 5));
+		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e, e->bn0, 5));
 		bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
-		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bn0.ab);
+		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bn0.ab, e->bf16);
 	}
 	stem_backward(e, t->cur_batch->images);
 	dp_allreduce_grads(e);

@@ -105,6 +105,19 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
 	    "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
 	    : "memory");
 }
+// same, bf16 inputs (kind::f16; the a/b formats in the instruction descriptor select bf16)
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+	    "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+template <bool BF16> __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	if constexpr (BF16) mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+	else mma_tf32_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+}
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
 	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -126,6 +139,27 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
 	for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+// two back-to-back 32-column loads (64 consecutive columns) behind ONE wait
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, float (&v)[64]) {
+	uint32_t r[64];
+#pragma unroll
+	for (int h = 0; h < 2; h++) {
+		uint32_t *q = r + 32 * h;
+		asm volatile(
+		    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+		    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		    : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]),
+		      "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]), "=r"(q[17]), "=r"(q[18]),
+		      "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]), "=r"(q[25]), "=r"(q[26]), "=r"(q[27]),
+		      "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+		    : "r"(taddr + (uint32_t)(32 * h))
+		    : "memory");
+	}
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 64; i++) v[i] = __uint_as_float(r[i]);
+}
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -141,17 +175,20 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate: c_format=F32 [4,6), a/b_format=TF32 [7,10)/[10,13),
 // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
-__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+// fmt: 2 = TF32 (kind::tf32), 1 = BF16, 0 = F16 (kind::f16).
+__host__ __device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, uint32_t fmt) {
 	uint32_t d = 0;
 	d |= 1u << 4;
-	d |= 2u << 7;
-	d |= 2u << 10;
+	d |= fmt << 7;
+	d |= fmt << 10;
 	d |= (uint32_t)(a_mn_major & 1) << 15;
 	d |= (uint32_t)(b_mn_major & 1) << 16;
 	d |= (uint32_t)(N >> 3) << 17;
 	d |= (uint32_t)(M >> 4) << 24;
 	return d;
 }
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) { return make_idesc(M, N, a_mn_major, b_mn_major, 2u); }
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) { return make_idesc(M, N, a_mn_major, b_mn_major, 1u); }
 
 }  // namespace ptx
 }  // namespace rb

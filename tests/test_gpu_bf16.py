@@ -1,0 +1,287 @@
+"""GPU parity tests of the bf16 storage mode (BASELINE configs 3-5): bf16 NHWC activations / activation gradients / packed
+weights, kind::f16 tcgen05 MMAs with fp32 accumulation, fp32 master weights, parameter gradients, statistics and head.
+
+The oracle is fed the SAME bf16-rounded inputs, so what is measured is the kernel: fp32 accumulation order plus ONE rounding
+of each stored output to bf16 (relative 2^-9 = 2e-3 of the element, i.e. <= 4e-3 of the tensor's max).  Bars:
+single operator <= 1e-2 of the tensor's max for bf16 outputs, 3e-3 for fp32 outputs (weight gradients, statistics);
+max-pool values and argmax indices bit-exact; whole step: argmax bit-exact, softmax max-abs <= 2e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import golden_cases as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF_OUT, F32_OUT = 1e-2, 3e-3
+
+
+@pytest.fixture(scope="module")
+def api():
+    from resnet_b200 import api as a
+    a.L()
+    return a
+
+
+def rel_max(a, b):
+    return float(np.abs(a - b).max() / max(1e-9, np.abs(b).max()))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.reshape(-1) - b.reshape(-1)) / max(1e-9, np.linalg.norm(b)))
+
+
+TC_CASES = [  # S, k, cin, cout, stride, N -- every (k, stride) kind of the network, ragged tiles, partial batches, 64..2048 channels
+    (8, 1, 64, 64, 1, 2), (8, 1, 64, 256, 1, 3), (8, 1, 256, 64, 1, 4), (8, 3, 64, 64, 1, 2), (8, 3, 128, 128, 2, 2),
+    (8, 3, 256, 512, 2, 2), (14, 3, 256, 256, 1, 3), (7, 3, 512, 512, 1, 2), (7, 1, 512, 2048, 1, 4), (28, 3, 128, 128, 1, 2),
+    (14, 3, 512, 512, 2, 2), (56, 3, 64, 64, 1, 1), (7, 1, 2048, 512, 1, 3),
+]
+
+
+@pytest.mark.parametrize("S,k,cin,cout,stride,N", TC_CASES)
+def test_conv_bf16_vs_oracle(api, S, k, cin, cout, stride, N):
+    rng = np.random.default_rng(S * 1000 + cin + cout + k)
+    R = api.bf16_round
+    x = R(rng.standard_normal((N, S, S, cin)).astype(np.float32))
+    w = R((rng.standard_normal((cout, cin, k, k)) * 0.1).astype(np.float32))
+    dy = R(rng.standard_normal((N, S // stride, S // stride, cout)).astype(np.float32))
+    base = R(rng.standard_normal(x.shape).astype(np.float32))
+    y = api.conv_forward(x, w, stride, impl=0, dtype="bf16")
+    assert rel_max(y, O.conv_fwd(x, w, stride)) < BF_OUT
+    din, dw = api.conv_backward(x, w, dy, stride, impl=0, dtype="bf16")
+    din_ref = O.conv_dgrad(w, dy, S, stride)
+    assert rel_max(din, din_ref) < BF_OUT
+    assert rel_max(dw, O.conv_wgrad(x, dy, k, stride)) < F32_OUT  # weight gradients leave the kernel in fp32
+    din2, _ = api.conv_backward(x, w, dy, stride, din_base=base, impl=0, dtype="bf16")  # TMA bf16 reduce-add (residual join)
+    assert rel_max(din2, base + din_ref) < BF_OUT
+
+
+@pytest.mark.parametrize("S,N", [(32, 4), (64, 3), (224, 2)])
+def test_stem_bf16_vs_oracle(api, S, N):
+    """7x7/2, Cin = 3 stem in bf16: fp32 batch -> zero-bordered bf16 NHWC4 copy, 16-tap overlapping-row tensor maps; fprop + wgrad."""
+    rng = np.random.default_rng(S + N)
+    x, _ = O.synthetic_batch(N, S, seed=S)
+    R = api.bf16_round
+    w = R(rng.normal(0, np.sqrt(2.0 / (49 * 67)), (64, 3, 7, 7)).astype(np.float32))
+    dy = R(rng.standard_normal((N, S // 2, S // 2, 64)).astype(np.float32))
+    y = api.conv_forward(x, w, 2, impl=0, dtype="bf16")
+    assert rel_max(y, O.conv_fwd(R(x), w, 2)) < BF_OUT
+    _, dw = api.conv_backward(x, w, dy, 2, want_din=False, impl=0, dtype="bf16")
+    assert rel_max(dw, O.conv_wgrad(R(x), dy, 7, 2)) < F32_OUT
+
+
+def test_conv_bf16_linearity_full_size(api):
+    """Size-independent property at a full ResNet-50 layer shape (3x3, 14x14, 256->256, batch 32): conv(2*x1 + x2) ==
+    2*conv(x1) + conv(x2) up to the output rounding, and agreement with the fp32 SIMT path on the same (bf16-exact) inputs."""
+    rng = np.random.default_rng(7)
+    N, S, cin, cout = 32, 14, 256, 256
+    R = api.bf16_round
+    x1 = R(rng.integers(-8, 9, (N, S, S, cin)).astype(np.float32) / 8)   # small dyadic values: 2*x1 + x2 is exact in bf16
+    x2 = R(rng.integers(-8, 9, (N, S, S, cin)).astype(np.float32) / 8)
+    w = R((rng.standard_normal((cout, cin, 3, 3)) * 0.05).astype(np.float32))
+    y1, y2 = api.conv_forward(x1, w, 1, dtype="bf16"), api.conv_forward(x2, w, 1, dtype="bf16")
+    y12 = api.conv_forward((2.0 * x1 + x2).astype(np.float32), w, 1, dtype="bf16")
+    assert rel_max(y12, 2.0 * y1 + y2) < 2e-2
+    assert rel_max(y1, api.conv_forward(x1, w, 1, impl=1)) < BF_OUT
+
+
+@pytest.mark.parametrize("N,S,Cc,relu", [(4, 8, 128, 1), (8, 16, 64, 1), (4, 8, 512, 0), (16, 14, 256, 1), (32, 28, 128, 1), (3, 7, 2048, 1)])
+def test_batchnorm_bf16_vs_oracle(api, N, S, Cc, relu):
+    rng = np.random.default_rng(N * 1000 + S * 10 + Cc)
+    R = api.bf16_round
+    x = R((rng.standard_normal((N, S, S, Cc)) * 1.5 + 0.3).astype(np.float32))
+    g = (1 + 0.2 * rng.standard_normal(Cc)).astype(np.float32)
+    b = (0.2 * rng.standard_normal(Cc)).astype(np.float32)
+    dy = R(rng.standard_normal(x.shape).astype(np.float32))
+    mu, var, y = api.batchnorm_forward(x, g, b, 1e-7, relu, dtype="bf16")
+    omu, ovar, oy, _, _ = O.bn_fwd(x, g, b, 1e-7, relu)
+    np.testing.assert_allclose(mu, omu, rtol=1e-4, atol=1e-5)       # statistics are fp32 sums of the bf16 inputs
+    np.testing.assert_allclose(var, ovar, rtol=1e-4, atol=1e-6)
+    assert rel_max(y, oy) < BF_OUT
+    # backward with the device's own (bf16) activation as the ReLU mask source
+    dg, db, dx = api.batchnorm_backward(x, g, 1e-7, omu, ovar, y, dy, relu, dtype="bf16")
+    odg, odb, odx = O.bn_bwd(x, g, 1e-7, omu, ovar, y, dy, relu)
+    np.testing.assert_allclose(db, odb, rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(dg, odg, rtol=1e-4, atol=1e-3)
+    assert rel_max(dx, odx) < BF_OUT
+
+
+def test_batchnorm_bf16_residual_join(api):
+    rng = np.random.default_rng(11)
+    R = api.bf16_round
+    x = R(rng.standard_normal((3, 7, 7, 2048)).astype(np.float32))
+    res = R(rng.standard_normal(x.shape).astype(np.float32))
+    g = (1 + 0.1 * rng.standard_normal(2048)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(2048)).astype(np.float32)
+    _, _, y = api.batchnorm_forward(x, g, b, 1e-7, True, residual=res, dtype="bf16")
+    _, _, n, _, _ = O.bn_fwd(x, g, b, 1e-7, False)
+    assert rel_max(y, np.maximum(n + res, 0)) < BF_OUT
+
+
+def test_pools_bf16(api):
+    """max pool is a selection: values and argmax indices are bit-exact on bf16-exact inputs; its backward is exact where one
+    window claims a pixel and one rounding away where several do; average pool accumulates in fp32."""
+    rng = np.random.default_rng(5)
+    R = api.bf16_round
+    x = R(rng.standard_normal((3, 16, 16, 64)).astype(np.float32))
+    x[0, 0:3, 0:3, 0] = 0.5  # ties: the first max of the row-major window scan wins (reference: resnet.cu:459-468)
+    out, inds = api.maxpool_forward(x, 3, 2, dtype="bf16")
+    oout, oinds = O.maxpool_fwd(x, 3, 2)
+    np.testing.assert_array_equal(inds, oinds)
+    np.testing.assert_array_equal(out, oout)
+    dout = R(rng.standard_normal(out.shape).astype(np.float32))
+    din = api.maxpool_backward(oinds, dout, x.shape, 3, 2, dtype="bf16")
+    assert rel_max(din, O.maxpool_bwd(oinds, dout, x.shape)) < BF_OUT
+    xa = R(rng.standard_normal((4, 7, 7, 2048)).astype(np.float32))
+    np.testing.assert_allclose(api.avgpool_forward(xa, dtype="bf16"), O.avgpool_fwd(xa), rtol=1e-5, atol=1e-6)
+    dp = rng.standard_normal((4, 2048)).astype(np.float32)
+    assert rel_max(api.avgpool_backward(dp, 7, dtype="bf16"), O.avgpool_bwd(dp, 7)) < BF_OUT
+
+
+def make_pair(cfg, keep_all=True):
+    from resnet_b200 import api
+    os.environ["RESNET_B200_KEEP_ALL"] = "1" if keep_all else "0"
+    try:
+        t = api.Trainer(input_dim=cfg["input_dim"], n_blocks=cfg["n_blocks"], reductions=cfg["reductions"], batch=cfg["batch"],
+                        output=cfg["output"], lr=cfg["lr"], wd=cfg["wd"], b1=cfg["b1"], b2=cfg["b2"], eps=cfg["eps"], dtype="bf16")
+    finally:
+        os.environ.pop("RESNET_B200_KEEP_ALL", None)
+    assert t.bf16 and t.uses_tensor_cores()
+    net = O.OracleNet(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], cfg["batch"], output=cfg["output"], lr=cfg["lr"],
+                      wd=cfg["wd"], b1=cfg["b1"], b2=cfg["b2"], eps=cfg["eps"])
+    shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
+    W = G.mini_weights(shapes)
+    t.set_params(W)
+    net.set_params([w.copy() for w in W])
+    return t, net
+
+
+@pytest.mark.parametrize("cfg_name", ["MINI4", "MINI"])
+def test_step_bf16_layerwise_self_consistency(cfg_name):
+    """Layer by layer on the trainer's OWN bf16 tensors (as tests/test_gpu_network.py does for fp32 / TF32): every conv and
+    BatchNorm of forward and backward is re-derived by the oracle from the inputs the trainer actually used, with the weights
+    rounded to bf16 as pack_weights does, so each layer is held to the single-kernel bar."""
+    from resnet_b200 import api
+    cfg = getattr(G, cfg_name)
+    t, net = make_pair(cfg)
+    img, lab = G.mini_batch(cfg)
+    t.set_batch(img, lab)
+    t.forward()
+    t.backward()
+    P = [p.reshape(s) for p, s in zip(t.get_params(0), net.shapes)]
+    Pb = [api.bf16_round(p) for p in P]
+    Gd = [g.reshape(s) for g, s in zip(t.get_params(1), net.shapes)]
+    N, eps = cfg["batch"], cfg["eps"]
+    tol, wtol = BF_OUT, F32_OUT
+    # stem: fp32 batch rounded to bf16 on the way into the padded copy
+    S0 = cfg["input_dim"]
+    X0 = t.activation("init_conv_applied").reshape(N, S0 // 2, S0 // 2, 64)
+    assert rel_max(X0, O.conv_fwd(api.bf16_round(img), Pb[0], 2)) < tol, "stem fprop"
+    dX0 = t.activation("init_conv_applied", deriv=True).reshape(X0.shape)
+    assert rel_max(Gd[0], O.conv_wgrad(api.bf16_round(img), dX0, 7, 2)) < wtol, "stem wgrad"
+    li = 3
+    x_in = t.activation("init_convblock_input").reshape(N, S0 // 4, S0 // 4, 64)
+    for bi, b in enumerate(net.plan):
+        pre = "b%d." % bi
+        S, So = b["spatial"], b["spatial"] // b["stride"]
+        A = lambda nm, shp, d=False: t.activation(pre + nm, deriv=d).reshape(shp)  # noqa: E731
+        red_in, red_out, exp_out = (N, S, S, b["reduced"]), (N, So, So, b["reduced"]), (N, So, So, b["expanded"])
+        Xr, Yr, Xs, Ys, Xe, OA = A("post_reduced", red_in), A("post_reduced_activated", red_in), A("post_spatial", red_out), \
+            A("post_spatial_activated", red_out), A("post_expanded", exp_out), A("output_activated", exp_out)
+        assert rel_max(Xr, O.conv_fwd(x_in, Pb[li], 1)) < tol, (bi, "reduce fprop")
+        assert rel_max(Xs, O.conv_fwd(Yr, Pb[li + 3], b["stride"])) < tol, (bi, "spatial fprop")
+        assert rel_max(Xe, O.conv_fwd(Ys, Pb[li + 6], 1)) < tol, (bi, "expand fprop")
+        # BatchNorm forward: statistics of the stored bf16 conv output, fused into the conv epilogue
+        mu_r, var_r = t.activation(pre + "norm_post_reduced.means"), t.activation(pre + "norm_post_reduced.vars")
+        omu, ovar, oYr, _, _ = O.bn_fwd(Xr, P[li + 1], P[li + 2], eps, True)
+        np.testing.assert_allclose(mu_r, omu, rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(var_r, ovar, rtol=1e-3, atol=1e-5)
+        assert rel_max(Yr, oYr) < tol, (bi, "reduce bn fwd")
+        dOA, dXe, dYs, dXs, dYr, dXr = A("output_activated", exp_out, True), A("post_expanded", exp_out, True), \
+            A("post_spatial_activated", red_out, True), A("post_spatial", red_out, True), A("post_reduced_activated", red_in, True), \
+            A("post_reduced", red_in, True)
+        mu_e, var_e = t.activation(pre + "norm_post_expanded.means"), t.activation(pre + "norm_post_expanded.vars")
+        dg, db, odXe = O.bn_bwd(Xe, P[li + 7], eps, mu_e, var_e, OA, dOA, True)
+        assert rel_max(dXe, odXe) < tol and rel_max(Gd[li + 7], dg) < wtol and rel_max(Gd[li + 8], db) < wtol, (bi, "expand bn bwd")
+        assert rel_max(dYs, O.conv_dgrad(Pb[li + 6], dXe, So, 1)) < tol, (bi, "expand dgrad")
+        assert rel_max(Gd[li + 6], O.conv_wgrad(Ys, dXe, 1, 1)) < wtol, (bi, "expand wgrad")
+        mu_s, var_s = t.activation(pre + "norm_post_spatial.means"), t.activation(pre + "norm_post_spatial.vars")
+        dg, db, odXs = O.bn_bwd(Xs, P[li + 4], eps, mu_s, var_s, Ys, dYs, True)
+        assert rel_max(dXs, odXs) < tol and rel_max(Gd[li + 4], dg) < wtol, (bi, "spatial bn bwd")
+        assert rel_max(dYr, O.conv_dgrad(Pb[li + 3], dXs, S, b["stride"])) < tol, (bi, "spatial dgrad")
+        assert rel_max(Gd[li + 3], O.conv_wgrad(Yr, dXs, 3, b["stride"])) < wtol, (bi, "spatial wgrad")
+        dg, db, odXr = O.bn_bwd(Xr, P[li + 1], eps, mu_r, var_r, Yr, dYr, True)
+        assert rel_max(dXr, odXr) < tol, (bi, "reduce bn bwd")
+        assert rel_max(Gd[li], O.conv_wgrad(x_in, dXr, 1, 1)) < wtol, (bi, "reduce wgrad")
+        dBI = (t.activation("init_convblock_input", deriv=True) if bi == 0 else t.activation("b%d.output_activated" % (bi - 1), deriv=True)).reshape(x_in.shape)
+        if b["proj"]:
+            Xp, dXp = A("transformed_residual", exp_out), A("transformed_residual", exp_out, True)
+            assert rel_max(Xp, O.conv_fwd(x_in, Pb[li + 9], b["stride"])) < tol, (bi, "proj fprop")
+            mu_p, var_p = t.activation(pre + "norm_post_projection.means"), t.activation(pre + "norm_post_projection.vars")
+            _, _, odXp = O.bn_bwd(Xp, P[li + 10], eps, mu_p, var_p, OA, dOA, True)
+            assert rel_max(dXp, odXp) < tol, (bi, "proj bn bwd")
+            assert rel_max(Gd[li + 9], O.conv_wgrad(x_in, dXp, b["proj_k"], b["stride"])) < wtol, (bi, "proj wgrad")
+            short = api.bf16_round(O.conv_dgrad(Pb[li + 9], dXp, S, b["stride"]))   # stored as bf16, then the reduce dgrad adds
+            li_next = li + 12
+        else:
+            short = O.relu_bwd(OA, dOA)
+            li_next = li + 9
+        assert rel_max(dBI, short + O.conv_dgrad(Pb[li], dXr, S, 1)) < 1.5 * tol, (bi, "block input gradient")
+        x_in, li = OA, li_next
+    t.close()
+
+
+@pytest.mark.parametrize("cfg_name", ["MINI4", "MINI5"])
+def test_step_bf16_vs_fp32_oracle(cfg_name):
+    """Whole step against the fp32 oracle (SURVEY.md 8d C3 bar for bf16): argmax bit-exact, softmax max-abs <= 2e-2, loss within
+    2 %, parameter gradients within 0.3 rel-L2 (bf16 noise flips ReLU masks of activations sitting at zero on these tiny
+    batches, as TF32 does: tests/test_gpu_network.py), Adam moves every parameter by at most 2.5 lr and zeroes the gradients."""
+    cfg = getattr(G, cfg_name)
+    t, net = make_pair(cfg, keep_all=False)
+    img, lab = G.mini_batch(cfg)
+    t.set_batch(img, lab)
+    pred = t.forward()
+    opred = net.forward(img, lab)
+    assert np.isfinite(pred).all()
+    assert (pred.argmax(1) == opred.argmax(1)).all()
+    assert np.abs(pred - opred).max() <= 2e-2
+    loss, nwrong = t.loss_accuracy()
+    oloss, onwrong = net.loss_acc()
+    assert abs(loss - oloss) < 2e-2 * abs(oloss) + 1e-3 and nwrong == onwrong
+    t.backward()
+    og = [g.copy() for g in net.backward()]
+    for i, (g, r) in enumerate(zip(t.get_params(1), og)):
+        assert np.isfinite(g).all()
+        assert rel_l2(g, r) < 3e-1, ("grad", i, net.shapes[i])
+    before = t.get_params(0)
+    t.update()
+    after = t.get_params(0)
+    for i, (a, b) in enumerate(zip(after, before)):
+        assert np.isfinite(a).all() and np.abs(a - b).max() <= 2.5 * cfg["lr"], ("param", i)
+    assert all((g == 0).all() for g in t.get_params(1))
+    t.close()
+
+
+def test_bf16_forward_only_batch_agreement():
+    """BASELINE config 3 shape of claim at a size the oracle finishes in seconds: forward-only, bf16, batch-statistics BatchNorm
+    (the reference has no inference mode: resnet_cudnn.cu:1679 passes NULL running stats): argmax agreement with the fp32
+    oracle and softmax max-abs <= 2e-2, plus bf16 == TF32 trainer argmax on the same weights."""
+    from resnet_b200 import api
+    cfg = dict(G.MINI5, batch=16)
+    t, net = make_pair(cfg, keep_all=False)
+    t32 = api.Trainer(input_dim=cfg["input_dim"], n_blocks=cfg["n_blocks"], reductions=cfg["reductions"], batch=cfg["batch"],
+                      output=cfg["output"], dtype="tf32")
+    assert not t32.bf16
+    t32.set_params(t.get_params(0))
+    img, lab = O.synthetic_batch(cfg["batch"], cfg["input_dim"], seed=77, n_classes=cfg["output"])
+    t.set_batch(img, lab)
+    t32.set_batch(img, lab)
+    pred, pred32, opred = t.forward(), t32.forward(), net.forward(img, lab)
+    assert (pred.argmax(1) == opred.argmax(1)).mean() >= 0.99
+    assert np.abs(pred - opred).max() <= 2e-2
+    assert (pred.argmax(1) == pred32.argmax(1)).all()
+    t.close()
+    t32.close()
