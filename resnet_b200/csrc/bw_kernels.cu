@@ -97,12 +97,16 @@ static int flat_grid(long long nvec, int V, int max_blocks, bool *fixed) {
 	}
 	return grid;
 }
+// every streaming kernel is compiled for a fixed number of resident blocks per SM (__launch_bounds__: 4, or 3 for the bf16
+// BatchNorm-backward kernels that carry 8 channels of coefficients per thread) and its grid is capped at whole waves of that: the bf16 BatchNorm-backward kernels at 80 registers fitted 3 blocks per SM, so a
+// 592-block grid ran as one full wave plus a 1-block-per-SM tail and reached 3 TB/s where the fp32 twin reached 6.4
+// (profiles/r01_ncu_all_kernels_bf16_summary.txt)
 constexpr int kMaxFlatBlocks = kNumSMs * 8;
 
 // ------------------------------------------------------------------------------------------- BN statistics
 // partials[blk][0][c] = sum x, partials[blk][1][c] = sum x^2 over the rows this block streamed.
 template <typename T, int VEC, bool FIXED, bool BWD>
-__global__ void __launch_bounds__(kThreads) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+__global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
                                                             const T *__restrict__ mask, const float *__restrict__ means,
                                                             long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab) {
 	extern __shared__ float sm[];  // [2][C]
@@ -249,7 +253,10 @@ static void launch_reduce(bool bwd, const void *x, const void *dy, const void *m
 	const int V = C / VEC;
 	const long long nvec = rows * V;
 	bool fixed;
-	int cap = max_blocks < kNumSMs * 4 ? max_blocks : kNumSMs * 4;  // the fold cost grows with the number of partial blocks
+	// one whole wave: the bf16 variants keep 8 channels of coefficients per thread and fit 3 blocks per SM, the fp32 ones 4
+	// (and the fold cost grows with the number of partial blocks)
+	const int wave = kNumSMs * (bf16 ? 3 : 4);
+	int cap = max_blocks < wave ? max_blocks : wave;
 	int grid = flat_grid(nvec, V, cap, &fixed);
 	if (VEC == 1) fixed = false;
 	const size_t smem = 2 * (size_t)C * sizeof(float);
@@ -284,7 +291,7 @@ void bn_stats(const void *x, long long rows, int C, const float *gamma, const fl
 
 // ------------------------------------------------------------------------------------------- BN apply (+ residual + ReLU)
 template <typename T, int VEC, bool FIXED>
-__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T *__restrict__ x, const float *__restrict__ ab, long long nvec, int V,
+__global__ void __launch_bounds__(kThreads, 4) bn_apply_kernel(const T *__restrict__ x, const float *__restrict__ ab, long long nvec, int V,
                                                            int relu, const T *__restrict__ res, const float *__restrict__ ab2,
                                                            T *__restrict__ y, int rnd) {
 	const int Cc = V * VEC;
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const T *__restrict_
 			a2[j] = ab2 ? ab2[c0 + j] : 1.f; b2[j] = ab2 ? ab2[Cc + c0 + j] : 0.f;
 		}
 	}
-#pragma unroll 4
+#pragma unroll(VEC == 8 ? 2 : 4)
 	for (long long i = g; i < nvec; i += TS) {
 		if constexpr (!FIXED) {
 			const int c0 = (int)(i % V) * VEC;
@@ -367,7 +374,7 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
 }
 
 template <typename T, int VEC, bool FIXED>
-__global__ void __launch_bounds__(kThreads) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
+__global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
                                                             const float *__restrict__ coef, long long nvec, int V, T *dx, int rnd,
                                                             const float *__restrict__ mab) {
 	const int Cc = V * VEC;
@@ -423,7 +430,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 	const int V = C / VEC;
 	const long long nvec = rows * V;
 	bool fixed;
-	int g2 = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
+	int g2 = flat_grid(nvec, V, bf16 ? kNumSMs * 6 : kMaxFlatBlocks, &fixed);  // two whole waves (3 / 4 resident blocks per SM)
 #define RB_DX(T_, VEC_, FIX_) \
 	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab)
 	if (bf16) { if (fixed) RB_DX(bf16_t, 8, true); else RB_DX(bf16_t, 8, false); }
@@ -436,7 +443,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 
 // ------------------------------------------------------------------------------------------- ReLU backward (identity shortcut)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const T *__restrict__ y, const T *__restrict__ dy, long long n, T *__restrict__ dx) {
+__global__ void __launch_bounds__(kThreads, 4) relu_bwd_kernel(const T *__restrict__ y, const T *__restrict__ dy, long long n, T *__restrict__ dx) {
 	const long long T_ = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	const long long nv = n / VEC;
@@ -755,22 +762,59 @@ void convert_bf16_to_f32(const void *s, long long n, float *d, cudaStream_t st) 
 	RB_LAUNCH_CHECK();
 }
 
-__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, int cin, int taps, float *__restrict__ dw) {
+// Three shapes of the same fixed-order sum (deterministic), chosen per layer from the ncu launch list of one step:
+//  * many splits (>= 48: the 56x56 / 28x28 layers, small dW): 32 outputs x 8 split lanes per block, lane y sums splits y, y+8, ...
+//    (independent coalesced loads), shared memory combines the 8 lanes;
+//  * few splits, 1x1: one thread per output, reads and writes both contiguous;
+//  * few splits, 3x3 (large dW): threads follow the OUTPUT order [co][ci][tap] so the 75 MB of writes are coalesced; the strided
+//    reads of partial[tap][co][ci] hit lines the neighbouring threads of the block use completely.
+constexpr int kWrX = 32, kWrY = 8;
+__global__ void __launch_bounds__(kWrX * kWrY) wgrad_reduce_lanes_kernel(const float *__restrict__ partial, int splits, int cout, int cin, int taps,
+                                                                          float *__restrict__ dw) {
+	__shared__ float sm[kWrY][kWrX];
 	const long long per = (long long)taps * cout * cin;
-	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
-		// i indexes partial [tap][co][ci]
-		const int ci = (int)(i % cin);
-		const int co = (int)((i / cin) % cout);
-		const int tap = (int)(i / ((long long)cin * cout));
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	for (long long base = (long long)blockIdx.x * kWrX; base < per; base += (long long)gridDim.x * kWrX) {
+		const long long i = base + tx;  // indexes partial [tap][co][ci]
 		float s = 0.f;
+		if (i < per) {
+#pragma unroll 4
+			for (int sp = ty; sp < splits; sp += kWrY) s += partial[(long long)sp * per + i];
+		}
+		sm[ty][tx] = s;
+		__syncthreads();
+		if (ty == 0 && i < per) {
+#pragma unroll
+			for (int y = 1; y < kWrY; y++) s += sm[y][tx];
+			const int ci = (int)(i % cin);
+			const int co = (int)((i / cin) % cout);
+			const int tap = (int)(i / ((long long)cin * cout));
+			dw[((long long)co * cin + ci) * taps + tap] = s;
+		}
+		__syncthreads();
+	}
+}
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, int cin, int taps, float *__restrict__ dw) {
+	const long long per = (long long)taps * cout * cin, cc = (long long)cout * cin;
+	for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < per; o += (long long)gridDim.x * blockDim.x) {
+		// o indexes dw [co][ci][tap]
+		const int tap = (int)(o % taps);
+		const long long i = (long long)tap * cc + o / taps;
+		float s = 0.f;
+#pragma unroll 4
 		for (int sp = 0; sp < splits; sp++) s += partial[(long long)sp * per + i];
-		dw[((long long)co * cin + ci) * taps + tap] = s;
+		dw[o] = s;
 	}
 }
 void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps, float *dw, cudaStream_t st) {
 	long long per = (long long)taps * cout * cin;
-	int grid = (int)((per + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
-	wgrad_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, cout, cin, taps, dw);
+	if (splits >= 48) {
+		int grid = (int)((per + kWrX - 1) / kWrX); grid = grid > kNumSMs * 32 ? kNumSMs * 32 : grid;
+		wgrad_reduce_lanes_kernel<<<grid, dim3(kWrX, kWrY), 0, st>>>(partial, splits, cout, cin, taps, dw);
+	} else {
+		int grid = (int)((per + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
+		wgrad_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, cout, cin, taps, dw);
+	}
 	RB_LAUNCH_CHECK();
 }
 

@@ -121,6 +121,7 @@ struct alignas(64) IgemmParams {
 	int kchunks, kelems;  // K chunks per tap and elements per chunk (one 128-byte swizzle row: 32 tf32 / 64 bf16)
 	int BN, n_tiles, Ncol;
 	int stages;
+	int nstaging;  // epilogue staging tiles (2..4): up to nstaging - 2 TMA stores stay in flight behind the chunk being staged
 	uint32_t a_bytes, b_bytes, a_tx_bytes;  // smem slot sizes; bytes one A box actually transfers (bw*bh*bn rows)
 	float *out;
 	int OH, OW, os, accumulate;
@@ -167,8 +168,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-	uint8_t *staging = base + (size_t)p.stages * stage_bytes;  // 2 x 16 KB epilogue tiles (128 rows x 32 fp32, 128B-swizzled)
-	uint64_t *full = reinterpret_cast<uint64_t *>(staging + 2 * kABytes);
+	uint8_t *staging = base + (size_t)p.stages * stage_bytes;  // nstaging x 16 KB epilogue tiles (128 rows x 128 B, 128B-swizzled)
+	uint64_t *full = reinterpret_cast<uint64_t *>(staging + p.nstaging * kABytes);
 	uint64_t *empty = full + p.stages;
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 		const int wq = row % p.bw, hq = (row / p.bw) % p.bh, nq = row / (p.bw * p.bh);
 		const bool issuer = (warp == 2 && lane == 0);
 		int acc = 0;
-		uint32_t accphase = 0, chunk_ctr = 0;
+		uint32_t accphase = 0, sbuf = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 			const int nt = tile % p.n_tiles;
 			int r = tile / p.n_tiles;
@@ -270,11 +271,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 				// TMEM -> registers -> swizzled smem tile -> one TMA tile store (or reduce-add for the residual join) per 128-byte
 				// column chunk: fully coalesced lines, rows outside the tensor are clipped by the TMA unit
 				constexpr int CW = BF16 ? 64 : 32;  // output columns per staged 128-byte row
-				for (int c = 0; c < p.BN / CW; c++, chunk_ctr++) {
+				for (int c = 0; c < p.BN / CW; c++, sbuf = (sbuf + 1 == (uint32_t)p.nstaging ? 0 : sbuf + 1)) {
 					float v[CW];
 					if constexpr (BF16) tmem_ld_32x64(taddr + (uint32_t)(c * CW), v);
 					else tmem_ld_32x32(taddr + (uint32_t)(c * CW), v);
-					uint8_t *buf = staging + (chunk_ctr & 1) * kABytes;
+					uint8_t *buf = staging + sbuf * kABytes;
 					uint8_t *rowp = buf + row * 128;
 					if (p.stats && !row_valid) {  // rows the TMA store clips must not pollute the fused statistics
 #pragma unroll
@@ -290,7 +291,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 							*reinterpret_cast<float4 *>(rowp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 					}
 					fence_proxy_async();
-					if (issuer) tma_wait_group_read0();  // the store that last read the OTHER buffer is done before anyone rewrites it
+					// the store that last read the NEXT buffer in the ring is done before anyone rewrites it; nstaging - 2 younger
+					// stores may still be in flight (the write-bound 1x1 layers were serialised on the store round trip with 2 tiles)
+					if (issuer) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }
 					named_barrier_sync(1, 128);
 					if (issuer) {
 						if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
@@ -524,6 +527,8 @@ struct TcPlan {
 	// fused BatchNorm statistics (fprop): rows of partial sums and their byte size
 	int stats_rows;
 	size_t stats_bytes;
+	double flops;  // algorithmic FLOPs of one launch: 2 * N * Ho * Wo * Cout * Cin * k^2
+	char what[40];
 };
 
 static const size_t kMaxDynSmem = 227 * 1024;
@@ -605,9 +610,14 @@ static void finish_kmajor(TcPlan *pl) {
 	p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128;
 	p.b_bytes = (uint32_t)p.BN * 128;
 	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-	int stages = (int)((kMaxDynSmem - 2048 - 2 * kABytes) / stage_bytes);
+	// short mainloops (1x1 layers with few K chunks) are bound by the epilogue's stores: give them a deeper store ring
+	int max_iters = 0;
+	for (int gi = 0; gi < p.ngroups; gi++) max_iters = std::max(max_iters, p.groups[gi].ntaps * p.kchunks);
+	p.nstaging = max_iters <= 8 ? 4 : 2;
+	if (const char *e = getenv("RESNET_B200_NSTAGING")) { int v = atoi(e); if (v >= 2 && v <= 4) p.nstaging = v; }
+	int stages = (int)((kMaxDynSmem - 2048 - p.nstaging * kABytes) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
-	pl->smem = (size_t)p.stages * stage_bytes + 2 * kABytes + 1024 + 256;
+	pl->smem = (size_t)p.stages * stage_bytes + p.nstaging * kABytes + 1024 + 256;
 	const int total = p.ngroups * p.m_tiles * p.n_tiles;
 	pl->grid = total < kNumSMs ? total : kNumSMs;
 	pl->kind = 0;
@@ -652,6 +662,8 @@ TcPlan *tc_make_fprop(const ConvGeom &g, const void *x, const void *wf, void *y,
 	gr.omap = 0;
 	p.tma_store = tma_store_enabled(bf16);
 	finish_kmajor(pl);
+	pl->flops = 2.0 * g.N * So * So * (double)g.cout * g.cin * g.taps();
+	snprintf(pl->what, sizeof(pl->what), "fprop %dx%d/%d %d->%d @%d", g.k, g.k, g.stride, g.cin, g.cout, g.S);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
@@ -713,6 +725,8 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const void *dy, const void *wd, void *d
 	if (g.k == 1 || g.stride == 1) for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
 	p.tma_store = tma_store_enabled(bf16);
 	finish_kmajor(pl);
+	pl->flops = 2.0 * g.N * So * So * (double)g.cout * g.cin * g.taps();
+	snprintf(pl->what, sizeof(pl->what), "dgrad %dx%d/%d %d->%d @%d", g.k, g.k, g.stride, g.cin, g.cout, g.S);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
@@ -807,6 +821,8 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 	pl->grid = total < kNumSMs ? total : kNumSMs;
 	pl->kind = 1;
 	pl->dw = dw; pl->cout = g.cout; pl->cin = g.cin; pl->taps = g.taps();
+	pl->flops = 2.0 * g.N * So * So * (double)g.cout * g.cin * g.taps();
+	snprintf(pl->what, sizeof(pl->what), "wgrad %dx%d/%d %d->%d @%d", g.k, g.k, g.stride, g.cin, g.cout, g.S);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
@@ -939,6 +955,8 @@ TcPlan *tc_make_stem_fprop(int N, int S, int cout, const void *xp, const void *w
 	gr.omap = 0;
 	p.tma_store = tma_store_enabled(bf16);
 	finish_kmajor(pl);
+	pl->flops = 2.0 * N * So * So * (double)cout * 3 * kStemK * kStemK;
+	snprintf(pl->what, sizeof(pl->what), "fprop 7x7/2 3->%d @%d", cout, S);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
@@ -979,12 +997,20 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	pl->grid = total < kNumSMs ? total : kNumSMs;
 	pl->kind = 2;
 	pl->dw = dw; pl->cout = cout; pl->cin = 3; pl->taps = kStemK * kStemK;
+	pl->flops = 2.0 * N * So * So * (double)cout * 3 * kStemK * kStemK;
+	snprintf(pl->what, sizeof(pl->what), "wgrad 7x7/2 3->%d @%d", cout, S);
 	if (!ok) { delete pl; return nullptr; }
 	return pl;
 }
 
 void tc_run(TcPlan *pl, cudaStream_t st) {
 	if (!pl) { set_error("tc_run: null plan"); return; }
+	static const bool trace = getenv("RESNET_B200_TRACE") != nullptr;  // one line per launch, in launch order (tools/ncu_summary.py joins it with ncu's list)
+	if (trace) {
+		char buf[256];
+		tc_describe(pl, buf, sizeof(buf));
+		fprintf(stderr, "[tc_run] %s flops=%.6g\n", buf, pl->flops);
+	}
 	static bool attr_set = false;
 	if (!attr_set) {
 		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
@@ -1027,12 +1053,12 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
-		snprintf(buf, n, "kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu", pl->bf16 ? "bf16" : "tf32",
+		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu", pl->what, pl->bf16 ? "bf16" : "tf32",
 		         p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem);
 	} else {
 		const WgradParams &p = pl->wp;
-		snprintf(buf, n, "wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
-		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
+		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
 	}
 }
 
