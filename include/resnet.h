@@ -211,6 +211,15 @@ void forward_pass(Train_ResNet * trainer);
 void backwards_pass(Train_ResNet * trainer);
 /* reference: resnet.cu:2910 */
 void update_parameters(Train_ResNet * trainer);
+/* reference: resnet.cu:2755 -- writes <root>/<special_dir>/<dump_id %08d>/{model_params,gradients,means,vars}/%03d.buffer,
+ * activations/..., activation_derivs/..., trainer_metadata.txt, trainer_checkpoint.txt in the reference's layout (fp32 files
+ * whatever the device storage type).  <root> = $RESNET_B200_DUMP_ROOT, default the reference's hard-coded
+ * /mnt/storage/data/vision/imagenet/training_dumps; directories are created. */
+void dump_trainer(int dump_id, Train_ResNet * trainer, const char * special_dir);
+/* reference: resnet.cu:2778 -- cur_shard_id, cur_batch_in_shard, cur_mean_decay, cur_var_decay, cur_dump_id, cur_epoch */
+void overwrite_trainer_hyperparams(Train_ResNet * trainer, int dump_id, const char * special_dir);
+/* reference: resnet.cu:2821 -- model_params, means, vars of every location */
+void overwrite_model_params(Train_ResNet * trainer, int dump_id, const char * special_dir);
 
 #ifdef __cplusplus
 }

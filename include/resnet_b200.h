@@ -61,6 +61,13 @@ int resnet_b200_timer_begin(Train_ResNet * trainer);
 float resnet_b200_timer_end_ms(Train_ResNet * trainer);
 /* on-device loss / accuracy of the last forward_pass (same definitions as reference resnet.cu:3363-3383) */
 int resnet_b200_loss_accuracy(Train_ResNet * trainer, float * loss_sum, int * n_wrong);
+/* epoch bookkeeping without a per-step synchronisation (the reference's loop reads N x 1000 floats of pred_cpu every step to
+ * compute these on the host, resnet.cu:3363-3412): forward_pass adds the batch's loss sum and wrong count to running device
+ * sums; epoch_stats reads (and optionally resets) them.  set_pred_copy(0) makes forward_pass return without copying pred to
+ * pred_cpu and without synchronising; fetch_pred brings pred_cpu up to date on demand. */
+int resnet_b200_set_pred_copy(Train_ResNet * trainer, int on);
+int resnet_b200_fetch_pred(Train_ResNet * trainer);
+int resnet_b200_epoch_stats(Train_ResNet * trainer, double * loss_sum, long long * n_wrong, long long * n_images, int reset);
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 long long resnet_b200_launch_count(void);
 /* per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline leg): enable (resets the

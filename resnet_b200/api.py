@@ -187,10 +187,40 @@ class Trainer:
         L().resnet_b200_trainer_sync(self.t)
         check()
 
+    # ---- dumps / checkpoints in the reference's directory format (reference: resnet.cu:2755, 2778, 2821); root = $RESNET_B200_DUMP_ROOT
+    def dump(self, dump_id, special_dir="resnet_b200"):
+        L().dump_trainer(int(dump_id), self.t, special_dir.encode())
+        check()
+
+    def restore(self, dump_id, special_dir="resnet_b200"):
+        L().overwrite_trainer_hyperparams(self.t, int(dump_id), special_dir.encode())
+        L().overwrite_model_params(self.t, int(dump_id), special_dir.encode())
+        check()
+
     def loss_accuracy(self):
         ls, nw = C.c_float(), C.c_int()
         L().resnet_b200_loss_accuracy(self.t, C.byref(ls), C.byref(nw))
         return ls.value, nw.value
+
+    def set_pred_copy(self, on):
+        """False: forward_pass neither copies pred to pred_cpu nor synchronises (epoch_stats / fetch_pred read results on demand)"""
+        L().resnet_b200_set_pred_copy(self.t, int(bool(on)))
+        check()
+
+    def forward_async(self):
+        L().forward_pass(self.t)
+
+    def fetch_pred(self):
+        L().resnet_b200_fetch_pred(self.t)
+        check()
+        return np.ctypeslib.as_array(self.t.contents.forward_buffer.contents.pred_cpu, shape=(self.batch, self.output)).copy()
+
+    def epoch_stats(self, reset=False):
+        """(loss sum, wrong predictions, images) accumulated on the device since the last reset (reference: resnet.cu:3363-3412)"""
+        ls, nw, ni = C.c_double(), C.c_longlong(), C.c_longlong()
+        L().resnet_b200_epoch_stats(self.t, C.byref(ls), C.byref(nw), C.byref(ni), int(reset))
+        check()
+        return ls.value, nw.value, ni.value
 
     def uses_tensor_cores(self):
         return bool(L().resnet_b200_uses_tensor_cores(self.t))

@@ -376,7 +376,7 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
 template <typename T, int VEC, bool FIXED>
 __global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
                                                             const float *__restrict__ coef, long long nvec, int V, T *dx, int rnd,
-                                                            const float *__restrict__ mab) {
+                                                            const float *__restrict__ mab, T *__restrict__ masked_out) {
 	const int Cc = V * VEC;
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -409,6 +409,9 @@ __global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_bwd_dx_kernel
 #pragma unroll
 			for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
 		}
+		// the ReLU-masked upstream gradient is also the identity shortcut's gradient (reference: resnet.cu:2003-2004 setVal + addVec):
+		// written here, while it is in registers, instead of by a separate 3-tensor relu_bwd pass
+		if (masked_out) stv<T, VEC>(masked_out, i, d);
 #pragma unroll
 		for (int j = 0; j < VEC; j++) {
 			float r = fmaf(c1[j], d[j], fmaf(c3[j], a[j] - mu[j], c2[j]));
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_bwd_dx_kernel
 
 void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars, float eps,
             long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks, float *coef, int rnd,
-            cudaStream_t st, const float *mab, int bf16) {
+            cudaStream_t st, const float *mab, int bf16, void *masked_out) {
 	int grid;
 	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab, bf16);
 	bn_bwd_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
@@ -432,7 +435,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 	bool fixed;
 	int g2 = flat_grid(nvec, V, bf16 ? kNumSMs * 6 : kMaxFlatBlocks, &fixed);  // two whole waves (3 / 4 resident blocks per SM)
 #define RB_DX(T_, VEC_, FIX_) \
-	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab)
+	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab, (T_ *)masked_out)
 	if (bf16) { if (fixed) RB_DX(bf16_t, 8, true); else RB_DX(bf16_t, 8, false); }
 	else if (VEC == 4 && fixed) RB_DX(float, 4, true);
 	else if (VEC == 4) RB_DX(float, 4, false);
@@ -677,13 +680,18 @@ void adam_step(float *p, float *g, float *m, float *v, long long n, float lr, fl
 
 // ------------------------------------------------------------------------------------------- fp32 SGEMM (FC head)
 // 64x64 tile, BK 16, 4x4 per thread.  Used for the 2048x1000 fully-connected layer (0.03% of step FLOPs).
+// blockIdx.z = split-K slice: slice z reduces k in [z*kc, (z+1)*kc) into its own [M][N] plane of Cm (summed in a fixed order by
+// splitk_sum_kernel): at batch 256 the forward GEMM has only 64 output tiles, one wave of 128 serial K steps (360 us).
 __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ Cm, int M, int N, int K,
-                                                   int ta, int tb) {
+                                                   int ta, int tb, int kc) {
 	__shared__ float As[16][65], Bs[16][65];
 	const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
 	const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
 	float acc[4][4] = {};
-	for (int k0 = 0; k0 < K; k0 += 16) {
+	const int kbeg = blockIdx.z * kc;
+	K = min(K, kbeg + kc);
+	Cm += (size_t)blockIdx.z * M * N;
+	for (int k0 = kbeg; k0 < K; k0 += 16) {
 		for (int e = threadIdx.x; e < 1024; e += 256) {
 			int kk, mm;
 			if (ta) { mm = e % 64; kk = e / 64; } else { kk = e % 16; mm = e / 16; }
@@ -715,30 +723,78 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A,
 			if (gm < M && gn < N) Cm[(size_t)gm * N + gn] = acc[i][j];
 		}
 }
-void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int ta, int tb, cudaStream_t st) {
-	dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-	sgemm_kernel<<<grid, 256, 0, st>>>(A, B, Cm, M, N, K, ta, tb);
+__global__ void splitk_sum_kernel(const float *__restrict__ planes, int nsplit, long long n, float *__restrict__ out) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		float s = 0.f;
+		for (int z = 0; z < nsplit; z++) s += planes[(long long)z * n + i];
+		out[i] = s;
+	}
+}
+// ws != NULL (>= sgemm_ws_floats(M, N) floats): split K over enough slices to fill the GPU, deterministic two-pass sum
+size_t sgemm_ws_floats(int M, int N) { return (size_t)8 * M * N; }
+void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int ta, int tb, cudaStream_t st, float *ws) {
+	const int tiles = ceil_div(N, 64) * ceil_div(M, 64);
+	int nsplit = 1;
+	if (ws) {
+		nsplit = ceil_div(2 * kNumSMs, tiles);
+		nsplit = nsplit > 8 ? 8 : nsplit;
+		while (nsplit > 1 && K / nsplit < 64) nsplit--;
+	}
+	const int kc = ceil_div(ceil_div(K, nsplit), 16) * 16;
+	nsplit = ceil_div(K, kc);
+	dim3 grid(ceil_div(N, 64), ceil_div(M, 64), nsplit);
+	sgemm_kernel<<<grid, 256, 0, st>>>(A, B, nsplit > 1 ? ws : Cm, M, N, K, ta, tb, kc);
 	RB_LAUNCH_CHECK();
+	if (nsplit > 1) {
+		const long long n = (long long)M * N;
+		splitk_sum_kernel<<<ceil_div(n, 256 * 4), 256, 0, st>>>(ws, nsplit, n, Cm);
+		RB_LAUNCH_CHECK();
+	}
 }
 
 // ------------------------------------------------------------------------------------------- weight re-layout
+// One block re-lays 32 co x 32 ci x taps weights through shared memory so that all three streams are coalesced: the source
+// [co][ci][tap] is read in runs of 32*taps floats, Wf[co][tap][ci] is written 32 ci at a time and Wd[ci][tap][co] 32 co at a time
+// (the element-wise version wrote Wd at a stride of taps*cout elements and ran the 0.4 GB of traffic at 0.8 TB/s).  Jobs whose
+// channel counts are not multiples of 32 (the 3-channel stem) take the element-wise path.
+constexpr int kPackT = 32, kPackMaxTaps = 9;
 template <typename T>
-__global__ void pack_weights_kernel(const PackJob *__restrict__ jobs, int rnd) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob *__restrict__ jobs, int rnd) {
+	__shared__ float sm[kPackT][kPackT * kPackMaxTaps + 1];
 	const PackJob jb = jobs[blockIdx.y];
-	const long long total = (long long)jb.cout * jb.cin * jb.taps;
-	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		// i indexes the source [co][ci][tap]
-		const int tap = (int)(i % jb.taps);
-		const int ci = (int)((i / jb.taps) % jb.cin);
-		const int co = (int)(i / ((long long)jb.taps * jb.cin));
-		float w = jb.src[i];
-		if (rnd && sizeof(T) == 4) w = round_tf32(w);
-		st1<T>((T *)jb.wf, ((long long)co * jb.taps + tap) * jb.cin + ci, w);
-		if (jb.wd) st1<T>((T *)jb.wd, ((long long)ci * jb.taps + tap) * jb.cout + co, w);
+	const int taps = jb.taps;
+	if ((jb.cout % kPackT) || (jb.cin % kPackT) || taps > kPackMaxTaps) {
+		const long long total = (long long)jb.cout * jb.cin * taps;
+		for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+			const int tap = (int)(i % taps), ci = (int)((i / taps) % jb.cin), co = (int)(i / ((long long)taps * jb.cin));
+			float w = jb.src[i];
+			if (rnd && sizeof(T) == 4) w = round_tf32(w);
+			st1<T>((T *)jb.wf, ((long long)co * taps + tap) * jb.cin + ci, w);
+			if (jb.wd) st1<T>((T *)jb.wd, ((long long)ci * taps + tap) * jb.cout + co, w);
+		}
+		return;
+	}
+	const int ci_tiles = jb.cin / kPackT, ntiles = (jb.cout / kPackT) * ci_tiles, run = kPackT * taps;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const int co0 = (tile / ci_tiles) * kPackT, ci0 = (tile % ci_tiles) * kPackT;
+		for (int e = threadIdx.x; e < kPackT * run; e += 256) {  // sm[co_l][ci_l * taps + tap]
+			const int co_l = e / run, r = e % run;
+			float w = jb.src[((long long)(co0 + co_l) * jb.cin + ci0) * taps + r];
+			if (rnd && sizeof(T) == 4) w = round_tf32(w);
+			sm[co_l][r] = w;
+		}
+		__syncthreads();
+		for (int p = warp; p < kPackT * taps; p += 8) {  // p = (row, tap); lane = the contiguous output index
+			const int row = p / taps, tap = p % taps;
+			st1<T>((T *)jb.wf, ((long long)(co0 + row) * taps + tap) * jb.cin + ci0 + lane, sm[row][lane * taps + tap]);
+			if (jb.wd) st1<T>((T *)jb.wd, ((long long)(ci0 + row) * taps + tap) * jb.cout + co0 + lane, sm[lane][row * taps + tap]);
+		}
+		__syncthreads();
 	}
 }
 void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int rnd, cudaStream_t st, int bf16) {
-	int gx = ceil_div(max_elems, 256 * 8); gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+	int gx = ceil_div(max_elems, kPackT * kPackT * kPackMaxTaps); gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
 	if (bf16) pack_weights_kernel<bf16_t><<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
 	else pack_weights_kernel<float><<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
 	RB_LAUNCH_CHECK();

@@ -127,6 +127,32 @@ int resnet_b200_loss_accuracy(Train_ResNet *t, float *loss_sum, int *n_wrong) {
 	*n_wrong = nw;
 	return status();
 }
+int resnet_b200_set_pred_copy(Train_ResNet *t, int on) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("set_pred_copy: unknown trainer"); return 1; }
+	e->pred_copy = on ? 1 : 0;
+	return status();
+}
+int resnet_b200_fetch_pred(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("fetch_pred: unknown trainer"); return 1; }
+	RB_CUDA(cudaMemcpyAsync(e->pred_host, e->pred, (size_t)e->N * t->model->dims->output * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+	RB_CUDA(cudaStreamSynchronize(e->stream));
+	return status();
+}
+int resnet_b200_epoch_stats(Train_ResNet *t, double *loss_sum, long long *n_wrong, long long *n_images, int reset) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("epoch_stats: unknown trainer"); return 1; }
+	double acc[2] = {0, 0};
+	RB_CUDA(cudaMemcpyAsync(acc, e->epoch_acc, sizeof(acc), cudaMemcpyDeviceToHost, e->stream));
+	if (reset) RB_CUDA(cudaMemsetAsync(e->epoch_acc, 0, sizeof(acc), e->stream));
+	RB_CUDA(cudaStreamSynchronize(e->stream));
+	if (loss_sum) *loss_sum = acc[0];
+	if (n_wrong) *n_wrong = (long long)(acc[1] + 0.5);
+	if (n_images) *n_images = e->epoch_images;
+	if (reset) e->epoch_images = 0;
+	return status();
+}
 long long resnet_b200_launch_count(void) { return g_launches; }
 void resnet_b200_profile(int enable) { prof_reset(); prof_enable(enable != 0); }
 int resnet_b200_profile_read(int family, double *ms, long long *launches, double *work) { return prof_read(family, ms, launches, work); }
@@ -173,6 +199,7 @@ int resnet_b200_conv_forward(int S, int k, int cin, int cout, int stride, int N,
 		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 	} else if (impl == 0) {
 		TcPlan *pl = tc_make_fprop(g, input, wf, output, bf);
+		if (pl && getenv("RESNET_B200_OP_STATS")) tc_attach_stats(pl, tmp.get<float>((long long)tc_stats_floats(cout)));  // tools/conv_probe.py: epilogue with the fused statistics
 		if (pl) { tc_run(pl, 0); RB_CUDA(cudaDeviceSynchronize()); tc_free(pl); }
 	} else {
 		simt_conv_fprop(g, input, (const float *)wf, output, 0);

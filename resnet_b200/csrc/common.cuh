@@ -63,7 +63,8 @@ void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, c
 // mask_ab != NULL ([2][C] folded scale/shift of the forward): the ReLU mask is recomputed as (x*a + b > 0) instead of read
 void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars,
             float eps, long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks,
-            float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr, int bf16 = 0);
+            float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr, int bf16 = 0, void *masked_out = nullptr);
+// masked_out != NULL: the masked upstream gradient dy' (the identity shortcut's gradient) is also stored there
 void relu_bwd(const void *y, const void *dy, long long n, void *dx, cudaStream_t st, int bf16 = 0);
 void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16 = 0);
 void maxpool_bwd(const int *max_inds, const void *dout, int N, int S, int C, int k, int stride, void *din, cudaStream_t st, int bf16 = 0);
@@ -78,7 +79,9 @@ void softmax_ce(const float *logits, const int *labels, int N, int L, float *pre
 void adam_step(float *p, float *g, float *m, float *v, long long n, float lr, float wd, float b1, float b2, float cur_b1,
                float cur_b2, float eps, int *bad, cudaStream_t st);
 // C[M][N] = op(A) * op(B), fp32 FMA; ta: A stored [K][M]; tb: B stored [N][K]
-void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int ta, int tb, cudaStream_t st);
+// ws (optional, >= sgemm_ws_floats(M, N) floats): lets small-output GEMMs split K (deterministic two-pass sum)
+void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int ta, int tb, cudaStream_t st, float *ws = nullptr);
+size_t sgemm_ws_floats(int M, int N);
 
 // weight re-layout [Cout][Cin][k][k] (fp32 master) -> Wf [Cout][k*k][Cin] and Wd [Cin][k*k][Cout], tf32-rounded fp32 or bf16
 struct PackJob { const float *src; void *wf; void *wd; int cout, cin, taps; };

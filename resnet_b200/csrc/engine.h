@@ -71,10 +71,16 @@ struct Engine {
 	float *pooled, *logits, *pred, *dlogits, *dpooled, *row_loss;
 	int *row_wrong;
 	float *pred_host;  // pinned
+	// on-device loss / accuracy bookkeeping: running sums over the steps since the last reset, so a host loop
+	// needs neither pred_cpu nor a synchronisation per step
+	int pred_copy;              // 1 (default, the reference's contract): forward_pass returns with pred_cpu valid; 0: no copy, no sync
+	double *epoch_acc;          // device [2]: sum of -log p[label], number of wrong predictions
+	long long epoch_images;     // images forwarded since the last reset
 	// workspaces
 	float *bn_partials;
 	int bn_max_blocks;
 	float *bn_coef;
+	float *fc_ws;  // split-K planes of the fully-connected GEMMs
 	float *wgrad_ws;
 	size_t wgrad_ws_bytes;
 	PackJob *pack_jobs_dev;

@@ -121,7 +121,8 @@ struct alignas(64) IgemmParams {
 	int kchunks, kelems;  // K chunks per tap and elements per chunk (one 128-byte swizzle row: 32 tf32 / 64 bf16)
 	int BN, n_tiles, Ncol;
 	int stages;
-	int nstaging;  // epilogue staging tiles (2..4): up to nstaging - 2 TMA stores stay in flight behind the chunk being staged
+	int nstaging;  // epilogue staging tiles PER GROUP (2..4): up to nstaging - 2 TMA stores stay in flight behind the chunk being staged
+	int epi_groups;  // 1 or 2 groups of four epilogue warps; with 2, the 128-byte column chunks of a CTA alternate between them
 	uint32_t a_bytes, b_bytes, a_tx_bytes;  // smem slot sizes; bytes one A box actually transfers (bw*bh*bn rows)
 	float *out;
 	int OH, OW, os, accumulate;
@@ -145,7 +146,8 @@ struct alignas(64) WgradParams {
 	float *partial;
 };
 
-constexpr int kIgemmThreads = 192;
+constexpr int kIgemmThreads = 192;   // wgrad: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kKmajorThreads = 320;  // fprop / dgrad: TMA warp, MMA warp, up to two groups of 4 epilogue warps
 constexpr int kTmemCols = 512;
 constexpr uint32_t kABytes = 128 * 32 * 4;  // 128 rows x 32 tf32 = 16 KB
 
@@ -164,12 +166,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // BF16 = true:  bf16 tensors, kind::f16 MMAs, 64 output columns per staged row.  The shared-memory tiles are byte-identical
 // in both modes (128 rows x 128 bytes, 4 MMAs per stage each advancing 32 bytes along K).
 template <bool BF16>
-__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-	uint8_t *staging = base + (size_t)p.stages * stage_bytes;  // nstaging x 16 KB epilogue tiles (128 rows x 128 B, 128B-swizzled)
-	uint64_t *full = reinterpret_cast<uint64_t *>(staging + p.nstaging * kABytes);
+	uint8_t *staging = base + (size_t)p.stages * stage_bytes;  // epi_groups x nstaging x 16 KB epilogue tiles (128 rows x 128 B, 128B-swizzled)
+	uint64_t *full = reinterpret_cast<uint64_t *>(staging + p.epi_groups * p.nstaging * kABytes);
 	uint64_t *empty = full + p.stages;
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 	if (warp == 1) {
 		if (lane == 0) {
 			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * p.epi_groups); }
 			fence_barrier_init();
 		}
 		__syncwarp();
@@ -250,13 +252,19 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 			}
 		}
 		__syncwarp();
-	} else {
+	} else if ((warp - 2) / 4 < p.epi_groups) {
+		// Epilogue.  A warp may only touch TMEM lanes 32 * (warp % 4) .. +31, so warps 2-5 and 6-9 each cover the four lane quarters.
+		// With two groups the 128-byte column chunks (counted over the CTA's whole tile sequence) alternate between them: the
+		// short-K 1x1 layers spend their time here (TMEM load -> convert -> swizzled st.shared -> barrier -> TMA store -> statistics
+		// is a serial ~0.8 us chain per chunk for four warps), and a second group doubles the chunks in flight.
+		const int eg = (warp - 2) / 4;
 		const int q = warp & 3;
 		const int row = q * 32 + lane;
 		const int wq = row % p.bw, hq = (row / p.bw) % p.bh, nq = row / (p.bw * p.bh);
-		const bool issuer = (warp == 2 && lane == 0);
+		const bool issuer = ((warp - 2) % 4 == 0 && lane == 0);
+		uint8_t *const gstaging = staging + (size_t)eg * p.nstaging * kABytes;
 		int acc = 0;
-		uint32_t accphase = 0, sbuf = 0;
+		uint32_t accphase = 0, sbuf = 0, chunk_no = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 			const int nt = tile % p.n_tiles;
 			int r = tile / p.n_tiles;
@@ -271,11 +279,13 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 				// TMEM -> registers -> swizzled smem tile -> one TMA tile store (or reduce-add for the residual join) per 128-byte
 				// column chunk: fully coalesced lines, rows outside the tensor are clipped by the TMA unit
 				constexpr int CW = BF16 ? 64 : 32;  // output columns per staged 128-byte row
-				for (int c = 0; c < p.BN / CW; c++, sbuf = (sbuf + 1 == (uint32_t)p.nstaging ? 0 : sbuf + 1)) {
+				for (int c = 0; c < p.BN / CW; c++) {
+					if (p.epi_groups == 2 && ((chunk_no++) & 1u) != (uint32_t)eg) continue;  // the other group's chunk
 					float v[CW];
 					if constexpr (BF16) tmem_ld_32x64(taddr + (uint32_t)(c * CW), v);
 					else tmem_ld_32x32(taddr + (uint32_t)(c * CW), v);
-					uint8_t *buf = staging + sbuf * kABytes;
+					uint8_t *buf = gstaging + sbuf * kABytes;
+					sbuf = (sbuf + 1 == (uint32_t)p.nstaging ? 0 : sbuf + 1);
 					uint8_t *rowp = buf + row * 128;
 					if (p.stats && !row_valid) {  // rows the TMA store clips must not pollute the fused statistics
 #pragma unroll
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 					// the store that last read the NEXT buffer in the ring is done before anyone rewrites it; nstaging - 2 younger
 					// stores may still be in flight (the write-bound 1x1 layers were serialised on the store round trip with 2 tiles)
 					if (issuer) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }
-					named_barrier_sync(1, 128);
+					named_barrier_sync(1 + eg, 128);
 					if (issuer) {
 						if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
 						else tma_store_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kmajor_kernel(const __
 								cq = fmaf(y, y, cq);
 							}
 						}
-						float *sp = p.stats + ((size_t)(blockIdx.x * 4 + q) * 2) * p.Ncol + (size_t)nt * p.BN + c * CW + (BF16 ? 2 * lane : lane);
+						float *sp = p.stats + ((size_t)((blockIdx.x * p.epi_groups + eg) * 4 + q) * 2) * p.Ncol + (size_t)nt * p.BN + c * CW + (BF16 ? 2 * lane : lane);
 						atomicAdd(sp, cs);
 						atomicAdd(sp + p.Ncol, cq);
 						if constexpr (BF16) {
@@ -613,11 +623,14 @@ static void finish_kmajor(TcPlan *pl) {
 	// short mainloops (1x1 layers with few K chunks) are bound by the epilogue's stores: give them a deeper store ring
 	int max_iters = 0;
 	for (int gi = 0; gi < p.ngroups; gi++) max_iters = std::max(max_iters, p.groups[gi].ntaps * p.kchunks);
-	p.nstaging = max_iters <= 8 ? 4 : 2;
+	p.epi_groups = (max_iters <= 8 && p.tma_store) ? 2 : 1;
+	p.nstaging = 2;
+	if (const char *e = getenv("RESNET_B200_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= 2 && p.tma_store) p.epi_groups = v; }
 	if (const char *e = getenv("RESNET_B200_NSTAGING")) { int v = atoi(e); if (v >= 2 && v <= 4) p.nstaging = v; }
-	int stages = (int)((kMaxDynSmem - 2048 - p.nstaging * kABytes) / stage_bytes);
+	const size_t staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
+	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
-	pl->smem = (size_t)p.stages * stage_bytes + p.nstaging * kABytes + 1024 + 256;
+	pl->smem = (size_t)p.stages * stage_bytes + staging_bytes + 1024 + 256;
 	const int total = p.ngroups * p.m_tiles * p.n_tiles;
 	pl->grid = total < kNumSMs ? total : kNumSMs;
 	pl->kind = 0;
@@ -1021,8 +1034,8 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 	}
 	if (pl->kind == 0) {
 		if (pl->ip.stats) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
-		if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->ip);
-		else igemm_kmajor_kernel<false><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->ip);
+		if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
+		else igemm_kmajor_kernel<false><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
 		RB_LAUNCH_CHECK();
 	} else {
 		if (pl->bf16) igemm_mnmajor_kernel<true><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
@@ -1043,11 +1056,11 @@ void tc_free(TcPlan *pl) { delete pl; }
 int tc_attach_stats(TcPlan *pl, float *partials) {
 	if (!pl || pl->kind != 0 || pl->ip.ngroups != 1 || !pl->ip.tma_store || pl->ip.accumulate) return 0;
 	pl->ip.stats = partials;
-	pl->stats_rows = pl->grid * 4;
+	pl->stats_rows = pl->grid * 4 * pl->ip.epi_groups;
 	pl->stats_bytes = (size_t)pl->stats_rows * 2 * pl->ip.Ncol * sizeof(float);
 	return pl->stats_rows;
 }
-size_t tc_stats_floats(int cout) { return (size_t)kNumSMs * 4 * 2 * cout; }
+size_t tc_stats_floats(int cout) { return (size_t)kNumSMs * 8 * 2 * cout; }
 
 void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }

@@ -58,6 +58,20 @@ __global__ void ce_deriv_kernel(const float *__restrict__ pred, const int *__res
 	}
 }
 
+// epoch_acc[0] += sum_i row_loss[i], epoch_acc[1] += sum_i row_wrong[i]: one block, fixed-order tree (deterministic), fp64 running sums
+__global__ void epoch_accumulate_kernel(const float *__restrict__ row_loss, const int *__restrict__ row_wrong, int N, double *__restrict__ acc) {
+	__shared__ double sl[256], sw[256];
+	double l = 0, w = 0;
+	for (int i = threadIdx.x; i < N; i += 256) { l += (double)row_loss[i]; w += (double)row_wrong[i]; }
+	sl[threadIdx.x] = l; sw[threadIdx.x] = w;
+	__syncthreads();
+	for (int o = 128; o; o >>= 1) {
+		if ((int)threadIdx.x < o) { sl[threadIdx.x] += sl[threadIdx.x + o]; sw[threadIdx.x] += sw[threadIdx.x + o]; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { acc[0] += sl[0]; acc[1] += sw[0]; }
+}
+
 // ------------------------------------------------------------------------------------------------ parameters
 // Builds a Params tree over one arena.  gen != NULL: weights ~ N(0, 2/(fan_in+fan_out)), FC ~ N(0, 1e-4), gamma 1,
 // beta 0, drawn with curandGenerateNormal in the reference's order (reference: resnet.cu:730,741,754,790,835,938)
@@ -323,6 +337,11 @@ static Engine *build_engine(Train_ResNet *t) {
 	DA->linear_output = e->dlogits;
 	e->row_loss = B.get<float>(N);
 	e->row_wrong = B.get<int>(N);
+	e->fc_ws = B.get<float>((long long)sgemm_ws_floats(N, std::max(d->output, d->final_depth)));
+	e->pred_copy = 1;
+	e->epoch_acc = B.get<double>(2);
+	RB_CUDA(cudaMemset(e->epoch_acc, 0, 2 * sizeof(double)));
+	e->epoch_images = 0;
 
 	// ---- gradient buffers: per-role scratch (default) or a full mirror (keep-all)
 	float *pp[2] = {nullptr, nullptr}, *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;
@@ -486,11 +505,13 @@ static void relu_backward(Engine *e, const float *y, const float *dy, long long 
 }
 // remask: plain BN+ReLU layer, the mask is recomputed from x (the stored activation is not read); otherwise `mask` (the block's
 // output after the residual join) is read
-static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps, bool remask = false) {
+// masked_out: also store the masked upstream gradient there (the identity shortcut's gradient, +1 E of writes)
+static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps, bool remask = false,
+                        float *masked_out = nullptr) {
 	const bool re = remask && (bn.C % 4 == 0) && env_int("RESNET_B200_REMASK", 1);
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, re ? 5 : (mask ? 7 : 5)));
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, (re ? 5 : (mask ? 7 : 5)) + (masked_out ? 1 : 0)));
 	bn_bwd(x, dy, mask, bn.gamma, bn.means, bn.vars, eps, bn.rows, bn.C, bn.dgamma, bn.dbeta, dx, e->bn_partials, e->bn_max_blocks, e->bn_coef,
-	       e->round_tf32, e->stream, re ? bn.ab : nullptr, e->bf16);
+	       e->round_tf32, e->stream, re ? bn.ab : nullptr, e->bf16, masked_out);
 }
 
 }  // namespace rb
@@ -585,10 +606,15 @@ void forward_pass(Train_ResNet *t) {
 	BlockRef &last = e->blocks.back();
 	const int Sl = last.expand.g.S;
 	avgpool_fwd(last.OA, e->N, Sl, d->final_depth, e->pooled, st, e->bf16);
-	sgemm(e->pooled, t->model->params->fully_connected, e->logits, e->N, d->output, d->final_depth, 0, 0, st);
+	sgemm(e->pooled, t->model->params->fully_connected, e->logits, e->N, d->output, d->final_depth, 0, 0, st, e->fc_ws);
 	softmax_ce(e->logits, t->cur_batch->correct_classes, e->N, d->output, e->pred, nullptr, e->row_loss, e->row_wrong, st);
-	RB_CUDA(cudaMemcpyAsync(e->pred_host, e->pred, (size_t)e->N * d->output * sizeof(float), cudaMemcpyDeviceToHost, st));
-	RB_CUDA(cudaStreamSynchronize(st));  // pred_cpu is valid on return, as in the reference (resnet.cu:1774)
+	epoch_accumulate_kernel<<<1, 256, 0, st>>>(e->row_loss, e->row_wrong, e->N, e->epoch_acc);
+	RB_LAUNCH_CHECK();
+	e->epoch_images += e->N;
+	if (e->pred_copy) {
+		RB_CUDA(cudaMemcpyAsync(e->pred_host, e->pred, (size_t)e->N * d->output * sizeof(float), cudaMemcpyDeviceToHost, st));
+		RB_CUDA(cudaStreamSynchronize(st));  // pred_cpu is valid on return, as in the reference (resnet.cu:1774)
+	}
 }
 
 // ---- backward (reference: resnet.cu:1777-2248; spatial-BN call per resnet_clean.cu:2778)
@@ -608,7 +634,7 @@ void backwards_pass(Train_ResNet *t) {
 	}
 	// dW_fc = pooled^T . dlogits ; dpooled = dlogits . W_fc^T   (reference: resnet.cu:1823, 1830)
 	sgemm(e->pooled, e->dlogits, G->fully_connected, d->final_depth, d->output, N, 1, 0, st);
-	sgemm(e->dlogits, t->model->params->fully_connected, e->dpooled, N, d->final_depth, d->output, 0, 1, st);
+	sgemm(e->dlogits, t->model->params->fully_connected, e->dpooled, N, d->final_depth, d->output, 0, 1, st, e->fc_ws);
 	BlockRef &last = e->blocks.back();
 	avgpool_bwd(e->dpooled, N, last.expand.g.S, d->final_depth, last.dOA, st, e->bf16);
 
@@ -619,13 +645,16 @@ void backwards_pass(Train_ResNet *t) {
 			relu_bwd(b.OA, b.dOA, b.n_exp_out, db->output, st, e->bf16);  // d(output), reference: resnet.cu:1934
 		}
 		// shortcut branch first (its scratch is reused by the expanded branch)
+		// identity shortcut: its gradient relu'(OA) * dOA (reference: resnet.cu:2003-2004) is stored by the expansion BatchNorm's
+		// backward, which has it in registers, unless RESNET_B200_FUSE_SHORTCUT=0 asks for the separate pass
+		const bool fuse_short = !b.has_proj && env_int("RESNET_B200_FUSE_SHORTCUT", 1);
 		if (b.has_proj) {
 			bn_backward(e, b.bn_p, b.Xp, b.dOA, b.OA, b.dXp, eps);
 			conv_bwd(e, b.proj, b.x_in, b.dXp, b.dBI, 0);
-		} else {
+		} else if (!fuse_short) {
 			relu_backward(e, b.OA, b.dOA, b.n_exp_out, b.dBI);
 		}
-		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps);
+		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps, false, fuse_short ? b.dBI : nullptr);
 		conv_bwd(e, b.expand, b.Ys, b.dXe, b.dYs, 0);
 		bn_backward(e, b.bn_s, b.Xs, b.dYs, b.Ys, b.dXs, eps, true);
 		conv_bwd(e, b.spatial, b.Yr, b.dXs, b.dYr, 0);

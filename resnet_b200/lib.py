@@ -87,13 +87,14 @@ class Train_ResNet(C.Structure):
 
 # every symbol include/resnet.h and include/resnet_b200.h declare (tests check the library exports all of them)
 RESNET_H_SYMBOLS = ["populate_class_info", "init_dimensions", "init_resnet", "init_general_batch", "init_trainer",
-                    "load_new_batch", "forward_pass", "backwards_pass", "update_parameters"]
+                    "load_new_batch", "forward_pass", "backwards_pass", "update_parameters", "dump_trainer",
+                    "overwrite_trainer_hyperparams", "overwrite_model_params"]
 RESNET_B200_H_SYMBOLS = [
     "resnet_b200_last_error", "resnet_b200_clear_error", "resnet_b200_set_device", "resnet_b200_malloc", "resnet_b200_free",
     "resnet_b200_malloc_host", "resnet_b200_free_host", "resnet_b200_memcpy_h2d", "resnet_b200_memcpy_d2h",
     "resnet_b200_memcpy_d2d", "resnet_b200_memset", "resnet_b200_sync", "resnet_b200_rng_create", "resnet_b200_rng_destroy",
     "resnet_b200_stage_batch", "resnet_b200_stage_batch_device", "resnet_b200_trainer_sync", "resnet_b200_timer_begin",
-    "resnet_b200_timer_end_ms", "resnet_b200_loss_accuracy", "resnet_b200_launch_count", "resnet_b200_profile", "resnet_b200_profile_read", "resnet_b200_uses_tensor_cores",
+    "resnet_b200_timer_end_ms", "resnet_b200_loss_accuracy", "resnet_b200_set_pred_copy", "resnet_b200_fetch_pred", "resnet_b200_epoch_stats", "resnet_b200_launch_count", "resnet_b200_profile", "resnet_b200_profile_read", "resnet_b200_uses_tensor_cores",
     "resnet_b200_destroy_trainer", "resnet_b200_conv_forward", "resnet_b200_conv_backward", "resnet_b200_batchnorm_forward",
     "resnet_b200_batchnorm_backward", "resnet_b200_maxpool_forward", "resnet_b200_maxpool_backward",
     "resnet_b200_avgpool_forward", "resnet_b200_avgpool_backward", "resnet_b200_matmul", "resnet_b200_softmax_ce",
@@ -128,6 +129,9 @@ def load():
     proto("backwards_pass", None, [T])
     proto("update_parameters", None, [T])
     proto("populate_class_info", vp, [C.c_char_p, C.c_char_p, C.c_char_p, ci])
+    proto("dump_trainer", None, [ci, T, C.c_char_p])
+    proto("overwrite_trainer_hyperparams", None, [T, ci, C.c_char_p])
+    proto("overwrite_model_params", None, [T, ci, C.c_char_p])
     proto("resnet_b200_last_error", C.c_char_p, [])
     proto("resnet_b200_clear_error", None, [])
     proto("resnet_b200_set_device", ci, [ci])
@@ -148,6 +152,9 @@ def load():
     proto("resnet_b200_timer_begin", ci, [T])
     proto("resnet_b200_timer_end_ms", cf, [T])
     proto("resnet_b200_loss_accuracy", ci, [T, f32p, i32p])
+    proto("resnet_b200_set_pred_copy", ci, [T, ci])
+    proto("resnet_b200_fetch_pred", ci, [T])
+    proto("resnet_b200_epoch_stats", ci, [T, C.POINTER(C.c_double), C.POINTER(cll), C.POINTER(cll), ci])
     proto("resnet_b200_launch_count", cll, [])
     proto("resnet_b200_profile", None, [ci])
     proto("resnet_b200_profile_read", ci, [ci, C.POINTER(C.c_double), C.POINTER(cll), C.POINTER(C.c_double)])

@@ -4,7 +4,8 @@ weights, kind::f16 tcgen05 MMAs with fp32 accumulation, fp32 master weights, par
 The oracle is fed the SAME bf16-rounded inputs, so what is measured is the kernel: fp32 accumulation order plus ONE rounding
 of each stored output to bf16 (relative 2^-9 = 2e-3 of the element, i.e. <= 4e-3 of the tensor's max).  Bars:
 single operator <= 1e-2 of the tensor's max for bf16 outputs, 3e-3 for fp32 outputs (weight gradients, statistics);
-max-pool values and argmax indices bit-exact; whole step: argmax bit-exact, softmax max-abs <= 2e-2.
+max-pool values and argmax indices bit-exact; whole step: argmax equal wherever the fp32 top-1 margin exceeds 2e-2, softmax
+max-abs <= 5e-2 and mean-abs <= 1e-2 (SOFTMAX_MAX below).
 """
 import os
 
@@ -17,6 +18,10 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 BF_OUT, F32_OUT = 1e-2, 3e-3
+# whole-network softmax error of the bf16 step against the fp32 oracle.  SURVEY.md 8d proposes max-abs <= 2e-2 for BASELINE
+# config 3 "to be tightened or relaxed once measured": measured on the 64x64 / batch 8-16 test networks it is 0.6-2.5e-2 depending
+# on the weights (batch-statistics BatchNorm over a few hundred values amplifies the 2^-9 storage rounding), mean-abs ~2e-3.
+SOFTMAX_MAX, SOFTMAX_MEAN = 5e-2, 1e-2
 
 
 @pytest.fixture(scope="module")
@@ -259,7 +264,7 @@ def test_step_bf16_vs_fp32_oracle():
     assert np.isfinite(pred).all()
     dec = decisive(opred)
     assert (pred.argmax(1) == opred.argmax(1))[dec].all()
-    assert np.abs(pred - opred).max() <= 2e-2
+    assert np.abs(pred - opred).max() <= SOFTMAX_MAX and np.abs(pred - opred).mean() <= SOFTMAX_MEAN
     loss, nwrong = t.loss_accuracy()
     oloss, onwrong = net.loss_acc()
     assert abs(loss - oloss) < 2e-2 * abs(oloss) + 1e-3 and abs(nwrong - onwrong) <= int((~dec).sum())
@@ -300,7 +305,7 @@ def test_bf16_forward_only_batch_agreement():
     pred, pred32, opred = t.forward(), t32.forward(), net.forward(img, lab)
     dec = decisive(opred)
     assert (pred.argmax(1) == opred.argmax(1))[dec].all() and (pred.argmax(1) == opred.argmax(1)).mean() >= 0.9
-    assert np.abs(pred - opred).max() <= 2e-2
+    assert np.abs(pred - opred).max() <= SOFTMAX_MAX and np.abs(pred - opred).mean() <= SOFTMAX_MEAN
     assert (pred.argmax(1) == pred32.argmax(1))[dec].all()
     t.close()
     t32.close()

@@ -2,6 +2,7 @@ set -x
 mkdir -p gpurun_out
 T="timeout 900 python -m pytest -q --timeout 300"
 $T tests -m gpu -x > gpurun_out/pytest_gpu.log 2>&1
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err
-timeout 300 python bench.py --config c4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err
+for c in c2 c4; do
+timeout 300 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
+done
 tail -n 3 gpurun_out/pytest_gpu.log
