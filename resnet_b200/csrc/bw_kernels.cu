@@ -28,6 +28,10 @@ void set_error(const char *fmt, ...) {
 const char *last_error() { return g_has_err ? g_err : ""; }
 void clear_error() { g_has_err = false; g_err[0] = 0; }
 bool has_error() { return g_has_err; }
+bool trace_on() {
+	static const bool on = getenv("RESNET_B200_TRACE") != nullptr;
+	return on;
+}
 
 // ------------------------------------------------------------------------------------------- helpers
 constexpr int kThreads = 256;
@@ -59,6 +63,29 @@ template <typename T, int VEC> __device__ __forceinline__ void stv(T *p, long lo
 	else if constexpr (VEC == 4) reinterpret_cast<float4 *>(p)[i] = make_float4(v[0], v[1], v[2], v[3]);
 	else p[i] = v[0];
 }
+// raw 128-bit loads first, unpacking later: lets a kernel put U loads per stream in flight before any of them is consumed
+template <int VEC> struct RawOf { using type = uint4; };
+template <> struct RawOf<1> { using type = float; };
+template <typename T, int VEC> __device__ __forceinline__ typename RawOf<VEC>::type ldraw(const T *p, long long i) {
+	if constexpr (VEC == 1) return p[i];
+	else return reinterpret_cast<const uint4 *>(p)[i];
+}
+template <typename T, int VEC> __device__ __forceinline__ void unpack(const typename RawOf<VEC>::type &r, float (&v)[VEC]) {
+	if constexpr (VEC == 1) v[0] = r;
+	else if constexpr (sizeof(T) == 2) {
+		v[0] = bf16_lo(r.x); v[1] = bf16_hi(r.x); v[2] = bf16_lo(r.y); v[3] = bf16_hi(r.y);
+		v[4] = bf16_lo(r.z); v[5] = bf16_hi(r.z); v[6] = bf16_lo(r.w); v[7] = bf16_hi(r.w);
+	} else {
+		v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+	}
+}
+// loads per stream kept in flight per thread by the BatchNorm-backward kernels (the bf16 variants carry 8 channels of
+// per-channel state in registers, so they afford fewer)
+// and the resident blocks per SM they are compiled for: fp32 3 loads x 3 blocks, bf16 4 loads x 2 blocks (8 channels of per-channel
+// state per thread): 256 threads x U x 3 streams x 16 B x blocks = 110 / 98 KB in flight per SM, above the ~55 KB that 6.5 TB/s needs
+template <int VEC> struct BatchOf { static constexpr int U = (VEC == 8) ? 4 : 3; static constexpr int kBlocks = (VEC == 8) ? 2 : 3; };
+static int bn_bwd_blocks_per_sm(int bf16) { return bf16 ? 2 : 3; }
+
 // scalar element access (small kernels)
 template <typename T> __device__ __forceinline__ float ld1(const T *p, long long i) {
 	if constexpr (sizeof(T) == 2) return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t *>(p)[i] << 16);
@@ -106,7 +133,7 @@ constexpr int kMaxFlatBlocks = kNumSMs * 8;
 // ------------------------------------------------------------------------------------------- BN statistics
 // partials[blk][0][c] = sum x, partials[blk][1][c] = sum x^2 over the rows this block streamed.
 template <typename T, int VEC, bool FIXED, bool BWD>
-__global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+__global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
                                                             const T *__restrict__ mask, const float *__restrict__ means,
                                                             long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab) {
 	extern __shared__ float sm[];  // [2][C]
@@ -131,38 +158,59 @@ __global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_reduce_kernel
 			mb[j] = remask ? mab[Cc + col0 + j] : 0.f;
 		}
 	}
-#pragma unroll 4
-	for (long long i = g; i < nvec; i += TS) {
-		float a[VEC];
-		ldv<T, VEC>(x, i, a);
-		if constexpr (!BWD) {
-			if constexpr (FIXED) {
+	// batches of U vectors per stream: all loads of a batch are issued before the first is consumed (the compiler kept only one
+	// or two in flight when load and use sat in the same unrolled body, and the bf16 kernels ran at 4.5 of 6.5 TB/s)
+	constexpr int U = BatchOf<VEC>::U;
+	using raw_t = typename RawOf<VEC>::type;
+	const bool rdmask = BWD && !remask && mask != nullptr;
+	for (long long i0 = g; i0 < nvec; i0 += TS * U) {
+		raw_t rx[U], rd[U], rm[U];
 #pragma unroll
-				for (int j = 0; j < VEC; j++) { s[j] += a[j]; q[j] += a[j] * a[j]; }
-			} else {
-				const int c = (int)(i % V) * VEC;
-#pragma unroll
-				for (int j = 0; j < VEC; j++) { atomicAdd(&sm[c + j], a[j]); atomicAdd(&sm[Cc + c + j], a[j] * a[j]); }
+		for (int u = 0; u < U; u++) {
+			const long long i = i0 + (long long)u * TS;
+			if (i < nvec) {
+				rx[u] = ldraw<T, VEC>(x, i);
+				if constexpr (BWD) {
+					rd[u] = ldraw<T, VEC>(dy, i);
+					if (rdmask) rm[u] = ldraw<T, VEC>(mask, i);
+				}
 			}
-		} else {
-			float d[VEC];
-			ldv<T, VEC>(dy, i, d);
-			if (remask) {
+		}
 #pragma unroll
-				for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
-			} else if (mask) {
-				float mk[VEC];
-				ldv<T, VEC>(mask, i, mk);
+		for (int u = 0; u < U; u++) {
+			const long long i = i0 + (long long)u * TS;
+			if (i >= nvec) break;
+			float a[VEC];
+			unpack<T, VEC>(rx[u], a);
+			if constexpr (!BWD) {
+				if constexpr (FIXED) {
 #pragma unroll
-				for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
-			}
-			if constexpr (FIXED) {
+					for (int j = 0; j < VEC; j++) { s[j] += a[j]; q[j] += a[j] * a[j]; }
+				} else {
+					const int c = (int)(i % V) * VEC;
 #pragma unroll
-				for (int j = 0; j < VEC; j++) { s[j] += d[j]; q[j] += d[j] * (a[j] - mu[j]); }
+					for (int j = 0; j < VEC; j++) { atomicAdd(&sm[c + j], a[j]); atomicAdd(&sm[Cc + c + j], a[j] * a[j]); }
+				}
 			} else {
-				const int c = (int)(i % V) * VEC;
+				float d[VEC];
+				unpack<T, VEC>(rd[u], d);
+				if (remask) {
 #pragma unroll
-				for (int j = 0; j < VEC; j++) { atomicAdd(&sm[c + j], d[j]); atomicAdd(&sm[Cc + c + j], d[j] * (a[j] - means[c + j])); }
+					for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
+				} else if (rdmask) {
+					float mk[VEC];
+					unpack<T, VEC>(rm[u], mk);
+#pragma unroll
+					for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
+				}
+				if constexpr (FIXED) {
+#pragma unroll
+					for (int j = 0; j < VEC; j++) { s[j] += d[j]; q[j] += d[j] * (a[j] - mu[j]); }
+				} else {
+					const int c = (int)(i % V) * VEC;
+#pragma unroll
+					for (int j = 0; j < VEC; j++) { atomicAdd(&sm[c + j], d[j]); atomicAdd(&sm[Cc + c + j], d[j] * (a[j] - means[c + j])); }
+				}
 			}
 		}
 	}
@@ -255,7 +303,7 @@ static void launch_reduce(bool bwd, const void *x, const void *dy, const void *m
 	bool fixed;
 	// one whole wave: the bf16 variants keep 8 channels of coefficients per thread and fit 3 blocks per SM, the fp32 ones 4
 	// (and the fold cost grows with the number of partial blocks)
-	const int wave = kNumSMs * (bf16 ? 3 : 4);
+	const int wave = kNumSMs * bn_bwd_blocks_per_sm(bf16);
 	int cap = max_blocks < wave ? max_blocks : wave;
 	int grid = flat_grid(nvec, V, cap, &fixed);
 	if (VEC == 1) fixed = false;
@@ -273,6 +321,7 @@ static void launch_reduce(bool bwd, const void *x, const void *dy, const void *m
 #undef RB_RED2
 #undef RB_RED
 	RB_LAUNCH_CHECK();
+	RB_TRACE("bn_reduce_kernel", "%s rows=%lld C=%d grid=%d", bwd ? "bwd" : "fwd", rows, C, grid);
 	*grid_out = grid;
 }
 
@@ -351,6 +400,7 @@ void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, c
 	else RB_APPLY(float, 1, false);
 #undef RB_APPLY
 	RB_LAUNCH_CHECK();
+	RB_TRACE("bn_apply_kernel", "rows=%lld C=%d res=%d grid=%d", rows, C, res ? (ab2 ? 2 : 1) : 0, grid);
 }
 
 // ------------------------------------------------------------------------------------------- BN backward
@@ -367,57 +417,75 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
 	dbeta[c] = (float)s1;
 	dgamma[c] = (float)(s2 * (double)rstd);
 	const double c1 = (double)gamma[c] * (double)rstd;
+	const double c2 = -c1 * s1 * inv_n, c3 = -c1 * (double)rstd * (double)rstd * s2 * inv_n;
 	coef[c] = (float)c1;
-	coef[Cc + c] = (float)(-c1 * s1 * inv_n);
-	coef[2 * Cc + c] = (float)(-c1 * (double)rstd * (double)rstd * s2 * inv_n);
-	coef[3 * Cc + c] = means[c];
+	coef[Cc + c] = (float)(c2 - c3 * (double)means[c]);  // dx = c1 dy' + c3 x + (c2 - c3 mean)
+	coef[2 * Cc + c] = (float)c3;
 }
 
+// coef [3][C]: dx = c1 * dy' + c3 * x + k with k = c2 - c3 * mean folded by the finalize kernel
 template <typename T, int VEC, bool FIXED>
-__global__ void __launch_bounds__(kThreads, (VEC == 8 ? 3 : 4)) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
+__global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
                                                             const float *__restrict__ coef, long long nvec, int V, T *dx, int rnd,
                                                             const float *__restrict__ mab, T *__restrict__ masked_out) {
 	const int Cc = V * VEC;
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
-	float c1[VEC], c2[VEC], c3[VEC], mu[VEC], ma[VEC], mb[VEC];
+	float c1[VEC], ck[VEC], c3[VEC], ma[VEC], mb[VEC];
 	const bool remask = FIXED && mab != nullptr;
+	const bool rdmask = !remask && mask != nullptr;
 	if constexpr (FIXED) {
 		const int c0 = (int)(g % V) * VEC;
 #pragma unroll
 		for (int j = 0; j < VEC; j++) {
-			c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j];
+			c1[j] = coef[c0 + j]; ck[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j];
 			ma[j] = remask ? mab[c0 + j] : 0.f; mb[j] = remask ? mab[Cc + c0 + j] : 0.f;
 		}
 	}
-#pragma unroll 4
-	for (long long i = g; i < nvec; i += TS) {
-		if constexpr (!FIXED) {
-			const int c0 = (int)(i % V) * VEC;
+	constexpr int U = BatchOf<VEC>::U;
+	using raw_t = typename RawOf<VEC>::type;
+	for (long long i0 = g; i0 < nvec; i0 += TS * U) {
+		raw_t rx[U], rd[U], rm[U];
 #pragma unroll
-			for (int j = 0; j < VEC; j++) { c1[j] = coef[c0 + j]; c2[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; mu[j] = coef[3 * Cc + c0 + j]; }
+		for (int u = 0; u < U; u++) {  // all loads of the batch first (dx may alias dy: every element is read before its own store)
+			const long long i = i0 + (long long)u * TS;
+			if (i < nvec) {
+				rx[u] = ldraw<T, VEC>(x, i);
+				rd[u] = ldraw<T, VEC>(dy, i);
+				if (rdmask) rm[u] = ldraw<T, VEC>(mask, i);
+			}
 		}
-		float a[VEC], d[VEC];
-		ldv<T, VEC>(x, i, a);
-		ldv<T, VEC>(dy, i, d);
-		if (remask) {
 #pragma unroll
-			for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
-		} else if (mask) {
-			float mk[VEC];
-			ldv<T, VEC>(mask, i, mk);
+		for (int u = 0; u < U; u++) {
+			const long long i = i0 + (long long)u * TS;
+			if (i >= nvec) break;
+			if constexpr (!FIXED) {
+				const int c0 = (int)(i % V) * VEC;
 #pragma unroll
-			for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
+				for (int j = 0; j < VEC; j++) { c1[j] = coef[c0 + j]; ck[j] = coef[Cc + c0 + j]; c3[j] = coef[2 * Cc + c0 + j]; }
+			}
+			float a[VEC], d[VEC];
+			unpack<T, VEC>(rx[u], a);
+			unpack<T, VEC>(rd[u], d);
+			if (remask) {
+#pragma unroll
+				for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
+			} else if (rdmask) {
+				float mk[VEC];
+				unpack<T, VEC>(rm[u], mk);
+#pragma unroll
+				for (int j = 0; j < VEC; j++) d[j] = mk[j] > 0.f ? d[j] : 0.f;
+			}
+			// the ReLU-masked upstream gradient is also the identity shortcut's gradient (reference: resnet.cu:2003-2004 setVal + addVec):
+			// written here, while it is in registers, instead of by a separate 3-tensor relu_bwd pass
+			if (masked_out) stv<T, VEC>(masked_out, i, d);
+#pragma unroll
+			for (int j = 0; j < VEC; j++) {
+				float r = fmaf(c1[j], d[j], fmaf(c3[j], a[j], ck[j]));
+				d[j] = rnd ? round_tf32(r) : r;
+			}
+			stv<T, VEC>(dx, i, d);
 		}
-		// the ReLU-masked upstream gradient is also the identity shortcut's gradient (reference: resnet.cu:2003-2004 setVal + addVec):
-		// written here, while it is in registers, instead of by a separate 3-tensor relu_bwd pass
-		if (masked_out) stv<T, VEC>(masked_out, i, d);
-#pragma unroll
-		for (int j = 0; j < VEC; j++) {
-			float r = fmaf(c1[j], d[j], fmaf(c3[j], a[j] - mu[j], c2[j]));
-			d[j] = rnd ? round_tf32(r) : r;
-		}
-		stv<T, VEC>(dx, i, d);
 	}
 }
 
@@ -433,7 +501,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 	const int V = C / VEC;
 	const long long nvec = rows * V;
 	bool fixed;
-	int g2 = flat_grid(nvec, V, bf16 ? kNumSMs * 6 : kMaxFlatBlocks, &fixed);  // two whole waves (3 / 4 resident blocks per SM)
+	int g2 = flat_grid(nvec, V, kNumSMs * bn_bwd_blocks_per_sm(bf16) * 2, &fixed);  // two whole waves
 #define RB_DX(T_, VEC_, FIX_) \
 	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab, (T_ *)masked_out)
 	if (bf16) { if (fixed) RB_DX(bf16_t, 8, true); else RB_DX(bf16_t, 8, false); }
@@ -442,6 +510,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 	else RB_DX(float, 1, false);
 #undef RB_DX
 	RB_LAUNCH_CHECK();
+	RB_TRACE("bn_bwd_dx_kernel", "rows=%lld C=%d mask=%s%s grid=%d", rows, C, mab ? "recomputed" : (mask_src ? "read" : "none"), masked_out ? "+shortcut" : "", g2);
 }
 
 // ------------------------------------------------------------------------------------------- ReLU backward (identity shortcut)
@@ -688,19 +757,18 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float *__restrict__ A,
 	const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
 	const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
 	float acc[4][4] = {};
-	const int kbeg = blockIdx.z * kc;
-	K = min(K, kbeg + kc);
+	const int kbeg = blockIdx.z * kc, kend = min(K, kbeg + kc);  // K stays the leading dimension of the operands
 	Cm += (size_t)blockIdx.z * M * N;
-	for (int k0 = kbeg; k0 < K; k0 += 16) {
+	for (int k0 = kbeg; k0 < kend; k0 += 16) {
 		for (int e = threadIdx.x; e < 1024; e += 256) {
 			int kk, mm;
 			if (ta) { mm = e % 64; kk = e / 64; } else { kk = e % 16; mm = e / 16; }
 			const int gm = m0 + mm, gk = k0 + kk;
-			As[kk][mm] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f;
+			As[kk][mm] = (gm < M && gk < kend) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f;
 			int kb, nn;
 			if (tb) { kb = e % 16; nn = e / 16; } else { nn = e % 64; kb = e / 64; }
 			const int gn = n0 + nn, gkb = k0 + kb;
-			Bs[kb][nn] = (gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f;
+			Bs[kb][nn] = (gn < N && gkb < kend) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f;
 		}
 		__syncthreads();
 #pragma unroll
@@ -758,14 +826,26 @@ void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int t
 // (the element-wise version wrote Wd at a stride of taps*cout elements and ran the 0.4 GB of traffic at 0.8 TB/s).  Jobs whose
 // channel counts are not multiples of 32 (the 3-channel stem) take the element-wise path.
 constexpr int kPackT = 32, kPackMaxTaps = 9;
+__host__ __device__ inline bool pack_tiled(int cout, int cin, int taps) { return !(cout % kPackT) && !(cin % kPackT) && taps <= kPackMaxTaps; }
+// number of blocks a job needs: one per 32 x 32 x taps tile, or one per 4096 elements on the element-wise path
+int pack_job_blocks(int cout, int cin, int taps) {
+	if (pack_tiled(cout, cin, taps)) return (cout / kPackT) * (cin / kPackT);
+	return ceil_div((long long)cout * cin * taps, 4096);
+}
 template <typename T>
-__global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob *__restrict__ jobs, int rnd) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob *__restrict__ jobs, int njobs, int rnd) {
 	__shared__ float sm[kPackT][kPackT * kPackMaxTaps + 1];
-	const PackJob jb = jobs[blockIdx.y];
-	const int taps = jb.taps;
-	if ((jb.cout % kPackT) || (jb.cin % kPackT) || taps > kPackMaxTaps) {
-		const long long total = (long long)jb.cout * jb.cin * taps;
-		for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+	// jobs[].first_block is the prefix sum of pack_job_blocks: find this block's job
+	int lo = 0, hi = njobs - 1;
+	while (lo < hi) {
+		const int mid = (lo + hi + 1) >> 1;
+		if (jobs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+	}
+	const PackJob jb = jobs[lo];
+	const int tile = blockIdx.x - jb.first_block, taps = jb.taps;
+	if (!pack_tiled(jb.cout, jb.cin, taps)) {
+		const long long total = (long long)jb.cout * jb.cin * taps, end = min(total, (long long)(tile + 1) * 4096);
+		for (long long i = (long long)tile * 4096 + threadIdx.x; i < end; i += 256) {
 			const int tap = (int)(i % taps), ci = (int)((i / taps) % jb.cin), co = (int)(i / ((long long)taps * jb.cin));
 			float w = jb.src[i];
 			if (rnd && sizeof(T) == 4) w = round_tf32(w);
@@ -774,29 +854,26 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJob *__rest
 		}
 		return;
 	}
-	const int ci_tiles = jb.cin / kPackT, ntiles = (jb.cout / kPackT) * ci_tiles, run = kPackT * taps;
+	const int ci_tiles = jb.cin / kPackT, run = kPackT * taps;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		const int co0 = (tile / ci_tiles) * kPackT, ci0 = (tile % ci_tiles) * kPackT;
-		for (int e = threadIdx.x; e < kPackT * run; e += 256) {  // sm[co_l][ci_l * taps + tap]
-			const int co_l = e / run, r = e % run;
-			float w = jb.src[((long long)(co0 + co_l) * jb.cin + ci0) * taps + r];
-			if (rnd && sizeof(T) == 4) w = round_tf32(w);
-			sm[co_l][r] = w;
-		}
-		__syncthreads();
-		for (int p = warp; p < kPackT * taps; p += 8) {  // p = (row, tap); lane = the contiguous output index
-			const int row = p / taps, tap = p % taps;
-			st1<T>((T *)jb.wf, ((long long)(co0 + row) * taps + tap) * jb.cin + ci0 + lane, sm[row][lane * taps + tap]);
-			if (jb.wd) st1<T>((T *)jb.wd, ((long long)(ci0 + row) * taps + tap) * jb.cout + co0 + lane, sm[lane][row * taps + tap]);
-		}
-		__syncthreads();
+	const int co0 = (tile / ci_tiles) * kPackT, ci0 = (tile % ci_tiles) * kPackT;
+	for (int e = threadIdx.x; e < kPackT * run; e += 256) {  // sm[co_l][ci_l * taps + tap]
+		const int co_l = e / run, r = e % run;
+		float w = jb.src[((long long)(co0 + co_l) * jb.cin + ci0) * taps + r];
+		if (rnd && sizeof(T) == 4) w = round_tf32(w);
+		sm[co_l][r] = w;
+	}
+	__syncthreads();
+	for (int p = warp; p < kPackT * taps; p += 8) {  // p = (row, tap); lane = the contiguous output index
+		const int row = p / taps, tap = p % taps;
+		st1<T>((T *)jb.wf, ((long long)(co0 + row) * taps + tap) * jb.cin + ci0 + lane, sm[row][lane * taps + tap]);
+		if (jb.wd) st1<T>((T *)jb.wd, ((long long)(ci0 + row) * taps + tap) * jb.cout + co0 + lane, sm[lane][row * taps + tap]);
 	}
 }
-void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int rnd, cudaStream_t st, int bf16) {
-	int gx = ceil_div(max_elems, kPackT * kPackT * kPackMaxTaps); gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
-	if (bf16) pack_weights_kernel<bf16_t><<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
-	else pack_weights_kernel<float><<<dim3(gx, njobs), 256, 0, st>>>(jobs_dev, rnd);
+void pack_weights(const PackJob *jobs_dev, int njobs, int total_blocks, int rnd, cudaStream_t st, int bf16) {
+	if (njobs <= 0 || total_blocks <= 0) return;
+	if (bf16) pack_weights_kernel<bf16_t><<<total_blocks, 256, 0, st>>>(jobs_dev, njobs, rnd);
+	else pack_weights_kernel<float><<<total_blocks, 256, 0, st>>>(jobs_dev, njobs, rnd);
 	RB_LAUNCH_CHECK();
 }
 

@@ -22,10 +22,10 @@ int g_op_bf16 = 0;  // element type of the activation tensors the single-operato
 
 // packs [Cout][Cin][k][k] into Wf / Wd on the default stream
 void pack_one(const float *w, void *wf, void *wd, int cout, int cin, int taps, int rnd, Tmp &tmp) {
-	PackJob job{w, wf, wd, cout, cin, taps};
+	PackJob job{w, wf, wd, cout, cin, taps, 0};
 	PackJob *jd = tmp.get<PackJob>(1);
 	RB_CUDA(cudaMemcpy(jd, &job, sizeof(job), cudaMemcpyHostToDevice));
-	pack_weights(jd, 1, cout * cin * taps, rnd, 0, g_op_bf16);
+	pack_weights(jd, 1, pack_job_blocks(cout, cin, taps), rnd, 0, g_op_bf16);
 }
 bool simt_in_bf16(int impl) {
 	if (impl != 0 && g_op_bf16) { set_error("the SIMT fp32 convolution has no bf16 variant (impl must be 0 when the op dtype is bf16)"); return true; }

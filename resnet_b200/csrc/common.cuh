@@ -29,6 +29,18 @@ extern long long g_launches;  // kernels launched by this library (bench.py gpu_
 		RB_CUDA(cudaGetLastError()); \
 	} while (0)
 
+// RESNET_B200_TRACE=1: one "[k] <kernel> <label>" line on stderr per instrumented launch, in launch order; tools/ncu_summary.py
+// joins them (one queue per kernel name) with ncu's launch list to label every kernel with its layer / tensor shape
+bool trace_on();
+#define RB_TRACE(kernel, ...)                     \
+	do {                                          \
+		if (rb::trace_on()) {                     \
+			fprintf(stderr, "[k] %s ", kernel);   \
+			fprintf(stderr, __VA_ARGS__);         \
+			fprintf(stderr, "\n");                \
+		}                                         \
+	} while (0)
+
 constexpr int kNumSMs = 148;  // B200
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -84,8 +96,10 @@ void sgemm(const float *A, const float *B, float *Cm, int M, int N, int K, int t
 size_t sgemm_ws_floats(int M, int N);
 
 // weight re-layout [Cout][Cin][k][k] (fp32 master) -> Wf [Cout][k*k][Cin] and Wd [Cin][k*k][Cout], tf32-rounded fp32 or bf16
-struct PackJob { const float *src; void *wf; void *wd; int cout, cin, taps; };
-void pack_weights(const PackJob *jobs_dev, int njobs, int max_elems, int round_tf32, cudaStream_t st, int bf16 = 0);
+// first_block: prefix sum of pack_job_blocks() over the job list (one launch covers all jobs, one block per 32x32xtaps tile)
+struct PackJob { const float *src; void *wf; void *wd; int cout, cin, taps; int first_block; };
+int pack_job_blocks(int cout, int cin, int taps);
+void pack_weights(const PackJob *jobs_dev, int njobs, int total_blocks, int round_tf32, cudaStream_t st, int bf16 = 0);
 // dW [Cout][Cin][k][k] = sum_s partial[s][tap][Cout][Cin]  (deterministic split-K reduce + re-layout)
 void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps, float *dw, cudaStream_t st);
 void convert_f32_to_bf16(const float *s, long long n, void *d, cudaStream_t st);

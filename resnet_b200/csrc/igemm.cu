@@ -1018,8 +1018,7 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 
 void tc_run(TcPlan *pl, cudaStream_t st) {
 	if (!pl) { set_error("tc_run: null plan"); return; }
-	static const bool trace = getenv("RESNET_B200_TRACE") != nullptr;  // one line per launch, in launch order (tools/ncu_summary.py joins it with ncu's list)
-	if (trace) {
+	if (trace_on()) {  // one line per launch, in launch order (tools/ncu_summary.py joins it with ncu's list)
 		char buf[256];
 		tc_describe(pl, buf, sizeof(buf));
 		fprintf(stderr, "[tc_run] %s flops=%.6g\n", buf, pl->flops);

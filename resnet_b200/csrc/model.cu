@@ -195,7 +195,7 @@ static void setup_conv(Engine *e, Bump &B, ConvRef &c, int N, int S, int cin, in
 	if (e->bf16 && !c.use_tc && k != 7) set_error("bf16 mode: conv %dx%d/%d %d->%d has no tensor-core plan (channels must be multiples of 64)", k, k, stride, cin, cout);
 	c.fprop = c.dgrad = c.wgrad = nullptr;
 	c.stats_rows = 0;
-	jobs.push_back(PackJob{c.w, c.wf, c.wd, cout, cin, k * k});
+	jobs.push_back(PackJob{c.w, c.wf, c.wd, cout, cin, k * k, 0});
 	if (c.use_tc) {
 		size_t ws = tc_wgrad_workspace_bytes(c.g, e->bf16);
 		if (ws > e->wgrad_ws_bytes) e->wgrad_ws_bytes = ws;
@@ -396,8 +396,8 @@ static Engine *build_engine(Train_ResNet *t) {
 	RB_CUDA(cudaMallocHost(&e->bad_host, sizeof(int)));
 	*e->bad_host = 0;
 	e->n_pack_jobs = (int)jobs.size();
-	e->pack_max_elems = 0;
-	for (auto &j : jobs) e->pack_max_elems = std::max(e->pack_max_elems, j.cout * j.cin * j.taps);
+	e->pack_max_elems = 0;  // total blocks of the one pack launch
+	for (auto &j : jobs) { j.first_block = e->pack_max_elems; e->pack_max_elems += pack_job_blocks(j.cout, j.cin, j.taps); }
 	e->pack_jobs_dev = (PackJob *)B.get<char>((long long)(jobs.size() * sizeof(PackJob)));
 	RB_CUDA(cudaMemcpyAsync(e->pack_jobs_dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, e->stream));
 	RB_CUDA(cudaStreamSynchronize(e->stream));

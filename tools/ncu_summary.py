@@ -32,11 +32,25 @@ if a.last_step:
     a.skip = starts[-1] if starts else 0
 ids = sorted(launch)[a.skip:]
 trace = []
+ktrace = collections.defaultdict(list)   # "[k] <kernel> <label>" lines, one queue per kernel name
 if a.trace:
     for l in open(a.trace):
         m = re.match(r"\[tc_run\] (.*?) \| .* flops=([0-9.e+]+)", l)
         if m:
             trace.append((m.group(1), float(m.group(2))))
+        m = re.match(r"\[k\] (\S+) (.*)", l)
+        if m:
+            ktrace[m.group(1)].append(m.group(2).strip())
+kcount = collections.Counter()
+for i in sorted(launch):
+    for k in ktrace:
+        if k in launch[i]["kernel"]:
+            kcount[k] += 1
+kpos = {k: len(ktrace[k]) - kcount[k] for k in ktrace}   # align queue tails with the captured launches
+for i in sorted(launch)[:a.skip]:
+    for k in ktrace:
+        if k in launch[i]["kernel"]:
+            kpos[k] += 1
 n_tc_total = sum(1 for i in sorted(launch) if "igemm" in launch[i]["kernel"])
 ti = len(trace) - n_tc_total if trace else 0   # the trace covers the whole run; align its tail with the captured launches
 for i in sorted(launch)[:a.skip]:
@@ -59,7 +73,12 @@ for i in ids:
         if "igemm" in d["kernel"]:
             ti += 1
         agg_key = d["kernel"]
-    print("%-34s %-30s %9.1f %6.1f %8.1f %6.1f %6s" % (d["kernel"][:34], layer, us, tp, gbs, 100 * gbs / a.hbm_peak, tf))
+        for k in ktrace:
+            if k in d["kernel"]:
+                if 0 <= kpos[k] < len(ktrace[k]):
+                    layer = ktrace[k][kpos[k]]
+                kpos[k] += 1
+    print("%-34s %-46s %9.1f %6.1f %8.1f %6.1f %6s" % (d["kernel"][:34], layer[:46], us, tp, gbs, 100 * gbs / a.hbm_peak, tf))
     g = agg[agg_key]
     g[0] += 1; g[1] += us; g[2] += tp * us; g[3] += gbs * us
 tot = sum(v[1] for v in agg.values())
