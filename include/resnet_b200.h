@@ -55,6 +55,10 @@ int resnet_b200_convert(const void * dev_src, void * dev_dst, long long n, int t
 /* asynchronous copies on the trainer's stream: host (pinned) -> cur_batch->images / correct_classes */
 int resnet_b200_stage_batch(Train_ResNet * trainer, const float * images_host, const int * labels_host);
 int resnet_b200_stage_batch_device(Train_ResNet * trainer, const float * images_dev, const int * labels_dev);
+/* overlapped variant: prefetch_batch starts the host (pinned) -> device copy of the NEXT batch on a copy stream while the
+ * current step computes; commit_batch (before forward_pass) orders the compute stream after it and moves it into cur_batch */
+int resnet_b200_prefetch_batch(Train_ResNet * trainer, const float * images_host, const int * labels_host);
+int resnet_b200_commit_batch(Train_ResNet * trainer);
 int resnet_b200_trainer_sync(Train_ResNet * trainer);   /* waits for the trainer's stream */
 /* CUDA-event bracket on the trainer's stream: begin / end-and-return-milliseconds */
 int resnet_b200_timer_begin(Train_ResNet * trainer);

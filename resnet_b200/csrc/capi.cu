@@ -91,6 +91,39 @@ int resnet_b200_stage_batch_device(Train_ResNet *t, const float *images_dev, con
 	RB_CUDA(cudaMemcpyAsync(b->correct_classes, labels_dev, (size_t)t->batch_size * sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
 	return status();
 }
+// Overlapped input path: prefetch_batch enqueues the host -> device copy of the NEXT batch on a copy stream (into a staging
+// buffer) while the current step computes; commit_batch makes the compute stream wait for it and moves it into cur_batch with a
+// device-to-device copy (0.05 ms for 154 MB).  The host buffers must be pinned and stay valid until commit_batch returns.
+int resnet_b200_prefetch_batch(Train_ResNet *t, const float *images_host, const int *labels_host) {
+	Engine *e = engine_of(t);
+	if (!e) { set_error("prefetch_batch: unknown trainer"); return 1; }
+	Batch *b = t->cur_batch;
+	const size_t ib = (size_t)t->batch_size * b->image_size * sizeof(float), lb = (size_t)t->batch_size * sizeof(int);
+	if (!e->copy_stream) {
+		RB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+		RB_CUDA(cudaMalloc(&e->stage_img, ib));
+		RB_CUDA(cudaMalloc(&e->stage_lab, lb));
+		RB_CUDA(cudaEventCreateWithFlags(&e->ev_staged, cudaEventDisableTiming));
+		RB_CUDA(cudaEventCreateWithFlags(&e->ev_consumed, cudaEventDisableTiming));
+		RB_CUDA(cudaEventRecord(e->ev_consumed, e->stream));
+	}
+	RB_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_consumed, 0));  // the previous commit has read the staging buffers
+	RB_CUDA(cudaMemcpyAsync(e->stage_img, images_host, ib, cudaMemcpyHostToDevice, e->copy_stream));
+	RB_CUDA(cudaMemcpyAsync(e->stage_lab, labels_host, lb, cudaMemcpyHostToDevice, e->copy_stream));
+	RB_CUDA(cudaEventRecord(e->ev_staged, e->copy_stream));
+	return status();
+}
+int resnet_b200_commit_batch(Train_ResNet *t) {
+	Engine *e = engine_of(t);
+	if (!e || !e->copy_stream) { set_error("commit_batch: no batch was prefetched"); return 1; }
+	Batch *b = t->cur_batch;
+	const size_t ib = (size_t)t->batch_size * b->image_size * sizeof(float), lb = (size_t)t->batch_size * sizeof(int);
+	RB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_staged, 0));
+	RB_CUDA(cudaMemcpyAsync(b->images, e->stage_img, ib, cudaMemcpyDeviceToDevice, e->stream));
+	RB_CUDA(cudaMemcpyAsync(b->correct_classes, e->stage_lab, lb, cudaMemcpyDeviceToDevice, e->stream));
+	RB_CUDA(cudaEventRecord(e->ev_consumed, e->stream));
+	return status();
+}
 int resnet_b200_trainer_sync(Train_ResNet *t) {
 	Engine *e = engine_of(t);
 	if (!e) { set_error("trainer_sync: unknown trainer"); return 1; }
@@ -177,6 +210,12 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 	for (Params *P : {t->backprop_buffer->param_derivs, t->backprop_buffer->prev_means, t->backprop_buffer->prev_vars}) {
 		ParamStore *ps = param_store_of(P);
 		if (ps) cudaFree(ps->base);
+	}
+	if (e->copy_stream) {
+		cudaStreamSynchronize(e->copy_stream);
+		cudaFree(e->stage_img); cudaFree(e->stage_lab);
+		cudaEventDestroy(e->ev_staged); cudaEventDestroy(e->ev_consumed);
+		cudaStreamDestroy(e->copy_stream);
 	}
 	cudaFreeHost(e->pred_host);
 	cudaFreeHost(e->bad_host);

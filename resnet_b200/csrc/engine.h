@@ -88,6 +88,11 @@ struct Engine {
 	float *ones, *zeros, *tmp_ab, *tmp_mv;  // keep-all helpers
 	int *bad_dev, *bad_host;
 	std::vector<void *> allocs;
+	// double-buffered host -> device staging of the next batch (resnet_b200_prefetch_batch / commit_batch), created lazily
+	cudaStream_t copy_stream;
+	float *stage_img;
+	int *stage_lab;
+	cudaEvent_t ev_staged, ev_consumed;
 	// data-parallel hook (dp.cu)
 	void *dp;
 	// step timing

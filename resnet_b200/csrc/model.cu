@@ -227,6 +227,7 @@ static Engine *build_engine(Train_ResNet *t) {
 	e->round_tf32 = (e->conv_mode == 0 && !e->bf16) ? env_int("RESNET_B200_TF32_ROUND", 1) : 0;
 	e->keep_all = env_int("RESNET_B200_KEEP_ALL", 0);
 	e->dp = nullptr;
+	e->copy_stream = nullptr; e->stage_img = nullptr; e->stage_lab = nullptr;
 	e->wgrad_ws_bytes = 0;
 	// a BLOCKING stream: it synchronises with the legacy default stream, so a host driver's plain cudaMemcpy / kernels on
 	// stream 0 (how the reference's own code touches these buffers) stay ordered with our launches

@@ -147,3 +147,37 @@ def test_on_device_epoch_bookkeeping():
     assert t.epoch_stats() == (0.0, 0, 0)
     t.set_pred_copy(True)
     t.close()
+
+
+def test_prefetch_commit_matches_blocking_copy():
+    """resnet_b200_prefetch_batch / commit_batch (double-buffered H2D on a copy stream) deliver exactly the bytes a blocking copy
+    does, including when the next batch is prefetched while the current one is still being consumed."""
+    import ctypes as C
+    from resnet_b200 import api
+    cfg = G.MINI
+    shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
+    t = make(cfg, "tf32", False)
+    t.set_params(G.mini_weights(shapes))
+    L = api.L()
+    batches = [G.mini_batch(cfg, seed=30 + i) for i in range(3)]
+    want = []
+    for img, lab in batches:
+        t.set_batch(img, lab)
+        want.append(t.forward())
+    pinned = []
+    for img, lab in batches:
+        hi, hl = L.resnet_b200_malloc_host(img.nbytes), L.resnet_b200_malloc_host(lab.nbytes)
+        C.memmove(hi, img.ctypes.data, img.nbytes)
+        C.memmove(hl, lab.ctypes.data, lab.nbytes)
+        pinned.append((hi, hl))
+    L.resnet_b200_prefetch_batch(t.t, *pinned[0])
+    for i in range(3):
+        L.resnet_b200_commit_batch(t.t)
+        if i + 1 < 3:
+            L.resnet_b200_prefetch_batch(t.t, *pinned[i + 1])   # overlaps with this step's forward
+        np.testing.assert_array_equal(t.forward(), want[i])
+    api.check()
+    for hi, hl in pinned:
+        L.resnet_b200_free_host(hi)
+        L.resnet_b200_free_host(hl)
+    t.close()
