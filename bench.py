@@ -239,7 +239,16 @@ def main():
         if rank == 0:
             L.resnet_b200_dp_unique_id(idbuf)
         idbuf = (C.c_char * 128)(*broadcast_bytes(dist, bytes(idbuf), 128))
-        L.resnet_b200_dp_init(t.t, idbuf, rank, world, 0)
+        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION is set in the environment; stdout carries exactly one
+        # JSON line (the driver parses it), so the communicator is created with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            L.resnet_b200_dp_init(t.t, idbuf, rank, world, 0)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
         api.check()
 
     from oracle import oracle as O  # synthetic batch generator only (shared with the tests)
