@@ -135,7 +135,8 @@ constexpr int kMaxFlatBlocks = kNumSMs * 8;
 template <typename T, int VEC, bool FIXED, bool BWD>
 __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
                                                             const T *__restrict__ mask, const float *__restrict__ means,
-                                                            long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab) {
+                                                            long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab,
+                                                            const uint8_t *__restrict__ mask_bits) {
 	extern __shared__ float sm[];  // [2][C]
 	const int Cc = V * VEC;
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) sm[i] = 0.f;
@@ -162,9 +163,13 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_ker
 	// or two in flight when load and use sat in the same unrolled body, and the bf16 kernels ran at 4.5 of 6.5 TB/s)
 	constexpr int U = BatchOf<VEC>::U;
 	using raw_t = typename RawOf<VEC>::type;
-	const bool rdmask = BWD && !remask && mask != nullptr;
+	// ReLU mask of a residual join: one bit per element written by the forward's bn_apply (one byte per 128-bit vector), or, when
+	// that is not available (single-operator calls), the sign of the stored block output
+	const bool rdbits = BWD && !remask && mask_bits != nullptr;
+	const bool rdmask = BWD && !remask && !rdbits && mask != nullptr;
 	for (long long i0 = g; i0 < nvec; i0 += TS * U) {
 		raw_t rx[U], rd[U], rm[U];
+		uint32_t rb[U];
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			const long long i = i0 + (long long)u * TS;
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_ker
 				if constexpr (BWD) {
 					rd[u] = ldraw<T, VEC>(dy, i);
 					if (rdmask) rm[u] = ldraw<T, VEC>(mask, i);
+					if (rdbits) rb[u] = mask_bits[i];
 				}
 			}
 		}
@@ -197,6 +203,9 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_ker
 				if (remask) {
 #pragma unroll
 					for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
+				} else if (rdbits) {
+#pragma unroll
+					for (int j = 0; j < VEC; j++) d[j] = ((rb[u] >> j) & 1u) ? d[j] : 0.f;
 				} else if (rdmask) {
 					float mk[VEC];
 					unpack<T, VEC>(rm[u], mk);
@@ -294,7 +303,8 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partials, int nblk,
 }
 
 static void launch_reduce(bool bwd, const void *x, const void *dy, const void *mask, const float *means, long long rows, int C,
-                          float *partials, int max_blocks, int *grid_out, cudaStream_t st, const float *mab, int bf16) {
+                          float *partials, int max_blocks, int *grid_out, cudaStream_t st, const float *mab, int bf16,
+                          const uint8_t *mask_bits = nullptr) {
 	const int VEC = vec_of(C, bf16);
 	*grid_out = 1;
 	if (!VEC) { set_error("BatchNorm over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
@@ -309,7 +319,7 @@ static void launch_reduce(bool bwd, const void *x, const void *dy, const void *m
 	if (VEC == 1) fixed = false;
 	const size_t smem = 2 * (size_t)C * sizeof(float);
 #define RB_RED(T_, VEC_, FIX_, BWD_) \
-	bn_reduce_kernel<T_, VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask, means, nvec, V, partials, mab)
+	bn_reduce_kernel<T_, VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask, means, nvec, V, partials, mab, mask_bits)
 #define RB_RED2(T_, VEC_) \
 	do { \
 		if (fixed) { if (bwd) RB_RED(T_, VEC_, true, true); else RB_RED(T_, VEC_, true, false); } \
@@ -342,7 +352,7 @@ void bn_stats(const void *x, long long rows, int C, const float *gamma, const fl
 template <typename T, int VEC, bool FIXED>
 __global__ void __launch_bounds__(kThreads, 4) bn_apply_kernel(const T *__restrict__ x, const float *__restrict__ ab, long long nvec, int V,
                                                            int relu, const T *__restrict__ res, const float *__restrict__ ab2,
-                                                           T *__restrict__ y, int rnd) {
+                                                           T *__restrict__ y, int rnd, uint8_t *__restrict__ bits_out) {
 	const int Cc = V * VEC;
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -381,11 +391,17 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_kernel(const T *__restri
 			if (rnd) v[j] = round_tf32(v[j]);
 		}
 		stv<T, VEC>(y, i, v);
+		if (bits_out) {  // sign bits of the activated output: what the backward pass needs of it (1 byte per vector)
+			uint32_t m = 0;
+#pragma unroll
+			for (int j = 0; j < VEC; j++) m |= (v[j] > 0.f ? 1u : 0u) << j;
+			bits_out[i] = (uint8_t)m;
+		}
 	}
 }
 
 void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, const void *res, const float *ab2, void *y,
-              int rnd, cudaStream_t st, int bf16) {
+              int rnd, cudaStream_t st, int bf16, uint8_t *bits_out) {
 	const int VEC = vec_of(C, bf16);
 	if (!VEC) { set_error("BatchNorm over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
 	const int V = C / VEC;
@@ -393,7 +409,7 @@ void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, c
 	bool fixed;
 	int grid = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
 #define RB_APPLY(T_, VEC_, FIX_) \
-	bn_apply_kernel<T_, VEC_, FIX_><<<grid, kThreads, 0, st>>>((const T_ *)x, ab, nvec, V, relu, (const T_ *)res, ab2, (T_ *)y, bf16 ? 0 : rnd)
+	bn_apply_kernel<T_, VEC_, FIX_><<<grid, kThreads, 0, st>>>((const T_ *)x, ab, nvec, V, relu, (const T_ *)res, ab2, (T_ *)y, bf16 ? 0 : rnd, bits_out)
 	if (bf16) { if (fixed) RB_APPLY(bf16_t, 8, true); else RB_APPLY(bf16_t, 8, false); }
 	else if (VEC == 4 && fixed) RB_APPLY(float, 4, true);
 	else if (VEC == 4) RB_APPLY(float, 4, false);
@@ -427,13 +443,15 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
 template <typename T, int VEC, bool FIXED>
 __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
                                                             const float *__restrict__ coef, long long nvec, int V, T *dx, int rnd,
-                                                            const float *__restrict__ mab, T *__restrict__ masked_out) {
+                                                            const float *__restrict__ mab, T *__restrict__ masked_out,
+                                                            const uint8_t *__restrict__ mask_bits) {
 	const int Cc = V * VEC;
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	float c1[VEC], ck[VEC], c3[VEC], ma[VEC], mb[VEC];
 	const bool remask = FIXED && mab != nullptr;
-	const bool rdmask = !remask && mask != nullptr;
+	const bool rdbits = !remask && mask_bits != nullptr;
+	const bool rdmask = !remask && !rdbits && mask != nullptr;
 	if constexpr (FIXED) {
 		const int c0 = (int)(g % V) * VEC;
 #pragma unroll
@@ -446,6 +464,7 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_ker
 	using raw_t = typename RawOf<VEC>::type;
 	for (long long i0 = g; i0 < nvec; i0 += TS * U) {
 		raw_t rx[U], rd[U], rm[U];
+		uint32_t rb[U];
 #pragma unroll
 		for (int u = 0; u < U; u++) {  // all loads of the batch first (dx may alias dy: every element is read before its own store)
 			const long long i = i0 + (long long)u * TS;
@@ -453,6 +472,7 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_ker
 				rx[u] = ldraw<T, VEC>(x, i);
 				rd[u] = ldraw<T, VEC>(dy, i);
 				if (rdmask) rm[u] = ldraw<T, VEC>(mask, i);
+				if (rdbits) rb[u] = mask_bits[i];
 			}
 		}
 #pragma unroll
@@ -470,6 +490,9 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_ker
 			if (remask) {
 #pragma unroll
 				for (int j = 0; j < VEC; j++) d[j] = fmaf(a[j], ma[j], mb[j]) > 0.f ? d[j] : 0.f;
+			} else if (rdbits) {
+#pragma unroll
+				for (int j = 0; j < VEC; j++) d[j] = ((rb[u] >> j) & 1u) ? d[j] : 0.f;
 			} else if (rdmask) {
 				float mk[VEC];
 				unpack<T, VEC>(rm[u], mk);
@@ -491,9 +514,9 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_ker
 
 void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars, float eps,
             long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks, float *coef, int rnd,
-            cudaStream_t st, const float *mab, int bf16, void *masked_out) {
+            cudaStream_t st, const float *mab, int bf16, void *masked_out, const uint8_t *mask_bits) {
 	int grid;
-	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab, bf16);
+	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab, bf16, mask_bits);
 	bn_bwd_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();
 	const int VEC = vec_of(C, bf16);
@@ -503,14 +526,14 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 	bool fixed;
 	int g2 = flat_grid(nvec, V, kNumSMs * bn_bwd_blocks_per_sm(bf16) * 2, &fixed);  // two whole waves
 #define RB_DX(T_, VEC_, FIX_) \
-	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab, (T_ *)masked_out)
+	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab, (T_ *)masked_out, mask_bits)
 	if (bf16) { if (fixed) RB_DX(bf16_t, 8, true); else RB_DX(bf16_t, 8, false); }
 	else if (VEC == 4 && fixed) RB_DX(float, 4, true);
 	else if (VEC == 4) RB_DX(float, 4, false);
 	else RB_DX(float, 1, false);
 #undef RB_DX
 	RB_LAUNCH_CHECK();
-	RB_TRACE("bn_bwd_dx_kernel", "rows=%lld C=%d mask=%s%s grid=%d", rows, C, mab ? "recomputed" : (mask_src ? "read" : "none"), masked_out ? "+shortcut" : "", g2);
+	RB_TRACE("bn_bwd_dx_kernel", "rows=%lld C=%d mask=%s%s grid=%d", rows, C, mab ? "recomputed" : (mask_bits ? "bits" : (mask_src ? "read" : "none")), masked_out ? "+shortcut" : "", g2);
 }
 
 // ------------------------------------------------------------------------------------------- ReLU backward (identity shortcut)

@@ -68,14 +68,18 @@ void bn_stats(const void *x, long long rows, int C, const float *gamma, const fl
 void bn_finalize(const float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
                  float *means, float *vars, float *ab, cudaStream_t st);
 // y = act(x*a + b [+ residual]);  residual: res (identity) or res*a2 + b2 (projected, ab2 != NULL)
+// bits_out != NULL: also stores the sign bits of y, one byte per 128-bit vector (bit j = element j of the vector is > 0): the
+// 1-bit ReLU mask BatchNorm backward needs of a residual join's output (bn_bwd mask_bits)
 void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, const void *res, const float *ab2, void *y,
-              int round_tf32, cudaStream_t st, int bf16 = 0);
+              int round_tf32, cudaStream_t st, int bf16 = 0, uint8_t *bits_out = nullptr);
 // BatchNorm backward.  mask_src != NULL: dy is masked where mask_src <= 0 (ReLU).  Produces dgamma, dbeta and
 // dx (may alias dy).  coef scratch [4][C].
 // mask_ab != NULL ([2][C] folded scale/shift of the forward): the ReLU mask is recomputed as (x*a + b > 0) instead of read
 void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars,
             float eps, long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks,
-            float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr, int bf16 = 0, void *masked_out = nullptr);
+            float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr, int bf16 = 0, void *masked_out = nullptr,
+            const uint8_t *mask_bits = nullptr);
+// mask_bits != NULL: the ReLU mask comes from bn_apply's bits_out instead of the sign of mask_src
 // masked_out != NULL: the masked upstream gradient dy' (the identity shortcut's gradient) is also stored there
 void relu_bwd(const void *y, const void *dy, long long n, void *dx, cudaStream_t st, int bf16 = 0);
 void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16 = 0);

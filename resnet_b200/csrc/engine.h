@@ -46,6 +46,7 @@ struct BlockRef {
 	// gradient buffers for this block (may alias scratch)
 	float *dOA, *dBI, *dXe, *dXp, *dYs, *dXs, *dYr, *dXr;
 	long long n_in, n_red_in, n_red_out, n_exp_out;
+	uint8_t *oa_bits;  // sign bits of OA, one byte per 128-bit vector (NULL: backward reads OA itself)
 };
 
 struct Engine {

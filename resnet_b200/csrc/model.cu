@@ -321,6 +321,8 @@ static Engine *build_engine(Train_ResNet *t) {
 		} else { b.Xp = NULL; }
 		ab->output = ka ? B.act(b.n_exp_out) : NULL;
 		b.OA = ab->output_activated = B.act(b.n_exp_out);
+		// 1-bit ReLU mask of the block output for the two BatchNorm backwards under the residual join (they read OA only for its sign)
+		b.oa_bits = env_int("RESNET_B200_BITMASK", 1) ? B.get<uint8_t>(b.n_exp_out / (e->bf16 ? 8 : 4)) : nullptr;
 		b.bn_r = mk_bnref(B, cb->norm_depth_reduction, gcb->norm_depth_reduction, ab->norm_post_reduced, (long long)N * Sin * Sin);
 		b.bn_s = mk_bnref(B, cb->norm_spatial, gcb->norm_spatial, ab->norm_post_spatial, (long long)N * Sout * Sout);
 		b.bn_e = mk_bnref(B, cb->norm_expansion, gcb->norm_expansion, ab->norm_post_expanded, (long long)N * Sout * Sout);
@@ -496,9 +498,9 @@ static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps, int stat
 		bn_apply(x, e->tmp_ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized_temp, 0, e->stream, e->bf16);
 	}
 }
-static void bn_act(Engine *e, BnRef &bn, const float *x, int relu, const float *res, const float *ab2, float *y, int rnd) {
+static void bn_act(Engine *e, BnRef &bn, const float *x, int relu, const float *res, const float *ab2, float *y, int rnd, uint8_t *bits_out = nullptr) {
 	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, res ? 3 : 2));
-	bn_apply(x, bn.ab, bn.rows, bn.C, relu, res, ab2, y, rnd, e->stream, e->bf16);
+	bn_apply(x, bn.ab, bn.rows, bn.C, relu, res, ab2, y, rnd, e->stream, e->bf16, bits_out);
 }
 static void relu_backward(Engine *e, const float *y, const float *dy, long long n, float *dx) {
 	ProfScope ps(e->stream, PROF_BN_ELTWISE, 3.0 * e->esz * (double)n);
@@ -507,12 +509,13 @@ static void relu_backward(Engine *e, const float *y, const float *dy, long long 
 // remask: plain BN+ReLU layer, the mask is recomputed from x (the stored activation is not read); otherwise `mask` (the block's
 // output after the residual join) is read
 // masked_out: also store the masked upstream gradient there (the identity shortcut's gradient, +1 E of writes)
+// mask_bits: the 1-bit mask bn_apply left for this tensor (then `mask` itself is not read)
 static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, const float *mask, float *dx, float eps, bool remask = false,
-                        float *masked_out = nullptr) {
+                        float *masked_out = nullptr, const uint8_t *mask_bits = nullptr) {
 	const bool re = remask && (bn.C % 4 == 0) && env_int("RESNET_B200_REMASK", 1);
-	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, (re ? 5 : (mask ? 7 : 5)) + (masked_out ? 1 : 0)));
+	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, (re || mask_bits ? 5 : (mask ? 7 : 5)) + (masked_out ? 1 : 0)));
 	bn_bwd(x, dy, mask, bn.gamma, bn.means, bn.vars, eps, bn.rows, bn.C, bn.dgamma, bn.dbeta, dx, e->bn_partials, e->bn_max_blocks, e->bn_coef,
-	       e->round_tf32, e->stream, re ? bn.ab : nullptr, e->bf16, masked_out);
+	       e->round_tf32, e->stream, re ? bn.ab : nullptr, e->bf16, masked_out, mask_bits);
 }
 
 }  // namespace rb
@@ -602,7 +605,7 @@ void forward_pass(Train_ResNet *t) {
 			bn_apply(b.Xe, b.bn_e.ab, b.bn_e.rows, b.bn_e.C, 0, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, ab->output, 0, st, e->bf16);
 		}
 		// output_activated = relu(bn(expanded) + shortcut)   (reference: resnet.cu:1670-1723, four kernels there)
-		bn_act(e, b.bn_e, b.Xe, 1, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, b.OA, rnd);
+		bn_act(e, b.bn_e, b.Xe, 1, b.has_proj ? b.Xp : b.x_in, b.has_proj ? b.bn_p.ab : nullptr, b.OA, rnd, b.oa_bits);
 	}
 	BlockRef &last = e->blocks.back();
 	const int Sl = last.expand.g.S;
@@ -650,12 +653,12 @@ void backwards_pass(Train_ResNet *t) {
 		// backward, which has it in registers, unless RESNET_B200_FUSE_SHORTCUT=0 asks for the separate pass
 		const bool fuse_short = !b.has_proj && env_int("RESNET_B200_FUSE_SHORTCUT", 1);
 		if (b.has_proj) {
-			bn_backward(e, b.bn_p, b.Xp, b.dOA, b.OA, b.dXp, eps);
+			bn_backward(e, b.bn_p, b.Xp, b.dOA, b.OA, b.dXp, eps, false, nullptr, b.oa_bits);
 			conv_bwd(e, b.proj, b.x_in, b.dXp, b.dBI, 0);
 		} else if (!fuse_short) {
 			relu_backward(e, b.OA, b.dOA, b.n_exp_out, b.dBI);
 		}
-		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps, false, fuse_short ? b.dBI : nullptr);
+		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps, false, fuse_short ? b.dBI : nullptr, b.oa_bits);
 		conv_bwd(e, b.expand, b.Ys, b.dXe, b.dYs, 0);
 		bn_backward(e, b.bn_s, b.Xs, b.dYs, b.Ys, b.dXs, eps, true);
 		conv_bwd(e, b.spatial, b.Yr, b.dXs, b.dYr, 0);
