@@ -1,0 +1,46 @@
+"""CPU tests of the host-side helpers around the C ABI (no GPU, no compute calls)."""
+import numpy as np
+
+
+def test_bf16_helpers_match_torch_rounding():
+    """api.to_bf16 / from_bf16 are what the bf16 tests feed the oracle with: round-to-nearest-even, as cvt.rn.bf16.f32 and
+    torch.bfloat16 do, including ties, subnormal neighbours, large values and signed zeros."""
+    import torch
+    from resnet_b200 import api
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.standard_normal(200000).astype(np.float32) * 100, rng.standard_normal(1000).astype(np.float32) * 1e-30,
+                        np.array([0.0, -0.0, 1.0, 1.00390625, 1.01171875, 3.3895314e38, -65504.0, 1e-38], np.float32)])
+    ours = api.from_bf16(api.to_bf16(a))
+    ref = torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    np.testing.assert_array_equal(ours.view(np.uint32), ref.view(np.uint32))
+    np.testing.assert_array_equal(api.bf16_round(a.reshape(-1, 8)).reshape(-1), ours)
+    assert api.to_bf16(a).dtype == np.uint16
+
+
+def test_bench_configs_match_baseline_json():
+    """bench.py --config names the BASELINE.json configurations: batch sizes, dtypes and the FLOP model of BASELINE.md section 3."""
+    import json
+    import os
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfgs = json.load(open(os.path.join(root, "BASELINE.json")))["configs"]
+    assert "batch 256" in cfgs[1] and "TF32" in cfgs[1] and bench.CONFIGS["c2"]["batch"] == 256 and bench.CONFIGS["c2"]["dtype"] == "tf32"
+    assert "batch 1024" in cfgs[2] and "bf16" in cfgs[2] and bench.CONFIGS["c3"]["batch"] == 1024 and bench.CONFIGS["c3"]["fwd_only"]
+    assert "batch 256/GPU" in cfgs[3] and bench.CONFIGS["c4"]["dtype"] == "bf16" and not bench.CONFIGS["c4"]["fwd_only"]
+    assert "ResNet-152" in cfgs[4] and "batch 128/GPU" in cfgs[4] and bench.CONFIGS["c5"]["batch"] == 128 and len(bench.CONFIGS["c5"]["red"]) == 50
+    # FLOP model: 2 N Ho Wo Cout Cin k^2 per pass; training = 3 x forward - stem dgrad
+    from oracle import oracle as O
+    def conv_gflop(n_blocks, red):
+        f = 2 * 112 * 112 * 64 * 3 * 49
+        stem = f
+        for b in O.block_plan(224, n_blocks, red):
+            S, So = b["spatial"], b["spatial"] // b["stride"]
+            f += 2 * S * S * b["reduced"] * b["incoming"] + 2 * So * So * b["reduced"] * b["reduced"] * 9 + 2 * So * So * b["expanded"] * b["reduced"]
+            if b["proj"]:
+                f += 2 * So * So * b["expanded"] * b["incoming"] * b["proj_k"] ** 2
+        return f / 1e9, stem / 1e9
+    f50, stem = conv_gflop(16, bench.R50_REDUCTIONS)
+    assert abs(f50 + 0.0041 - bench.CONFIGS["c3"]["gflop"]) < 0.02
+    assert abs(3 * (f50 + 0.0041) - stem - bench.CONFIGS["c2"]["gflop"]) < 0.05
+    f152, _ = conv_gflop(50, bench.R152_REDUCTIONS)
+    assert abs(3 * (f152 + 0.0041) - stem - bench.CONFIGS["c5"]["gflop"]) < 0.1
