@@ -133,9 +133,10 @@ constexpr int kMaxFlatBlocks = kNumSMs * 8;
 // ------------------------------------------------------------------------------------------- BN statistics
 // partials[blk][0][c] = sum x, partials[blk][1][c] = sum x^2 over the rows this block streamed.
 template <typename T, int VEC, bool FIXED, bool BWD>
-__device__ __forceinline__ void bn_reduce_body(const T *__restrict__ x, const T *__restrict__ dy, const T *__restrict__ mask,
-                                               const float *__restrict__ means, long long nvec, int V, float *__restrict__ partials,
-                                               const float *__restrict__ mab, const uint8_t *__restrict__ mask_bits) {
+__global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+                                                            const T *__restrict__ mask, const float *__restrict__ means,
+                                                            long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab,
+                                                            const uint8_t *__restrict__ mask_bits) {
 	extern __shared__ float sm[];  // [2][C]
 	const int Cc = V * VEC;
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) sm[i] = 0.f;
@@ -251,13 +252,6 @@ __device__ __forceinline__ void bn_reduce_body(const T *__restrict__ x, const T 
 	__syncthreads();
 	float *out = partials + (size_t)blockIdx.x * 2 * Cc;
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) out[i] = sm[i];
-}
-template <typename T, int VEC, bool FIXED, bool BWD>
-__global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_kernel(const T *__restrict__ x, const T *__restrict__ dy,
-                                                            const T *__restrict__ mask, const float *__restrict__ means,
-                                                            long long nvec, int V, float *__restrict__ partials, const float *__restrict__ mab,
-                                                            const uint8_t *__restrict__ mask_bits) {
-	bn_reduce_body<T, VEC, FIXED, BWD>(x, dy, mask, means, nvec, V, partials, mab, mask_bits);
 }
 
 // Fold of the per-block partials in fp64.  8 channels x 128 slices per block: slice sy sums partial blocks sy, sy+128, ... (32-byte
@@ -447,9 +441,10 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
 
 // coef [3][C]: dx = c1 * dy' + c3 * x + k with k = c2 - c3 * mean folded by the finalize kernel
 template <typename T, int VEC, bool FIXED>
-__device__ __forceinline__ void bn_bwd_dx_body(const T *__restrict__ x, const T *dy, const T *__restrict__ mask, const float *coef, long long nvec,
-                                               int V, T *dx, int rnd, const float *__restrict__ mab, T *__restrict__ masked_out,
-                                               const uint8_t *__restrict__ mask_bits) {
+__global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
+                                                            const float *__restrict__ coef, long long nvec, int V, T *dx, int rnd,
+                                                            const float *__restrict__ mab, T *__restrict__ masked_out,
+                                                            const uint8_t *__restrict__ mask_bits) {
 	const int Cc = V * VEC;
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -517,124 +512,10 @@ __device__ __forceinline__ void bn_bwd_dx_body(const T *__restrict__ x, const T 
 	}
 }
 
-template <typename T, int VEC, bool FIXED>
-__global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_kernel(const T *__restrict__ x, const T *dy, const T *__restrict__ mask,
-                                                            const float *__restrict__ coef, long long nvec, int V, T *dx, int rnd,
-                                                            const float *__restrict__ mab, T *__restrict__ masked_out,
-                                                            const uint8_t *__restrict__ mask_bits) {
-	bn_bwd_dx_body<T, VEC, FIXED>(x, dy, mask, coef, nvec, V, dx, rnd, mab, masked_out, mask_bits);
-}
-
-// ---- the three phases of BatchNorm backward in ONE launch: reduce -> grid barrier -> fold (8 channels per block) -> grid barrier ->
-// dx.  Saves two launches per layer (159 per ResNet-50 step with the forward's folds, each ~4-8 us of drain + launch + ramp on
-// kernels that last 15-25 us for the 14x14 / 7x7 tensors) and lets the second read of x and dy hit L2 where the tensors fit.
-// The grid is at most one wave of resident blocks (checked with the occupancy API at first use), so every block is scheduled
-// without waiting for another block of this grid to exit and the software barrier cannot deadlock; kernels of other streams
-// (the NCCL allreduce) only delay it.  bar[0] = arrivals of the current barrier, bar[1] = generation.
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned nblocks) {
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		__threadfence();
-		const unsigned gen = *reinterpret_cast<volatile unsigned *>(bar + 1);
-		if (atomicAdd(bar, 1u) == nblocks - 1) {
-			atomicExch(bar, 0u);
-			__threadfence();
-			atomicAdd(bar + 1, 1u);
-		} else {
-			while (*reinterpret_cast<volatile unsigned *>(bar + 1) == gen) __nanosleep(64);
-		}
-		__threadfence();
-	}
-	__syncthreads();
-}
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_fused_kernel(
-    const T *__restrict__ x, const T *dy, const T *__restrict__ mask, const uint8_t *__restrict__ mask_bits, const float *__restrict__ mab,
-    const float *__restrict__ gamma, const float *__restrict__ means, const float *__restrict__ vars, float eps, double inv_n, long long nvec, int V,
-    float *partials, float *coef, float *__restrict__ dgamma, float *__restrict__ dbeta, T *dx, int rnd, T *__restrict__ masked_out, unsigned *bar) {
-	const int Cc = V * VEC;
-	bn_reduce_body<T, VEC, true, true>(x, dy, mask, means, nvec, V, partials, mab, mask_bits);
-	grid_barrier(bar, gridDim.x);
-	{
-		// fold: 8 channels x 32 slices per block (fixed shuffle tree + fixed-order sum of the 8 warps), fp64
-		__shared__ double fs[kThreads / 32][2][8];
-		const int cx = threadIdx.x & 7, sy = threadIdx.x >> 3, nblk = (int)gridDim.x;
-		for (int job = blockIdx.x; job * 8 < Cc; job += gridDim.x) {
-			const int c = job * 8 + cx;
-			double s1 = 0, s2 = 0;
-			if (c < Cc) {
-#pragma unroll 4
-				for (int b = sy; b < nblk; b += 32) {
-					s1 += (double)__ldcg(partials + (size_t)b * 2 * Cc + c);
-					s2 += (double)__ldcg(partials + (size_t)b * 2 * Cc + Cc + c);
-				}
-			}
-			s1 += __shfl_xor_sync(0xffffffffu, s1, 8);  s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-			s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-			if ((sy & 3) == 0) { fs[sy >> 2][0][cx] = s1; fs[sy >> 2][1][cx] = s2; }
-			__syncthreads();
-			if (sy == 0 && c < Cc) {
-				s1 = 0; s2 = 0;
-#pragma unroll
-				for (int j = 0; j < kThreads / 32; j++) { s1 += fs[j][0][cx]; s2 += fs[j][1][cx]; }
-				const float rstd = 1.0f / sqrtf(vars[c] + eps);
-				dbeta[c] = (float)s1;
-				dgamma[c] = (float)(s2 * (double)rstd);
-				const double c1 = (double)gamma[c] * (double)rstd;
-				const double c2 = -c1 * s1 * inv_n, c3 = -c1 * (double)rstd * (double)rstd * s2 * inv_n;
-				coef[c] = (float)c1;
-				coef[Cc + c] = (float)(c2 - c3 * (double)means[c]);
-				coef[2 * Cc + c] = (float)c3;
-			}
-			__syncthreads();
-		}
-	}
-	grid_barrier(bar, gridDim.x);
-	bn_bwd_dx_body<T, VEC, true>(x, dy, mask, coef, nvec, V, dx, rnd, mab, masked_out, mask_bits);
-}
-// resident blocks of the fused kernel on this device (0 = unavailable)
-template <typename T, int VEC> static int fused_wave(size_t smem) {
-	static size_t cached_smem[8];
-	static int cached_wave[8], ncached = 0;  // a handful of channel counts per network; one stream of launches per process
-	for (int i = 0; i < ncached; i++) if (cached_smem[i] == smem) return cached_wave[i];
-	int per_sm = 0, dev = 0, sms = 0;
-	if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-	if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_bwd_fused_kernel<T, VEC>, kThreads, smem) != cudaSuccess) return 0;
-	if (ncached < 8) { cached_smem[ncached] = smem; cached_wave[ncached] = per_sm * sms; ncached++; }
-	return per_sm * sms;
-}
-
 void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars, float eps,
             long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks, float *coef, int rnd,
-            cudaStream_t st, const float *mab, int bf16, void *masked_out, const uint8_t *mask_bits, unsigned *barrier) {
+            cudaStream_t st, const float *mab, int bf16, void *masked_out, const uint8_t *mask_bits) {
 	int grid;
-	if (barrier) {  // one launch for reduce + fold + dx when the fixed-column mapping applies
-		const int VEC = vec_of(C, bf16);
-		if (VEC == 4 || VEC == 8) {
-			const int V = C / VEC;
-			const long long nvec = rows * V;
-			bool fixed;
-			const int wave = kNumSMs * bn_bwd_blocks_per_sm(bf16);
-			int g = flat_grid(nvec, V, max_blocks < wave ? max_blocks : wave, &fixed);
-			const size_t smem = 2 * (size_t)C * sizeof(float);
-			const int resident = bf16 ? fused_wave<bf16_t, 8>(smem) : fused_wave<float, 4>(smem);
-			if (fixed && g <= resident) {
-				if (bf16)
-					bn_bwd_fused_kernel<bf16_t, 8><<<g, kThreads, smem, st>>>((const bf16_t *)x, (const bf16_t *)dy, (const bf16_t *)mask_src, mask_bits, mab, gamma, means,
-					                                                        vars, eps, 1.0 / (double)rows, nvec, V, partials, coef, dgamma, dbeta, (bf16_t *)dx, 0,
-					                                                        (bf16_t *)masked_out, barrier);
-				else
-					bn_bwd_fused_kernel<float, 4><<<g, kThreads, smem, st>>>((const float *)x, (const float *)dy, (const float *)mask_src, mask_bits, mab, gamma, means, vars,
-					                                                       eps, 1.0 / (double)rows, nvec, V, partials, coef, dgamma, dbeta, (float *)dx, rnd,
-					                                                       (float *)masked_out, barrier);
-				RB_LAUNCH_CHECK();
-				RB_TRACE("bn_bwd_fused_kernel", "rows=%lld C=%d mask=%s%s grid=%d", rows, C, mab ? "recomputed" : (mask_bits ? "bits" : (mask_src ? "read" : "none")),
-				         masked_out ? "+shortcut" : "", g);
-				return;
-			}
-		}
-	}
 	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab, bf16, mask_bits);
 	bn_bwd_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();

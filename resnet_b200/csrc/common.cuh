@@ -78,10 +78,8 @@ void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, c
 void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *gamma, const float *means, const float *vars,
             float eps, long long rows, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks,
             float *coef, int round_tf32, cudaStream_t st, const float *mask_ab = nullptr, int bf16 = 0, void *masked_out = nullptr,
-            const uint8_t *mask_bits = nullptr, unsigned *barrier = nullptr);
+            const uint8_t *mask_bits = nullptr);
 // mask_bits != NULL: the ReLU mask comes from bn_apply's bits_out instead of the sign of mask_src
-// barrier != NULL (2 zero-initialised unsigned in device memory, private to the stream): reduce + fold + dx run as ONE launch
-// with a software grid barrier when the geometry allows; otherwise three launches
 // masked_out != NULL: the masked upstream gradient dy' (the identity shortcut's gradient) is also stored there
 void relu_bwd(const void *y, const void *dy, long long n, void *dx, cudaStream_t st, int bf16 = 0);
 void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16 = 0);

@@ -81,7 +81,6 @@ struct Engine {
 	float *bn_partials;
 	int bn_max_blocks;
 	float *bn_coef;
-	unsigned *bn_barrier;  // grid-barrier words of the fused BatchNorm-backward kernel (NULL: three launches)
 	float *fc_ws;  // split-K planes of the fully-connected GEMMs
 	float *wgrad_ws;
 	size_t wgrad_ws_bytes;

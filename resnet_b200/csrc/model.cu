@@ -390,8 +390,6 @@ static Engine *build_engine(Train_ResNet *t) {
 	int maxC = d->final_depth > F ? d->final_depth : F;
 	e->bn_partials = B.get<float>((long long)e->bn_max_blocks * 2 * maxC);
 	e->bn_coef = B.get<float>(4LL * maxC);
-	e->bn_barrier = env_int("RESNET_B200_FUSED_BN_BWD", 1) ? B.get<unsigned>(2) : nullptr;
-	if (e->bn_barrier) RB_CUDA(cudaMemset(e->bn_barrier, 0, 2 * sizeof(unsigned)));
 	e->ones = B.get<float>(maxC); e->zeros = B.get<float>(maxC); e->tmp_ab = B.get<float>(2LL * maxC); e->tmp_mv = B.get<float>(2LL * maxC);
 	fill(e->ones, maxC, 1.f, e->stream);
 	fill(e->zeros, maxC, 0.f, e->stream);
@@ -517,7 +515,7 @@ static void bn_backward(Engine *e, BnRef &bn, const float *x, const float *dy, c
 	const bool re = remask && (bn.C % 4 == 0) && env_int("RESNET_B200_REMASK", 1);
 	ProfScope ps(e->stream, PROF_BN_ELTWISE, bn_bytes(e, bn, (re || mask_bits ? 5 : (mask ? 7 : 5)) + (masked_out ? 1 : 0)));
 	bn_bwd(x, dy, mask, bn.gamma, bn.means, bn.vars, eps, bn.rows, bn.C, bn.dgamma, bn.dbeta, dx, e->bn_partials, e->bn_max_blocks, e->bn_coef,
-	       e->round_tf32, e->stream, re ? bn.ab : nullptr, e->bf16, masked_out, mask_bits, e->bn_barrier);
+	       e->round_tf32, e->stream, re ? bn.ab : nullptr, e->bf16, masked_out, mask_bits);
 }
 
 }  // namespace rb
@@ -673,7 +671,7 @@ void backwards_pass(Train_ResNet *t) {
 	{
 		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e, e->bn0, 5));
 		bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
-		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bn0.ab, e->bf16, nullptr, nullptr, e->bn_barrier);
+		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bn0.ab, e->bf16);
 	}
 	stem_backward(e, t->cur_batch->images);
 	dp_allreduce_grads(e);
