@@ -349,10 +349,13 @@ void bn_stats(const void *x, long long rows, int C, const float *gamma, const fl
 }
 
 // ------------------------------------------------------------------------------------------- BN apply (+ residual + ReLU)
-template <typename T, int VEC, bool FIXED>
+// BITS: also store the sign bits of y (one byte per 128-bit vector, bit j = element j > 0): the 1-bit ReLU mask BatchNorm backward
+// needs of a residual join's output.  Four neighbouring lanes own four consecutive vectors, so the group leader stores one 32-bit
+// word (per-thread byte stores made the join 40 % slower); needs nvec % 32 == 0, which keeps `i < nvec` warp-uniform.
+template <typename T, int VEC, bool FIXED, bool BITS>
 __global__ void __launch_bounds__(kThreads, 4) bn_apply_kernel(const T *__restrict__ x, const float *__restrict__ ab, long long nvec, int V,
                                                            int relu, const T *__restrict__ res, const float *__restrict__ ab2,
-                                                           T *__restrict__ y, int rnd, uint8_t *__restrict__ bits_out) {
+                                                           T *__restrict__ y, int rnd, uint32_t *__restrict__ bits_out) {
 	const int Cc = V * VEC;
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -391,11 +394,12 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_kernel(const T *__restri
 			if (rnd) v[j] = round_tf32(v[j]);
 		}
 		stv<T, VEC>(y, i, v);
-		if (bits_out) {  // sign bits of the activated output: what the backward pass needs of it (1 byte per vector)
+		if constexpr (BITS) {
 			uint32_t m = 0;
 #pragma unroll
 			for (int j = 0; j < VEC; j++) m |= (v[j] > 0.f ? 1u : 0u) << j;
-			bits_out[i] = (uint8_t)m;
+			const uint32_t m1 = __shfl_down_sync(0xffffffffu, m, 1), m2 = __shfl_down_sync(0xffffffffu, m, 2), m3 = __shfl_down_sync(0xffffffffu, m, 3);
+			if ((threadIdx.x & 3) == 0) bits_out[i >> 2] = m | (m1 << 8) | (m2 << 16) | (m3 << 24);
 		}
 	}
 }
@@ -408,15 +412,17 @@ void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, c
 	const long long nvec = rows * V;
 	bool fixed;
 	int grid = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
-#define RB_APPLY(T_, VEC_, FIX_) \
-	bn_apply_kernel<T_, VEC_, FIX_><<<grid, kThreads, 0, st>>>((const T_ *)x, ab, nvec, V, relu, (const T_ *)res, ab2, (T_ *)y, bf16 ? 0 : rnd, bits_out)
-	if (bf16) { if (fixed) RB_APPLY(bf16_t, 8, true); else RB_APPLY(bf16_t, 8, false); }
-	else if (VEC == 4 && fixed) RB_APPLY(float, 4, true);
-	else if (VEC == 4) RB_APPLY(float, 4, false);
-	else RB_APPLY(float, 1, false);
+	if (bits_out && !(fixed && VEC >= 4 && nvec % 32 == 0)) { set_error("bn_apply: mask bits need the fixed-column vector path and nvec %% 32 == 0 (rows %lld, C %d)", rows, C); return; }
+#define RB_APPLY(T_, VEC_, FIX_, BITS_) \
+	bn_apply_kernel<T_, VEC_, FIX_, BITS_><<<grid, kThreads, 0, st>>>((const T_ *)x, ab, nvec, V, relu, (const T_ *)res, ab2, (T_ *)y, bf16 ? 0 : rnd, (uint32_t *)bits_out)
+	if (bf16) { if (bits_out) RB_APPLY(bf16_t, 8, true, true); else if (fixed) RB_APPLY(bf16_t, 8, true, false); else RB_APPLY(bf16_t, 8, false, false); }
+	else if (VEC == 4 && bits_out) RB_APPLY(float, 4, true, true);
+	else if (VEC == 4 && fixed) RB_APPLY(float, 4, true, false);
+	else if (VEC == 4) RB_APPLY(float, 4, false, false);
+	else RB_APPLY(float, 1, false, false);
 #undef RB_APPLY
 	RB_LAUNCH_CHECK();
-	RB_TRACE("bn_apply_kernel", "rows=%lld C=%d res=%d grid=%d", rows, C, res ? (ab2 ? 2 : 1) : 0, grid);
+	RB_TRACE("bn_apply_kernel", "rows=%lld C=%d res=%d%s grid=%d", rows, C, res ? (ab2 ? 2 : 1) : 0, bits_out ? " +bits" : "", grid);
 }
 
 // ------------------------------------------------------------------------------------------- BN backward

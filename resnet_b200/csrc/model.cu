@@ -322,7 +322,10 @@ static Engine *build_engine(Train_ResNet *t) {
 		ab->output = ka ? B.act(b.n_exp_out) : NULL;
 		b.OA = ab->output_activated = B.act(b.n_exp_out);
 		// 1-bit ReLU mask of the block output for the two BatchNorm backwards under the residual join (they read OA only for its sign)
-		b.oa_bits = env_int("RESNET_B200_BITMASK", 1) ? B.get<uint8_t>(b.n_exp_out / (e->bf16 ? 8 : 4)) : nullptr;
+		// (needs whole warps of vectors per row group: expanded_depth / vector width a multiple of 32, true for every ResNet width)
+		const int vecw = e->bf16 ? 8 : 4;
+		const bool bits_ok = cb->expanded_depth % (32 * vecw) == 0 && (256 % (cb->expanded_depth / vecw) == 0 || (cb->expanded_depth / vecw) % 256 == 0);
+		b.oa_bits = (bits_ok && env_int("RESNET_B200_BITMASK", 1)) ? B.get<uint8_t>(b.n_exp_out / vecw) : nullptr;
 		b.bn_r = mk_bnref(B, cb->norm_depth_reduction, gcb->norm_depth_reduction, ab->norm_post_reduced, (long long)N * Sin * Sin);
 		b.bn_s = mk_bnref(B, cb->norm_spatial, gcb->norm_spatial, ab->norm_post_spatial, (long long)N * Sout * Sout);
 		b.bn_e = mk_bnref(B, cb->norm_expansion, gcb->norm_expansion, ab->norm_post_expanded, (long long)N * Sout * Sout);

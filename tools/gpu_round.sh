@@ -3,5 +3,5 @@ mkdir -p gpurun_out
 T="timeout 900 python -m pytest -q --timeout 300"
 $T tests -m gpu -x > gpurun_out/pytest_gpu.log 2>&1
 for c in c2 c4; do
-timeout 300 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
+timeout 300 python bench.py --config $c --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
 done

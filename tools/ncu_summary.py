@@ -15,6 +15,7 @@ ap.add_argument("csv")
 ap.add_argument("--trace")
 ap.add_argument("--skip", type=int, default=0, help="ignore the first N launches (warm-up step)")
 ap.add_argument("--last-step", action="store_true", help="start at the last pack_weights launch (the first kernel of forward_pass)")
+ap.add_argument("--json", help="also write per-family DRAM traffic per launch (bench.py's roofline.traffic) to this file")
 ap.add_argument("--hbm-peak", type=float, default=6539.2)
 a = ap.parse_args()
 
@@ -85,3 +86,21 @@ tot = sum(v[1] for v in agg.values())
 print("\nper kernel (time-weighted averages), total %.3f ms over %d launches" % (tot / 1e3, len(ids)))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%-44s n=%4d total=%8.3f ms %5.1f%%  avg=%8.1f us  tensor %5.1f%%  DRAM %7.1f GB/s" % (k[:44], v[0], v[1] / 1e3, 100 * v[1] / tot, v[1] / v[0], v[2] / v[1], v[3] / v[1]))
+
+if a.json:
+    import json
+    fam = {"kmajor": ["igemm_kmajor_kernel"], "wgrad": ["igemm_mnmajor_kernel", "wgrad_reduce"],
+           "bn_eltwise": ["bn_apply_kernel", "bn_reduce_kernel", "bn_bwd_dx_kernel", "relu_bwd_kernel", "bn_finalize_kernel", "bn_bwd_finalize_kernel"]}
+    out = {"source": a.csv, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, one step under ncu (cold caches, serialised)"}
+    for f, pats in fam.items():
+        n, by, us = 0, 0.0, 0.0
+        for i in ids:
+            d = launch[i]
+            if any(p in d["kernel"] for p in pats):
+                # the family's launch count follows bench.py's ProfScope granularity: reduces / finalizes ride inside their parent's scope
+                main = any(p in d["kernel"] for p in pats[:1]) if f != "bn_eltwise" else ("finalize" not in d["kernel"] and not ("bn_reduce" in d["kernel"]))
+                n += 1 if main else 0
+                by += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+                us += d.get("gpu__time_duration.sum", 0.0) / 1e3
+        out[f] = {"launches": n, "dram_bytes_per_launch": by / max(n, 1), "dram_bytes_per_step": by, "kernel_us_per_step": us}
+    json.dump(out, open(a.json, "w"), indent=1)
