@@ -368,38 +368,55 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_kernel(const T *__restri
 			a2[j] = ab2 ? ab2[c0 + j] : 1.f; b2[j] = ab2 ? ab2[Cc + c0 + j] : 0.f;
 		}
 	}
-#pragma unroll(VEC == 8 ? 2 : 4)
-	for (long long i = g; i < nvec; i += TS) {
-		if constexpr (!FIXED) {
-			const int c0 = (int)(i % V) * VEC;
+	// batches of U vectors per stream, all loads first (the warp shuffles of the BITS variant otherwise fence every iteration's
+	// loads behind the previous iteration's stores: one load pair in flight instead of U)
+	constexpr int U = (VEC == 8) ? 2 : 4;
+	using raw_t = typename RawOf<VEC>::type;
+	for (long long i0 = g; i0 < nvec; i0 += TS * U) {
+		raw_t rx[U], rr[U];
 #pragma unroll
-			for (int j = 0; j < VEC; j++) {
-				a[j] = ab[c0 + j]; b[j] = ab[Cc + c0 + j];
-				a2[j] = ab2 ? ab2[c0 + j] : 1.f; b2[j] = ab2 ? ab2[Cc + c0 + j] : 0.f;
+		for (int u = 0; u < U; u++) {
+			const long long i = i0 + (long long)u * TS;
+			if (i < nvec) {
+				rx[u] = ldraw<T, VEC>(x, i);
+				if (res) rr[u] = ldraw<T, VEC>(res, i);
 			}
 		}
-		float v[VEC];
-		ldv<T, VEC>(x, i, v);
 #pragma unroll
-		for (int j = 0; j < VEC; j++) v[j] = fmaf(v[j], a[j], b[j]);
-		if (res) {
-			float r[VEC];
-			ldv<T, VEC>(res, i, r);
+		for (int u = 0; u < U; u++) {
+			const long long i = i0 + (long long)u * TS;
+			if (i >= nvec) break;  // warp-uniform in the BITS variant (nvec % 32 == 0)
+			if constexpr (!FIXED) {
+				const int c0 = (int)(i % V) * VEC;
 #pragma unroll
-			for (int j = 0; j < VEC; j++) v[j] += fmaf(r[j], a2[j], b2[j]);
-		}
+				for (int j = 0; j < VEC; j++) {
+					a[j] = ab[c0 + j]; b[j] = ab[Cc + c0 + j];
+					a2[j] = ab2 ? ab2[c0 + j] : 1.f; b2[j] = ab2 ? ab2[Cc + c0 + j] : 0.f;
+				}
+			}
+			float v[VEC];
+			unpack<T, VEC>(rx[u], v);
 #pragma unroll
-		for (int j = 0; j < VEC; j++) {
-			if (relu) v[j] = fmaxf(v[j], 0.f);
-			if (rnd) v[j] = round_tf32(v[j]);
-		}
-		stv<T, VEC>(y, i, v);
-		if constexpr (BITS) {
-			uint32_t m = 0;
+			for (int j = 0; j < VEC; j++) v[j] = fmaf(v[j], a[j], b[j]);
+			if (res) {
+				float r[VEC];
+				unpack<T, VEC>(rr[u], r);
 #pragma unroll
-			for (int j = 0; j < VEC; j++) m |= (v[j] > 0.f ? 1u : 0u) << j;
-			const uint32_t m1 = __shfl_down_sync(0xffffffffu, m, 1), m2 = __shfl_down_sync(0xffffffffu, m, 2), m3 = __shfl_down_sync(0xffffffffu, m, 3);
-			if ((threadIdx.x & 3) == 0) bits_out[i >> 2] = m | (m1 << 8) | (m2 << 16) | (m3 << 24);
+				for (int j = 0; j < VEC; j++) v[j] += fmaf(r[j], a2[j], b2[j]);
+			}
+#pragma unroll
+			for (int j = 0; j < VEC; j++) {
+				if (relu) v[j] = fmaxf(v[j], 0.f);
+				if (rnd) v[j] = round_tf32(v[j]);
+			}
+			stv<T, VEC>(y, i, v);
+			if constexpr (BITS) {
+				uint32_t m = 0;
+#pragma unroll
+				for (int j = 0; j < VEC; j++) m |= (v[j] > 0.f ? 1u : 0u) << j;
+				const uint32_t m1 = __shfl_down_sync(0xffffffffu, m, 1), m2 = __shfl_down_sync(0xffffffffu, m, 2), m3 = __shfl_down_sync(0xffffffffu, m, 3);
+				if ((threadIdx.x & 3) == 0) bits_out[i >> 2] = m | (m1 << 8) | (m2 << 16) | (m3 << 24);
+			}
 		}
 	}
 }
