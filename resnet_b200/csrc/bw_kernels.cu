@@ -621,12 +621,110 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const T *__restri
 		} else inds[i] = mi[0];
 	}
 }
+// k = 3, stride = 2 (the only pooling the network uses, reference: resnet.cu:3248): the nine window loads are issued before the
+// first comparison (the generic loop above serialises load -> compare -> branch nine times: 3.1 of 6.5 TB/s), comparisons keep the
+// reference's row-major order so ties resolve identically.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads, 3) maxpool3s2_fwd_kernel(const T *__restrict__ x, int N, int S, int C, int *__restrict__ inds, T *__restrict__ out) {
+	using raw_t = typename RawOf<VEC>::type;
+	const int So = S / 2, V = C / VEC;
+	const long long total = (long long)N * So * So * V;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+		const int cv = (int)(i % V);
+		long long p = i / V;
+		const int ow = (int)(p % So); p /= So;
+		const int oh = (int)(p % So);
+		const int n = (int)(p / So);
+		raw_t rv[9];
+		bool ok[9];
+		int base[9];
+#pragma unroll
+		for (int t = 0; t < 9; t++) {
+			const int h = 2 * oh + t / 3 - 1, w = 2 * ow + t % 3 - 1;
+			ok[t] = h >= 0 && h < S && w >= 0 && w < S;
+			base[t] = (int)((((long long)n * S + h) * S + w) * C + (long long)cv * VEC);  // flat input index (int, as the reference's max_inds)
+			if (ok[t]) rv[t] = ldraw<T, VEC>(x, base[t] / VEC);
+		}
+		float mv[VEC]; int mi[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++) { mv[j] = -1024.f; mi[j] = -1024; }
+#pragma unroll
+		for (int t = 0; t < 9; t++) {
+			if (!ok[t]) continue;
+			float v[VEC];
+			unpack<T, VEC>(rv[t], v);
+#pragma unroll
+			for (int j = 0; j < VEC; j++) if (v[j] > mv[j]) { mv[j] = v[j]; mi[j] = base[t] + j; }
+		}
+		stv<T, VEC>(out, i, mv);
+#pragma unroll
+		for (int h = 0; h < VEC / 4; h++) reinterpret_cast<int4 *>(inds)[i * (VEC / 4) + h] = make_int4(mi[4 * h], mi[4 * h + 1], mi[4 * h + 2], mi[4 * h + 3]);
+	}
+}
+// backward twin: an input pixel belongs to at most 2 x 2 windows; their argmax vectors and gradients are loaded together, then summed
+// in ascending (oh, ow) order like the generic kernel
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads, 3) maxpool3s2_bwd_kernel(const int *__restrict__ inds, const T *__restrict__ dout, int N, int S, int C, T *__restrict__ din) {
+	using raw_t = typename RawOf<VEC>::type;
+	const int So = S / 2, V = C / VEC;
+	const long long total = (long long)N * S * S * V;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+		const int cv = (int)(i % V);
+		long long p = i / V;
+		const int w = (int)(p % S); p /= S;
+		const int h = (int)(p % S);
+		const int n = (int)(p / S);
+		// windows oh with 2*oh - 1 <= h <= 2*oh + 1: oh = h/2 for even h; (h-1)/2 and (h+1)/2 for odd h
+		const int oh0 = h >> 1, ow0 = w >> 1;
+		const bool two_h = (h & 1) && oh0 + 1 < So, two_w = (w & 1) && ow0 + 1 < So;
+		raw_t rd[4];
+		int4 ri[4][VEC / 4];
+		bool ok[4];
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			const int oh = oh0 + (t >> 1), ow = ow0 + (t & 1);
+			ok[t] = ((t >> 1) == 0 || two_h) && ((t & 1) == 0 || two_w);
+			if (ok[t]) {
+				const long long o = ((((long long)n * So + oh) * So + ow) * C) / VEC + cv;
+				rd[t] = ldraw<T, VEC>(dout, o);
+#pragma unroll
+				for (int q = 0; q < VEC / 4; q++) ri[t][q] = reinterpret_cast<const int4 *>(inds)[o * (VEC / 4) + q];
+			}
+		}
+		const int me = (int)(i * VEC);
+		float acc[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++) acc[j] = 0.f;
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			if (!ok[t]) continue;
+			float d[VEC];
+			unpack<T, VEC>(rd[t], d);
+#pragma unroll
+			for (int q = 0; q < VEC / 4; q++) {
+				if (ri[t][q].x == me + 4 * q) acc[4 * q] += d[4 * q];
+				if (ri[t][q].y == me + 4 * q + 1) acc[4 * q + 1] += d[4 * q + 1];
+				if (ri[t][q].z == me + 4 * q + 2) acc[4 * q + 2] += d[4 * q + 2];
+				if (ri[t][q].w == me + 4 * q + 3) acc[4 * q + 3] += d[4 * q + 3];
+			}
+		}
+		stv<T, VEC>(din, i, acc);
+	}
+}
+
 void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16) {
 	const int So = S / stride;
 	const int VEC = vec_of(C, bf16);
 	if (!VEC) { set_error("max pool over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
 	long long total = (long long)N * So * So * (C / VEC);
 	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
+	if (k == 3 && stride == 2 && S % 2 == 0 && VEC >= 4 && (long long)N * S * S * C < (1LL << 31)) {
+		grid = grid > kNumSMs * 3 * 4 ? kNumSMs * 3 * 4 : grid;
+		if (bf16) maxpool3s2_fwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>((const bf16_t *)x, N, S, C, max_inds, (bf16_t *)out);
+		else maxpool3s2_fwd_kernel<float, 4><<<grid, kThreads, 0, st>>>((const float *)x, N, S, C, max_inds, (float *)out);
+		RB_LAUNCH_CHECK();
+		return;
+	}
 	if (bf16) maxpool_fwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>((const bf16_t *)x, N, S, C, k, stride, max_inds, (bf16_t *)out);
 	else if (VEC == 4) maxpool_fwd_kernel<float, 4><<<grid, kThreads, 0, st>>>((const float *)x, N, S, C, k, stride, max_inds, (float *)out);
 	else maxpool_fwd_kernel<float, 1><<<grid, kThreads, 0, st>>>((const float *)x, N, S, C, k, stride, max_inds, (float *)out);
@@ -680,6 +778,13 @@ void maxpool_bwd(const int *max_inds, const void *dout, int N, int S, int C, int
 	if (!VEC) { set_error("max pool over bf16 tensors needs C %% 8 == 0 (C = %d)", C); return; }
 	long long total = (long long)N * S * S * (C / VEC);
 	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 8 ? kMaxFlatBlocks * 8 : grid;
+	if (k == 3 && stride == 2 && S % 2 == 0 && VEC >= 4 && (long long)N * S * S * C < (1LL << 31)) {
+		grid = grid > kNumSMs * 3 * 8 ? kNumSMs * 3 * 8 : grid;
+		if (bf16) maxpool3s2_bwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>(max_inds, (const bf16_t *)dout, N, S, C, (bf16_t *)din);
+		else maxpool3s2_bwd_kernel<float, 4><<<grid, kThreads, 0, st>>>(max_inds, (const float *)dout, N, S, C, (float *)din);
+		RB_LAUNCH_CHECK();
+		return;
+	}
 	if (bf16) maxpool_bwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>(max_inds, (const bf16_t *)dout, N, S, C, k, stride, (bf16_t *)din);
 	else if (VEC == 4) maxpool_bwd_kernel<float, 4><<<grid, kThreads, 0, st>>>(max_inds, (const float *)dout, N, S, C, k, stride, (float *)din);
 	else maxpool_bwd_kernel<float, 1><<<grid, kThreads, 0, st>>>(max_inds, (const float *)dout, N, S, C, k, stride, (float *)din);
