@@ -340,8 +340,20 @@ def main():
                            "ms_per_step": fam[2]["ms"] / prof_steps, "launches_per_step": fam[2]["launches"] / prof_steps,
                            "bytes_per_launch": fam[2]["work"] / fam[2]["launches"]})
         dom = max(rl_all, key=lambda r: r["ms_per_step"])
+        # DRAM traffic per launch of the dominant family from the committed ncu capture of one step of this configuration's dtype
+        # (profiles/r01_traffic_<dtype>.json, written by tools/ncu_summary.py --json; batch 256 ResNet-50 only)
+        traffic, traffic_src = None, None
+        tfile = os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % cfg["dtype"])
+        if os.path.exists(tfile) and args.config in ("c2", "c4") and N == 256:
+            try:
+                tj = json.load(open(tfile))
+                key = "kmajor" if "kmajor" in dom["kernel"] else ("wgrad" if "mnmajor" in dom["kernel"] else "bn_eltwise")
+                traffic = tj[key]["dram_bytes_per_step"] / dom["launches_per_step"]
+                traffic_src = "profiles/r01_traffic_%s.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one step / launches of the family)" % cfg["dtype"]
+            except Exception:
+                traffic = None
         roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
-                    "traffic": None, "kernel": dom["kernel"],
+                    "traffic": traffic, "traffic_source": traffic_src, "kernel": dom["kernel"],
                     "peak_source": ("MEASURED_PEAKS.json (%s): " % pk["src"]) + (("bf16_tflops_sustained (kernel timed inside a long step)" if t.bf16 else
                                                                                   "bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate; kernel timed inside a long step)")
                                                                                  if dom["bound"] == "tensor" else "hbm_gbs copy bandwidth"),

@@ -206,6 +206,8 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 			if (c->dgrad) tc_free(c->dgrad);
 			if (c->wgrad) tc_free(c->wgrad);
 		}
+	if (e->stem_fprop) tc_free(e->stem_fprop);
+	if (e->stem_wgrad) tc_free(e->stem_wgrad);
 	for (void *p : e->allocs) cudaFree(p);
 	for (Params *P : {t->backprop_buffer->param_derivs, t->backprop_buffer->prev_means, t->backprop_buffer->prev_vars}) {
 		ParamStore *ps = param_store_of(P);
