@@ -2,8 +2,9 @@
 // residual join, max / average pooling, softmax cross-entropy, fused Adam, weight re-layout.
 //
 // Roofline: HBM bandwidth (MEASURED_PEAKS.json hbm_gbs).  Every tensor pass is a flat, fully coalesced
-// 128-bit grid-stride stream; per-channel quantities ride in registers because the grid stride is a multiple
-// of C/4, so a thread always sees the same four channels (NHWC: C is the contiguous axis).
+// 128-bit grid-stride stream over fp32 (4 elements per access) or bf16 (8 per access) tensors with fp32 arithmetic;
+// per-channel quantities ride in registers because the grid stride is a multiple of the vectors per row, so a thread
+// always sees the same channels (NHWC: C is the contiguous axis).
 // Reference semantics: resnet.cu:289-342 (BN fwd), 350-426 (BN bwd), 433-494 (max pool), 500-542 (avg pool),
 // 545-602 (ReLU, softmax, CE), 605-662 (Adam).
 #include "common.cuh"
@@ -124,10 +125,9 @@ static int flat_grid(long long nvec, int V, int max_blocks, bool *fixed) {
 	}
 	return grid;
 }
-// every streaming kernel is compiled for a fixed number of resident blocks per SM (__launch_bounds__: 4, or 3 for the bf16
-// BatchNorm-backward kernels that carry 8 channels of coefficients per thread) and its grid is capped at whole waves of that: the bf16 BatchNorm-backward kernels at 80 registers fitted 3 blocks per SM, so a
-// 592-block grid ran as one full wave plus a 1-block-per-SM tail and reached 3 TB/s where the fp32 twin reached 6.4
-// (profiles/r01_ncu_all_kernels_bf16_summary.txt)
+// every streaming kernel is compiled for a fixed number of resident blocks per SM (__launch_bounds__) and its grid is capped at
+// whole waves of that: the bf16 BatchNorm-backward kernels at 80 registers once fitted 3 blocks per SM, so a 592-block grid ran as
+// one full wave plus a 1-block-per-SM tail and reached 3 TB/s where the fp32 twin reached 6.4
 constexpr int kMaxFlatBlocks = kNumSMs * 8;
 
 // ------------------------------------------------------------------------------------------- BN statistics

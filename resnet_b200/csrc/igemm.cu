@@ -1,28 +1,30 @@
 // igemm.cu -- tcgen05 / TMA implicit-GEMM convolution for sm_100a: fprop, dgrad (K-major operands) and wgrad
-// (MN-major operands), TF32 inputs with fp32 accumulation in TMEM.
+// (MN-major operands); fp32 tensors with kind::tf32 MMAs or bf16 tensors with kind::f16 MMAs, fp32 accumulation in TMEM.
 //
 // Replaces the reference's doConvolution / convolutionDerivInput / convolutionDerivWeights
 // (reference: resnet.cu:109-156, 166-219, 227-281 and their launchers 1386-1429).
 //
-// Data layout (DESIGN.md "HBM layout"): activations NHWC fp32; packed weights Wf[Cout][tap][Cin] (fprop) and
-// Wd[Cin][tap][Cout] (dgrad), both K-major for the GEMM that reads them.
+// Data layout: activations NHWC (fp32 or bf16); packed weights Wf[Cout][tap][Cin] (fprop) and
+// Wd[Cin][tap][Cout] (dgrad), both K-major for the GEMM that reads them.  A "K chunk" is one 128-byte swizzle row:
+// 32 tf32 or 64 bf16 elements; the shared-memory tiles are byte-identical in the two modes.
 //
-// fprop / dgrad kernel (igemm_kmajor_kernel): D[128 pixels x BN] += A[128 x 32] * B[BN x 32]^T per pipeline stage.
+// fprop / dgrad kernel (igemm_kmajor_kernel<BF16>): D[128 pixels x BN] += A[128 x chunk] * B[BN x chunk]^T per pipeline stage.
 //   * A tile = a (bw x bh x bn) box of output pixels; for filter tap (kh, kw) the SAME box shifted by the tap
-//     offset is fetched by ONE 4-D TMA tiled load {32 ch, bw, bh, bn}; out-of-bounds coordinates are zero-filled
+//     offset is fetched by ONE 4-D TMA tiled load {chunk, bw, bh, bn}; out-of-bounds coordinates are zero-filled
 //     by the TMA unit, which is exactly the convolution's zero padding (im2col never exists in memory).
 //     Stride-2 layers read through four "parity" tensor maps (even/odd rows x even/odd cols of the input), so
 //     every tap is again a dense shifted box.  Stride-2 dgrad is decomposed into the four output parities
 //     (1 + 2 + 2 + 4 taps): no multiply by structural zeros.
-//   * B tile = BN weight rows x 32 k via a 2-D TMA load.  Both tiles land in 128-byte-swizzled K-major layout,
+//   * B tile = BN weight rows x chunk via a 2-D TMA load.  Both tiles land in 128-byte-swizzled K-major layout,
 //     the canonical operand layout of tcgen05.mma (UMMA) descriptors.
-//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (4 x K=8 MMAs per stage);
-//     warps 2-5: epilogue (tcgen05.ld TMEM -> registers -> global), overlapped with the next tile's mainloop
-//     through a double-buffered TMEM accumulator (2 x BN <= 512 columns).  Persistent: one CTA per SM.
+//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (4 MMAs per stage, K = 8 tf32 / 16 bf16);
+//     warps 2-5 (and 6-9 on short-K layers): epilogue -- tcgen05.ld TMEM -> registers -> swizzled smem staging tile -> TMA
+//     tile store / reduce-add, plus the fused BatchNorm statistics -- overlapped with the next tile's mainloop through a
+//     double-buffered TMEM accumulator (2 x BN <= 512 columns).  Persistent: one CTA per SM.
 //
-// wgrad kernel (igemm_mnmajor_kernel): dW[tap][128 co x BN ci] += dY[32 px x 128 co]^T * X_tap[32 px x BN ci].
-//   The reduction (GEMM K) runs over pixels, so both operands are MN-major straight out of NHWC memory:
-//   a TMA box of 32 pixels x 32 channels is one 128B-swizzled MN-major atom column.  Split-K over pixel ranges
+// wgrad kernel (igemm_mnmajor_kernel<BF16>): dW[tap][128 co x BN ci] += dY[px x 128 co]^T * X_tap[px x BN ci], px = 32 (tf32) /
+//   64 (bf16) pixels per stage.  The reduction (GEMM K) runs over pixels, so both operands are MN-major straight out of NHWC
+//   memory: a TMA box of px pixels x 128 bytes of channels is one swizzled MN-major atom column.  Split-K over pixel ranges
 //   into a workspace, reduced deterministically (and re-laid to [Cout][Cin][kh][kw]) by wgrad_reduce.
 #include "common.cuh"
 #include "ptx.cuh"
