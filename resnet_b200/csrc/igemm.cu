@@ -126,6 +126,12 @@ struct alignas(64) IgemmParams {
 	int nstaging;  // epilogue staging tiles PER GROUP (2..4): up to nstaging - 2 TMA stores stay in flight behind the chunk being staged
 	int epi_groups;  // 1 or 2 groups of four epilogue warps; with 2, the 128-byte column chunks of a CTA alternate between them
 	uint32_t a_bytes, b_bytes, a_tx_bytes;  // smem slot sizes; bytes one A box actually transfers (bw*bh*bn rows)
+	// resident_b: the CTA's whole weight operand (all taps x K chunks of its one N tile, resb_bytes) is loaded ONCE into shared memory
+	// ahead of the pipeline stages, which then carry activation tiles only.  Used when it fits and every tile of a CTA has the same
+	// N tile (gridDim.x % n_tiles == 0): the 64-channel 3x3 layers and the stem re-fetched their few KB of weights for every tile
+	// and sat at the ~10-12 TB/s the TMA / L2 path delivers chip-wide.
+	int resident_b;
+	uint32_t resb_bytes;
 	float *out;
 	int OH, OW, os, accumulate;
 	int tma_store;  // epilogue: 1 = swizzled smem staging + TMA tile store (reduce-add when accumulate), 0 = per-thread row stores
@@ -171,13 +177,16 @@ template <bool BF16>
 __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
-	const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-	uint8_t *staging = base + (size_t)p.stages * stage_bytes;  // epi_groups x nstaging x 16 KB epilogue tiles (128 rows x 128 B, 128B-swizzled)
+	const uint32_t stage_bytes = p.resident_b ? p.a_bytes : p.a_bytes + p.b_bytes;
+	uint8_t *resb = base;                                           // resident weight slots [tap * kchunks + kc] (resb_bytes, 0 when unused)
+	uint8_t *stage0 = base + p.resb_bytes;
+	uint8_t *staging = stage0 + (size_t)p.stages * stage_bytes;  // epi_groups x nstaging x 16 KB epilogue tiles (128 rows x 128 B, 128B-swizzled)
 	uint64_t *full = reinterpret_cast<uint64_t *>(staging + p.epi_groups * p.nstaging * kABytes);
 	uint64_t *empty = full + p.stages;
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+	uint64_t *bfull = tempty + 2;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (warp == 0 && lane == 0) {
@@ -189,6 +198,7 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 		if (lane == 0) {
 			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
 			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * p.epi_groups); }
+			mbar_init(bfull, 1);
 			fence_barrier_init();
 		}
 		__syncwarp();
@@ -206,6 +216,14 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 		if (lane == 0) {
 			int stage = 0;
 			uint32_t phase = 0;
+			if (p.resident_b && (int)blockIdx.x < total_tiles) {  // the weights of this CTA's N tile, once
+				const GroupDesc &g = p.groups[0];
+				const int nt = (int)blockIdx.x % p.n_tiles;
+				mbar_expect_tx(bfull, p.resb_bytes);
+				for (int t = 0; t < g.ntaps; t++)
+					for (int kc = 0; kc < p.kchunks; kc++)
+						tma_load_2d(resb + (size_t)(t * p.kchunks + kc) * p.b_bytes, &p.bmap, bfull, g.taps[t].bcol + kc * p.kelems, nt * p.BN);
+			}
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 				const int nt = tile % p.n_tiles;
 				int r = tile / p.n_tiles;
@@ -216,10 +234,10 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 					const TapDesc tp = g.taps[t];
 					for (int kc = 0; kc < p.kchunks; kc++) {
 						mbar_wait(&empty[stage], phase ^ 1);
-						uint8_t *sa = base + (size_t)stage * stage_bytes;
-						mbar_expect_tx(&full[stage], p.a_tx_bytes + p.b_bytes);
+						uint8_t *sa = stage0 + (size_t)stage * stage_bytes;
+						mbar_expect_tx(&full[stage], p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + p.b_bytes);
 						tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * p.kelems, ow0 + tp.dx, oh0 + tp.dy, n0);
-						tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * p.kelems, nt * p.BN);
+						if (!p.resident_b) tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * p.kelems, nt * p.BN);
 						if (++stage == p.stages) { stage = 0; phase ^= 1; }
 					}
 				}
@@ -231,6 +249,7 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
+			if (p.resident_b && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0);
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 				const GroupDesc &g = p.groups[(tile / p.n_tiles) / p.m_tiles];
 				const int iters = g.ntaps * p.kchunks;
@@ -240,9 +259,9 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 				for (int it = 0; it < iters; it++) {
 					mbar_wait(&full[stage], phase);
 					tc_fence_after();
-					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
+					const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
 					const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-					const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, 16, 1024);
+					const uint64_t bdesc = make_smem_desc(p.resident_b ? smem_u32(resb + (size_t)it * p.b_bytes) : a_addr + p.a_bytes, 16, 1024);
 #pragma unroll
 					for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
 					mma_commit(&empty[stage]);
@@ -630,11 +649,19 @@ static void finish_kmajor(TcPlan *pl) {
 	if (const char *e = getenv("RESNET_B200_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= 2 && p.tma_store) p.epi_groups = v; }
 	if (const char *e = getenv("RESNET_B200_NSTAGING")) { int v = atoi(e); if (v >= 2 && v <= 4) p.nstaging = v; }
 	const size_t staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
-	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes) / stage_bytes);
-	p.stages = stages > 8 ? 8 : stages;
-	pl->smem = (size_t)p.stages * stage_bytes + staging_bytes + 1024 + 256;
 	const int total = p.ngroups * p.m_tiles * p.n_tiles;
 	pl->grid = total < kNumSMs ? total : kNumSMs;
+	// weights resident in shared memory when they fit next to >= 4 activation stages and every tile of a CTA shares one N tile
+	const size_t resb = (size_t)p.groups[0].ntaps * p.kchunks * p.b_bytes;
+	int want_res = 1;
+	if (const char *e = getenv("RESNET_B200_RESIDENT_B")) want_res = atoi(e);
+	p.resident_b = want_res && p.ngroups == 1 && pl->grid % p.n_tiles == 0 && resb <= 80 * 1024 && total >= 2 * pl->grid &&
+	               kMaxDynSmem - 2048 - staging_bytes - resb >= 4 * (size_t)p.a_bytes;
+	p.resb_bytes = p.resident_b ? (uint32_t)resb : 0;
+	const uint32_t pipe_stage = p.resident_b ? p.a_bytes : stage_bytes;
+	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
+	p.stages = stages > 8 ? 8 : stages;
+	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
 }
 
@@ -1069,8 +1096,8 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
-		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu", pl->what, pl->bf16 ? "bf16" : "tf32",
-		         p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu resB=%u", pl->what,
+		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem, p.resb_bytes);
 	} else {
 		const WgradParams &p = pl->wp;
 		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
