@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python tools/probe_resident.py > gpurun_out/probe2.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:igemm --csv --log-file gpurun_out/probe2_ncu.csv python tools/probe_resident.py > gpurun_out/probe2_ncu.log 2>&1
+timeout 900 python -m pytest -q -s --timeout 600 tests/test_gpu_network.py -k "full_geometry" > gpurun_out/fullgeo.log 2>&1
+tail -n 30 gpurun_out/fullgeo.log
