@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest -q -s --timeout 600 tests/test_gpu_network.py -k "full_geometry" > gpurun_out/fullgeo.log 2>&1
-tail -n 30 gpurun_out/fullgeo.log
+free -g | head -2 > gpurun_out/parity_batch32.txt
+timeout 1200 python tools/parity_batch.py 32 >> gpurun_out/parity_batch32.txt 2>&1
+tail -n 20 gpurun_out/parity_batch32.txt
