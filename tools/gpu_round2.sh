@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-free -g | head -2 > gpurun_out/parity_batch32.txt
-timeout 1200 python tools/parity_batch.py 32 >> gpurun_out/parity_batch32.txt 2>&1
-tail -n 20 gpurun_out/parity_batch32.txt
+timeout 900 python -m pytest -q --timeout 600 tests/test_gpu_bf16.py -k "overfits" > gpurun_out/overfit.log 2>&1
+tail -n 12 gpurun_out/overfit.log
