@@ -148,6 +148,7 @@ struct alignas(64) WgradParams {
 	int tpt;  // filter taps per tile (they share the dY tile of each stage); tpt * BN <= 256 TMEM columns
 	int co_tiles, ci_tiles, BN, cin, cout;
 	int a_blocks, cb;  // 128-byte channel blocks per 128-channel A tile (4 tf32 / 2 bf16), channels per block (32 / 64)
+	int merge_taps;    // the taps of a group sit back to back in shared memory AND in TMEM: one MMA of N = ntaps * BN covers them all
 	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
 	int stages;
 	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
@@ -484,12 +485,22 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 					tc_fence_after();
 					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
 					const uint64_t adesc = make_smem_desc(a_addr, p.lbo, p.sbo, p.layout_type);
-					for (int t = 0; t < ntg; t++) {
-						const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
+					if (p.merge_taps) {
+						// the group's B tiles are contiguous [tap][channel block][px][128 B] with one LBO pitch, and its accumulators are
+						// contiguous TMEM columns: issue the whole group as ONE N = ntg * BN MMA per K step instead of ntg narrow ones
+						const uint32_t idesc_g = BF16 ? make_idesc_bf16(128, ntg * p.BN, 1, 1) : make_idesc_tf32(128, ntg * p.BN, 1, 1);
+						const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-						for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
-							mma_ss<BF16>(d_tmem + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
-							             (uint32_t)((kb > kb0) || (k != 0)));
+						for (int k = 0; k < 4; k++)
+							mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc_g, (uint32_t)((kb > kb0) || (k != 0)));
+					} else {
+						for (int t = 0; t < ntg; t++) {
+							const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
+#pragma unroll
+							for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
+								mma_ss<BF16>(d_tmem + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
+								             (uint32_t)((kb > kb0) || (k != 0)));
+						}
 					}
 					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -813,6 +824,8 @@ static CUtensorMapSwizzle wgrad_layout(WgradParams &p, int bf16) {
 	p.kadv = bf16 ? 128 : 64;         // 16 / 8 pixel rows of 128 B per MMA, in 16-byte units
 	p.a_bytes = 128 * 128;            // 128 co x px pixels: 4 x [32 px][32 fp32] or 2 x [64 px][64 bf16]
 	p.b_bytes = (uint32_t)p.BN * 128;
+	p.merge_taps = 1;
+	if (const char *e = getenv("RESNET_B200_WGRAD_MERGE")) p.merge_taps = atoi(e) != 0;
 	return bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 }
 
