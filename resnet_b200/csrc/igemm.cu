@@ -148,6 +148,11 @@ struct alignas(64) WgradParams {
 	int tpt;  // filter taps per tile (they share the dY tile of each stage); tpt * BN <= 256 TMEM columns
 	int co_tiles, ci_tiles, BN, cin, cout;
 	int a_blocks, cb;  // 128-byte channel blocks per 128-channel A tile (4 tf32 / 2 bf16), channels per block (32 / 64)
+	// m_pair = 2: one work item covers TWO 128-row co tiles that share the X tile of every stage (A = 256 co x px, two M = 128 MMAs
+	// per K step against the same B descriptor, accumulators in all 512 TMEM columns, single-buffered: a work item runs for hundreds
+	// of stages, so its one epilogue need not overlap).  Cuts the bytes the TMA path must deliver per MAC by a third on the layers
+	// that are bound by it (every wgrad with Cout >= 256 sat at the ~42 B/clk/SM the TMA / L2 path delivers chip-wide).
+	int m_pair, co_items;  // co_items = co_tiles / m_pair
 	int merge_taps;    // the taps of a group sit back to back in shared memory AND in TMEM: one MMA of N = ntaps * BN covers them all
 	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
 	int stages;
@@ -434,9 +439,11 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	// tile = ((tap_group * co_tiles + cot) * ci_tiles + cit) * splits + split; a tap group shares one dY (A) tile per
 	// stage between up to `tpt` filter taps, each with its own BN-column accumulator (tpt * BN <= 256 TMEM columns)
 	const int n_groups = (p.ntaps + p.tpt - 1) / p.tpt;
-	const int total_tiles = n_groups * p.co_tiles * p.ci_tiles * p.splits;
+	const int total_tiles = n_groups * p.co_items * p.ci_tiles * p.splits;
 	const int nb_boxes = p.BN / p.cb;  // [px][128 B of channels] boxes per B tile
-	const uint32_t acc_cols = (uint32_t)(p.tpt * p.BN);
+	const uint32_t grp_cols = (uint32_t)(p.tpt * p.BN);          // accumulator columns of one 128-row co tile
+	const uint32_t acc_cols = grp_cols * (uint32_t)p.m_pair;     // ... of one work item
+	const int nbuf = (2 * acc_cols <= (uint32_t)kTmemCols) ? 2 : 1;  // TMEM accumulator buffers
 
 	if (warp == 0) {
 		if (lane == 0) {
@@ -446,8 +453,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 				const int split = tile % p.splits;
 				int r = tile / p.splits;
 				const int cit = r % p.ci_tiles; r /= p.ci_tiles;
-				const int cot = r % p.co_tiles;
-				const int tap0 = (r / p.co_tiles) * p.tpt;
+				const int cot = r % p.co_items;
+				const int tap0 = (r / p.co_items) * p.tpt;
 				const int ntg = min(p.tpt, p.ntaps - tap0);
 				const int kb0 = split * p.boxes_per_split;
 				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 					mbar_wait(&empty[stage], phase ^ 1);
 					uint8_t *sa = base + (size_t)stage * stage_bytes;
 					mbar_expect_tx(&full[stage], p.a_bytes + (uint32_t)ntg * p.b_bytes);
-					tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * p.a_blocks);  // all [px][128 B of co] boxes in one op
+					tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * p.a_blocks * p.m_pair);  // all [px][128 B of co] boxes in one op
 					for (int t = 0; t < ntg; t++) {
 						const TapDesc tp = p.taps[tap0 + t];
 						tma_load_5d(sa + p.a_bytes + (size_t)t * p.b_bytes, &p.bmap[tp.amap], &full[stage], 0, ow0 + tp.dx, oh0 + tp.dy, n0, cit * nb_boxes);
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			uint32_t phase = 0, accphase = 0;
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 				const int split = tile % p.splits;
-				const int tap0 = ((tile / p.splits) / p.ci_tiles / p.co_tiles) * p.tpt;
+				const int tap0 = ((tile / p.splits) / p.ci_tiles / p.co_items) * p.tpt;
 				const int ntg = min(p.tpt, p.ntaps - tap0);
 				const int kb0 = split * p.boxes_per_split;
 				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
@@ -484,30 +491,32 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 					mbar_wait(&full[stage], phase);
 					tc_fence_after();
 					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
-					const uint64_t adesc = make_smem_desc(a_addr, p.lbo, p.sbo, p.layout_type);
-					if (p.merge_taps) {
-						// the group's B tiles are contiguous [tap][channel block][px][128 B] with one LBO pitch, and its accumulators are
-						// contiguous TMEM columns: issue the whole group as ONE N = ntg * BN MMA per K step instead of ntg narrow ones
-						const uint32_t idesc_g = BF16 ? make_idesc_bf16(128, ntg * p.BN, 1, 1) : make_idesc_tf32(128, ntg * p.BN, 1, 1);
-						const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
+					for (int m = 0; m < p.m_pair; m++) {  // the 128-row co tiles of the item: same B tiles, own A rows and accumulators
+						const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)m * kABytes, p.lbo, p.sbo, p.layout_type);
+						const uint32_t d_m = d_tmem + (uint32_t)m * grp_cols;
+						if (p.merge_taps) {
+							// the group's B tiles are contiguous [tap][channel block][px][128 B] with one LBO pitch, and its accumulators are
+							// contiguous TMEM columns: issue the whole group as ONE N = ntg * BN MMA per K step instead of ntg narrow ones
+							const uint32_t idesc_g = BF16 ? make_idesc_bf16(128, ntg * p.BN, 1, 1) : make_idesc_tf32(128, ntg * p.BN, 1, 1);
+							const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-						for (int k = 0; k < 4; k++)
-							mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc_g, (uint32_t)((kb > kb0) || (k != 0)));
-					} else {
-						for (int t = 0; t < ntg; t++) {
-							const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
+							for (int k = 0; k < 4; k++)
+								mma_ss<BF16>(d_m, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc_g, (uint32_t)((kb > kb0) || (k != 0)));
+						} else {
+							for (int t = 0; t < ntg; t++) {
+								const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-							for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
-								mma_ss<BF16>(d_tmem + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
-								             (uint32_t)((kb > kb0) || (k != 0)));
+								for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
+									mma_ss<BF16>(d_m + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
+									             (uint32_t)((kb > kb0) || (k != 0)));
+							}
 						}
 					}
 					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
 				mma_commit(&tfull[acc]);
-				acc ^= 1;
-				if (acc == 0) accphase ^= 1;
+				if (++acc == nbuf) { acc = 0; accphase ^= 1; }
 			}
 		}
 		__syncwarp();
@@ -520,31 +529,32 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			const int split = tile % p.splits;
 			int r = tile / p.splits;
 			const int cit = r % p.ci_tiles; r /= p.ci_tiles;
-			const int cot = r % p.co_tiles;
-			const int tap0 = (r / p.co_tiles) * p.tpt;
+			const int cot = r % p.co_items;
+			const int tap0 = (r / p.co_items) * p.tpt;
 			const int ntg = min(p.tpt, p.ntaps - tap0);
-			const int co = cot * 128 + row;
-			const bool valid = co < p.cout;
 			mbar_wait(&tfull[acc], accphase);
 			tc_fence_after();
-			for (int t = 0; t < ntg; t++) {
-				float *dst = p.partial + (((size_t)split * p.ntaps + tap0 + t) * p.cout + co) * p.cin + (size_t)cit * p.BN;
-				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(t * p.BN);
-				for (int c = 0; c < p.BN / 32; c++) {
-					float v[32];
-					tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-					if (valid) {
-						float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
+			for (int m = 0; m < p.m_pair; m++) {
+				const int co = (cot * p.m_pair + m) * 128 + row;
+				const bool valid = co < p.cout;
+				for (int t = 0; t < ntg; t++) {
+					float *dst = p.partial + (((size_t)split * p.ntaps + tap0 + t) * p.cout + co) * p.cin + (size_t)cit * p.BN;
+					const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)m * grp_cols + (uint32_t)(t * p.BN);
+					for (int c = 0; c < p.BN / 32; c++) {
+						float v[32];
+						tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+						if (valid) {
+							float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
 #pragma unroll
-						for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+							for (int j = 0; j < 8; j++) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+						}
 					}
 				}
 			}
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&tempty[acc]);
-			acc ^= 1;
-			if (acc == 0) accphase ^= 1;
+			if (++acc == nbuf) { acc = 0; accphase ^= 1; }
 		}
 	}
 	tc_fence_before();
@@ -786,7 +796,7 @@ TcPlan *tc_make_dgrad(const ConvGeom &g, const void *dy, const void *wd, void *d
 
 // shape decisions of a wgrad launch, shared by the workspace query and the plan builder.  One pipeline stage reduces over a box
 // of `px` pixels = 4 MMAs: 32 pixels (tf32, K = 8) or 64 pixels (bf16, K = 16).
-struct WgradShape { int bw, bh, bn, tiles_w, tiles_h, tiles_b, k_boxes, BN, ci_tiles, co_tiles, ntaps, tpt, splits, boxes_per_split; };
+struct WgradShape { int bw, bh, bn, tiles_w, tiles_h, tiles_b, k_boxes, BN, ci_tiles, co_tiles, ntaps, tpt, splits, boxes_per_split, m_pair, co_items; };
 static WgradShape wgrad_shape(int Wm, int Hm, int Nn, bool flat, int cin_cols, int cout, int ntaps, int bf16) {
 	WgradShape w;
 	const int px = bf16 ? 64 : 32;
@@ -801,14 +811,26 @@ static WgradShape wgrad_shape(int Wm, int Hm, int Nn, bool flat, int cin_cols, i
 	w.tpt = 256 / w.BN;  // double-buffered accumulators: 2 * tpt * BN <= 512 TMEM columns
 	if (w.tpt > ntaps) w.tpt = ntaps;
 	if (w.tpt < 1) w.tpt = 1;
-	const int tiles = ceil_div(ntaps, w.tpt) * w.co_tiles * w.ci_tiles;
-	// two whole waves of the persistent grid: floor, not ceil -- 3 tiles x 99 splits = 297 work items ran as three rounds with the
-	// last one 1 % full (wave efficiency 0.67-0.81 on 13 of the 22 layer shapes)
-	int splits = (2 * kNumSMs) / tiles;
-	if (splits > w.k_boxes) splits = w.k_boxes;
-	if (splits < 1) splits = 1;
-	w.boxes_per_split = ceil_div(w.k_boxes, splits);
-	w.splits = ceil_div(w.k_boxes, w.boxes_per_split);
+	// two co tiles per work item (WgradParams::m_pair) when there is an even number of them AND the items stay long: pairing halves
+	// the tile count, so the split count doubles and an item gets half the stages, while its epilogue (512 TMEM columns, not
+	// overlapped with the next item) doubles.  Measured (profiles/r01_conv_probe_wgrad_mpair.txt): -15..20 % on the three large
+	// projections (196 stages per item), +10..40 % on the 14x14 / 7x7 layers (11-25 stages per item).  RESNET_B200_WGRAD_MPAIR=0 / 2
+	// forces it off / on.
+	int force = -1;
+	if (const char *e = getenv("RESNET_B200_WGRAD_MPAIR")) force = atoi(e);
+	for (int pair = (w.co_tiles % 2 == 0 && force != 0) ? 2 : 1; pair >= 1; pair--) {
+		w.m_pair = pair;
+		w.co_items = w.co_tiles / pair;
+		const int tiles = ceil_div(ntaps, w.tpt) * w.co_items * w.ci_tiles;
+		// two whole waves of the persistent grid: floor, not ceil -- 3 tiles x 99 splits = 297 work items ran as three rounds with the
+		// last one 1 % full (wave efficiency 0.67-0.81 on 13 of the 22 layer shapes)
+		int splits = (2 * kNumSMs) / tiles;
+		if (splits > w.k_boxes) splits = w.k_boxes;
+		if (splits < 1) splits = 1;
+		w.boxes_per_split = ceil_div(w.k_boxes, splits);
+		w.splits = ceil_div(w.k_boxes, w.boxes_per_split);
+		if (pair == 1 || force == 2 || w.boxes_per_split >= 64) break;
+	}
 	return w;
 }
 
@@ -822,7 +844,7 @@ static CUtensorMapSwizzle wgrad_layout(WgradParams &p, int bf16) {
 	p.sbo = bf16 ? 1024 : 512;        // pitch of the swizzle atoms along the pixel (K) axis
 	p.layout_type = bf16 ? 2 : 1;
 	p.kadv = bf16 ? 128 : 64;         // 16 / 8 pixel rows of 128 B per MMA, in 16-byte units
-	p.a_bytes = 128 * 128;            // 128 co x px pixels: 4 x [32 px][32 fp32] or 2 x [64 px][64 bf16]
+	p.a_bytes = (uint32_t)p.m_pair * 128 * 128;  // m_pair x (128 co x px pixels): 4 x [32 px][32 fp32] or 2 x [64 px][64 bf16] each
 	p.b_bytes = (uint32_t)p.BN * 128;
 	p.merge_taps = 1;
 	if (const char *e = getenv("RESNET_B200_WGRAD_MERGE")) p.merge_taps = atoi(e) != 0;
@@ -849,8 +871,8 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 	                    : wgrad_shape(So, So, g.N, false, g.cin, g.cout, g.taps(), bf16);
 	p.bw = w.bw; p.bh = w.bh; p.bn = w.bn; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_b = w.tiles_b; p.k_boxes = w.k_boxes;
 	p.cin = g.cin; p.cout = g.cout; p.BN = w.BN; p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles; p.ntaps = w.ntaps; p.tpt = w.tpt;
-	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split;
-	const int tiles = ceil_div(p.ntaps, p.tpt) * p.co_tiles * p.ci_tiles;
+	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split; p.m_pair = w.m_pair; p.co_items = w.co_items;
+	const int tiles = ceil_div(p.ntaps, p.tpt) * p.co_items * p.ci_tiles;
 	if ((size_t)p.splits * p.ntaps * g.cout * g.cin * sizeof(float) > ws_bytes) { set_error("tc_make_wgrad: workspace too small"); delete pl; return nullptr; }
 	CUtensorMapSwizzle swz = wgrad_layout(p, bf16);
 	const int box[4] = {p.cb, p.bw, p.bh, p.bn};
@@ -858,7 +880,7 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 		unsigned a, b, c, d;
 		if (sscanf(e, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) { p.lbo = a; p.sbo = b; p.layout_type = c; swz = (CUtensorMapSwizzle)d; }
 	}
-	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat, bf16, swz, p.a_blocks);
+	bool ok = make_input_maps(&p.amap, dy, g.N, So, g.cout, 1, box, flat, bf16, swz, p.a_blocks * p.m_pair);
 	ok = ok && make_input_maps(p.bmap, x, g.N, g.S, g.cin, g.stride, box, flat, bf16, swz, p.BN / p.cb);
 	if (g.stride == 1) for (int i = 1; i < 4; i++) p.bmap[i] = p.bmap[0];
 	for (int kh = 0; kh < g.k; kh++)
@@ -1033,11 +1055,11 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	WgradShape w = wgrad_shape(So, So, N, false, RE, cout, kStemK, bf16);
 	p.bw = w.bw; p.bh = w.bh; p.bn = w.bn; p.tiles_w = w.tiles_w; p.tiles_h = w.tiles_h; p.tiles_b = w.tiles_b; p.k_boxes = w.k_boxes;
 	p.cin = RE; p.cout = cout; p.BN = w.BN; p.ci_tiles = w.ci_tiles; p.co_tiles = w.co_tiles; p.ntaps = w.ntaps; p.tpt = w.tpt;
-	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split;
+	p.splits = w.splits; p.boxes_per_split = w.boxes_per_split; p.m_pair = w.m_pair; p.co_items = w.co_items;
 	if ((size_t)p.splits * kStemK * cout * RE * sizeof(float) > ws_bytes) { set_error("tc_make_stem_wgrad: workspace too small"); delete pl; return nullptr; }
 	const CUtensorMapSwizzle swz = wgrad_layout(p, bf16);
 	const int box[4] = {p.cb, p.bw, p.bh, p.bn};
-	bool ok = make_input_maps(&p.amap, dy, N, So, cout, 1, box, false, bf16, swz, p.a_blocks);
+	bool ok = make_input_maps(&p.amap, dy, N, So, cout, 1, box, false, bf16, swz, p.a_blocks * p.m_pair);
 	ok = ok && make_stem_maps(p.bmap, xp, N, S, box, bf16, swz, 1);
 	p.bmap[2] = p.bmap[0]; p.bmap[3] = p.bmap[1];
 	for (int kh = 0; kh < kStemK; kh++) {
@@ -1050,7 +1072,7 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	p.stages = stages > 8 ? 8 : stages;
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-	const int total = ceil_div(p.ntaps, p.tpt) * p.co_tiles * p.ci_tiles * p.splits;
+	const int total = ceil_div(p.ntaps, p.tpt) * p.co_items * p.ci_tiles * p.splits;
 	pl->grid = total < kNumSMs ? total : kNumSMs;
 	pl->kind = 2;
 	pl->dw = dw; pl->cout = cout; pl->cin = 3; pl->taps = kStemK * kStemK;
@@ -1113,8 +1135,8 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem, p.resb_bytes);
 	} else {
 		const WgradParams &p = pl->wp;
-		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
-		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
+		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.m_pair, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
 	}
 }
 
