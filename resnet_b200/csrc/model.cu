@@ -260,6 +260,9 @@ static Engine *build_engine(Train_ResNet *t) {
 	std::vector<PackJob> jobs;
 	const int S0 = d->input, S1 = d->input / d->init_conv_stride, S2 = S1 / d->init_maxpool_stride, F = d->init_conv_filters;
 	const long long n_x0 = (long long)N * S1 * S1 * F, n_p0 = (long long)N * S2 * S2 * F;
+	// max_inds holds flat int32 indices into init_conv_activated (reference: resnet.cu:459-468) and Cache_BatchNorm::input_size is an
+	// int: the largest tensor of the network must stay below 2^31 elements (batch 2674 at 224 x 224 x 64 filters)
+	if (n_x0 >= (1LL << 31)) set_error("batch %d: init_conv_activated has %lld elements, above the int32 index range of max_inds", N, n_x0);
 	setup_conv(e, B, e->stem, N, S0, 3, F, d->init_kernel_dim, d->init_conv_stride, 0, P, G, jobs);
 	e->stem_tc = (e->conv_mode == 0) && (e->bf16 || env_int("RESNET_B200_STEM_TC", 1)) && tc_stem_supported(S0, d->init_kernel_dim, 3, F, d->init_conv_stride, e->bf16);
 	if (e->bf16 && !e->stem_tc) set_error("bf16 mode: the stem must be 7x7/2 with a multiple of 64 filters (<= 128)");

@@ -349,3 +349,31 @@ def test_resnet152_bf16_geometry_runs():
     t.update()
     assert all(np.isfinite(x).all() for x in t.get_params(0))
     t.close()
+
+
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+def test_batch_of_one_and_odd_batches(dtype):
+    """Ragged ends of every tiling: batch 1 (BatchNorm over a handful of pixels, one-row GEMM tiles, a single split) and batch 3
+    (pixel boxes that overhang the batch) run a full step with finite results, and batch 3 agrees with the oracle's softmax."""
+    from resnet_b200 import api
+    for N in (1, 3):
+        cfg = dict(G.MINI, batch=N)
+        t = api.Trainer(input_dim=cfg["input_dim"], n_blocks=cfg["n_blocks"], reductions=cfg["reductions"], batch=N, output=cfg["output"],
+                        lr=cfg["lr"], dtype=dtype)
+        shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
+        W = G.mini_weights(shapes)
+        t.set_params(W)
+        img, lab = G.mini_batch(cfg)
+        t.set_batch(img, lab)
+        pred = t.forward()
+        assert np.isfinite(pred).all() and abs(pred.sum(1) - 1).max() < 1e-4
+        t.backward()
+        assert all(np.isfinite(g).all() for g in t.get_params(1))
+        t.update()
+        assert all(np.isfinite(p).all() for p in t.get_params(0))
+        if N == 3:
+            net = O.OracleNet(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], N, output=cfg["output"], lr=cfg["lr"])
+            net.set_params([w.copy() for w in W])
+            opred = net.forward(img, lab)
+            assert np.abs(pred - opred).max() < (2e-2 if dtype == "tf32" else 1e-1)
+        t.close()
