@@ -332,3 +332,26 @@ def test_training_overfits_a_fixed_batch(dtype):
     assert last < first / 10, (first, last)
     assert losses[-1][1] == 0, losses[-1]
     t.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 3e-3), ("bf16", 3e-3)])
+@pytest.mark.parametrize("S,k,cin,cout,stride,N", [(14, 3, 256, 512, 2, 4), (8, 1, 128, 256, 1, 3), (7, 3, 512, 512, 1, 2)])
+def test_wgrad_paired_co_tiles_forced(api, dtype, tol, S, k, cin, cout, stride, N):
+    """The wgrad variant the large projections use at batch 256 (two 128-row co tiles per work item, all 512 TMEM columns,
+    single-buffered; chosen only when a work item keeps >= 64 stages) forced on small problems with RESNET_B200_WGRAD_MPAIR=2,
+    against the oracle and against the one-tile-per-item variant."""
+    rng = np.random.default_rng(S + cin + cout)
+    R = api.bf16_round if dtype == "bf16" else (lambda a: a)
+    x = R(rng.standard_normal((N, S, S, cin)).astype(np.float32))
+    w = R((rng.standard_normal((cout, cin, k, k)) * 0.1).astype(np.float32))
+    dy = R(rng.standard_normal((N, S // stride, S // stride, cout)).astype(np.float32))
+    ref = O.conv_wgrad(x, dy, k, stride)
+    out = {}
+    for mode in ("2", "0"):
+        os.environ["RESNET_B200_WGRAD_MPAIR"] = mode
+        try:
+            _, out[mode] = api.conv_backward(x, w, dy, stride, want_din=False, impl=0, dtype=dtype)
+        finally:
+            os.environ.pop("RESNET_B200_WGRAD_MPAIR", None)
+        assert rel_max(out[mode], ref) < tol, mode
+    assert rel_max(out["2"], out["0"]) < 1e-4   # same products, different split-K partition
