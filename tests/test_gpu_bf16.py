@@ -355,3 +355,32 @@ def test_wgrad_paired_co_tiles_forced(api, dtype, tol, S, k, cin, cout, stride, 
             os.environ.pop("RESNET_B200_WGRAD_MPAIR", None)
         assert rel_max(out[mode], ref) < tol, mode
     assert rel_max(out["2"], out["0"]) < 1e-4   # same products, different split-K partition
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 3e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("S,k,cin,cout,stride,N", [(8, 3, 64, 64, 1, 2), (16, 1, 64, 256, 1, 3), (14, 3, 64, 128, 2, 2), (64, 7, 3, 64, 2, 3)])
+def test_resident_weight_operand_forced(api, dtype, tol, S, k, cin, cout, stride, N):
+    """fprop / dgrad with the CTA's whole weight operand resident in shared memory (what the 64-channel layers and the stem use at
+    batch 256, where a CTA runs many tiles) forced on small problems with RESNET_B200_RESIDENT_B=2; bit-identical to the
+    re-fetching variant."""
+    rng = np.random.default_rng(S + cin + cout)
+    R = api.bf16_round if dtype == "bf16" else (lambda a: a)
+    x = O.synthetic_batch(N, S, seed=S)[0] if cin == 3 else R(rng.standard_normal((N, S, S, cin)).astype(np.float32))
+    w = R((rng.standard_normal((cout, cin, k, k)) * 0.1).astype(np.float32))
+    dy = R(rng.standard_normal((N, S // stride, S // stride, cout)).astype(np.float32))
+    xr = R(x) if cin == 3 else x
+    out = {}
+    for mode in ("2", "0"):
+        os.environ["RESNET_B200_RESIDENT_B"] = mode
+        try:
+            y = api.conv_forward(x, w, stride, impl=0, dtype=dtype)
+            din = api.conv_backward(x, w, dy, stride, impl=0, dtype=dtype)[0] if cin != 3 else None
+        finally:
+            os.environ.pop("RESNET_B200_RESIDENT_B", None)
+        assert rel_max(y, O.conv_fwd(xr, w, stride)) < tol, mode
+        if din is not None:
+            assert rel_max(din, O.conv_dgrad(w, dy, S, stride)) < tol, mode
+        out[mode] = (y, din)
+    np.testing.assert_array_equal(out["2"][0], out["0"][0])
+    if out["2"][1] is not None:
+        np.testing.assert_array_equal(out["2"][1], out["0"][1])
