@@ -588,6 +588,10 @@ static inline int kelems_of(int bf16) { return bf16 ? 64 : 32; }  // elements pe
 
 // choose a pixel box (bw, bh, bn) with product <= cap (exact == cap if exact) maximising coverage of (W, H, N)
 static void choose_box(int W, int H, int N, int cap, bool exact, int *bw, int *bh, int *bn) {
+	if (const char *e = getenv("RESNET_B200_BOX")) {  // bring-up / tuning aid: "bw,bh,bn" for the 128-pixel boxes of fprop / dgrad
+		int a, b, c;
+		if (!exact && sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a * b * c <= cap && a >= 1 && b >= 1 && c >= 1) { *bw = a; *bh = b; *bn = c; return; }
+	}
 	double best = -1;
 	*bw = 1; *bh = 1; *bn = cap;
 	for (int w = 1; w <= cap; w++) {
