@@ -132,6 +132,7 @@ struct alignas(64) IgemmParams {
 	// and sat at the ~10-12 TB/s the TMA / L2 path delivers chip-wide.
 	int resident_b;
 	uint32_t resb_bytes;
+	int debug;  // profiling aid (RESNET_B200_DEBUG_SKIP): bit 0 = issue no MMAs (feed only), bit 1 = epilogue drains TMEM but stores nothing
 	float *out;
 	int OH, OW, os, accumulate;
 	int tma_store;  // epilogue: 1 = swizzled smem staging + TMA tile store (reduce-add when accumulate), 0 = per-thread row stores
@@ -268,8 +269,10 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 					const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
 					const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
 					const uint64_t bdesc = make_smem_desc(p.resident_b ? smem_u32(resb + (size_t)it * p.b_bytes) : a_addr + p.a_bytes, 16, 1024);
+					if (!(p.debug & 1)) {
 #pragma unroll
-					for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+						for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+					}
 					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
@@ -302,7 +305,9 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			mbar_wait(&tfull[acc], accphase);
 			tc_fence_after();
 			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-			if (p.tma_store) {
+			if (p.debug & 2) {
+				// feed-only profiling: nothing to drain
+			} else if (p.tma_store) {
 				// TMEM -> registers -> swizzled smem tile -> one TMA tile store (or reduce-add for the residual join) per 128-byte
 				// column chunk: fully coalesced lines, rows outside the tensor are clipped by the TMA unit
 				constexpr int CW = BF16 ? 64 : 32;  // output columns per staged 128-byte row
@@ -662,6 +667,7 @@ static int tma_store_enabled(int bf16) {
 
 static void finish_kmajor(TcPlan *pl) {
 	IgemmParams &p = pl->ip;
+	int max_stages_override = 0;  // RESNET_B200_STAGES: profiling aid
 	p.a_bytes = kABytes;
 	p.a_tx_bytes = (uint32_t)(p.bw * p.bh * p.bn) * 128;
 	p.b_bytes = (uint32_t)p.BN * 128;
@@ -684,9 +690,13 @@ static void finish_kmajor(TcPlan *pl) {
 	p.resident_b = want_res && p.ngroups == 1 && pl->grid % p.n_tiles == 0 && resb <= 80 * 1024 && (total >= 2 * pl->grid || want_res == 2) &&
 	               kMaxDynSmem - 2048 - staging_bytes - resb >= 4 * (size_t)p.a_bytes;
 	p.resb_bytes = p.resident_b ? (uint32_t)resb : 0;
+	p.debug = 0;
+	if (const char *e = getenv("RESNET_B200_DEBUG_SKIP")) p.debug = atoi(e);
+	if (const char *e = getenv("RESNET_B200_STAGES")) { int v = atoi(e); if (v >= 1) max_stages_override = v; }
 	const uint32_t pipe_stage = p.resident_b ? p.a_bytes : stage_bytes;
 	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
 	p.stages = stages > 8 ? 8 : stages;
+	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
 }
