@@ -712,6 +712,64 @@ __global__ void __launch_bounds__(kThreads, 3) maxpool3s2_bwd_kernel(const int *
 	}
 }
 
+// The same sums with each pooled vector read four times instead of nine: a thread owns the 2 x 2 input block (2a..2a+1, 2b..2b+1),
+// whose pixels belong to windows (a, b), (a, b+1), (a+1, b), (a+1, b+1) only -- four (gradient, argmax) vector pairs in, four input
+// gradient vectors out, summed in the same ascending (oh, ow) order (bit-identical to the per-pixel kernel above, which ran at
+// 2.1-2.5 TB/s of DRAM traffic on its L1 / L2 request rate: 2.25 pooled vector pairs per input vector).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads, 3) maxpool3s2_bwd_block_kernel(const int *__restrict__ inds, const T *__restrict__ dout, int N, int S, int C, T *__restrict__ din) {
+	using raw_t = typename RawOf<VEC>::type;
+	const int So = S / 2, V = C / VEC;
+	const long long total = (long long)N * So * So * V;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+		const int cv = (int)(i % V);
+		long long p = i / V;
+		const int b = (int)(p % So); p /= So;
+		const int a = (int)(p % So);
+		const int n = (int)(p / So);
+		raw_t rd[4];
+		int4 ri[4][VEC / 4];
+		bool ok[4];
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			const int oh = a + (t >> 1), ow = b + (t & 1);
+			ok[t] = oh < So && ow < So;
+			if (ok[t]) {
+				const long long o = ((((long long)n * So + oh) * So + ow) * C) / VEC + cv;
+				rd[t] = ldraw<T, VEC>(dout, o);
+#pragma unroll
+				for (int q = 0; q < VEC / 4; q++) ri[t][q] = reinterpret_cast<const int4 *>(inds)[o * (VEC / 4) + q];
+			}
+		}
+		float d[4][VEC];
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			if (ok[t]) unpack<T, VEC>(rd[t], d[t]);
+		}
+#pragma unroll
+		for (int px = 0; px < 4; px++) {  // input pixel (2a + px / 2, 2b + px % 2) collects from windows t with (t / 2 <= px / 2) and (t % 2 <= px % 2)
+			const int h = 2 * a + (px >> 1), w = 2 * b + (px & 1);
+			const long long vi = (((long long)n * S + h) * S + w) * V + cv;
+			const int me = (int)(vi * VEC);
+			float acc[VEC];
+#pragma unroll
+			for (int j = 0; j < VEC; j++) acc[j] = 0.f;
+#pragma unroll
+			for (int t = 0; t < 4; t++) {
+				if ((t >> 1) > (px >> 1) || (t & 1) > (px & 1) || !ok[t]) continue;
+#pragma unroll
+				for (int q = 0; q < VEC / 4; q++) {
+					if (ri[t][q].x == me + 4 * q) acc[4 * q] += d[t][4 * q];
+					if (ri[t][q].y == me + 4 * q + 1) acc[4 * q + 1] += d[t][4 * q + 1];
+					if (ri[t][q].z == me + 4 * q + 2) acc[4 * q + 2] += d[t][4 * q + 2];
+					if (ri[t][q].w == me + 4 * q + 3) acc[4 * q + 3] += d[t][4 * q + 3];
+				}
+			}
+			stv<T, VEC>(din, vi, acc);
+		}
+	}
+}
+
 void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16) {
 	const int So = S / stride;
 	const int VEC = vec_of(C, bf16);
@@ -779,6 +837,14 @@ void maxpool_bwd(const int *max_inds, const void *dout, int N, int S, int C, int
 	long long total = (long long)N * S * S * (C / VEC);
 	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kMaxFlatBlocks * 8 ? kMaxFlatBlocks * 8 : grid;
 	if (k == 3 && stride == 2 && S % 2 == 0 && VEC >= 4 && (long long)N * S * S * C < (1LL << 31)) {
+		if (!getenv("RESNET_B200_POOL_BWD_PIXEL")) {  // one thread per 2 x 2 input block
+			const long long blocks = ((long long)N * (S / 2) * (S / 2) * (C / VEC) + kThreads - 1) / kThreads;
+			const int g2 = (int)(blocks > kNumSMs * 3 * 8 ? kNumSMs * 3 * 8 : blocks);
+			if (bf16) maxpool3s2_bwd_block_kernel<bf16_t, 8><<<g2, kThreads, 0, st>>>(max_inds, (const bf16_t *)dout, N, S, C, (bf16_t *)din);
+			else maxpool3s2_bwd_block_kernel<float, 4><<<g2, kThreads, 0, st>>>(max_inds, (const float *)dout, N, S, C, (float *)din);
+			RB_LAUNCH_CHECK();
+			return;
+		}
 		grid = grid > kNumSMs * 3 * 8 ? kNumSMs * 3 * 8 : grid;
 		if (bf16) maxpool3s2_bwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>(max_inds, (const bf16_t *)dout, N, S, C, (bf16_t *)din);
 		else maxpool3s2_bwd_kernel<float, 4><<<grid, kThreads, 0, st>>>(max_inds, (const float *)dout, N, S, C, (float *)din);
@@ -1090,11 +1156,62 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 		dw[o] = s;
 	}
 }
+// The same sums (same order: bit-identical) with 128-bit accesses on both sides.  A block owns kWvPairs consecutive (co, ci) pairs:
+// thread (tap, quad) sums the float4 of pairs 4*quad..+3 of its tap plane over the splits (a tap plane's 32 quads are 512 contiguous
+// bytes; four loads in flight per thread), the [pair][tap] re-layout goes through shared memory, and the block's kWvPairs * TAPS outputs
+// -- contiguous in dW -- leave as float4 rows.  The scalar kernel above ran the 1x1 / large 3x3 reduces at ~2.2 TB/s.
+constexpr int kWvPairs = 128;
+template <int TAPS, int GROUPS>  // GROUPS independent 128-pair groups per block (TAPS = 1: 8 groups = 256 threads)
+__global__ void __launch_bounds__(32 * TAPS * GROUPS) wgrad_reduce_vec_kernel(const float *__restrict__ partial, int splits, long long cc, float *__restrict__ dw) {
+	__shared__ float sm[TAPS == 1 ? 1 : kWvPairs * TAPS];
+	static_assert(TAPS == 1 || GROUPS == 1, "the shared-memory re-layout is per block");
+	const long long per = cc * TAPS;
+	const int grp = threadIdx.x / (32 * TAPS), tap = (threadIdx.x / 32) % TAPS, quad = threadIdx.x % 32;
+	for (long long p0 = ((long long)blockIdx.x * GROUPS + grp) * kWvPairs; p0 < cc; p0 += (long long)gridDim.x * GROUPS * kWvPairs) {
+		const float4 *src = reinterpret_cast<const float4 *>(partial + (long long)tap * cc + p0) + quad;
+		const long long step = per / 4;
+		float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+		int sp = 0;
+		for (; sp + 4 <= splits; sp += 4) {
+			const float4 a = src[(long long)sp * step], b = src[(long long)(sp + 1) * step], c = src[(long long)(sp + 2) * step], d = src[(long long)(sp + 3) * step];
+			s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+			s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+			s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+			s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+		}
+		for (; sp < splits; sp++) {
+			const float4 a = src[(long long)sp * step];
+			s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+		}
+		if (TAPS == 1) {
+			reinterpret_cast<float4 *>(dw + p0)[quad] = s;
+		} else {
+			__syncthreads();  // the previous round's readers are done
+			sm[(4 * quad) * TAPS + tap] = s.x;
+			sm[(4 * quad + 1) * TAPS + tap] = s.y;
+			sm[(4 * quad + 2) * TAPS + tap] = s.z;
+			sm[(4 * quad + 3) * TAPS + tap] = s.w;
+			__syncthreads();
+			// kWvPairs * TAPS floats = 32 * TAPS float4: one per thread
+			reinterpret_cast<float4 *>(dw + p0 * TAPS)[threadIdx.x] = reinterpret_cast<const float4 *>(sm)[threadIdx.x];
+		}
+	}
+}
 void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps, float *dw, cudaStream_t st) {
 	long long per = (long long)taps * cout * cin;
 	if (splits >= 48) {
 		int grid = (int)((per + kWrX - 1) / kWrX); grid = grid > kNumSMs * 32 ? kNumSMs * 32 : grid;
 		wgrad_reduce_lanes_kernel<<<grid, dim3(kWrX, kWrY), 0, st>>>(partial, splits, cout, cin, taps, dw);
+	} else if ((taps == 1 || taps == 9) && ((long long)cout * cin) % (8 * kWvPairs) == 0 && (uintptr_t)partial % 16 == 0 && (uintptr_t)dw % 16 == 0 &&
+	           !getenv("RESNET_B200_WGRAD_REDUCE_SCALAR")) {
+		const long long cc = (long long)cout * cin;
+		if (taps == 1) {
+			int grid = (int)(cc / (8 * kWvPairs)); grid = grid > kNumSMs * 8 ? kNumSMs * 8 : grid;
+			wgrad_reduce_vec_kernel<1, 8><<<grid, 256, 0, st>>>(partial, splits, cc, dw);
+		} else {
+			int grid = (int)(cc / kWvPairs); grid = grid > kNumSMs * 7 ? kNumSMs * 7 : grid;
+			wgrad_reduce_vec_kernel<9, 1><<<grid, 32 * 9, 0, st>>>(partial, splits, cc, dw);
+		}
 	} else {
 		int grid = (int)((per + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
 		wgrad_reduce_kernel<<<grid, 256, 0, st>>>(partial, splits, cout, cin, taps, dw);

@@ -133,6 +133,11 @@ struct alignas(64) IgemmParams {
 	int resident_b;
 	uint32_t resb_bytes;
 	int debug;  // profiling aid (RESNET_B200_DEBUG_SKIP): bit 0 = issue no MMAs (feed only), bit 1 = epilogue drains TMEM but stores nothing
+	// halo = 1 (igemm_halo_kernel, stride-1 3x3): the activation patch of a tile -- (bh + 2) x (bw + 2) pixels, PH x PW -- is fetched
+	// ONCE per K chunk (a_tx_bytes) into an a_bytes slot of an `stages`-deep ring, and the nine taps address it through descriptor
+	// start offsets; the weight tiles of the (K chunk, tap) pairs travel through their own `bstages`-deep ring unless resident_b.
+	int halo, PW, PH, bstages;
+	int desc_base_off;  // bring-up aid (RESNET_B200_HALO_BASEOFF): also set the descriptor's base-offset field to (start >> 7) & 7
 	float *out;
 	int OH, OW, os, accumulate;
 	int tma_store;  // epilogue: 1 = swizzled smem staging + TMA tile store (reduce-add when accumulate), 0 = per-thread row stores
@@ -400,6 +405,228 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			if (acc == 0) accphase ^= 1;
 		}
 		if (issuer) tma_wait_group0();  // shared memory must outlive the last store's reads; global writes complete before exit
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tc_fence_after();
+		tmem_dealloc(tmem_base, kTmemCols);
+	}
+}
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad, stride-1 3x3, haloed patch
+// The per-tap kernel above fetches every activation nine times (one shifted 128-pixel box per filter tap), and the layers with
+// few channels (64 at 56x56, 128 at 28x28) are bound by those activation bytes into shared memory, not by the MMAs
+// (profiles/r01_conv_probe_feed_only.txt).  Here a tile's activations are fetched ONCE per K chunk: the (bh + 2) x (bw + 2) pixel
+// patch around a bh x bw output tile lands as [PH][PW] rows of 128 bytes (TMA zero-fills the out-of-image border = the padding),
+// and tap (kh, kw) is the SAME shared memory read from row kh * PW + kw on: accumulator row r (r = 0..127) belongs to patch
+// position r = h * PW + w, and reads patch row r + kh * PW + kw = pixel (h + kh, w + kw).  Rows with w >= bw (the two halo columns
+// of every patch row) or h >= bh are computed and dropped (14 x 8 and 28 x 4 tiles: 112 of 128 rows useful).  The 128-byte swizzle is a
+// function of the shared-memory address bits, so a descriptor whose start address is moved by whole 128-byte rows still meets the
+// pattern the TMA unit wrote.  The epilogue compacts the useful rows into a dense [bh][bw] staging tile for the TMA store.
+template <bool BF16>
+__global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __grid_constant__ IgemmParams p) {
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t *base = align1024(smem_raw);
+	uint8_t *resb = base;                                                       // resident weight tiles [kc][tap] (resb_bytes, 0 when unused)
+	uint8_t *aring = base + p.resb_bytes;                                       // `stages` activation patches
+	uint8_t *bring = aring + (size_t)p.stages * p.a_bytes;                      // `bstages` weight tiles (none when resident)
+	uint8_t *staging = bring + (size_t)p.bstages * p.b_bytes;                   // epi_groups x nstaging x 16 KB epilogue tiles
+	uint64_t *afull = reinterpret_cast<uint64_t *>(staging + p.epi_groups * p.nstaging * kABytes);
+	uint64_t *aempty = afull + p.stages;
+	uint64_t *bfull = aempty + p.stages;
+	uint64_t *bempty = bfull + p.bstages;
+	uint64_t *tfull = bempty + p.bstages;
+	uint64_t *tempty = tfull + 2;
+	uint64_t *resfull = tempty + 2;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(resfull + 1);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (warp == 0 && lane == 0) {
+		prefetch_tmap(&p.amap[0]);
+		prefetch_tmap(&p.bmap);
+		prefetch_tmap(&p.omap[0]);
+	}
+	if (warp == 1) {
+		if (lane == 0) {
+			for (int i = 0; i < p.stages; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+			for (int i = 0; i < p.bstages; i++) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * p.epi_groups); }
+			mbar_init(resfull, 1);
+			fence_barrier_init();
+		}
+		__syncwarp();
+		tmem_alloc(tmem_slot, kTmemCols);
+		tmem_relinquish();
+	}
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	const int total_tiles = p.m_tiles * p.n_tiles;
+	const GroupDesc &g = p.groups[0];
+
+	if (warp == 0) {
+		if (lane == 0) {
+			int as = 0, bs = 0;
+			uint32_t aph = 0, bph = 0;
+			if (p.resident_b && (int)blockIdx.x < total_tiles) {  // the weights of this CTA's N tile, once
+				const int nt = (int)blockIdx.x % p.n_tiles;
+				mbar_expect_tx(resfull, p.resb_bytes);
+				for (int kc = 0; kc < p.kchunks; kc++)
+					for (int t = 0; t < g.ntaps; t++)
+						tma_load_2d(resb + (size_t)(kc * g.ntaps + t) * p.b_bytes, &p.bmap, resfull, g.taps[t].bcol + kc * p.kelems, nt * p.BN);
+			}
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+				const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = mt / (p.tiles_w * p.tiles_h);
+				for (int kc = 0; kc < p.kchunks; kc++) {
+					mbar_wait(&aempty[as], aph ^ 1);
+					mbar_expect_tx(&afull[as], p.a_tx_bytes);
+					tma_load_4d(aring + (size_t)as * p.a_bytes, &p.amap[0], &afull[as], kc * p.kelems, ow0 - 1, oh0 - 1, n0);
+					if (++as == p.stages) { as = 0; aph ^= 1; }
+					if (!p.resident_b) {
+						for (int t = 0; t < g.ntaps; t++) {
+							mbar_wait(&bempty[bs], bph ^ 1);
+							mbar_expect_tx(&bfull[bs], p.b_bytes);
+							tma_load_2d(bring + (size_t)bs * p.b_bytes, &p.bmap, &bfull[bs], g.taps[t].bcol + kc * p.kelems, nt * p.BN);
+							if (++bs == p.bstages) { bs = 0; bph ^= 1; }
+						}
+					}
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == 1) {
+		if (lane == 0) {
+			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
+			int as = 0, bs = 0, acc = 0;
+			uint32_t aph = 0, bph = 0, accphase = 0;
+			if (p.resident_b && (int)blockIdx.x < total_tiles) mbar_wait(resfull, 0);
+			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+				mbar_wait(&tempty[acc], accphase ^ 1);
+				tc_fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+				for (int kc = 0; kc < p.kchunks; kc++) {
+					mbar_wait(&afull[as], aph);
+					tc_fence_after();
+					const uint32_t a_base = smem_u32(aring + (size_t)as * p.a_bytes);
+					for (int t = 0; t < g.ntaps; t++) {
+						const TapDesc tp = g.taps[t];
+						uint32_t b_addr;
+						if (p.resident_b) b_addr = smem_u32(resb + (size_t)(kc * g.ntaps + t) * p.b_bytes);
+						else {
+							mbar_wait(&bfull[bs], bph);
+							tc_fence_after();
+							b_addr = smem_u32(bring + (size_t)bs * p.b_bytes);
+						}
+						const uint32_t a_addr = a_base + (uint32_t)(((tp.dy + 1) * p.PW + (tp.dx + 1)) * 128);  // the patch from row (kh, kw) on
+						uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+						if (p.desc_base_off) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+						const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
+#pragma unroll
+						for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kc | t | k) != 0));
+						if (!p.resident_b) {
+							mma_commit(&bempty[bs]);
+							if (++bs == p.bstages) { bs = 0; bph ^= 1; }
+						}
+					}
+					mma_commit(&aempty[as]);
+					if (++as == p.stages) { as = 0; aph ^= 1; }
+				}
+				mma_commit(&tfull[acc]);
+				acc ^= 1;
+				if (acc == 0) accphase ^= 1;
+			}
+		}
+		__syncwarp();
+	} else if ((warp - 2) / 4 < p.epi_groups) {
+		// Epilogue (see igemm_kmajor_kernel): accumulator row `pos` is patch position (pos / PW, pos % PW); the useful rows are
+		// compacted to staging row h * bw + w, so ONE TMA store of a dense {columns, bw, bh, 1} box writes the tile.
+		constexpr int CW = BF16 ? 64 : 32;
+		const int eg = (warp - 2) / 4;
+		const int q = warp & 3;
+		const int pos = q * 32 + lane;
+		const int hq = pos / p.PW, wq = pos - hq * p.PW;
+		const bool in_box = (wq < p.bw) && (hq < p.bh);
+		const int crow = hq * p.bw + wq;
+		const int nrows = p.bw * p.bh;
+		const bool issuer = ((warp - 2) % 4 == 0 && lane == 0);
+		uint8_t *const gstaging = staging + (size_t)eg * p.nstaging * kABytes;
+		int acc = 0;
+		uint32_t accphase = 0, sbuf = 0, chunk_no = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+			const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = mt / (p.tiles_w * p.tiles_h);
+			const bool row_valid = in_box && (ow0 + wq < p.Wm) && (oh0 + hq < p.Hm);
+			mbar_wait(&tfull[acc], accphase);
+			tc_fence_after();
+			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+			for (int c = 0; c < p.BN / CW; c++) {
+				if (p.epi_groups == 2 && ((chunk_no++) & 1u) != (uint32_t)eg) continue;  // the other group's chunk
+				float v[CW];
+				if constexpr (BF16) tmem_ld_32x64(taddr + (uint32_t)(c * CW), v);
+				else tmem_ld_32x32(taddr + (uint32_t)(c * CW), v);
+				uint8_t *buf = gstaging + sbuf * kABytes;
+				sbuf = (sbuf + 1 == (uint32_t)p.nstaging ? 0 : sbuf + 1);
+				if (in_box) {
+					uint8_t *rowp = buf + crow * 128;
+					if (p.stats && !row_valid) {  // rows the TMA store clips must not pollute the fused statistics
+#pragma unroll
+						for (int j = 0; j < CW; j++) v[j] = 0.f;
+					}
+#pragma unroll
+					for (int j = 0; j < 8; j++) {
+						if constexpr (BF16)
+							*reinterpret_cast<uint4 *>(rowp + ((j ^ (crow & 7)) << 4)) =
+							    make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+							               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+						else
+							*reinterpret_cast<float4 *>(rowp + ((j ^ (crow & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+					}
+				}
+				fence_proxy_async();
+				if (issuer) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }
+				named_barrier_sync(1 + eg, 128);
+				if (issuer) {
+					if (p.accumulate) tma_reduce_add_4d(&p.omap[0], buf, nt * p.BN + c * CW, ow0, oh0, n0);
+					else tma_store_4d(&p.omap[0], buf, nt * p.BN + c * CW, ow0, oh0, n0);
+					tma_commit_group();
+				}
+				if (p.stats) {  // fused BatchNorm statistics over the staged rows (see igemm_kmajor_kernel)
+					float cs = 0.f, cq = 0.f, cs1 = 0.f, cq1 = 0.f;
+					const int r_end = min(32, nrows - q * 32);
+#pragma unroll 8
+					for (int rr = 0; rr < r_end; rr++) {
+						const int r2 = q * 32 + rr;
+						const uint32_t w = *reinterpret_cast<const uint32_t *>(buf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7)) << 4) | ((lane & 3) << 2)));
+						if constexpr (BF16) {
+							const float y0 = __uint_as_float(w << 16), y1 = __uint_as_float(w & 0xffff0000u);
+							cs += y0; cq = fmaf(y0, y0, cq);
+							cs1 += y1; cq1 = fmaf(y1, y1, cq1);
+						} else {
+							const float y = __uint_as_float(w);
+							cs += y;
+							cq = fmaf(y, y, cq);
+						}
+					}
+					float *sp = p.stats + ((size_t)((blockIdx.x * p.epi_groups + eg) * 4 + q) * 2) * p.Ncol + (size_t)nt * p.BN + c * CW + (BF16 ? 2 * lane : lane);
+					atomicAdd(sp, cs);
+					atomicAdd(sp + p.Ncol, cq);
+					if constexpr (BF16) {
+						atomicAdd(sp + 1, cs1);
+						atomicAdd(sp + p.Ncol + 1, cq1);
+					}
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&tempty[acc]);
+			acc ^= 1;
+			if (acc == 0) accphase ^= 1;
+		}
+		if (issuer) tma_wait_group0();
 	}
 	tc_fence_before();
 	__syncthreads();
@@ -701,8 +928,124 @@ static void finish_kmajor(TcPlan *pl) {
 	pl->kind = 0;
 }
 
+// ---- haloed-patch plans (igemm_halo_kernel): stride-1 3x3 fprop / dgrad
+// output tile bw x bh with bh * (bw + 2) <= 128 patch positions; picks the shape with the largest useful fraction of the 128 MMA
+// rows over the whole S x S map (ties: the smaller patch)
+static double choose_halo_tile(int S, int *bw, int *bh) {
+	double best = -1;
+	int best_rows = 0;
+	*bw = *bh = 0;
+	for (int w = 1; w <= 126 && w <= S; w++) {
+		const int hmax = 128 / (w + 2);
+		for (int h = 1; h <= hmax && h <= S; h++) {
+			const double frac = (double)S * S / ((double)ceil_div(S, w) * ceil_div(S, h) * 128.0);
+			const int rows = (w + 2) * (h + 2);
+			if (frac > best + 1e-9 || (frac > best - 1e-9 && rows < best_rows)) { best = frac; best_rows = rows; *bw = w; *bh = h; }
+		}
+	}
+	return best;
+}
+// RESNET_B200_HALO: 0 (default) = never, 1 = the layers it was written for (<= 128 output columns per tile and >= 85 % useful MMA
+// rows, i.e. the 64-channel 56x56 and 128-channel 28x28 layers of ResNet-50 / 152), 2 = every stride-1 3x3 (tests).
+// Off by default: measured on B200 (profiles/r01_conv_probe_halo.txt) it is bit-compatible and moves 6x fewer activation bytes, but
+// it is 25-50 % SLOWER than the per-tap kernel on exactly those layers -- a tcgen05.mma in SS mode costs >= ~115 clocks whatever
+// its N (profiles/r01_mma_rate.txt), so a 64- or 128-column MMA cannot use more than 28 % / 55 % of the tensor pipe however it is
+// fed, and the patch tiling wastes 12.5 % of the rows on top.  Kept as the feed half of the N = pixels (swapped operand) plan of
+// DESIGN.md 8.
+static int halo_mode() {
+	if (const char *e = getenv("RESNET_B200_HALO")) return atoi(e);
+	return 0;
+}
+static bool halo_wanted(const ConvGeom &g, int ncol, int bf16, int *bw, int *bh) {
+	const int mode = halo_mode();
+	if (mode <= 0 || g.k != 3 || g.stride != 1 || !tma_store_enabled(bf16)) return false;
+	const double frac = choose_halo_tile(g.S, bw, bh);
+	if (*bw < 1) return false;
+	if (mode >= 2) return true;
+	return frac >= 0.85 && pick_bn(ncol, bf16) <= 128;
+}
+
+// in: the tensor the taps read ([N][S][S][K]); wk: packed weights [ncol][tap][K]; out: [N][S][S][ncol].  tap t reads pixel + (dx[t], dy[t]).
+static TcPlan *make_halo_plan(const ConvGeom &g, const void *in, int K, const void *wk, void *out, int ncol, const int *tdx, const int *tdy,
+                              int accumulate, int bw, int bh, int bf16, const char *what) {
+	TcPlan *pl = new TcPlan();
+	memset(pl, 0, sizeof(*pl));
+	pl->bf16 = bf16;
+	IgemmParams &p = pl->ip;
+	const int S = g.S, ke = kelems_of(bf16);
+	p.halo = 1;
+	p.Wm = S; p.Hm = S; p.Nn = g.N;
+	p.bw = bw; p.bh = bh; p.bn = 1;
+	p.PW = bw + 2; p.PH = bh + 2;
+	p.tiles_w = ceil_div(S, bw); p.tiles_h = ceil_div(S, bh); p.tiles_b = g.N;
+	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+	p.Ncol = ncol; p.BN = pick_bn(ncol, bf16); p.n_tiles = ncol / p.BN;
+	p.kelems = ke; p.kchunks = K / ke;
+	const long long dims_in[4] = {K, S, S, g.N}, str_in[3] = {K, (long long)S * K, (long long)S * S * K};
+	const int box_in[4] = {ke, p.PW, p.PH, 1};
+	bool ok = make_map4(&p.amap[0], in, dims_in, str_in, box_in, bf16);
+	for (int i = 1; i < 4; i++) p.amap[i] = p.amap[0];
+	ok = ok && make_map2(&p.bmap, wk, 9LL * K, ncol, 9LL * K, ke, p.BN, bf16);
+	const long long dims_out[4] = {ncol, S, S, g.N}, str_out[3] = {ncol, (long long)S * ncol, (long long)S * S * ncol};
+	const int box_out[4] = {ke, bw, bh, 1};
+	ok = ok && make_map4(&p.omap[0], out, dims_out, str_out, box_out, bf16);
+	for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
+	p.ngroups = 1;
+	GroupDesc &gr = p.groups[0];
+	gr.ntaps = 9; gr.oh_off = gr.ow_off = 0; gr.omap = 0;
+	for (int t = 0; t < 9; t++) gr.taps[t] = TapDesc{tdx[t], tdy[t], 0, t * K};
+	p.out = (float *)out; p.OH = S; p.OW = S; p.os = 1; p.accumulate = accumulate;
+	p.tma_store = 1;
+	// shared memory: [resident weights] [A ring] [B ring] [staging] [barriers]
+	p.a_bytes = (uint32_t)(((2 * p.PW + 2 + 128) * 128 + 1023) / 1024 * 1024);  // every row a tap's 128-row window can touch
+	p.a_tx_bytes = (uint32_t)(p.PW * p.PH) * 128;
+	p.b_bytes = (uint32_t)p.BN * 128;
+	// one tile's MMAs take ~ 9 * kchunks * 4 * BN / 2 clocks, one staged 128-byte column chunk ~ 1500 clocks of one epilogue group
+	const int cw = bf16 ? 64 : 32;
+	p.epi_groups = ((p.BN / cw) * 1500 > 9 * p.kchunks * 2 * p.BN) ? 2 : 1;
+	if (const char *e = getenv("RESNET_B200_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= 2) p.epi_groups = v; }
+	p.nstaging = 2;
+	const int total = p.m_tiles * p.n_tiles;
+	pl->grid = total < kNumSMs ? total : kNumSMs;
+	const size_t resb = (size_t)9 * p.kchunks * p.b_bytes;
+	int want_res = 1;
+	if (const char *e = getenv("RESNET_B200_RESIDENT_B")) want_res = atoi(e);
+	size_t staging_bytes = 0;
+	for (;; p.epi_groups = 1) {  // a second epilogue group only where its staging tiles leave room for the operand rings
+		staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
+		const size_t budget = kMaxDynSmem - 2048 - staging_bytes;
+		p.resident_b = want_res && pl->grid % p.n_tiles == 0 && (total >= 2 * pl->grid || want_res == 2) && resb + 3 * (size_t)p.a_bytes <= budget;
+		if (p.resident_b) {
+			p.resb_bytes = (uint32_t)resb;
+			p.stages = (int)std::min<size_t>(6, (budget - resb) / p.a_bytes);
+			p.bstages = 0;
+			break;
+		}
+		p.resb_bytes = 0;
+		p.stages = p.kchunks >= 2 ? 3 : 2;
+		p.bstages = (int)std::min<size_t>(16, (budget - (size_t)p.stages * p.a_bytes) / p.b_bytes);
+		if (p.bstages >= 4 || p.epi_groups == 1) break;
+	}
+	if (!p.resident_b && p.bstages < 2) { set_error("make_halo_plan: no room for the weight ring"); ok = false; }
+	if (const char *e = getenv("RESNET_B200_HALO_BASEOFF")) p.desc_base_off = atoi(e);
+	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * p.a_bytes + (size_t)p.bstages * p.b_bytes + staging_bytes + 1024 + 512;
+	pl->kind = 0;
+	pl->flops = 2.0 * g.N * S * S * (double)g.cout * g.cin * 9;
+	snprintf(pl->what, sizeof(pl->what), "%s 3x3/1 %d->%d @%d", what, g.cin, g.cout, g.S);
+	if (!ok || pl->smem > kMaxDynSmem) { if (ok) set_error("make_halo_plan: shared memory plan too large"); delete pl; return nullptr; }
+	return pl;
+}
+
 TcPlan *tc_make_fprop(const ConvGeom &g, const void *x, const void *wf, void *y, int bf16) {
 	if (!tc_supported(g, bf16)) { set_error("tc_make_fprop: unsupported geometry"); return nullptr; }
+	{
+		int hbw, hbh;
+		if (halo_wanted(g, g.cout, bf16, &hbw, &hbh)) {  // y(h, w) += Wf[kh][kw] . x(h + kh - 1, w + kw - 1)
+			int tdx[9], tdy[9];
+			for (int t = 0; t < 9; t++) { tdx[t] = t % 3 - 1; tdy[t] = t / 3 - 1; }
+			return make_halo_plan(g, x, g.cin, wf, y, g.cout, tdx, tdy, 0, hbw, hbh, bf16, "fprop");
+		}
+	}
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
 	pl->bf16 = bf16;
@@ -748,6 +1091,14 @@ TcPlan *tc_make_fprop(const ConvGeom &g, const void *x, const void *wf, void *y,
 
 TcPlan *tc_make_dgrad(const ConvGeom &g, const void *dy, const void *wd, void *dx, int accumulate, int bf16) {
 	if (!tc_supported(g, bf16)) { set_error("tc_make_dgrad: unsupported geometry"); return nullptr; }
+	{
+		int hbw, hbh;
+		if (halo_wanted(g, g.cin, bf16, &hbw, &hbh)) {  // dx(h, w) += Wd[kh][kw] . dy(h + 1 - kh, w + 1 - kw)
+			int tdx[9], tdy[9];
+			for (int t = 0; t < 9; t++) { tdx[t] = 1 - t % 3; tdy[t] = 1 - t / 3; }
+			return make_halo_plan(g, dy, g.cout, wd, dx, g.cin, tdx, tdy, accumulate, hbw, hbh, bf16, "dgrad");
+		}
+	}
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
 	pl->bf16 = bf16;
@@ -970,15 +1321,27 @@ __global__ void stem_pack_weights_kernel(const float *__restrict__ w, int cout, 
 		}
 	}
 }
-// dw [Cout][3][7][7] = sum_s partial[s][kh][Cout][kw*4 + c]
-__global__ void stem_wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, int RE, float *__restrict__ dw) {
+// dw [Cout][3][7][7] = sum_s partial[s][kh][Cout][kw*4 + c].  The stem's one wgrad tile is split ~300 ways, so a block sums 32
+// outputs over 8 split lanes (lane y takes splits y, y + 8, ...: independent loads) and combines the lanes in a fixed order
+// (deterministic); one thread per output walked the splits as one serial chain of dependent-latency loads (145 us for 9408 outputs).
+constexpr int kSwrX = 32, kSwrY = 8;
+__global__ void __launch_bounds__(kSwrX * kSwrY) stem_wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int cout, int RE, float *__restrict__ dw) {
+	__shared__ float sm[kSwrY][kSwrX];
 	const int total = cout * 3 * kStemK * kStemK;
 	const long long per = (long long)kStemK * cout * RE;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+	const int i = blockIdx.x * kSwrX + threadIdx.x, ty = threadIdx.y;
+	float s = 0.f;
+	if (i < total) {
 		const int kw = i % kStemK, kh = (i / kStemK) % kStemK, c = (i / (kStemK * kStemK)) % 3, co = i / (3 * kStemK * kStemK);
 		const long long src = ((long long)kh * cout + co) * RE + kw * 4 + c;
-		float s = 0.f;
-		for (int sp = 0; sp < splits; sp++) s += partial[sp * per + src];
+#pragma unroll 4
+		for (int sp = ty; sp < splits; sp += kSwrY) s += partial[sp * per + src];
+	}
+	sm[ty][threadIdx.x] = s;
+	__syncthreads();
+	if (ty == 0 && i < total) {
+#pragma unroll
+		for (int y = 1; y < kSwrY; y++) s += sm[y][threadIdx.x];
 		dw[i] = s;
 	}
 }
@@ -1110,11 +1473,16 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		RB_CUDA(cudaFuncSetAttribute(igemm_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		RB_CUDA(cudaFuncSetAttribute(igemm_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		attr_set = true;
 	}
 	if (pl->kind == 0) {
 		if (pl->ip.stats) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
-		if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
+		if (pl->ip.halo) {
+			if (pl->bf16) igemm_halo_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
+			else igemm_halo_kernel<false><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
+		} else if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
 		else igemm_kmajor_kernel<false><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
 		RB_LAUNCH_CHECK();
 	} else {
@@ -1123,7 +1491,7 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 		RB_LAUNCH_CHECK();
 		if (pl->kind == 1) wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
 		else {
-			stem_wgrad_reduce_kernel<<<ceil_div(pl->cout * 3 * kStemK * kStemK, 256), 256, 0, st>>>(pl->wp.partial, pl->wp.splits, pl->cout, pl->wp.cin, pl->dw);
+			stem_wgrad_reduce_kernel<<<ceil_div(pl->cout * 3 * kStemK * kStemK, kSwrX), dim3(kSwrX, kSwrY), 0, st>>>(pl->wp.partial, pl->wp.splits, pl->cout, pl->wp.cin, pl->dw);
 			RB_LAUNCH_CHECK();
 		}
 	}
@@ -1146,6 +1514,10 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
+		if (p.halo)
+			snprintf(buf, n, "%s | halo %s tile=(%d,%d) m_tiles=%d n_tiles=%d BN=%d kchunks=%d astages=%d bstages=%d epi=%d grid=%d smem=%zu resB=%u", pl->what,
+			         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.m_tiles, p.n_tiles, p.BN, p.kchunks, p.stages, p.bstages, p.epi_groups, pl->grid, pl->smem, p.resb_bytes);
+		else
 		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu resB=%u", pl->what,
 		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem, p.resb_bytes);
 	} else {
