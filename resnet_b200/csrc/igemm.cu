@@ -137,6 +137,12 @@ struct alignas(64) IgemmParams {
 	// ONCE per K chunk (a_tx_bytes) into an a_bytes slot of an `stages`-deep ring, and the nine taps address it through descriptor
 	// start offsets; the weight tiles of the (K chunk, tap) pairs travel through their own `bstages`-deep ring unless resident_b.
 	int halo, PW, PH, bstages;
+	// issuers (1, 2 or 4): threads issuing the tile's MMAs.  One thread cannot issue a tcgen05.mma more often than every ~115 clocks
+	// (171 at N = 256) whatever the instruction's size, two / four threads interleaving on the SAME accumulator reach 62 / 57 clocks at
+	// N = 64, 86 / 77 at N = 128, 150 / 141 at N = 256 (profiles/r01_mma_rate.txt; results exact).  Issuer x takes the pipeline
+	// stages (halo kernel: taps) with index = x (mod issuers); issuer 0's first MMA overwrites the accumulator and is committed to
+	// `zinit` before the others may accumulate.
+	int issuers;
 	int desc_base_off;  // bring-up aid (RESNET_B200_HALO_BASEOFF): also set the descriptor's base-offset field to (start >> 7) & 7
 	float *out;
 	int OH, OW, os, accumulate;
@@ -162,12 +168,13 @@ struct alignas(64) WgradParams {
 	int merge_taps;    // the taps of a group sit back to back in shared memory AND in TMEM: one MMA of N = ntaps * BN covers them all
 	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
 	int stages;
+	int issuers;       // MMA-issuing threads (see IgemmParams::issuers): issuer x takes the stages kb - kb0 = x (mod issuers) of every work item
 	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
 	float *partial;
 };
 
-constexpr int kIgemmThreads = 192;   // wgrad: TMA warp, MMA warp, 4 epilogue warps
-constexpr int kKmajorThreads = 320;  // fprop / dgrad: TMA warp, MMA warp, up to two groups of 4 epilogue warps
+constexpr int kIgemmThreads = 288;   // wgrad: TMA warp, MMA warp, 4 epilogue warps, up to 3 more MMA-issuing warps (6-8)
+constexpr int kKmajorThreads = 416;  // fprop / dgrad: TMA warp, MMA warp, up to two groups of 4 epilogue warps, up to 3 more MMA-issuing warps (10-12)
 constexpr int kTmemCols = 512;
 constexpr uint32_t kABytes = 128 * 32 * 4;  // 128 rows x 32 tf32 = 16 KB
 
@@ -198,7 +205,8 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
 	uint64_t *bfull = tempty + 2;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
+	uint64_t *zinit = bfull + 1;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(zinit + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (warp == 0 && lane == 0) {
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 	if (warp == 1) {
 		if (lane == 0) {
 			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * p.epi_groups); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], p.issuers); mbar_init(&tempty[i], 4 * p.epi_groups); mbar_init(&zinit[i], 1); }
 			mbar_init(bfull, 1);
 			fence_barrier_init();
 		}
@@ -256,8 +264,9 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			}
 		}
 		__syncwarp();
-	} else if (warp == 1) {
+	} else if (warp == 1 || (warp >= 10 && warp - 9 < p.issuers)) {
 		if (lane == 0) {
+			const int x = warp == 1 ? 0 : warp - 9, I = p.issuers;  // this issuer takes the stages it = x (mod I) of every tile
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
@@ -265,20 +274,27 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 				const GroupDesc &g = p.groups[(tile / p.n_tiles) / p.m_tiles];
 				const int iters = g.ntaps * p.kchunks;
-				mbar_wait(&tempty[acc], accphase ^ 1);
+				// issuer 0 waits for the epilogue to drain the accumulator and overwrites it with its first MMA; the others wait for that MMA
+				if (x == 0) mbar_wait(&tempty[acc], accphase ^ 1);
+				else mbar_wait(&zinit[acc], accphase);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
 				for (int it = 0; it < iters; it++) {
-					mbar_wait(&full[stage], phase);
-					tc_fence_after();
-					const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
-					const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-					const uint64_t bdesc = make_smem_desc(p.resident_b ? smem_u32(resb + (size_t)it * p.b_bytes) : a_addr + p.a_bytes, 16, 1024);
-					if (!(p.debug & 1)) {
+					if (I == 1 || it % I == x) {
+						mbar_wait(&full[stage], phase);
+						tc_fence_after();
+						const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
+						const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+						const uint64_t bdesc = make_smem_desc(p.resident_b ? smem_u32(resb + (size_t)it * p.b_bytes) : a_addr + p.a_bytes, 16, 1024);
+						if (!(p.debug & 1)) {
 #pragma unroll
-						for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+							for (int k = 0; k < 4; k++) {
+								mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+								if (I > 1 && it == 0 && k == 0) mma_commit(&zinit[acc]);
+							}
+						} else if (I > 1 && it == 0) mma_commit(&zinit[acc]);
+						mma_commit(&empty[stage]);
 					}
-					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
 				mma_commit(&tfull[acc]);
@@ -439,7 +455,8 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __g
 	uint64_t *tfull = bempty + p.bstages;
 	uint64_t *tempty = tfull + 2;
 	uint64_t *resfull = tempty + 2;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(resfull + 1);
+	uint64_t *zinit = resfull + 1;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(zinit + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (warp == 0 && lane == 0) {
@@ -449,9 +466,9 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __g
 	}
 	if (warp == 1) {
 		if (lane == 0) {
-			for (int i = 0; i < p.stages; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+			for (int i = 0; i < p.stages; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], p.issuers); }
 			for (int i = 0; i < p.bstages; i++) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * p.epi_groups); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], p.issuers); mbar_init(&tempty[i], 4 * p.epi_groups); mbar_init(&zinit[i], 1); }
 			mbar_init(resfull, 1);
 			fence_barrier_init();
 		}
@@ -498,14 +515,16 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __g
 			}
 		}
 		__syncwarp();
-	} else if (warp == 1) {
+	} else if (warp == 1 || (warp >= 10 && warp - 9 < p.issuers)) {
 		if (lane == 0) {
+			const int x = warp == 1 ? 0 : warp - 9, I = p.issuers;  // this issuer takes the taps t = x (mod I) of every K chunk
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int as = 0, bs = 0, acc = 0;
 			uint32_t aph = 0, bph = 0, accphase = 0;
 			if (p.resident_b && (int)blockIdx.x < total_tiles) mbar_wait(resfull, 0);
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				mbar_wait(&tempty[acc], accphase ^ 1);
+				if (x == 0) mbar_wait(&tempty[acc], accphase ^ 1);
+				else mbar_wait(&zinit[acc], accphase);  // issuer 0's overwriting first MMA is done
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
 				for (int kc = 0; kc < p.kchunks; kc++) {
@@ -513,24 +532,27 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __g
 					tc_fence_after();
 					const uint32_t a_base = smem_u32(aring + (size_t)as * p.a_bytes);
 					for (int t = 0; t < g.ntaps; t++) {
-						const TapDesc tp = g.taps[t];
-						uint32_t b_addr;
-						if (p.resident_b) b_addr = smem_u32(resb + (size_t)(kc * g.ntaps + t) * p.b_bytes);
-						else {
-							mbar_wait(&bfull[bs], bph);
-							tc_fence_after();
-							b_addr = smem_u32(bring + (size_t)bs * p.b_bytes);
-						}
-						const uint32_t a_addr = a_base + (uint32_t)(((tp.dy + 1) * p.PW + (tp.dx + 1)) * 128);  // the patch from row (kh, kw) on
-						uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-						if (p.desc_base_off) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-						const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
+						if (I == 1 || t % I == x) {
+							const TapDesc tp = g.taps[t];
+							uint32_t b_addr;
+							if (p.resident_b) b_addr = smem_u32(resb + (size_t)(kc * g.ntaps + t) * p.b_bytes);
+							else {
+								mbar_wait(&bfull[bs], bph);
+								tc_fence_after();
+								b_addr = smem_u32(bring + (size_t)bs * p.b_bytes);
+							}
+							const uint32_t a_addr = a_base + (uint32_t)(((tp.dy + 1) * p.PW + (tp.dx + 1)) * 128);  // the patch from row (kh, kw) on
+							uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+							if (p.desc_base_off) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+							const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-						for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kc | t | k) != 0));
-						if (!p.resident_b) {
-							mma_commit(&bempty[bs]);
-							if (++bs == p.bstages) { bs = 0; bph ^= 1; }
+							for (int k = 0; k < 4; k++) {
+								mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kc | t | k) != 0));
+								if (I > 1 && (kc | t | k) == 0) mma_commit(&zinit[acc]);
+							}
+							if (!p.resident_b) mma_commit(&bempty[bs]);
 						}
+						if (!p.resident_b) { if (++bs == p.bstages) { bs = 0; bph ^= 1; } }
 					}
 					mma_commit(&aempty[as]);
 					if (++as == p.stages) { as = 0; aph ^= 1; }
@@ -646,7 +668,8 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	uint64_t *empty = full + p.stages;
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+	uint64_t *zinit = tempty + 2;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(zinit + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (warp == 0 && lane == 0) {
@@ -656,7 +679,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	if (warp == 1) {
 		if (lane == 0) {
 			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], p.issuers); mbar_init(&tempty[i], 4); mbar_init(&zinit[i], 1); }
 			fence_barrier_init();
 		}
 		__syncwarp();
@@ -705,8 +728,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			}
 		}
 		__syncwarp();
-	} else if (warp == 1) {
+	} else if (warp == 1 || (warp >= 6 && warp - 5 < p.issuers)) {
 		if (lane == 0) {
+			const int x = warp == 1 ? 0 : warp - 5, I = p.issuers;
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 1, 1) : make_idesc_tf32(128, p.BN, 1, 1);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
@@ -716,35 +740,40 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 				const int ntg = min(p.tpt, p.ntaps - tap0);
 				const int kb0 = split * p.boxes_per_split;
 				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
-				mbar_wait(&tempty[acc], accphase ^ 1);
+				// issuer 0 waits for the drained accumulator and overwrites it with the MMAs of the item's first stage; the others wait for those
+				if (x == 0) mbar_wait(&tempty[acc], accphase ^ 1);
+				else mbar_wait(&zinit[acc], accphase);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
 				for (int kb = kb0; kb < kb1; kb++) {
-					mbar_wait(&full[stage], phase);
-					tc_fence_after();
-					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
-					for (int m = 0; m < p.m_pair; m++) {  // the 128-row co tiles of the item: same B tiles, own A rows and accumulators
-						const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)m * kABytes, p.lbo, p.sbo, p.layout_type);
-						const uint32_t d_m = d_tmem + (uint32_t)m * grp_cols;
-						if (p.merge_taps) {
-							// the group's B tiles are contiguous [tap][channel block][px][128 B] with one LBO pitch, and its accumulators are
-							// contiguous TMEM columns: issue the whole group as ONE N = ntg * BN MMA per K step instead of ntg narrow ones
-							const uint32_t idesc_g = BF16 ? make_idesc_bf16(128, ntg * p.BN, 1, 1) : make_idesc_tf32(128, ntg * p.BN, 1, 1);
-							const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
+					if (I == 1 || (kb - kb0) % I == x) {
+						mbar_wait(&full[stage], phase);
+						tc_fence_after();
+						const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
+						for (int m = 0; m < p.m_pair; m++) {  // the 128-row co tiles of the item: same B tiles, own A rows and accumulators
+							const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)m * kABytes, p.lbo, p.sbo, p.layout_type);
+							const uint32_t d_m = d_tmem + (uint32_t)m * grp_cols;
+							if (p.merge_taps) {
+								// the group's B tiles are contiguous [tap][channel block][px][128 B] with one LBO pitch, and its accumulators are
+								// contiguous TMEM columns: issue the whole group as ONE N = ntg * BN MMA per K step instead of ntg narrow ones
+								const uint32_t idesc_g = BF16 ? make_idesc_bf16(128, ntg * p.BN, 1, 1) : make_idesc_tf32(128, ntg * p.BN, 1, 1);
+								const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-							for (int k = 0; k < 4; k++)
-								mma_ss<BF16>(d_m, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc_g, (uint32_t)((kb > kb0) || (k != 0)));
-						} else {
-							for (int t = 0; t < ntg; t++) {
-								const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
+								for (int k = 0; k < 4; k++)
+									mma_ss<BF16>(d_m, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc_g, (uint32_t)((kb > kb0) || (k != 0)));
+							} else {
+								for (int t = 0; t < ntg; t++) {
+									const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-								for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
-									mma_ss<BF16>(d_m + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
-									             (uint32_t)((kb > kb0) || (k != 0)));
+									for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
+										mma_ss<BF16>(d_m + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
+										             (uint32_t)((kb > kb0) || (k != 0)));
+								}
 							}
 						}
+						if (I > 1 && kb == kb0) mma_commit(&zinit[acc]);
+						mma_commit(&empty[stage]);
 					}
-					mma_commit(&empty[stage]);
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
 				mma_commit(&tfull[acc]);
@@ -752,7 +781,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			}
 		}
 		__syncwarp();
-	} else {
+	} else if (warp >= 2 && warp < 6) {
 		const int q = warp & 3;
 		const int row = q * 32 + lane;
 		int acc = 0;
@@ -816,6 +845,20 @@ struct TcPlan {
 };
 
 static const size_t kMaxDynSmem = 227 * 1024;
+// MMA-issuing threads per CTA (IgemmParams::issuers): RESNET_B200_ISSUERS = 1 (default), 2 or 4.
+// EXPERIMENTAL above 1.  The microbenchmark (tools/mma_rate.cu, profiles/r01_mma_rate.txt) shows what it is worth -- one thread issues a
+// tcgen05.mma at most every ~115 clocks (171 at N = 256), two / four threads on the same accumulator reach 62 / 57 (N = 64), 86 / 77
+// (N = 128), 150 / 141 (N = 256) with exact results -- and the unit tests pass with 2 and 4 issuers, but the full batch-256 step
+// does not survive it yet: fprop 1x1 256->1024 (3 stages, 4 iterations per tile) hangs and the stem's wgrad faults after a few
+// hundred launches (profiles/r01_issuers_status.txt).  It also gives up bitwise reproducibility (the order in which two threads' MMAs
+// reach the accumulator depends on timing).  Round-2 item 1 in DESIGN.md 8.
+static int issuers_default(int dflt, const char *family_env = nullptr) {
+	for (const char *name : {family_env, "RESNET_B200_ISSUERS"}) {  // per-family override first (bring-up): RESNET_B200_ISSUERS_K / _W
+		if (!name) continue;
+		if (const char *e = getenv(name)) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) return v; }
+	}
+	return dflt;
+}
 static inline int kelems_of(int bf16) { return bf16 ? 64 : 32; }  // elements per 128-byte swizzle row
 
 // choose a pixel box (bw, bh, bn) with product <= cap (exact == cap if exact) maximising coverage of (W, H, N)
@@ -926,6 +969,7 @@ static void finish_kmajor(TcPlan *pl) {
 	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
+	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");
 }
 
 // ---- haloed-patch plans (igemm_halo_kernel): stride-1 3x3 fprop / dgrad
@@ -1028,6 +1072,7 @@ static TcPlan *make_halo_plan(const ConvGeom &g, const void *in, int K, const vo
 	}
 	if (!p.resident_b && p.bstages < 2) { set_error("make_halo_plan: no room for the weight ring"); ok = false; }
 	if (const char *e = getenv("RESNET_B200_HALO_BASEOFF")) p.desc_base_off = atoi(e);
+	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * p.a_bytes + (size_t)p.bstages * p.b_bytes + staging_bytes + 1024 + 512;
 	pl->kind = 0;
 	pl->flops = 2.0 * g.N * S * S * (double)g.cout * g.cin * 9;
@@ -1214,6 +1259,7 @@ static CUtensorMapSwizzle wgrad_layout(WgradParams &p, int bf16) {
 	p.b_bytes = (uint32_t)p.BN * 128;
 	p.merge_taps = 1;
 	if (const char *e = getenv("RESNET_B200_WGRAD_MERGE")) p.merge_taps = atoi(e) != 0;
+	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_W");
 	return bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 }
 
@@ -1515,15 +1561,15 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
 		if (p.halo)
-			snprintf(buf, n, "%s | halo %s tile=(%d,%d) m_tiles=%d n_tiles=%d BN=%d kchunks=%d astages=%d bstages=%d epi=%d grid=%d smem=%zu resB=%u", pl->what,
-			         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.m_tiles, p.n_tiles, p.BN, p.kchunks, p.stages, p.bstages, p.epi_groups, pl->grid, pl->smem, p.resb_bytes);
+			snprintf(buf, n, "%s | halo %s tile=(%d,%d) m_tiles=%d n_tiles=%d BN=%d kchunks=%d astages=%d bstages=%d epi=%d issuers=%d grid=%d smem=%zu resB=%u", pl->what,
+			         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.m_tiles, p.n_tiles, p.BN, p.kchunks, p.stages, p.bstages, p.epi_groups, p.issuers, pl->grid, pl->smem, p.resb_bytes);
 		else
-		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d grid=%d smem=%zu resB=%u", pl->what,
-		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, pl->grid, pl->smem, p.resb_bytes);
+		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d issuers=%d grid=%d smem=%zu resB=%u", pl->what,
+		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, p.issuers, pl->grid, pl->smem, p.resb_bytes);
 	} else {
 		const WgradParams &p = pl->wp;
-		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
-		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.m_pair, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d issuers=%d grid=%d smem=%zu",
+		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.m_pair, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, p.issuers, pl->grid, pl->smem);
 	}
 }
 

@@ -372,11 +372,13 @@ def test_resident_weight_operand_forced(api, dtype, tol, S, k, cin, cout, stride
     out = {}
     for mode in ("2", "0"):
         os.environ["RESNET_B200_RESIDENT_B"] = mode
+        os.environ["RESNET_B200_ISSUERS"] = "1"   # one MMA-issuing thread: a fixed summation order, so the variants can be compared bit for bit
         try:
             y = api.conv_forward(x, w, stride, impl=0, dtype=dtype)
             din = api.conv_backward(x, w, dy, stride, impl=0, dtype=dtype)[0] if cin != 3 else None
         finally:
             os.environ.pop("RESNET_B200_RESIDENT_B", None)
+            os.environ.pop("RESNET_B200_ISSUERS", None)
         assert rel_max(y, O.conv_fwd(xr, w, stride)) < tol, mode
         if din is not None:
             assert rel_max(din, O.conv_dgrad(w, dy, S, stride)) < tol, mode
@@ -420,3 +422,34 @@ def test_halo_patch_conv_forced(api, dtype, tol, S, cin, cout, N):
         lim = 3e-5 if dtype == "f32" else 8e-3   # bf16 outputs: the two summation orders may round to neighbouring values
         assert rel_max(out[key][0], out[("0", "1")][0]) < lim
         assert rel_max(out[key][1], out[("0", "1")][1]) < lim
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 3e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("S,k,cin,cout,stride,N", [(14, 3, 256, 256, 1, 3), (28, 3, 128, 256, 2, 2), (16, 1, 256, 64, 1, 3), (12, 3, 64, 64, 1, 2), (28, 3, 128, 128, 1, 48), (28, 1, 64, 256, 1, 40)])
+@pytest.mark.skipif(os.environ.get("RESNET_B200_TEST_ISSUERS") != "1",
+                    reason="multi-issuer MMA is experimental (passes here, but hangs / faults in the full batch-256 step: profiles/r01_issuers_status.txt); "
+                           "set RESNET_B200_TEST_ISSUERS=1 to run")
+def test_mma_issuer_counts(api, dtype, tol, S, k, cin, cout, stride, N):
+    """fprop, dgrad and wgrad with one (default), two and four MMA-issuing threads per CTA (RESNET_B200_ISSUERS; a thread cannot issue
+    a tcgen05.mma more often than every ~115 clocks, several threads interleave on the same accumulator; profiles/r01_mma_rate.txt):
+    each against the oracle, and against the single-issuer result up to the fp32 summation order."""
+    rng = np.random.default_rng(S + cin + cout)
+    R = api.bf16_round if dtype == "bf16" else (lambda a: a)
+    x = R(rng.standard_normal((N, S, S, cin)).astype(np.float32))
+    w = R((rng.standard_normal((cout, cin, k, k)) * 0.1).astype(np.float32))
+    dy = R(rng.standard_normal((N, S // stride, S // stride, cout)).astype(np.float32))
+    yo, do, wo = O.conv_fwd(x, w, stride), O.conv_dgrad(w, dy, S, stride), O.conv_wgrad(x, dy, k, stride)
+    out = {}
+    for iss in ("1", "2", "4"):
+        os.environ["RESNET_B200_ISSUERS"] = iss
+        try:
+            y = api.conv_forward(x, w, stride, impl=0, dtype=dtype)
+            din, dw = api.conv_backward(x, w, dy, stride, impl=0, dtype=dtype)
+        finally:
+            os.environ.pop("RESNET_B200_ISSUERS", None)
+        assert rel_max(y, yo) < tol and rel_max(din, do) < tol and rel_max(dw, wo) < 3e-3, iss
+        out[iss] = (y, din, dw)
+    lim = 3e-5 if dtype == "f32" else 8e-3
+    for iss in ("2", "4"):
+        assert rel_max(out[iss][0], out["1"][0]) < lim and rel_max(out[iss][1], out["1"][1]) < lim
+        assert rel_max(out[iss][2], out["1"][2]) < 3e-5
