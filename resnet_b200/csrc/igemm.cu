@@ -173,8 +173,10 @@ struct alignas(64) WgradParams {
 	float *partial;
 };
 
-constexpr int kIgemmThreads = 288;   // wgrad: TMA warp, MMA warp, 4 epilogue warps, up to 3 more MMA-issuing warps (6-8)
-constexpr int kKmajorThreads = 416;  // fprop / dgrad: TMA warp, MMA warp, up to two groups of 4 epilogue warps, up to 3 more MMA-issuing warps (10-12)
+// Block sizes.  MI = the experimental multi-issuer instantiation (IgemmParams::issuers > 1): up to three more MMA-issuing warps.  The
+// default single-issuer instantiation is compiled without any of that (the issuing thread's loop is the critical path of every conv).
+constexpr int kIgemmThreads = 192, kIgemmThreadsMI = 288;    // wgrad: TMA warp, MMA warp, 4 epilogue warps (+ warps 6-8)
+constexpr int kKmajorThreads = 320, kKmajorThreadsMI = 416;  // fprop / dgrad: TMA warp, MMA warp, up to two groups of 4 epilogue warps (+ warps 10-12)
 constexpr int kTmemCols = 512;
 constexpr uint32_t kABytes = 128 * 32 * 4;  // 128 rows x 32 tf32 = 16 KB
 
@@ -192,8 +194,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // BF16 = false: fp32 tensors, kind::tf32 MMAs, 32 output columns per staged 128-byte row;
 // BF16 = true:  bf16 tensors, kind::f16 MMAs, 64 output columns per staged row.  The shared-memory tiles are byte-identical
 // in both modes (128 rows x 128 bytes, 4 MMAs per stage each advancing 32 bytes along K).
-template <bool BF16>
-__global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+template <bool BF16, bool MI>
+__global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.resident_b ? p.a_bytes : p.a_bytes + p.b_bytes;
@@ -264,9 +266,9 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			}
 		}
 		__syncwarp();
-	} else if (warp == 1 || (warp >= 10 && warp - 9 < p.issuers)) {
+	} else if (warp == 1 || (MI && warp >= 10 && warp - 9 < p.issuers)) {
 		if (lane == 0) {
-			const int x = warp == 1 ? 0 : warp - 9, I = p.issuers;  // this issuer takes the stages it = x (mod I) of every tile
+			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;  // this issuer takes the stages it = x (mod I) of every tile
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
@@ -440,8 +442,8 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 // of every patch row) or h >= bh are computed and dropped (14 x 8 and 28 x 4 tiles: 112 of 128 rows useful).  The 128-byte swizzle is a
 // function of the shared-memory address bits, so a descriptor whose start address is moved by whole 128-byte rows still meets the
 // pattern the TMA unit wrote.  The epilogue compacts the useful rows into a dense [bh][bw] staging tile for the TMA store.
-template <bool BF16>
-__global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __grid_constant__ IgemmParams p) {
+template <bool BF16, bool MI>
+__global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) igemm_halo_kernel(const __grid_constant__ IgemmParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	uint8_t *resb = base;                                                       // resident weight tiles [kc][tap] (resb_bytes, 0 when unused)
@@ -515,9 +517,9 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __g
 			}
 		}
 		__syncwarp();
-	} else if (warp == 1 || (warp >= 10 && warp - 9 < p.issuers)) {
+	} else if (warp == 1 || (MI && warp >= 10 && warp - 9 < p.issuers)) {
 		if (lane == 0) {
-			const int x = warp == 1 ? 0 : warp - 9, I = p.issuers;  // this issuer takes the taps t = x (mod I) of every K chunk
+			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;  // this issuer takes the taps t = x (mod I) of every K chunk
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int as = 0, bs = 0, acc = 0;
 			uint32_t aph = 0, bph = 0, accphase = 0;
@@ -659,8 +661,8 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_halo_kernel(const __g
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
-template <bool BF16>
-__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const __grid_constant__ WgradParams p) {
+template <bool BF16, bool MI>
+__global__ void __launch_bounds__(MI ? kIgemmThreadsMI : kIgemmThreads, 1) igemm_mnmajor_kernel(const __grid_constant__ WgradParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
@@ -728,9 +730,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			}
 		}
 		__syncwarp();
-	} else if (warp == 1 || (warp >= 6 && warp - 5 < p.issuers)) {
+	} else if (warp == 1 || (MI && warp >= 6 && warp - 5 < p.issuers)) {
 		if (lane == 0) {
-			const int x = warp == 1 ? 0 : warp - 5, I = p.issuers;
+			const int x = (!MI || warp == 1) ? 0 : warp - 5, I = MI ? p.issuers : 1;
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 1, 1) : make_idesc_tf32(128, p.BN, 1, 1);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
@@ -1515,25 +1517,30 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 	}
 	static bool attr_set = false;
 	if (!attr_set) {
-		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-		RB_CUDA(cudaFuncSetAttribute(igemm_kmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-		RB_CUDA(cudaFuncSetAttribute(igemm_mnmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-		RB_CUDA(cudaFuncSetAttribute(igemm_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-		RB_CUDA(cudaFuncSetAttribute(igemm_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+		const void *kernels[] = {(const void *)igemm_kmajor_kernel<false, false>, (const void *)igemm_kmajor_kernel<true, false>,
+		                         (const void *)igemm_kmajor_kernel<false, true>,  (const void *)igemm_kmajor_kernel<true, true>,
+		                         (const void *)igemm_halo_kernel<false, false>,   (const void *)igemm_halo_kernel<true, false>,
+		                         (const void *)igemm_halo_kernel<false, true>,    (const void *)igemm_halo_kernel<true, true>,
+		                         (const void *)igemm_mnmajor_kernel<false, false>, (const void *)igemm_mnmajor_kernel<true, false>,
+		                         (const void *)igemm_mnmajor_kernel<false, true>,  (const void *)igemm_mnmajor_kernel<true, true>};
+		for (const void *k : kernels) RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		attr_set = true;
 	}
 	if (pl->kind == 0) {
 		if (pl->ip.stats) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
+		const bool mi = pl->ip.issuers > 1;
+		const int threads = mi ? kKmajorThreadsMI : kKmajorThreads;
 		if (pl->ip.halo) {
-			if (pl->bf16) igemm_halo_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
-			else igemm_halo_kernel<false><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
-		} else if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
-		else igemm_kmajor_kernel<false><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
+			if (pl->bf16) { if (mi) igemm_halo_kernel<true, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_halo_kernel<true, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
+			else { if (mi) igemm_halo_kernel<false, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_halo_kernel<false, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
+		} else if (pl->bf16) { if (mi) igemm_kmajor_kernel<true, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_kmajor_kernel<true, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
+		else { if (mi) igemm_kmajor_kernel<false, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_kmajor_kernel<false, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
 		RB_LAUNCH_CHECK();
 	} else {
-		if (pl->bf16) igemm_mnmajor_kernel<true><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
-		else igemm_mnmajor_kernel<false><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
+		const bool mi = pl->wp.issuers > 1;
+		const int threads = mi ? kIgemmThreadsMI : kIgemmThreads;
+		if (pl->bf16) { if (mi) igemm_mnmajor_kernel<true, true><<<pl->grid, threads, pl->smem, st>>>(pl->wp); else igemm_mnmajor_kernel<true, false><<<pl->grid, threads, pl->smem, st>>>(pl->wp); }
+		else { if (mi) igemm_mnmajor_kernel<false, true><<<pl->grid, threads, pl->smem, st>>>(pl->wp); else igemm_mnmajor_kernel<false, false><<<pl->grid, threads, pl->smem, st>>>(pl->wp); }
 		RB_LAUNCH_CHECK();
 		if (pl->kind == 1) wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
 		else {
