@@ -854,6 +854,12 @@ static const size_t kMaxDynSmem = 227 * 1024;
 // does not survive it yet: fprop 1x1 256->1024 (3 stages, 4 iterations per tile) hangs and the stem's wgrad faults after a few
 // hundred launches (profiles/r01_issuers_status.txt).  It also gives up bitwise reproducibility (the order in which two threads' MMAs
 // reach the accumulator depends on timing).  Round-2 item 1 in DESIGN.md 8.
+// more issuers than ring stages would let an issuer wait for a slot whose previous pass has not been filled yet (the parity test of
+// mbarrier.try_wait cannot tell "two phases behind" from "done": tools/issuer_protocol_sim.py) -- clamp to the stage count
+static int clamp_issuers(int issuers, int stages) {
+	while (issuers > 1 && issuers > stages) issuers /= 2;
+	return issuers;
+}
 static int issuers_default(int dflt, const char *family_env = nullptr) {
 	for (const char *name : {family_env, "RESNET_B200_ISSUERS"}) {  // per-family override first (bring-up): RESNET_B200_ISSUERS_K / _W
 		if (!name) continue;
@@ -971,7 +977,7 @@ static void finish_kmajor(TcPlan *pl) {
 	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
-	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");
+	p.issuers = clamp_issuers(issuers_default(1, "RESNET_B200_ISSUERS_K"), p.stages);
 }
 
 // ---- haloed-patch plans (igemm_halo_kernel): stride-1 3x3 fprop / dgrad
@@ -1074,7 +1080,7 @@ static TcPlan *make_halo_plan(const ConvGeom &g, const void *in, int K, const vo
 	}
 	if (!p.resident_b && p.bstages < 2) { set_error("make_halo_plan: no room for the weight ring"); ok = false; }
 	if (const char *e = getenv("RESNET_B200_HALO_BASEOFF")) p.desc_base_off = atoi(e);
-	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");
+	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");  // (halo: issuers split the taps of ONE resident patch, no ring aliasing)
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * p.a_bytes + (size_t)p.bstages * p.b_bytes + staging_bytes + 1024 + 512;
 	pl->kind = 0;
 	pl->flops = 2.0 * g.N * S * S * (double)g.cout * g.cin * 9;
@@ -1308,6 +1314,7 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
+	p.issuers = clamp_issuers(p.issuers, p.stages);
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = tiles * p.splits;
@@ -1496,6 +1503,7 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
+	p.issuers = clamp_issuers(p.issuers, p.stages);
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = ceil_div(p.ntaps, p.tpt) * p.co_items * p.ci_tiles * p.splits;

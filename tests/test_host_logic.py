@@ -44,3 +44,21 @@ def test_bench_configs_match_baseline_json():
     assert abs(3 * (f50 + 0.0041) - stem - bench.CONFIGS["c2"]["gflop"]) < 0.05
     f152, _ = conv_gflop(50, bench.R152_REDUCTIONS)
     assert abs(3 * (f152 + 0.0041) - stem - bench.CONFIGS["c5"]["gflop"]) < 0.1
+
+
+def test_multi_issuer_barrier_protocol_model():
+    """The mbarrier protocol of the (experimental) multi-issuer convolution kernels, model-checked under random schedules
+    (tools/issuer_protocol_sim.py): sound whenever issuers <= ring stages -- no deadlock, no issuer passes `full` onto a stale slot, no
+    accumulator is touched by the wrong tile -- and broken by phase aliasing with 4 issuers on a 3-stage ring, which is why igemm.cu
+    clamps the issuer count to the stage count."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("issuer_protocol_sim", os.path.join(os.path.dirname(__file__), "..", "tools", "issuer_protocol_sim.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    res = sim.sweep(seeds=12, tiles=8)
+    for cfg, failing in res.items():
+        if cfg == (3, 4, 4):
+            assert failing > 0, "the model no longer shows the issuers > stages aliasing it documents"
+        else:
+            assert failing == 0, (cfg, failing)
