@@ -978,6 +978,10 @@ static void finish_kmajor(TcPlan *pl) {
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
 	p.issuers = clamp_issuers(issuers_default(1, "RESNET_B200_ISSUERS_K"), p.stages);
+	// measured on the batch-256 step (profiles/r01_issuers_status.txt): with rings of >= 4 stages everywhere two issuers run the whole
+	// step; plans with a 3-stage ring (the short-K 1x1 layers with two epilogue groups, or RESNET_B200_STAGES=3) hang or fault.  Those
+	// plans are bound by their stores, not by MMA issue, so they keep one issuer.
+	if (p.stages < 4) p.issuers = 1;
 }
 
 // ---- haloed-patch plans (igemm_halo_kernel): stride-1 3x3 fprop / dgrad
