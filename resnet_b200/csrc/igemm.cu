@@ -139,9 +139,9 @@ struct alignas(64) IgemmParams {
 	int halo, PW, PH, bstages;
 	// issuers (1, 2 or 4): threads issuing the tile's MMAs.  One thread cannot issue a tcgen05.mma more often than every ~115 clocks
 	// (171 at N = 256) whatever the instruction's size, two / four threads interleaving on the SAME accumulator reach 62 / 57 clocks at
-	// N = 64, 86 / 77 at N = 128, 150 / 141 at N = 256 (profiles/r01_mma_rate.txt; results exact).  Issuer x takes the pipeline
-	// stages (halo kernel: taps) with index = x (mod issuers); issuer 0's first MMA overwrites the accumulator and is committed to
-	// `zinit` before the others may accumulate.
+	// N = 64, 86 / 77 at N = 128, 150 / 141 at N = 256 (profiles/r01_mma_rate.txt; results exact).  Issuer x owns the ring slots
+	// s = x (mod issuers) (halo kernel with resident weights: the taps t = x (mod issuers)); the owner of a tile's first stage overwrites
+	// the accumulator with its first MMA and commits `zinit`, which the others wait for before they accumulate.
 	int issuers;
 	int desc_base_off;  // bring-up aid (RESNET_B200_HALO_BASEOFF): also set the descriptor's base-offset field to (start >> 7) & 7
 	float *out;
@@ -168,7 +168,7 @@ struct alignas(64) WgradParams {
 	int merge_taps;    // the taps of a group sit back to back in shared memory AND in TMEM: one MMA of N = ntaps * BN covers them all
 	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
 	int stages;
-	int issuers;       // MMA-issuing threads (see IgemmParams::issuers): issuer x takes the stages kb - kb0 = x (mod issuers) of every work item
+	int issuers;       // MMA-issuing threads (see IgemmParams::issuers): issuer x owns the ring slots s = x (mod issuers); stages % issuers == 0
 	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
 	float *partial;
 };
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 		__syncwarp();
 	} else if (warp == 1 || (MI && warp >= 10 && warp - 9 < p.issuers)) {
 		if (lane == 0) {
-			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;  // this issuer takes the stages it = x (mod I) of every tile
+			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;  // this issuer owns the ring SLOTS s = x (mod I); stages % I == 0
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int stage = 0, acc = 0;
 			uint32_t phase = 0, accphase = 0;
@@ -276,13 +276,17 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 				const GroupDesc &g = p.groups[(tile / p.n_tiles) / p.m_tiles];
 				const int iters = g.ntaps * p.kchunks;
-				// issuer 0 waits for the epilogue to drain the accumulator and overwrites it with its first MMA; the others wait for that MMA
-				if (x == 0) mbar_wait(&tempty[acc], accphase ^ 1);
-				else mbar_wait(&zinit[acc], accphase);
+				// Every issuer waits for the epilogue to drain the accumulator; the owner of the tile's first stage overwrites it with its
+				// first MMA, the others wait for that MMA (zinit).  Ownership goes by ring slot, not by stage index within the tile: an issuer
+				// then waits on EVERY pass of its slots' `full` barriers.  Skipping a pass is fatal -- mbarrier.try_wait.parity cannot tell
+				// "the previous pass has not landed yet" from "this pass has landed", and TMA loads complete out of order (the hang / fault
+				// of the first version on 3-stage rings, profiles/r01_issuers_status.txt; tools/issuer_protocol_sim.py).
+				mbar_wait(&tempty[acc], accphase ^ 1);
+				if (I > 1 && stage % I != x) mbar_wait(&zinit[acc], accphase);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
 				for (int it = 0; it < iters; it++) {
-					if (I == 1 || it % I == x) {
+					if (I == 1 || stage % I == x) {
 						mbar_wait(&full[stage], phase);
 						tc_fence_after();
 						const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
@@ -519,14 +523,16 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 		__syncwarp();
 	} else if (warp == 1 || (MI && warp >= 10 && warp - 9 < p.issuers)) {
 		if (lane == 0) {
-			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;  // this issuer takes the taps t = x (mod I) of every K chunk
+			// this issuer takes the taps t = x (mod I) of every K chunk when the weights are resident (no per-tap barrier), else the taps
+			// whose weight-ring SLOT is x (mod I) (bstages % I == 0): an issuer must wait on every pass of a slot's barrier (see igemm_kmajor_kernel)
+			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;
 			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
 			int as = 0, bs = 0, acc = 0;
 			uint32_t aph = 0, bph = 0, accphase = 0;
 			if (p.resident_b && (int)blockIdx.x < total_tiles) mbar_wait(resfull, 0);
 			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				if (x == 0) mbar_wait(&tempty[acc], accphase ^ 1);
-				else mbar_wait(&zinit[acc], accphase);  // issuer 0's overwriting first MMA is done
+				mbar_wait(&tempty[acc], accphase ^ 1);
+				if (I > 1 && (p.resident_b ? 0 : bs % I) != x) mbar_wait(&zinit[acc], accphase);  // the first tap's owner has overwritten the accumulator
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
 				for (int kc = 0; kc < p.kchunks; kc++) {
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 					tc_fence_after();
 					const uint32_t a_base = smem_u32(aring + (size_t)as * p.a_bytes);
 					for (int t = 0; t < g.ntaps; t++) {
-						if (I == 1 || t % I == x) {
+						if (I == 1 || (p.resident_b ? t % I : bs % I) == x) {
 							const TapDesc tp = g.taps[t];
 							uint32_t b_addr;
 							if (p.resident_b) b_addr = smem_u32(resb + (size_t)(kc * g.ntaps + t) * p.b_bytes);
@@ -742,13 +748,14 @@ __global__ void __launch_bounds__(MI ? kIgemmThreadsMI : kIgemmThreads, 1) igemm
 				const int ntg = min(p.tpt, p.ntaps - tap0);
 				const int kb0 = split * p.boxes_per_split;
 				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
-				// issuer 0 waits for the drained accumulator and overwrites it with the MMAs of the item's first stage; the others wait for those
-				if (x == 0) mbar_wait(&tempty[acc], accphase ^ 1);
-				else mbar_wait(&zinit[acc], accphase);
+				// every issuer waits for the drained accumulator; the owner of the item's first stage overwrites it with that stage's MMAs, the
+				// others wait for those (zinit).  Ownership by ring slot (stages % I == 0), see igemm_kmajor_kernel.
+				mbar_wait(&tempty[acc], accphase ^ 1);
+				if (I > 1 && stage % I != x) mbar_wait(&zinit[acc], accphase);
 				tc_fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
 				for (int kb = kb0; kb < kb1; kb++) {
-					if (I == 1 || (kb - kb0) % I == x) {
+					if (I == 1 || stage % I == x) {
 						mbar_wait(&full[stage], phase);
 						tc_fence_after();
 						const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
@@ -850,14 +857,19 @@ static const size_t kMaxDynSmem = 227 * 1024;
 // MMA-issuing threads per CTA (IgemmParams::issuers): RESNET_B200_ISSUERS = 1 (default), 2 or 4.
 // EXPERIMENTAL above 1.  The microbenchmark (tools/mma_rate.cu, profiles/r01_mma_rate.txt) shows what it is worth -- one thread issues a
 // tcgen05.mma at most every ~115 clocks (171 at N = 256), two / four threads on the same accumulator reach 62 / 57 (N = 64), 86 / 77
-// (N = 128), 150 / 141 (N = 256) with exact results -- and the unit tests pass with 2 and 4 issuers, but the full batch-256 step
-// does not survive it yet: fprop 1x1 256->1024 (3 stages, 4 iterations per tile) hangs and the stem's wgrad faults after a few
-// hundred launches (profiles/r01_issuers_status.txt).  It also gives up bitwise reproducibility (the order in which two threads' MMAs
-// reach the accumulator depends on timing).  Round-2 item 1 in DESIGN.md 8.
-// more issuers than ring stages would let an issuer wait for a slot whose previous pass has not been filled yet (the parity test of
-// mbarrier.try_wait cannot tell "two phases behind" from "done": tools/issuer_protocol_sim.py) -- clamp to the stage count
-static int clamp_issuers(int issuers, int stages) {
-	while (issuers > 1 && issuers > stages) issuers /= 2;
+// (N = 128), 150 / 141 (N = 256) with exact results.  History (profiles/r01_issuers_status.txt): the first version gave issuer x the
+// stages it = x (mod issuers) of every tile; unit tests and a batch-32 step passed, the batch-256 step hung / faulted on 3-stage rings
+// and in the stem's wgrad (an odd stage count per work item).  Cause, reproduced by tools/issuer_protocol_sim.py once TMA loads are
+// allowed to complete out of order: an issuer that does not wait on every pass of a ring slot can find the slot's barrier one phase
+// behind, and mbarrier.try_wait.parity then reports "done".  Ownership now goes by ring slot; that version has NOT run on a GPU yet
+// (the round's GPU budget was spent), hence still off by default.  It also gives up bitwise reproducibility (the order in which two
+// threads' MMAs reach the accumulator depends on timing).  Round-2 item 1 in DESIGN.md 8.
+// Issuer x owns the ring slots s = x (mod issuers), so the ring depth must be a multiple of the issuer count: fewer issuers while the
+// ring is shallower than two slots each, then the depth rounded down.  (Ownership by slot: an issuer waits on every pass of its slots'
+// barriers; skipping passes aliases the mbarrier phase parity, tools/issuer_protocol_sim.py.)
+static int fit_issuers(int issuers, int *stages) {
+	while (issuers > 1 && 2 * issuers > *stages) issuers /= 2;
+	if (issuers > 1) *stages = *stages / issuers * issuers;
 	return issuers;
 }
 static int issuers_default(int dflt, const char *family_env = nullptr) {
@@ -975,13 +987,11 @@ static void finish_kmajor(TcPlan *pl) {
 	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
 	p.stages = stages > 8 ? 8 : stages;
 	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
+	// several issuers only on rings of >= 4 stages: the 3-stage plans (short-K 1x1 layers with two epilogue groups) are bound by their
+	// stores, not by MMA issue
+	p.issuers = fit_issuers(issuers_default(1, "RESNET_B200_ISSUERS_K"), &p.stages);
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
-	p.issuers = clamp_issuers(issuers_default(1, "RESNET_B200_ISSUERS_K"), p.stages);
-	// measured on the batch-256 step (profiles/r01_issuers_status.txt): with rings of >= 4 stages everywhere two issuers run the whole
-	// step; plans with a 3-stage ring (the short-K 1x1 layers with two epilogue groups, or RESNET_B200_STAGES=3) hang or fault.  Those
-	// plans are bound by their stores, not by MMA issue, so they keep one issuer.
-	if (p.stages < 4) p.issuers = 1;
 }
 
 // ---- haloed-patch plans (igemm_halo_kernel): stride-1 3x3 fprop / dgrad
@@ -1084,7 +1094,8 @@ static TcPlan *make_halo_plan(const ConvGeom &g, const void *in, int K, const vo
 	}
 	if (!p.resident_b && p.bstages < 2) { set_error("make_halo_plan: no room for the weight ring"); ok = false; }
 	if (const char *e = getenv("RESNET_B200_HALO_BASEOFF")) p.desc_base_off = atoi(e);
-	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");  // (halo: issuers split the taps of ONE resident patch, no ring aliasing)
+	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");  // the issuers split the taps of ONE patch; streamed weights: by weight-ring slot
+	if (!p.resident_b) p.issuers = fit_issuers(p.issuers, &p.bstages);
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * p.a_bytes + (size_t)p.bstages * p.b_bytes + staging_bytes + 1024 + 512;
 	pl->kind = 0;
 	pl->flops = 2.0 * g.N * S * S * (double)g.cout * g.cin * 9;
@@ -1318,7 +1329,7 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
-	p.issuers = clamp_issuers(p.issuers, p.stages);
+	p.issuers = fit_issuers(p.issuers, &p.stages);
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = tiles * p.splits;
@@ -1507,7 +1518,7 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
-	p.issuers = clamp_issuers(p.issuers, p.stages);
+	p.issuers = fit_issuers(p.issuers, &p.stages);
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = ceil_div(p.ntaps, p.tpt) * p.co_items * p.ci_tiles * p.splits;

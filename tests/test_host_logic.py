@@ -47,18 +47,18 @@ def test_bench_configs_match_baseline_json():
 
 
 def test_multi_issuer_barrier_protocol_model():
-    """The mbarrier protocol of the (experimental) multi-issuer convolution kernels, model-checked under random schedules
-    (tools/issuer_protocol_sim.py): sound whenever issuers <= ring stages -- no deadlock, no issuer passes `full` onto a stale slot, no
-    accumulator is touched by the wrong tile -- and broken by phase aliasing with 4 issuers on a 3-stage ring, which is why igemm.cu
-    clamps the issuer count to the stage count."""
+    """The mbarrier protocol of the (experimental) multi-issuer convolution kernels, model-checked under random schedules with TMA loads
+    completing out of order (tools/issuer_protocol_sim.py).  Ownership by ring slot -- what igemm.cu does -- never deadlocks, never lets
+    an issuer onto a stale slot, never touches an accumulator another tile owns.  Ownership by stage index -- the first version -- fails
+    on 3-stage rings and on work items with an odd stage count, the two places where the batch-256 step hung / faulted on the GPU
+    (profiles/r01_issuers_status.txt)."""
     import importlib.util
     import os
     spec = importlib.util.spec_from_file_location("issuer_protocol_sim", os.path.join(os.path.dirname(__file__), "..", "tools", "issuer_protocol_sim.py"))
     sim = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(sim)
-    res = sim.sweep(seeds=12, tiles=8)
-    for cfg, failing in res.items():
-        if cfg == (3, 4, 4):
-            assert failing > 0, "the model no longer shows the issuers > stages aliasing it documents"
-        else:
-            assert failing == 0, (cfg, failing)
+    for cfg, failing in sim.sweep(seeds=10, tiles=6).items():
+        assert failing == 0, ("by slot", cfg, failing)
+    old = sim.sweep(seeds=20, tiles=6, by_slot=False, configs=[(3, 8, 2), (4, 339, 2), (4, 8, 2)])
+    assert old[(3, 8, 2)] > 0 and old[(4, 339, 2)] > 0, old      # the hardware failures, reproduced
+    assert old[(4, 8, 2)] == 0, old                               # ... and the configuration that ran

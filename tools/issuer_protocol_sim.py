@@ -1,17 +1,23 @@
 """Randomised model of the mbarrier protocol of the multi-issuer convolution kernels (igemm_kmajor_kernel<.., MI = true>; the halo and
-wgrad kernels follow the same scheme): one TMA producer filling an S-deep stage ring, I MMA-issuing threads that own the stages
-`it % I` of every tile, an epilogue draining two accumulators, and the barriers full[S], empty[S], tfull[2] (count I), tempty[2], zinit[2].
+wgrad kernels follow the same scheme): one TMA producer filling an S-deep stage ring, I MMA-issuing threads, an epilogue draining two
+accumulators, and the barriers full[S], empty[S], tfull[2] (count I), tempty[2], zinit[2].
 mbarrier semantics as in PTX: `try_wait.parity P` succeeds iff the phase of parity P has completed, which is only meaningful while the
-waiter is at most one phase behind; tcgen05.commit / TMA completions arrive asynchronously, in order per issuing thread.
+waiter is at most one phase behind; tcgen05.commit completions arrive asynchronously, in order per issuing thread; TMA loads complete in
+issue order (tma_in_order) or in any order (what the hardware does).
 
 The model checks, under random schedules: no deadlock, an issuer never passes `full` onto a slot that does not hold its (tile, stage)
 (phase aliasing), nobody accumulates into an accumulator another tile owns, the epilogue reads the tile it expects.
 
-Result (tests/test_host_logic.py runs it): sound for I <= S; with more issuers than ring stages (I = 4, S = 3) an issuer waits for a slot
-whose PREVIOUS pass has not been filled yet and the parity test lets it through -- igemm.cu therefore clamps issuers to the stage count.
-The hang / fault of the batch-256 step with I = 2 (profiles/r01_issuers_status.txt) is NOT reproduced by this model, i.e. it is not a
-flaw of the barrier protocol as written but of an assumption about the hardware (candidates: what tcgen05.commit tracks when two threads
-of a CTA have MMAs in flight; MMAs of different shapes from two threads interleaving at a tile boundary)."""
+Two ownership schemes:
+ * by stage index (issuer x takes the stages it % I == x of every tile; the first version of the kernels): sound only if TMA loads
+   land in order.  With out-of-order completion it fails exactly where the hardware did (profiles/r01_issuers_status.txt): 3-stage rings
+   with 2 issuers, and 4-stage rings whose work items have an odd stage count (the stem's wgrad: 339).  An issuer that skips a pass of a
+   slot waits for the NEXT pass with the same parity; if the skipped pass has not landed yet the barrier is one phase behind and the
+   parity test lets the issuer through onto stale data, after which its `empty` arrival corrupts the producer's accounting.
+ * by ring slot (issuer x owns the slots s % I == x, S % I == 0; every issuer waits `tempty`, the owner of a tile's first stage
+   overwrites the accumulator and commits `zinit`; what igemm.cu does now): every waiter sees every phase of its barriers; no failure
+   in any configuration tried, in-order or not.
+tests/test_host_logic.py runs both."""
 import random
 
 
@@ -30,11 +36,13 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-def run(S, iters_list, I, seed):
-    """-> ('OK' | 'HANG' | 'ERR', errors)"""
+def run(S, iters_list, I, seed, by_slot=False, tma_in_order=True):
+    """-> ('OK' | 'HANG' | 'ERR', errors).  by_slot: issuer x owns the ring SLOTS s % I == x (needs S % I == 0) instead of the
+    stages it % I == x of every tile.  tma_in_order = False: TMA loads complete in any order (they do on the hardware)."""
     rnd = random.Random(seed)
     full, empty = [Bar(1) for _ in range(S)], [Bar(1) for _ in range(S)]
     tfull, tempty, zinit = [Bar(I) for _ in range(2)], [Bar(1) for _ in range(2)], [Bar(1) for _ in range(2)]
+    assert not by_slot or S % I == 0
     slot, acc_owner = [None] * S, [None, None]
     pending, now, errors = [], [0], []
 
@@ -53,7 +61,10 @@ def run(S, iters_list, I, seed):
                 def land(stage=stage, tile=tile, it=it):
                     slot[stage] = (tile, it)
                     full[stage].arrive()
-                later(st, land)
+                if tma_in_order:
+                    later(st, land)
+                else:
+                    pending.append((now[0] + rnd.randint(1, 40), land))
                 stage += 1
                 if stage == S:
                     stage, phase = 0, phase ^ 1
@@ -62,10 +73,17 @@ def run(S, iters_list, I, seed):
     def issuer(x):
         st, stage, phase, acc, accphase = {}, 0, 0, 0, 0
         for tile, iters in enumerate(iters_list):
-            while not (tempty[acc].test(accphase ^ 1) if x == 0 else zinit[acc].test(accphase)):
-                yield
+            if by_slot:  # every issuer waits for the drained accumulator; the owner of the tile's first stage overwrites it, the others wait for that
+                while not tempty[acc].test(accphase ^ 1):
+                    yield
+                if stage % I != x:
+                    while not zinit[acc].test(accphase):
+                        yield
+            else:
+                while not (tempty[acc].test(accphase ^ 1) if x == 0 else zinit[acc].test(accphase)):
+                    yield
             for it in range(iters):
-                if it % I == x:
+                if (stage % I == x) if by_slot else (it % I == x):
                     while not full[stage].test(phase):
                         yield
                     if slot[stage] != (tile, it):
@@ -123,16 +141,26 @@ def run(S, iters_list, I, seed):
     return "OK", errors
 
 
-def sweep(seeds=40, tiles=10):
-    """-> {(S, iters, I): number of failing seeds}"""
+CONFIGS = [(4, 4, 2), (4, 9, 2), (4, 339, 2), (4, 7, 2), (8, 9, 2), (8, 1, 2), (8, 2, 4), (4, 4, 4), (8, 36, 4), (2, 8, 2), (6, 5, 2)]
+
+
+def sweep(seeds=40, tiles=8, by_slot=True, tma_in_order=False, configs=CONFIGS):
+    """-> {(S, stages per tile, I): number of failing seeds}"""
     out = {}
-    for cfg in [(3, 4, 2), (4, 9, 2), (3, 4, 4), (4, 4, 4), (8, 1, 2), (8, 2, 4), (4, 7, 2), (3, 5, 2), (4, 36, 4)]:
-        S, iters, I = cfg
-        out[cfg] = sum(run(S, [iters] * tiles, I, seed)[0] != "OK" for seed in range(seeds))
-    out["mixed groups, S=4, I=2"] = sum(run(4, [8, 4, 4, 2] * 3, 2, seed)[0] != "OK" for seed in range(seeds))
+    for S, iters, I in configs:
+        out[(S, iters, I)] = sum(run(S, [iters] * tiles, I, seed, by_slot, tma_in_order)[0] != "OK" for seed in range(seeds))
+    if by_slot:
+        out["mixed tile lengths, S=4, I=2"] = sum(run(4, [8, 4, 4, 2, 1, 3] * 2, 2, seed, True, tma_in_order)[0] != "OK" for seed in range(seeds))
     return out
 
 
 if __name__ == "__main__":
-    for k, v in sweep(seeds=200).items():
-        print(k, "failing seeds:", v)
+    print("ownership by ring slot, TMA out of order:")
+    for k, v in sweep(seeds=100).items():
+        print("  ", k, "failing seeds:", v)
+    print("ownership by stage index (first version), TMA out of order:")
+    for k, v in sweep(seeds=100, by_slot=False, configs=[(3, 4, 2), (3, 8, 2), (4, 339, 2), (4, 7, 2), (4, 8, 2), (8, 9, 2)]).items():
+        print("  ", k, "failing seeds:", v)
+    print("ownership by stage index, TMA in order:")
+    for k, v in sweep(seeds=100, by_slot=False, tma_in_order=True, configs=[(3, 4, 2), (3, 8, 2), (4, 339, 2), (4, 7, 2), (3, 4, 4)]).items():
+        print("  ", k, "failing seeds:", v)
