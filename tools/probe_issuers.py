@@ -9,10 +9,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from resnet_b200 import api  # noqa: E402
 
-SHAPES = [(28, 3, 512, 1024, 2), (14, 3, 256, 256, 1), (28, 3, 128, 128, 1), (56, 3, 64, 64, 1), (14, 1, 1024, 256, 1), (14, 1, 256, 1024, 1)]
-N = 256
+# (the first run of this tool at batch 256 with six shapes x two dtypes did not finish in 5 GPU-minutes: the host side of api.conv_* -- numpy
+# conversions and PCIe copies of 100-400 MB tensors per call -- dominates; batch 128 and four shapes keep every CTA at >= 2 tiles)
+SHAPES = [(28, 3, 512, 1024, 2), (14, 3, 256, 256, 1), (28, 3, 128, 128, 1), (56, 3, 64, 64, 1)]
+N = 128
 rng = np.random.default_rng(0)
-dtypes = sys.argv[1:] or ["bf16", "f32"]
+dtypes = sys.argv[1:] or ["bf16"]
 for (S, k, cin, cout, stride) in SHAPES:
     x = rng.standard_normal((N, S, S, cin), dtype=np.float32)
     w = rng.standard_normal((cout, cin, k, k), dtype=np.float32) * 0.05
