@@ -91,7 +91,7 @@ static void dump_bn_cache(Engine *e, const std::string &dir, Cache_BatchNorm *c)
 }
 // reference: resnet.cu:2351-2513
 static void dump_block(Engine *e, const std::string &root, Activation_ConvBlock *b, int ind, bool deriv) {
-	char nn[8];
+	char nn[16];
 	snprintf(nn, sizeof(nn), "%02d/", ind);
 	const std::string sub = deriv ? "activation_derivs/" : "activations/";
 	const std::string dir = root + sub + "conv_blocks/" + nn, bn = root + sub + "batch_norms/" + nn;
