@@ -62,6 +62,8 @@ def test_multi_issuer_barrier_protocol_model():
     old = sim.sweep(seeds=20, tiles=6, by_slot=False, configs=[(3, 8, 2), (4, 339, 2), (4, 8, 2)])
     assert old[(3, 8, 2)] > 0 and old[(4, 339, 2)] > 0, old      # the hardware failures, reproduced
     assert old[(4, 8, 2)] == 0, old                               # ... and the configuration that ran
+    for cfg, failing in sim.sweep_halo(seeds=8, tiles=4).items():   # the haloed-patch kernel's two rings
+        assert failing == 0, ("halo", cfg, failing)
 
 
 def _halo_emulation(x, wk, tdx, tdy, bw, bh):

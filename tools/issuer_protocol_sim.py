@@ -154,6 +154,139 @@ def sweep(seeds=40, tiles=8, by_slot=True, tma_in_order=False, configs=CONFIGS):
     return out
 
 
+
+
+def run_halo(AS, BS, kchunks, ntaps, tiles, I, seed, resident=False):
+    """The same model for igemm_halo_kernel: an A ring of AS patches (one per K chunk, read by ALL issuers: afull waited by everyone, aempty
+    count I) and a B ring of BS weight tiles (one per (K chunk, tap), owned by slot: bs % I == x; resident weights: taps t % I == x, no B ring)."""
+    rnd = random.Random(seed)
+    afull, aempty = [Bar(1) for _ in range(AS)], [Bar(I) for _ in range(AS)]
+    bfull, bempty = [Bar(1) for _ in range(max(BS, 1))], [Bar(1) for _ in range(max(BS, 1))]
+    tfull, tempty, zinit = [Bar(I) for _ in range(2)], [Bar(1) for _ in range(2)], [Bar(1) for _ in range(2)]
+    aslot, bslot, acc_owner = [None] * AS, [None] * max(BS, 1), [None, None]
+    pending, now, errors = [], [0], []
+    assert resident or BS % I == 0
+
+    def later(state, fn):
+        t = max(state.get("last", 0), now[0]) + rnd.randint(1, 6)
+        state["last"] = t
+        pending.append((t, fn))
+
+    def producer():
+        a, aph, b, bph = 0, 0, 0, 0
+        for tile in range(tiles):
+            for kc in range(kchunks):
+                while not aempty[a].test(aph ^ 1):
+                    yield
+
+                def landa(a=a, tile=tile, kc=kc):
+                    aslot[a] = (tile, kc)
+                    afull[a].arrive()
+                pending.append((now[0] + rnd.randint(1, 40), landa))
+                a += 1
+                if a == AS:
+                    a, aph = 0, aph ^ 1
+                if not resident:
+                    for t in range(ntaps):
+                        while not bempty[b].test(bph ^ 1):
+                            yield
+
+                        def landb(b=b, tile=tile, kc=kc, t=t):
+                            bslot[b] = (tile, kc, t)
+                            bfull[b].arrive()
+                        pending.append((now[0] + rnd.randint(1, 40), landb))
+                        b += 1
+                        if b == BS:
+                            b, bph = 0, bph ^ 1
+                        yield
+                yield
+
+    def issuer(x):
+        st, a, aph, b, bph, acc, accphase = {}, 0, 0, 0, 0, 0, 0
+        for tile in range(tiles):
+            while not tempty[acc].test(accphase ^ 1):
+                yield
+            if (0 if resident else b % I) != x:
+                while not zinit[acc].test(accphase):
+                    yield
+            for kc in range(kchunks):
+                while not afull[a].test(aph):
+                    yield
+                if aslot[a] != (tile, kc):
+                    errors.append(("stale patch", x, tile, kc, aslot[a]))
+                for t in range(ntaps):
+                    if (t % I if resident else b % I) == x:
+                        if not resident:
+                            while not bfull[b].test(bph):
+                                yield
+                            if bslot[b] != (tile, kc, t):
+                                errors.append(("stale weights", x, tile, kc, t, bslot[b]))
+                        if kc == 0 and t == 0:
+                            acc_owner[acc] = tile
+                            if I > 1:
+                                later(st, lambda c=acc: zinit[c].arrive())
+                        elif acc_owner[acc] != tile:
+                            errors.append(("accumulator hazard", x, tile, kc, t, acc_owner[acc]))
+                        if not resident:
+                            later(st, lambda s_=b: bempty[s_].arrive())
+                        yield
+                    if not resident:
+                        b += 1
+                        if b == BS:
+                            b, bph = 0, bph ^ 1
+                later(st, lambda s_=a: aempty[s_].arrive())
+                a += 1
+                if a == AS:
+                    a, aph = 0, aph ^ 1
+            later(st, lambda c=acc: tfull[c].arrive())
+            acc ^= 1
+            if acc == 0:
+                accphase ^= 1
+            yield
+
+    def epilogue():
+        acc, accphase = 0, 0
+        for tile in range(tiles):
+            while not tfull[acc].test(accphase):
+                yield
+            if acc_owner[acc] != tile:
+                errors.append(("epilogue reads another tile", tile, acc_owner[acc]))
+            for _ in range(rnd.randint(0, 8)):
+                yield
+            tempty[acc].arrive()
+            acc ^= 1
+            if acc == 0:
+                accphase ^= 1
+            yield
+
+    threads = [producer()] + [issuer(x) for x in range(I)] + [epilogue()]
+    alive, steps = [True] * len(threads), 0
+    while any(alive):
+        now[0] += 1
+        for p in sorted([p for p in pending if p[0] <= now[0]], key=lambda q: q[0]):
+            pending.remove(p)
+            p[1]()
+        i = rnd.randrange(len(threads))
+        if alive[i]:
+            try:
+                next(threads[i])
+            except StopIteration:
+                alive[i] = False
+        steps += 1
+        if errors:
+            return "ERR", errors
+        if steps > 400000:
+            return "HANG", errors
+    return "OK", errors
+
+
+def sweep_halo(seeds=20, tiles=5):
+    out = {}
+    for AS, BS, kc, I, res in [(4, 0, 1, 2, True), (4, 0, 1, 4, True), (3, 12, 2, 2, False), (3, 6, 4, 2, False), (3, 12, 2, 4, False), (3, 8, 4, 4, False), (2, 4, 1, 2, False)]:
+        out[(AS, BS, kc, I, "resident" if res else "streamed")] = sum(run_halo(AS, BS, kc, 9, tiles, I, seed, res)[0] != "OK" for seed in range(seeds))
+    return out
+
+
 if __name__ == "__main__":
     print("ownership by ring slot, TMA out of order:")
     for k, v in sweep(seeds=100).items():
@@ -163,4 +296,7 @@ if __name__ == "__main__":
         print("  ", k, "failing seeds:", v)
     print("ownership by stage index, TMA in order:")
     for k, v in sweep(seeds=100, by_slot=False, tma_in_order=True, configs=[(3, 4, 2), (3, 8, 2), (4, 339, 2), (4, 7, 2), (3, 4, 4)]).items():
+        print("  ", k, "failing seeds:", v)
+    print("igemm_halo_kernel (A ring read by all issuers, weight ring owned by slot / resident weights split by tap), TMA out of order:")
+    for k, v in sweep_halo(seeds=100).items():
         print("  ", k, "failing seeds:", v)
