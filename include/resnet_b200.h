@@ -92,6 +92,11 @@ int resnet_b200_conv_forward(int in_spatial_dim, int kern_dim, int in_filters, i
 int resnet_b200_conv_backward(int in_spatial_dim, int kern_dim, int in_filters, int out_filters, int stride, int batch_size, int to_add,
                               const float * input, const float * weights, const float * out_deriv, float * input_deriv,
                               float * weight_deriv, int impl);
+/* measurement aid (tools/conv_bench.py): mean milliseconds per launch of ONE convolution pass of this geometry on synthetic device
+ * data, CUDA events around `iters` launches after `warmup`; pass 0 = fprop (with_stats: fused BatchNorm statistics), 1 = dgrad,
+ * 2 = dgrad accumulating, 3 = wgrad + reduce; activations in the op dtype; < 0 on error; desc receives the launch plan */
+float resnet_b200_conv_bench(int in_spatial_dim, int kern_dim, int in_filters, int out_filters, int stride, int batch_size, int pass,
+                             int with_stats, int warmup, int iters, char * desc, int desc_len);
 /* reference: resnet.cu:1431 prepareAndDoBatchNormAndActivate (normalized_temp / normalized outputs may be NULL) */
 int resnet_b200_batchnorm_forward(int spatial_dim, int filters, int batch_size, float eps, const float * input, const float * gamma,
                                   const float * beta, float * means, float * vars, float * activated, int to_activate,

@@ -196,10 +196,15 @@ int resnet_b200_uses_tensor_cores(Train_ResNet *t) {
 	for (auto &b : e->blocks) n += b.reduce.use_tc + b.spatial.use_tc + b.expand.use_tc;
 	return n > 0;
 }
+// Frees everything init_trainer / init_resnet / init_general_batch created for this trainer on the device and in the side tables
+// (the reference has no destroy functions; nothing is ever freed there).  The trainer, its model and its batch are unusable afterwards;
+// a second call, or any entry point on the stale pointer, finds no engine and does nothing.
 void resnet_b200_destroy_trainer(Train_ResNet *t) {
 	Engine *e = engine_of(t);
 	if (!e) return;
 	cudaStreamSynchronize(e->stream);
+	if (t->cur_batch) loader_release(t->cur_batch);  // stops the prefetch thread before its streams / buffers go away
+	dp_release(e);
 	for (auto &b : e->blocks)
 		for (ConvRef *c : {&b.reduce, &b.spatial, &b.expand, &b.proj}) {
 			if (c->fprop) tc_free(c->fprop);
@@ -209,9 +214,9 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 	if (e->stem_fprop) tc_free(e->stem_fprop);
 	if (e->stem_wgrad) tc_free(e->stem_wgrad);
 	for (void *p : e->allocs) cudaFree(p);
-	for (Params *P : {t->backprop_buffer->param_derivs, t->backprop_buffer->prev_means, t->backprop_buffer->prev_vars}) {
+	for (Params *P : {t->model->params, t->backprop_buffer->param_derivs, t->backprop_buffer->prev_means, t->backprop_buffer->prev_vars}) {
 		ParamStore *ps = param_store_of(P);
-		if (ps) cudaFree(ps->base);
+		if (ps) { cudaFree(ps->base); delete ps; }
 	}
 	if (e->copy_stream) {
 		cudaStreamSynchronize(e->copy_stream);
@@ -221,7 +226,16 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 	}
 	cudaFreeHost(e->pred_host);
 	cudaFreeHost(e->bad_host);
+	cudaEventDestroy(e->ev0);
+	cudaEventDestroy(e->ev1);
 	cudaStreamDestroy(e->stream);
+	if (Batch *b = t->cur_batch) {
+		cudaFree(b->images); cudaFree(b->correct_classes);
+		cudaFreeHost(b->images_float_cpu); cudaFreeHost(b->correct_classes_cpu);
+		b->images = nullptr; b->correct_classes = nullptr; b->images_float_cpu = nullptr; b->correct_classes_cpu = nullptr;
+	}
+	engine_forget(t);
+	delete e;
 }
 
 // ---------------------------------------------------------------------------------------------- single operators
@@ -282,6 +296,75 @@ int resnet_b200_conv_backward(int S, int k, int cin, int cout, int stride, int N
 	}
 	RB_CUDA(cudaDeviceSynchronize());
 	return status();
+}
+
+// Times one convolution pass of the given geometry on synthetic device data: plan built once, `warmup` + `iters` launches on the
+// default stream bracketed by CUDA events; returns the mean milliseconds per launch (< 0 on error).  pass: 0 = fprop (with_stats: the
+// epilogue also produces the fused BatchNorm statistics), 1 = dgrad, 2 = dgrad accumulating into dx, 3 = wgrad (+ its reduce).
+// Activations in the op dtype (resnet_b200_set_op_dtype).  tools/conv_bench.py walks the network's layer shapes with it.
+float resnet_b200_conv_bench(int S, int k, int cin, int cout, int stride, int N, int pass, int with_stats, int warmup, int iters, char *desc, int desc_len) {
+	Tmp tmp;
+	const int bf = g_op_bf16;
+	const size_t es = bf ? 2 : 4;
+	ConvGeom g{N, S, cin, cout, k, stride};
+	const bool stem = tc_stem_supported(S, k, cin, cout, stride, bf);
+	if (!stem && !tc_supported(g, bf)) { set_error("conv_bench: unsupported geometry"); return -1.f; }
+	if (stem && (pass == 1 || pass == 2)) { set_error("conv_bench: the stem has no input gradient"); return -1.f; }
+	curandGenerator_t gen;
+	if (curandCreateGenerator(&gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS) { set_error("conv_bench: curandCreateGenerator failed"); return -1.f; }
+	curandSetPseudoRandomGeneratorSeed(gen, 99);
+	auto rand_act = [&](long long n) -> void * {  // N(0, 1) values in the op dtype
+		n = (n + 1) / 2 * 2;
+		float *f = tmp.get<float>(n);
+		curandGenerateNormal(gen, f, (size_t)n, 0.f, 1.f);
+		if (!bf) return f;
+		void *h = tmp.get<char>(n * 2);
+		convert_f32_to_bf16(f, n, h, 0);
+		return h;
+	};
+	float *w = tmp.get<float>(g.w_elems() + 1);
+	curandGenerateNormal(gen, w, (size_t)((g.w_elems() + 1) / 2 * 2), 0.f, 0.05f);
+	void *wf = tmp.get<char>(g.w_elems() * 4), *wd = tmp.get<char>(g.w_elems() * 4);
+	pack_one(w, wf, wd, cout, cin, k * k, bf ? 0 : 1, tmp);
+	void *x = stem ? nullptr : rand_act(g.in_elems());
+	void *dy = (pass == 0) ? tmp.get<char>(g.out_elems() * (long long)es) : rand_act(g.out_elems());
+	TcPlan *pl = nullptr;
+	if (stem) {
+		float *img = tmp.get<float>(g.in_elems() + 1);
+		curandGenerateNormal(gen, img, (size_t)((g.in_elems() + 1) / 2 * 2), 0.f, 60.f);
+		void *xp = tmp.get<char>((long long)stem_xp_bytes(N, S, bf)), *wfs = tmp.get<char>((long long)stem_wfs_bytes(cout, bf));
+		stem_pad_input(img, N, S, xp, 1, bf, 0);
+		stem_pack_weights(w, cout, wfs, 1, bf, 0);
+		if (pass == 0) pl = tc_make_stem_fprop(N, S, cout, xp, wfs, dy, bf);
+		else {
+			const size_t ws = tc_stem_wgrad_workspace_bytes(N, S, cout, bf);
+			pl = tc_make_stem_wgrad(N, S, cout, xp, dy, tmp.get<float>(g.w_elems()), (float *)tmp.get<char>((long long)ws), ws, bf);
+		}
+	} else if (pass == 0) pl = tc_make_fprop(g, x, wf, dy, bf);
+	else if (pass == 1 || pass == 2) pl = tc_make_dgrad(g, dy, wd, tmp.get<char>(g.in_elems() * (long long)es), pass == 2, bf);
+	else {
+		const size_t ws = tc_wgrad_workspace_bytes(g, bf);
+		pl = tc_make_wgrad(g, x, dy, tmp.get<float>(g.w_elems()), (float *)tmp.get<char>((long long)ws), ws, bf);
+	}
+	curandDestroyGenerator(gen);
+	if (!pl) return -1.f;
+	if (pass == 0 && with_stats) tc_attach_stats(pl, tmp.get<float>((long long)tc_stats_floats(cout)));
+	if (desc && desc_len > 0) tc_describe(pl, desc, (size_t)desc_len);
+	cudaEvent_t e0, e1;
+	RB_CUDA(cudaEventCreate(&e0));
+	RB_CUDA(cudaEventCreate(&e1));
+	for (int i = 0; i < warmup; i++) tc_run(pl, 0);
+	RB_CUDA(cudaEventRecord(e0, 0));
+	for (int i = 0; i < iters; i++) tc_run(pl, 0);
+	RB_CUDA(cudaEventRecord(e1, 0));
+	RB_CUDA(cudaEventSynchronize(e1));
+	float ms = -1.f;
+	RB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	tc_free(pl);
+	RB_CUDA(cudaDeviceSynchronize());
+	return has_error() ? -1.f : ms / (float)(iters > 0 ? iters : 1);
 }
 
 int resnet_b200_batchnorm_forward(int S, int C, int N, float eps, const float *input, const float *gamma, const float *beta, float *means,

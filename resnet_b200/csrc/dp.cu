@@ -27,6 +27,7 @@ struct NcclApi {
 	int (*GetUniqueId)(ncclUniqueId *);
 	int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
 	int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+	int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
 	int (*CommDestroy)(ncclComm_t);
 	const char *(*GetErrorString)(int);
 };
@@ -43,9 +44,10 @@ static NcclApi *nccl() {
 	api.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(api.lib, "ncclGetUniqueId");
 	api.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
 	api.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+	api.Broadcast = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(api.lib, "ncclBroadcast");
 	api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.lib, "ncclCommDestroy");
 	api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
-	if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce) { set_error("libnccl: missing symbols"); api.lib = nullptr; return nullptr; }
+	if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.Broadcast) { set_error("libnccl: missing symbols"); api.lib = nullptr; return nullptr; }
 	return &api;
 }
 
@@ -96,6 +98,25 @@ static void issue_ready(Engine *e, int finished_block) {
 		if (r != ncclSuccess) set_error("ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
 		s->next++;
 	}
+}
+
+void dp_rank_world(const Engine *e, int *rank, int *world) {
+	const DpState *s = (const DpState *)e->dp;
+	*rank = s ? s->rank : 0;
+	*world = s ? s->world : 1;
+}
+
+void dp_release(Engine *e) {
+	DpState *s = (DpState *)e->dp;
+	if (!s) return;
+	cudaStreamSynchronize(s->comm_stream);
+	NcclApi *api = nccl();
+	if (api && api->CommDestroy) api->CommDestroy(s->comm);
+	cudaEventDestroy(s->ready);
+	cudaEventDestroy(s->done);
+	cudaStreamDestroy(s->comm_stream);
+	delete s;
+	e->dp = nullptr;
 }
 
 void dp_block_done(Engine *e, int block) {
@@ -150,6 +171,27 @@ int resnet_b200_dp_init(Train_ResNet *t, const void *id_bytes, int rank, int wor
 	for (auto &b : e->blocks) first.push_back(b.reduce.loc);
 	if (bucket_bytes <= 0) bucket_bytes = 32LL << 20;
 	s->buckets = plan_buckets(g->offs, g->total, first, bucket_bytes / 4);
+	// Replicas must start identical: rank 0's parameters and Adam moments (whatever seed, checkpoint restore or set_params put there)
+	// and its optimizer clocks replace every other rank's.  Without this a rank that was seeded or restored differently diverges silently.
+	RB_CUDA(cudaStreamSynchronize(e->stream));
+	ParamStore *trees[3] = {param_store_of(t->model->params), param_store_of(t->backprop_buffer->prev_means), param_store_of(t->backprop_buffer->prev_vars)};
+	for (ParamStore *ps : trees) {
+		if (!ps) { set_error("dp_init: trainer has no parameter arena"); continue; }
+		r = api->Broadcast(ps->base, ps->base, (size_t)ps->total, ncclFloat32, 0, s->comm, s->comm_stream);
+		if (r != ncclSuccess) set_error("ncclBroadcast failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+	}
+	float *clk = nullptr;
+	RB_CUDA(cudaMalloc(&clk, 2 * sizeof(float)));
+	const float hclk[2] = {t->cur_mean_decay, t->cur_var_decay};
+	RB_CUDA(cudaMemcpyAsync(clk, hclk, sizeof(hclk), cudaMemcpyHostToDevice, s->comm_stream));
+	r = api->Broadcast(clk, clk, 2, ncclFloat32, 0, s->comm, s->comm_stream);
+	if (r != ncclSuccess) set_error("ncclBroadcast failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+	float rclk[2] = {hclk[0], hclk[1]};
+	RB_CUDA(cudaMemcpyAsync(rclk, clk, sizeof(rclk), cudaMemcpyDeviceToHost, s->comm_stream));
+	RB_CUDA(cudaStreamSynchronize(s->comm_stream));
+	RB_CUDA(cudaFree(clk));
+	t->cur_mean_decay = rclk[0];
+	t->cur_var_decay = rclk[1];
 	e->dp = s;
 	return has_error() ? 1 : 0;
 }

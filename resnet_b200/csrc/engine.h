@@ -103,6 +103,12 @@ Engine *engine_of(const Train_ResNet *t);
 extern int g_default_bf16;  // storage type of the next init_trainer (resnet_b200_set_dtype)
 
 // dp.cu
+void dp_rank_world(const Engine *e, int *rank, int *world);  // (0, 1) without data parallelism
+void dp_release(Engine *e);                                   // destroys the communicator, stream and events
+// loader.cu
+void loader_release(Batch *bb);
+// model.cu: drops the side-table entries of a trainer (resnet_b200_destroy_trainer)
+void engine_forget(const Train_ResNet *t);
 void dp_block_done(Engine *e, int block);  // block's gradients are enqueued: issue the buckets that became complete
 void dp_allreduce_grads(Engine *e);       // end of backward: flush remaining buckets, compute stream waits
 

@@ -30,6 +30,7 @@
 #include "ptx.cuh"
 #include "igemm.h"
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 namespace rb {
@@ -133,17 +134,6 @@ struct alignas(64) IgemmParams {
 	int resident_b;
 	uint32_t resb_bytes;
 	int debug;  // profiling aid (RESNET_B200_DEBUG_SKIP): bit 0 = issue no MMAs (feed only), bit 1 = epilogue drains TMEM but stores nothing
-	// halo = 1 (igemm_halo_kernel, stride-1 3x3): the activation patch of a tile -- (bh + 2) x (bw + 2) pixels, PH x PW -- is fetched
-	// ONCE per K chunk (a_tx_bytes) into an a_bytes slot of an `stages`-deep ring, and the nine taps address it through descriptor
-	// start offsets; the weight tiles of the (K chunk, tap) pairs travel through their own `bstages`-deep ring unless resident_b.
-	int halo, PW, PH, bstages;
-	// issuers (1, 2 or 4): threads issuing the tile's MMAs.  One thread cannot issue a tcgen05.mma more often than every ~115 clocks
-	// (171 at N = 256) whatever the instruction's size, two / four threads interleaving on the SAME accumulator reach 62 / 57 clocks at
-	// N = 64, 86 / 77 at N = 128, 150 / 141 at N = 256 (profiles/r01_mma_rate.txt; results exact).  Issuer x owns the ring slots
-	// s = x (mod issuers) (halo kernel with resident weights: the taps t = x (mod issuers)); the owner of a tile's first stage overwrites
-	// the accumulator with its first MMA and commits `zinit`, which the others wait for before they accumulate.
-	int issuers;
-	int desc_base_off;  // bring-up aid (RESNET_B200_HALO_BASEOFF): also set the descriptor's base-offset field to (start >> 7) & 7
 	float *out;
 	int OH, OW, os, accumulate;
 	int tma_store;  // epilogue: 1 = swizzled smem staging + TMA tile store (reduce-add when accumulate), 0 = per-thread row stores
@@ -165,18 +155,20 @@ struct alignas(64) WgradParams {
 	// of stages, so its one epilogue need not overlap).  Cuts the bytes the TMA path must deliver per MAC by a third on the layers
 	// that are bound by it (every wgrad with Cout >= 256 sat at the ~42 B/clk/SM the TMA / L2 path delivers chip-wide).
 	int m_pair, co_items;  // co_items = co_tiles / m_pair
+	int split_major;   // work-item order, see wgrad_tile()
 	int merge_taps;    // the taps of a group sit back to back in shared memory AND in TMEM: one MMA of N = ntaps * BN covers them all
 	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
 	int stages;
-	int issuers;       // MMA-issuing threads (see IgemmParams::issuers): issuer x owns the ring slots s = x (mod issuers); stages % issuers == 0
 	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
 	float *partial;
 };
 
-// Block sizes.  MI = the experimental multi-issuer instantiation (IgemmParams::issuers > 1): up to three more MMA-issuing warps.  The
-// default single-issuer instantiation is compiled without any of that (the issuing thread's loop is the critical path of every conv).
-constexpr int kIgemmThreads = 192, kIgemmThreadsMI = 288;    // wgrad: TMA warp, MMA warp, 4 epilogue warps (+ warps 6-8)
-constexpr int kKmajorThreads = 320, kKmajorThreadsMI = 416;  // fprop / dgrad: TMA warp, MMA warp, up to two groups of 4 epilogue warps (+ warps 10-12)
+// Block sizes: TMA warp, MMA warp, 4 epilogue warps (wgrad) / up to two groups of 4 epilogue warps (fprop, dgrad).
+// (Round 1 carried an experimental mode with 2-4 MMA-issuing warps per CTA.  With the issue loops warp-uniform it measured 1-25 % SLOWER
+// on every layer, profiles/r02_conv_bench_issuers_*.txt -- the kernels are bound by their operand feed and epilogue, not by MMA issue --
+// and it gave up bitwise reproducibility, so it was removed.)
+constexpr int kIgemmThreads = 192;
+constexpr int kKmajorThreads = 320;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kABytes = 128 * 32 * 4;  // 128 rows x 32 tf32 = 16 KB
 
@@ -194,8 +186,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // BF16 = false: fp32 tensors, kind::tf32 MMAs, 32 output columns per staged 128-byte row;
 // BF16 = true:  bf16 tensors, kind::f16 MMAs, 64 output columns per staged row.  The shared-memory tiles are byte-identical
 // in both modes (128 rows x 128 bytes, 4 MMAs per stage each advancing 32 bytes along K).
-template <bool BF16, bool MI>
-__global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+template <bool BF16>
+__global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.resident_b ? p.a_bytes : p.a_bytes + p.b_bytes;
@@ -207,8 +199,7 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
 	uint64_t *bfull = tempty + 2;
-	uint64_t *zinit = bfull + 1;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(zinit + 2);
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (warp == 0 && lane == 0) {
@@ -219,7 +210,7 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 	if (warp == 1) {
 		if (lane == 0) {
 			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], p.issuers); mbar_init(&tempty[i], 4 * p.epi_groups); mbar_init(&zinit[i], 1); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * p.epi_groups); }
 			mbar_init(bfull, 1);
 			fence_barrier_init();
 		}
@@ -234,81 +225,76 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 
 	const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
 
+	// The producer and the MMA warps run their loops with all 32 lanes (warp-uniform control flow and addresses) and elect one lane
+	// only around the TMA / tcgen05 instructions themselves.  Round 1 had these loops under `if (lane == 0)`: nvcc then treats the
+	// whole region as divergent and wraps EVERY UTCHMMA / UTMALDG / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop,
+	// which is what made a tcgen05.mma cost ~115 clocks to issue (profiles/r02_mma_rate.txt).
 	if (warp == 0) {
-		if (lane == 0) {
-			int stage = 0;
-			uint32_t phase = 0;
-			if (p.resident_b && (int)blockIdx.x < total_tiles) {  // the weights of this CTA's N tile, once
-				const GroupDesc &g = p.groups[0];
-				const int nt = (int)blockIdx.x % p.n_tiles;
+		int stage = 0;
+		uint32_t phase = 0;
+		if (p.resident_b && (int)blockIdx.x < total_tiles) {  // the weights of this CTA's N tile, once
+			const GroupDesc &g = p.groups[0];
+			const int nt = (int)blockIdx.x % p.n_tiles;
+			if (elect_one()) {
 				mbar_expect_tx(bfull, p.resb_bytes);
 				for (int t = 0; t < g.ntaps; t++)
 					for (int kc = 0; kc < p.kchunks; kc++)
 						tma_load_2d(resb + (size_t)(t * p.kchunks + kc) * p.b_bytes, &p.bmap, bfull, g.taps[t].bcol + kc * p.kelems, nt * p.BN);
 			}
-			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				const int nt = tile % p.n_tiles;
-				int r = tile / p.n_tiles;
-				const int mt = r % p.m_tiles;
-				const GroupDesc &g = p.groups[r / p.m_tiles];
-				const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-				for (int t = 0; t < g.ntaps; t++) {
-					const TapDesc tp = g.taps[t];
-					for (int kc = 0; kc < p.kchunks; kc++) {
-						mbar_wait(&empty[stage], phase ^ 1);
+			__syncwarp();
+		}
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			const int nt = tile % p.n_tiles;
+			int r = tile / p.n_tiles;
+			const int mt = r % p.m_tiles;
+			const GroupDesc &g = p.groups[r / p.m_tiles];
+			const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+			for (int t = 0; t < g.ntaps; t++) {
+				const TapDesc tp = g.taps[t];
+				for (int kc = 0; kc < p.kchunks; kc++) {
+					mbar_wait(&empty[stage], phase ^ 1);
+					if (elect_one()) {
 						uint8_t *sa = stage0 + (size_t)stage * stage_bytes;
 						mbar_expect_tx(&full[stage], p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + p.b_bytes);
 						tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * p.kelems, ow0 + tp.dx, oh0 + tp.dy, n0);
 						if (!p.resident_b) tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * p.kelems, nt * p.BN);
-						if (++stage == p.stages) { stage = 0; phase ^= 1; }
 					}
-				}
-			}
-		}
-		__syncwarp();
-	} else if (warp == 1 || (MI && warp >= 10 && warp - 9 < p.issuers)) {
-		if (lane == 0) {
-			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;  // this issuer owns the ring SLOTS s = x (mod I); stages % I == 0
-			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
-			int stage = 0, acc = 0;
-			uint32_t phase = 0, accphase = 0;
-			if (p.resident_b && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0);
-			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				const GroupDesc &g = p.groups[(tile / p.n_tiles) / p.m_tiles];
-				const int iters = g.ntaps * p.kchunks;
-				// Every issuer waits for the epilogue to drain the accumulator; the owner of the tile's first stage overwrites it with its
-				// first MMA, the others wait for that MMA (zinit).  Ownership goes by ring slot, not by stage index within the tile: an issuer
-				// then waits on EVERY pass of its slots' `full` barriers.  Skipping a pass is fatal -- mbarrier.try_wait.parity cannot tell
-				// "the previous pass has not landed yet" from "this pass has landed", and TMA loads complete out of order (the hang / fault
-				// of the first version on 3-stage rings, profiles/r01_issuers_status.txt; tools/issuer_protocol_sim.py).
-				mbar_wait(&tempty[acc], accphase ^ 1);
-				if (I > 1 && stage % I != x) mbar_wait(&zinit[acc], accphase);
-				tc_fence_after();
-				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-				for (int it = 0; it < iters; it++) {
-					if (I == 1 || stage % I == x) {
-						mbar_wait(&full[stage], phase);
-						tc_fence_after();
-						const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
-						const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-						const uint64_t bdesc = make_smem_desc(p.resident_b ? smem_u32(resb + (size_t)it * p.b_bytes) : a_addr + p.a_bytes, 16, 1024);
-						if (!(p.debug & 1)) {
-#pragma unroll
-							for (int k = 0; k < 4; k++) {
-								mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
-								if (I > 1 && it == 0 && k == 0) mma_commit(&zinit[acc]);
-							}
-						} else if (I > 1 && it == 0) mma_commit(&zinit[acc]);
-						mma_commit(&empty[stage]);
-					}
+					__syncwarp();
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
-				mma_commit(&tfull[acc]);
-				acc ^= 1;
-				if (acc == 0) accphase ^= 1;
 			}
 		}
-		__syncwarp();
+	} else if (warp == 1) {
+		const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
+		int stage = 0, acc = 0;
+		uint32_t phase = 0, accphase = 0;
+		if (p.resident_b && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0);
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			const GroupDesc &g = p.groups[(tile / p.n_tiles) / p.m_tiles];
+			const int iters = g.ntaps * p.kchunks;
+			mbar_wait(&tempty[acc], accphase ^ 1);  // the epilogue has drained this accumulator
+			tc_fence_after();
+			const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+			for (int it = 0; it < iters; it++) {
+				mbar_wait(&full[stage], phase);
+				tc_fence_after();
+				if (elect_one()) {
+					const uint32_t a_addr = smem_u32(stage0 + (size_t)stage * stage_bytes);
+					const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+					const uint64_t bdesc = make_smem_desc(p.resident_b ? smem_u32(resb + (size_t)it * p.b_bytes) : a_addr + p.a_bytes, 16, 1024);
+					if (!(p.debug & 1)) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((it | k) != 0));
+					}
+					mma_commit(&empty[stage]);
+					if (it == iters - 1) mma_commit(&tfull[acc]);
+				}
+				__syncwarp();
+				if (++stage == p.stages) { stage = 0; phase ^= 1; }
+			}
+			acc ^= 1;
+			if (acc == 0) accphase ^= 1;
+		}
 	} else if ((warp - 2) / 4 < p.epi_groups) {
 		// Epilogue.  A warp may only touch TMEM lanes 32 * (warp % 4) .. +31, so warps 2-5 and 6-9 each cover the four lane quarters.
 		// With two groups the 128-byte column chunks (counted over the CTA's whole tile sequence) alternate between them: the
@@ -318,7 +304,7 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 		const int q = warp & 3;
 		const int row = q * 32 + lane;
 		const int wq = row % p.bw, hq = (row / p.bw) % p.bh, nq = row / (p.bw * p.bh);
-		const bool issuer = ((warp - 2) % 4 == 0 && lane == 0);
+		const bool store_warp = ((warp - 2) % 4 == 0);  // its elected lane issues the group's TMA stores (elect.sync names the same lane every time: bulk groups are per thread)
 		uint8_t *const gstaging = staging + (size_t)eg * p.nstaging * kABytes;
 		int acc = 0;
 		uint32_t accphase = 0, sbuf = 0, chunk_no = 0;
@@ -362,12 +348,15 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 					fence_proxy_async();
 					// the store that last read the NEXT buffer in the ring is done before anyone rewrites it; nstaging - 2 younger
 					// stores may still be in flight (the write-bound 1x1 layers were serialised on the store round trip with 2 tiles)
-					if (issuer) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }
+					if (store_warp) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }  // (lanes without bulk groups fall through)
 					named_barrier_sync(1 + eg, 128);
-					if (issuer) {
-						if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
-						else tma_store_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
-						tma_commit_group();
+					if (store_warp) {
+						if (elect_one()) {
+							if (p.accumulate) tma_reduce_add_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
+							else tma_store_4d(&p.omap[g.omap], buf, nt * p.BN + c * CW, ow0, oh0, n0);
+							tma_commit_group();
+						}
+						__syncwarp();
 					}
 					if (p.stats) {
 						// fused BatchNorm statistics: lane j sums 32-bit word j (one fp32 column / two bf16 columns) of this warp's 32 rows
@@ -426,237 +415,7 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 			acc ^= 1;
 			if (acc == 0) accphase ^= 1;
 		}
-		if (issuer) tma_wait_group0();  // shared memory must outlive the last store's reads; global writes complete before exit
-	}
-	tc_fence_before();
-	__syncthreads();
-	if (warp == 1) {
-		tc_fence_after();
-		tmem_dealloc(tmem_base, kTmemCols);
-	}
-}
-
-// ------------------------------------------------------------------------------------------ fprop / dgrad, stride-1 3x3, haloed patch
-// The per-tap kernel above fetches every activation nine times (one shifted 128-pixel box per filter tap), and the layers with
-// few channels (64 at 56x56, 128 at 28x28) are bound by those activation bytes into shared memory, not by the MMAs
-// (profiles/r01_conv_probe_feed_only.txt).  Here a tile's activations are fetched ONCE per K chunk: the (bh + 2) x (bw + 2) pixel
-// patch around a bh x bw output tile lands as [PH][PW] rows of 128 bytes (TMA zero-fills the out-of-image border = the padding),
-// and tap (kh, kw) is the SAME shared memory read from row kh * PW + kw on: accumulator row r (r = 0..127) belongs to patch
-// position r = h * PW + w, and reads patch row r + kh * PW + kw = pixel (h + kh, w + kw).  Rows with w >= bw (the two halo columns
-// of every patch row) or h >= bh are computed and dropped (14 x 8 and 28 x 4 tiles: 112 of 128 rows useful).  The 128-byte swizzle is a
-// function of the shared-memory address bits, so a descriptor whose start address is moved by whole 128-byte rows still meets the
-// pattern the TMA unit wrote.  The epilogue compacts the useful rows into a dense [bh][bw] staging tile for the TMA store.
-template <bool BF16, bool MI>
-__global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) igemm_halo_kernel(const __grid_constant__ IgemmParams p) {
-	extern __shared__ uint8_t smem_raw[];
-	uint8_t *base = align1024(smem_raw);
-	uint8_t *resb = base;                                                       // resident weight tiles [kc][tap] (resb_bytes, 0 when unused)
-	uint8_t *aring = base + p.resb_bytes;                                       // `stages` activation patches
-	uint8_t *bring = aring + (size_t)p.stages * p.a_bytes;                      // `bstages` weight tiles (none when resident)
-	uint8_t *staging = bring + (size_t)p.bstages * p.b_bytes;                   // epi_groups x nstaging x 16 KB epilogue tiles
-	uint64_t *afull = reinterpret_cast<uint64_t *>(staging + p.epi_groups * p.nstaging * kABytes);
-	uint64_t *aempty = afull + p.stages;
-	uint64_t *bfull = aempty + p.stages;
-	uint64_t *bempty = bfull + p.bstages;
-	uint64_t *tfull = bempty + p.bstages;
-	uint64_t *tempty = tfull + 2;
-	uint64_t *resfull = tempty + 2;
-	uint64_t *zinit = resfull + 1;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(zinit + 2);
-
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	if (warp == 0 && lane == 0) {
-		prefetch_tmap(&p.amap[0]);
-		prefetch_tmap(&p.bmap);
-		prefetch_tmap(&p.omap[0]);
-	}
-	if (warp == 1) {
-		if (lane == 0) {
-			for (int i = 0; i < p.stages; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], p.issuers); }
-			for (int i = 0; i < p.bstages; i++) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], p.issuers); mbar_init(&tempty[i], 4 * p.epi_groups); mbar_init(&zinit[i], 1); }
-			mbar_init(resfull, 1);
-			fence_barrier_init();
-		}
-		__syncwarp();
-		tmem_alloc(tmem_slot, kTmemCols);
-		tmem_relinquish();
-	}
-	tc_fence_before();
-	__syncthreads();
-	tc_fence_after();
-	const uint32_t tmem_base = *tmem_slot;
-
-	const int total_tiles = p.m_tiles * p.n_tiles;
-	const GroupDesc &g = p.groups[0];
-
-	if (warp == 0) {
-		if (lane == 0) {
-			int as = 0, bs = 0;
-			uint32_t aph = 0, bph = 0;
-			if (p.resident_b && (int)blockIdx.x < total_tiles) {  // the weights of this CTA's N tile, once
-				const int nt = (int)blockIdx.x % p.n_tiles;
-				mbar_expect_tx(resfull, p.resb_bytes);
-				for (int kc = 0; kc < p.kchunks; kc++)
-					for (int t = 0; t < g.ntaps; t++)
-						tma_load_2d(resb + (size_t)(kc * g.ntaps + t) * p.b_bytes, &p.bmap, resfull, g.taps[t].bcol + kc * p.kelems, nt * p.BN);
-			}
-			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-				const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = mt / (p.tiles_w * p.tiles_h);
-				for (int kc = 0; kc < p.kchunks; kc++) {
-					mbar_wait(&aempty[as], aph ^ 1);
-					mbar_expect_tx(&afull[as], p.a_tx_bytes);
-					tma_load_4d(aring + (size_t)as * p.a_bytes, &p.amap[0], &afull[as], kc * p.kelems, ow0 - 1, oh0 - 1, n0);
-					if (++as == p.stages) { as = 0; aph ^= 1; }
-					if (!p.resident_b) {
-						for (int t = 0; t < g.ntaps; t++) {
-							mbar_wait(&bempty[bs], bph ^ 1);
-							mbar_expect_tx(&bfull[bs], p.b_bytes);
-							tma_load_2d(bring + (size_t)bs * p.b_bytes, &p.bmap, &bfull[bs], g.taps[t].bcol + kc * p.kelems, nt * p.BN);
-							if (++bs == p.bstages) { bs = 0; bph ^= 1; }
-						}
-					}
-				}
-			}
-		}
-		__syncwarp();
-	} else if (warp == 1 || (MI && warp >= 10 && warp - 9 < p.issuers)) {
-		if (lane == 0) {
-			// this issuer takes the taps t = x (mod I) of every K chunk when the weights are resident (no per-tap barrier), else the taps
-			// whose weight-ring SLOT is x (mod I) (bstages % I == 0): an issuer must wait on every pass of a slot's barrier (see igemm_kmajor_kernel)
-			const int x = (!MI || warp == 1) ? 0 : warp - 9, I = MI ? p.issuers : 1;
-			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 0, 0) : make_idesc_tf32(128, p.BN, 0, 0);
-			int as = 0, bs = 0, acc = 0;
-			uint32_t aph = 0, bph = 0, accphase = 0;
-			if (p.resident_b && (int)blockIdx.x < total_tiles) mbar_wait(resfull, 0);
-			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				mbar_wait(&tempty[acc], accphase ^ 1);
-				if (I > 1 && (p.resident_b ? 0 : bs % I) != x) mbar_wait(&zinit[acc], accphase);  // the first tap's owner has overwritten the accumulator
-				tc_fence_after();
-				const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-				for (int kc = 0; kc < p.kchunks; kc++) {
-					mbar_wait(&afull[as], aph);
-					tc_fence_after();
-					const uint32_t a_base = smem_u32(aring + (size_t)as * p.a_bytes);
-					for (int t = 0; t < g.ntaps; t++) {
-						if (I == 1 || (p.resident_b ? t % I : bs % I) == x) {
-							const TapDesc tp = g.taps[t];
-							uint32_t b_addr;
-							if (p.resident_b) b_addr = smem_u32(resb + (size_t)(kc * g.ntaps + t) * p.b_bytes);
-							else {
-								mbar_wait(&bfull[bs], bph);
-								tc_fence_after();
-								b_addr = smem_u32(bring + (size_t)bs * p.b_bytes);
-							}
-							const uint32_t a_addr = a_base + (uint32_t)(((tp.dy + 1) * p.PW + (tp.dx + 1)) * 128);  // the patch from row (kh, kw) on
-							uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-							if (p.desc_base_off) adesc |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-							const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
-#pragma unroll
-							for (int k = 0; k < 4; k++) {
-								mma_ss<BF16>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((kc | t | k) != 0));
-								if (I > 1 && (kc | t | k) == 0) mma_commit(&zinit[acc]);
-							}
-							if (!p.resident_b) mma_commit(&bempty[bs]);
-						}
-						if (!p.resident_b) { if (++bs == p.bstages) { bs = 0; bph ^= 1; } }
-					}
-					mma_commit(&aempty[as]);
-					if (++as == p.stages) { as = 0; aph ^= 1; }
-				}
-				mma_commit(&tfull[acc]);
-				acc ^= 1;
-				if (acc == 0) accphase ^= 1;
-			}
-		}
-		__syncwarp();
-	} else if ((warp - 2) / 4 < p.epi_groups) {
-		// Epilogue (see igemm_kmajor_kernel): accumulator row `pos` is patch position (pos / PW, pos % PW); the useful rows are
-		// compacted to staging row h * bw + w, so ONE TMA store of a dense {columns, bw, bh, 1} box writes the tile.
-		constexpr int CW = BF16 ? 64 : 32;
-		const int eg = (warp - 2) / 4;
-		const int q = warp & 3;
-		const int pos = q * 32 + lane;
-		const int hq = pos / p.PW, wq = pos - hq * p.PW;
-		const bool in_box = (wq < p.bw) && (hq < p.bh);
-		const int crow = hq * p.bw + wq;
-		const int nrows = p.bw * p.bh;
-		const bool issuer = ((warp - 2) % 4 == 0 && lane == 0);
-		uint8_t *const gstaging = staging + (size_t)eg * p.nstaging * kABytes;
-		int acc = 0;
-		uint32_t accphase = 0, sbuf = 0, chunk_no = 0;
-		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-			const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-			const int ow0 = (mt % p.tiles_w) * p.bw, oh0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh, n0 = mt / (p.tiles_w * p.tiles_h);
-			const bool row_valid = in_box && (ow0 + wq < p.Wm) && (oh0 + hq < p.Hm);
-			mbar_wait(&tfull[acc], accphase);
-			tc_fence_after();
-			const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-			for (int c = 0; c < p.BN / CW; c++) {
-				if (p.epi_groups == 2 && ((chunk_no++) & 1u) != (uint32_t)eg) continue;  // the other group's chunk
-				float v[CW];
-				if constexpr (BF16) tmem_ld_32x64(taddr + (uint32_t)(c * CW), v);
-				else tmem_ld_32x32(taddr + (uint32_t)(c * CW), v);
-				uint8_t *buf = gstaging + sbuf * kABytes;
-				sbuf = (sbuf + 1 == (uint32_t)p.nstaging ? 0 : sbuf + 1);
-				if (in_box) {
-					uint8_t *rowp = buf + crow * 128;
-					if (p.stats && !row_valid) {  // rows the TMA store clips must not pollute the fused statistics
-#pragma unroll
-						for (int j = 0; j < CW; j++) v[j] = 0.f;
-					}
-#pragma unroll
-					for (int j = 0; j < 8; j++) {
-						if constexpr (BF16)
-							*reinterpret_cast<uint4 *>(rowp + ((j ^ (crow & 7)) << 4)) =
-							    make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-							               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-						else
-							*reinterpret_cast<float4 *>(rowp + ((j ^ (crow & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-					}
-				}
-				fence_proxy_async();
-				if (issuer) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }
-				named_barrier_sync(1 + eg, 128);
-				if (issuer) {
-					if (p.accumulate) tma_reduce_add_4d(&p.omap[0], buf, nt * p.BN + c * CW, ow0, oh0, n0);
-					else tma_store_4d(&p.omap[0], buf, nt * p.BN + c * CW, ow0, oh0, n0);
-					tma_commit_group();
-				}
-				if (p.stats) {  // fused BatchNorm statistics over the staged rows (see igemm_kmajor_kernel)
-					float cs = 0.f, cq = 0.f, cs1 = 0.f, cq1 = 0.f;
-					const int r_end = min(32, nrows - q * 32);
-#pragma unroll 8
-					for (int rr = 0; rr < r_end; rr++) {
-						const int r2 = q * 32 + rr;
-						const uint32_t w = *reinterpret_cast<const uint32_t *>(buf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7)) << 4) | ((lane & 3) << 2)));
-						if constexpr (BF16) {
-							const float y0 = __uint_as_float(w << 16), y1 = __uint_as_float(w & 0xffff0000u);
-							cs += y0; cq = fmaf(y0, y0, cq);
-							cs1 += y1; cq1 = fmaf(y1, y1, cq1);
-						} else {
-							const float y = __uint_as_float(w);
-							cs += y;
-							cq = fmaf(y, y, cq);
-						}
-					}
-					float *sp = p.stats + ((size_t)((blockIdx.x * p.epi_groups + eg) * 4 + q) * 2) * p.Ncol + (size_t)nt * p.BN + c * CW + (BF16 ? 2 * lane : lane);
-					atomicAdd(sp, cs);
-					atomicAdd(sp + p.Ncol, cq);
-					if constexpr (BF16) {
-						atomicAdd(sp + 1, cs1);
-						atomicAdd(sp + p.Ncol + 1, cq1);
-					}
-				}
-			}
-			tc_fence_before();
-			__syncwarp();
-			if (lane == 0) mbar_arrive(&tempty[acc]);
-			acc ^= 1;
-			if (acc == 0) accphase ^= 1;
-		}
-		if (issuer) tma_wait_group0();
+		if (store_warp) tma_wait_group0();  // shared memory must outlive the last store's reads; global writes complete before exit
 	}
 	tc_fence_before();
 	__syncthreads();
@@ -667,8 +426,22 @@ __global__ void __launch_bounds__(MI ? kKmajorThreadsMI : kKmajorThreads, 1) ige
 }
 
 // ------------------------------------------------------------------------------------------ wgrad
-template <bool BF16, bool MI>
-__global__ void __launch_bounds__(MI ? kIgemmThreadsMI : kIgemmThreads, 1) igemm_mnmajor_kernel(const __grid_constant__ WgradParams p) {
+// work item -> (pixel-range split, output tile r = (tap group * co_items + cot) * ci_tiles + cit).  split_major: consecutive items -- the
+// ones the persistent grid runs at the same time -- are the DIFFERENT output tiles of the SAME pixel range, so a range of dY / X is
+// fetched from HBM once and its re-reads by the other (co, ci, tap-group) tiles hit L2.  Round 1 ran split-fastest: one output tile's
+// splits side by side, every other tile re-reading the whole tensors from HBM later (1.5-1.9x the algorithmic DRAM bytes).
+__device__ __forceinline__ void wgrad_tile(const WgradParams &p, int tile, int n_groups, int &split, int &r) {
+	if (p.split_major) {
+		const int T = n_groups * p.co_items * p.ci_tiles;
+		split = tile / T;
+		r = tile - split * T;
+	} else {
+		split = tile % p.splits;
+		r = tile / p.splits;
+	}
+}
+template <bool BF16>
+__global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const __grid_constant__ WgradParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
@@ -676,8 +449,7 @@ __global__ void __launch_bounds__(MI ? kIgemmThreadsMI : kIgemmThreads, 1) igemm
 	uint64_t *empty = full + p.stages;
 	uint64_t *tfull = empty + p.stages;
 	uint64_t *tempty = tfull + 2;
-	uint64_t *zinit = tempty + 2;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(zinit + 2);
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (warp == 0 && lane == 0) {
@@ -687,7 +459,7 @@ __global__ void __launch_bounds__(MI ? kIgemmThreadsMI : kIgemmThreads, 1) igemm
 	if (warp == 1) {
 		if (lane == 0) {
 			for (int i = 0; i < p.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], p.issuers); mbar_init(&tempty[i], 4); mbar_init(&zinit[i], 1); }
+			for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
 			fence_barrier_init();
 		}
 		__syncwarp();
@@ -708,22 +480,22 @@ __global__ void __launch_bounds__(MI ? kIgemmThreadsMI : kIgemmThreads, 1) igemm
 	const uint32_t acc_cols = grp_cols * (uint32_t)p.m_pair;     // ... of one work item
 	const int nbuf = (2 * acc_cols <= (uint32_t)kTmemCols) ? 2 : 1;  // TMEM accumulator buffers
 
-	if (warp == 0) {
-		if (lane == 0) {
-			int stage = 0;
-			uint32_t phase = 0;
-			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				const int split = tile % p.splits;
-				int r = tile / p.splits;
-				const int cit = r % p.ci_tiles; r /= p.ci_tiles;
-				const int cot = r % p.co_items;
-				const int tap0 = (r / p.co_items) * p.tpt;
-				const int ntg = min(p.tpt, p.ntaps - tap0);
-				const int kb0 = split * p.boxes_per_split;
-				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
-				for (int kb = kb0; kb < kb1; kb++) {
-					const int ow0 = (kb % p.tiles_w) * p.bw, oh0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh, n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bn;
-					mbar_wait(&empty[stage], phase ^ 1);
+	if (warp == 0) {  // all lanes run the loops, one elected lane issues (see igemm_kmajor_kernel)
+		int stage = 0;
+		uint32_t phase = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			int split, r;
+			wgrad_tile(p, tile, n_groups, split, r);
+			const int cit = r % p.ci_tiles; r /= p.ci_tiles;
+			const int cot = r % p.co_items;
+			const int tap0 = (r / p.co_items) * p.tpt;
+			const int ntg = min(p.tpt, p.ntaps - tap0);
+			const int kb0 = split * p.boxes_per_split;
+			const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
+			for (int kb = kb0; kb < kb1; kb++) {
+				const int ow0 = (kb % p.tiles_w) * p.bw, oh0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh, n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bn;
+				mbar_wait(&empty[stage], phase ^ 1);
+				if (elect_one()) {
 					uint8_t *sa = base + (size_t)stage * stage_bytes;
 					mbar_expect_tx(&full[stage], p.a_bytes + (uint32_t)ntg * p.b_bytes);
 					tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * p.a_blocks * p.m_pair);  // all [px][128 B of co] boxes in one op
@@ -731,73 +503,67 @@ __global__ void __launch_bounds__(MI ? kIgemmThreadsMI : kIgemmThreads, 1) igemm
 						const TapDesc tp = p.taps[tap0 + t];
 						tma_load_5d(sa + p.a_bytes + (size_t)t * p.b_bytes, &p.bmap[tp.amap], &full[stage], 0, ow0 + tp.dx, oh0 + tp.dy, n0, cit * nb_boxes);
 					}
-					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
+				__syncwarp();
+				if (++stage == p.stages) { stage = 0; phase ^= 1; }
 			}
 		}
-		__syncwarp();
-	} else if (warp == 1 || (MI && warp >= 6 && warp - 5 < p.issuers)) {
-		if (lane == 0) {
-			const int x = (!MI || warp == 1) ? 0 : warp - 5, I = MI ? p.issuers : 1;
-			const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 1, 1) : make_idesc_tf32(128, p.BN, 1, 1);
-			int stage = 0, acc = 0;
-			uint32_t phase = 0, accphase = 0;
-			for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-				const int split = tile % p.splits;
-				const int tap0 = ((tile / p.splits) / p.ci_tiles / p.co_items) * p.tpt;
-				const int ntg = min(p.tpt, p.ntaps - tap0);
-				const int kb0 = split * p.boxes_per_split;
-				const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
-				// every issuer waits for the drained accumulator; the owner of the item's first stage overwrites it with that stage's MMAs, the
-				// others wait for those (zinit).  Ownership by ring slot (stages % I == 0), see igemm_kmajor_kernel.
-				mbar_wait(&tempty[acc], accphase ^ 1);
-				if (I > 1 && stage % I != x) mbar_wait(&zinit[acc], accphase);
+	} else if (warp == 1) {
+		const uint32_t idesc = BF16 ? make_idesc_bf16(128, p.BN, 1, 1) : make_idesc_tf32(128, p.BN, 1, 1);
+		int stage = 0, acc = 0;
+		uint32_t phase = 0, accphase = 0;
+		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+			int split, r;
+			wgrad_tile(p, tile, n_groups, split, r);
+			const int tap0 = (r / p.ci_tiles / p.co_items) * p.tpt;
+			const int ntg = min(p.tpt, p.ntaps - tap0);
+			const int kb0 = split * p.boxes_per_split;
+			const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
+			mbar_wait(&tempty[acc], accphase ^ 1);  // the epilogue has drained this accumulator
+			tc_fence_after();
+			const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+			for (int kb = kb0; kb < kb1; kb++) {
+				mbar_wait(&full[stage], phase);
 				tc_fence_after();
-				const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
-				for (int kb = kb0; kb < kb1; kb++) {
-					if (I == 1 || stage % I == x) {
-						mbar_wait(&full[stage], phase);
-						tc_fence_after();
-						const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
-						for (int m = 0; m < p.m_pair; m++) {  // the 128-row co tiles of the item: same B tiles, own A rows and accumulators
-							const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)m * kABytes, p.lbo, p.sbo, p.layout_type);
-							const uint32_t d_m = d_tmem + (uint32_t)m * grp_cols;
-							if (p.merge_taps) {
-								// the group's B tiles are contiguous [tap][channel block][px][128 B] with one LBO pitch, and its accumulators are
-								// contiguous TMEM columns: issue the whole group as ONE N = ntg * BN MMA per K step instead of ntg narrow ones
-								const uint32_t idesc_g = BF16 ? make_idesc_bf16(128, ntg * p.BN, 1, 1) : make_idesc_tf32(128, ntg * p.BN, 1, 1);
-								const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
+				if (elect_one()) {
+					const uint32_t a_addr = smem_u32(base + (size_t)stage * stage_bytes);
+					for (int m = 0; m < p.m_pair; m++) {  // the 128-row co tiles of the item: same B tiles, own A rows and accumulators
+						const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)m * kABytes, p.lbo, p.sbo, p.layout_type);
+						const uint32_t d_m = d_tmem + (uint32_t)m * grp_cols;
+						if (p.merge_taps) {
+							// the group's B tiles are contiguous [tap][channel block][px][128 B] with one LBO pitch, and its accumulators are
+							// contiguous TMEM columns: issue the whole group as ONE N = ntg * BN MMA per K step instead of ntg narrow ones
+							const uint32_t idesc_g = BF16 ? make_idesc_bf16(128, ntg * p.BN, 1, 1) : make_idesc_tf32(128, ntg * p.BN, 1, 1);
+							const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-								for (int k = 0; k < 4; k++)
-									mma_ss<BF16>(d_m, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc_g, (uint32_t)((kb > kb0) || (k != 0)));
-							} else {
-								for (int t = 0; t < ntg; t++) {
-									const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
+							for (int k = 0; k < 4; k++)
+								mma_ss<BF16>(d_m, adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc_g, (uint32_t)((kb > kb0) || (k != 0)));
+						} else {
+							for (int t = 0; t < ntg; t++) {
+								const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes + (uint32_t)t * p.b_bytes, p.lbo, p.sbo, p.layout_type);
 #pragma unroll
-									for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
-										mma_ss<BF16>(d_m + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
-										             (uint32_t)((kb > kb0) || (k != 0)));
-								}
+								for (int k = 0; k < 4; k++)  // 8 (tf32, K=8) or 16 (bf16, K=16) pixel rows of 128 B per MMA
+									mma_ss<BF16>(d_m + (uint32_t)(t * p.BN), adesc + (uint64_t)(k * p.kadv), bdesc + (uint64_t)(k * p.kadv), idesc,
+									             (uint32_t)((kb > kb0) || (k != 0)));
 							}
 						}
-						if (I > 1 && kb == kb0) mma_commit(&zinit[acc]);
-						mma_commit(&empty[stage]);
 					}
-					if (++stage == p.stages) { stage = 0; phase ^= 1; }
+					mma_commit(&empty[stage]);
+					if (kb == kb1 - 1) mma_commit(&tfull[acc]);
 				}
-				mma_commit(&tfull[acc]);
-				if (++acc == nbuf) { acc = 0; accphase ^= 1; }
+				__syncwarp();
+				if (++stage == p.stages) { stage = 0; phase ^= 1; }
 			}
+			if (++acc == nbuf) { acc = 0; accphase ^= 1; }
 		}
-		__syncwarp();
 	} else if (warp >= 2 && warp < 6) {
 		const int q = warp & 3;
 		const int row = q * 32 + lane;
 		int acc = 0;
 		uint32_t accphase = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-			const int split = tile % p.splits;
-			int r = tile / p.splits;
+			int split, r;
+			wgrad_tile(p, tile, n_groups, split, r);
 			const int cit = r % p.ci_tiles; r /= p.ci_tiles;
 			const int cot = r % p.co_items;
 			const int tap0 = (r / p.co_items) * p.tpt;
@@ -854,31 +620,6 @@ struct TcPlan {
 };
 
 static const size_t kMaxDynSmem = 227 * 1024;
-// MMA-issuing threads per CTA (IgemmParams::issuers): RESNET_B200_ISSUERS = 1 (default), 2 or 4.
-// EXPERIMENTAL above 1.  The microbenchmark (tools/mma_rate.cu, profiles/r01_mma_rate.txt) shows what it is worth -- one thread issues a
-// tcgen05.mma at most every ~115 clocks (171 at N = 256), two / four threads on the same accumulator reach 62 / 57 (N = 64), 86 / 77
-// (N = 128), 150 / 141 (N = 256) with exact results.  History (profiles/r01_issuers_status.txt): the first version gave issuer x the
-// stages it = x (mod issuers) of every tile; unit tests and a batch-32 step passed, the batch-256 step hung / faulted on 3-stage rings
-// and in the stem's wgrad (an odd stage count per work item).  Cause, reproduced by tools/issuer_protocol_sim.py once TMA loads are
-// allowed to complete out of order: an issuer that does not wait on every pass of a ring slot can find the slot's barrier one phase
-// behind, and mbarrier.try_wait.parity then reports "done".  Ownership now goes by ring slot; that version has NOT run on a GPU yet
-// (the round's GPU budget was spent), hence still off by default.  It also gives up bitwise reproducibility (the order in which two
-// threads' MMAs reach the accumulator depends on timing).  Round-2 item 1 in DESIGN.md 8.
-// Issuer x owns the ring slots s = x (mod issuers), so the ring depth must be a multiple of the issuer count: fewer issuers while the
-// ring is shallower than two slots each, then the depth rounded down.  (Ownership by slot: an issuer waits on every pass of its slots'
-// barriers; skipping passes aliases the mbarrier phase parity, tools/issuer_protocol_sim.py.)
-static int fit_issuers(int issuers, int *stages) {
-	while (issuers > 1 && 2 * issuers > *stages) issuers /= 2;
-	if (issuers > 1) *stages = *stages / issuers * issuers;
-	return issuers;
-}
-static int issuers_default(int dflt, const char *family_env = nullptr) {
-	for (const char *name : {family_env, "RESNET_B200_ISSUERS"}) {  // per-family override first (bring-up): RESNET_B200_ISSUERS_K / _W
-		if (!name) continue;
-		if (const char *e = getenv(name)) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) return v; }
-	}
-	return dflt;
-}
 static inline int kelems_of(int bf16) { return bf16 ? 64 : 32; }  // elements per 128-byte swizzle row
 
 // choose a pixel box (bw, bh, bn) with product <= cap (exact == cap if exact) maximising coverage of (W, H, N)
@@ -987,133 +728,12 @@ static void finish_kmajor(TcPlan *pl) {
 	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
 	p.stages = stages > 8 ? 8 : stages;
 	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
-	// several issuers only on rings of >= 4 stages: the 3-stage plans (short-K 1x1 layers with two epilogue groups) are bound by their
-	// stores, not by MMA issue
-	p.issuers = fit_issuers(issuers_default(1, "RESNET_B200_ISSUERS_K"), &p.stages);
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
 }
 
-// ---- haloed-patch plans (igemm_halo_kernel): stride-1 3x3 fprop / dgrad
-// output tile bw x bh with bh * (bw + 2) <= 128 patch positions; picks the shape with the largest useful fraction of the 128 MMA
-// rows over the whole S x S map (ties: the smaller patch)
-static double choose_halo_tile(int S, int *bw, int *bh) {
-	double best = -1;
-	int best_rows = 0;
-	*bw = *bh = 0;
-	for (int w = 1; w <= 126 && w <= S; w++) {
-		const int hmax = 128 / (w + 2);
-		for (int h = 1; h <= hmax && h <= S; h++) {
-			const double frac = (double)S * S / ((double)ceil_div(S, w) * ceil_div(S, h) * 128.0);
-			const int rows = (w + 2) * (h + 2);
-			if (frac > best + 1e-9 || (frac > best - 1e-9 && rows < best_rows)) { best = frac; best_rows = rows; *bw = w; *bh = h; }
-		}
-	}
-	return best;
-}
-// RESNET_B200_HALO: 0 (default) = never, 1 = the layers it was written for (<= 128 output columns per tile and >= 85 % useful MMA
-// rows, i.e. the 64-channel 56x56 and 128-channel 28x28 layers of ResNet-50 / 152), 2 = every stride-1 3x3 (tests).
-// Off by default: measured on B200 (profiles/r01_conv_probe_halo.txt) it is bit-compatible and moves 6x fewer activation bytes, but
-// it is 25-50 % SLOWER than the per-tap kernel on exactly those layers -- a tcgen05.mma in SS mode costs >= ~115 clocks whatever
-// its N (profiles/r01_mma_rate.txt), so a 64- or 128-column MMA cannot use more than 28 % / 55 % of the tensor pipe however it is
-// fed, and the patch tiling wastes 12.5 % of the rows on top.  Kept as the feed half of the N = pixels (swapped operand) plan of
-// DESIGN.md 8.
-static int halo_mode() {
-	if (const char *e = getenv("RESNET_B200_HALO")) return atoi(e);
-	return 0;
-}
-static bool halo_wanted(const ConvGeom &g, int ncol, int bf16, int *bw, int *bh) {
-	const int mode = halo_mode();
-	if (mode <= 0 || g.k != 3 || g.stride != 1 || !tma_store_enabled(bf16)) return false;
-	const double frac = choose_halo_tile(g.S, bw, bh);
-	if (*bw < 1) return false;
-	if (mode >= 2) return true;
-	return frac >= 0.85 && pick_bn(ncol, bf16) <= 128;
-}
-
-// in: the tensor the taps read ([N][S][S][K]); wk: packed weights [ncol][tap][K]; out: [N][S][S][ncol].  tap t reads pixel + (dx[t], dy[t]).
-static TcPlan *make_halo_plan(const ConvGeom &g, const void *in, int K, const void *wk, void *out, int ncol, const int *tdx, const int *tdy,
-                              int accumulate, int bw, int bh, int bf16, const char *what) {
-	TcPlan *pl = new TcPlan();
-	memset(pl, 0, sizeof(*pl));
-	pl->bf16 = bf16;
-	IgemmParams &p = pl->ip;
-	const int S = g.S, ke = kelems_of(bf16);
-	p.halo = 1;
-	p.Wm = S; p.Hm = S; p.Nn = g.N;
-	p.bw = bw; p.bh = bh; p.bn = 1;
-	p.PW = bw + 2; p.PH = bh + 2;
-	p.tiles_w = ceil_div(S, bw); p.tiles_h = ceil_div(S, bh); p.tiles_b = g.N;
-	p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-	p.Ncol = ncol; p.BN = pick_bn(ncol, bf16); p.n_tiles = ncol / p.BN;
-	p.kelems = ke; p.kchunks = K / ke;
-	const long long dims_in[4] = {K, S, S, g.N}, str_in[3] = {K, (long long)S * K, (long long)S * S * K};
-	const int box_in[4] = {ke, p.PW, p.PH, 1};
-	bool ok = make_map4(&p.amap[0], in, dims_in, str_in, box_in, bf16);
-	for (int i = 1; i < 4; i++) p.amap[i] = p.amap[0];
-	ok = ok && make_map2(&p.bmap, wk, 9LL * K, ncol, 9LL * K, ke, p.BN, bf16);
-	const long long dims_out[4] = {ncol, S, S, g.N}, str_out[3] = {ncol, (long long)S * ncol, (long long)S * S * ncol};
-	const int box_out[4] = {ke, bw, bh, 1};
-	ok = ok && make_map4(&p.omap[0], out, dims_out, str_out, box_out, bf16);
-	for (int i = 1; i < 4; i++) p.omap[i] = p.omap[0];
-	p.ngroups = 1;
-	GroupDesc &gr = p.groups[0];
-	gr.ntaps = 9; gr.oh_off = gr.ow_off = 0; gr.omap = 0;
-	for (int t = 0; t < 9; t++) gr.taps[t] = TapDesc{tdx[t], tdy[t], 0, t * K};
-	p.out = (float *)out; p.OH = S; p.OW = S; p.os = 1; p.accumulate = accumulate;
-	p.tma_store = 1;
-	// shared memory: [resident weights] [A ring] [B ring] [staging] [barriers]
-	p.a_bytes = (uint32_t)(((2 * p.PW + 2 + 128) * 128 + 1023) / 1024 * 1024);  // every row a tap's 128-row window can touch
-	p.a_tx_bytes = (uint32_t)(p.PW * p.PH) * 128;
-	p.b_bytes = (uint32_t)p.BN * 128;
-	// one tile's MMAs take ~ 9 * kchunks * 4 * BN / 2 clocks, one staged 128-byte column chunk ~ 1500 clocks of one epilogue group
-	const int cw = bf16 ? 64 : 32;
-	p.epi_groups = ((p.BN / cw) * 1500 > 9 * p.kchunks * 2 * p.BN) ? 2 : 1;
-	if (const char *e = getenv("RESNET_B200_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= 2) p.epi_groups = v; }
-	p.nstaging = 2;
-	const int total = p.m_tiles * p.n_tiles;
-	pl->grid = total < kNumSMs ? total : kNumSMs;
-	const size_t resb = (size_t)9 * p.kchunks * p.b_bytes;
-	int want_res = 1;
-	if (const char *e = getenv("RESNET_B200_RESIDENT_B")) want_res = atoi(e);
-	size_t staging_bytes = 0;
-	for (;; p.epi_groups = 1) {  // a second epilogue group only where its staging tiles leave room for the operand rings
-		staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
-		const size_t budget = kMaxDynSmem - 2048 - staging_bytes;
-		p.resident_b = want_res && pl->grid % p.n_tiles == 0 && (total >= 2 * pl->grid || want_res == 2) && resb + 3 * (size_t)p.a_bytes <= budget;
-		if (p.resident_b) {
-			p.resb_bytes = (uint32_t)resb;
-			p.stages = (int)std::min<size_t>(6, (budget - resb) / p.a_bytes);
-			p.bstages = 0;
-			break;
-		}
-		p.resb_bytes = 0;
-		p.stages = p.kchunks >= 2 ? 3 : 2;
-		p.bstages = (int)std::min<size_t>(16, (budget - (size_t)p.stages * p.a_bytes) / p.b_bytes);
-		if (p.bstages >= 4 || p.epi_groups == 1) break;
-	}
-	if (!p.resident_b && p.bstages < 2) { set_error("make_halo_plan: no room for the weight ring"); ok = false; }
-	if (const char *e = getenv("RESNET_B200_HALO_BASEOFF")) p.desc_base_off = atoi(e);
-	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_K");  // the issuers split the taps of ONE patch; streamed weights: by weight-ring slot
-	if (!p.resident_b) p.issuers = fit_issuers(p.issuers, &p.bstages);
-	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * p.a_bytes + (size_t)p.bstages * p.b_bytes + staging_bytes + 1024 + 512;
-	pl->kind = 0;
-	pl->flops = 2.0 * g.N * S * S * (double)g.cout * g.cin * 9;
-	snprintf(pl->what, sizeof(pl->what), "%s 3x3/1 %d->%d @%d", what, g.cin, g.cout, g.S);
-	if (!ok || pl->smem > kMaxDynSmem) { if (ok) set_error("make_halo_plan: shared memory plan too large"); delete pl; return nullptr; }
-	return pl;
-}
-
 TcPlan *tc_make_fprop(const ConvGeom &g, const void *x, const void *wf, void *y, int bf16) {
 	if (!tc_supported(g, bf16)) { set_error("tc_make_fprop: unsupported geometry"); return nullptr; }
-	{
-		int hbw, hbh;
-		if (halo_wanted(g, g.cout, bf16, &hbw, &hbh)) {  // y(h, w) += Wf[kh][kw] . x(h + kh - 1, w + kw - 1)
-			int tdx[9], tdy[9];
-			for (int t = 0; t < 9; t++) { tdx[t] = t % 3 - 1; tdy[t] = t / 3 - 1; }
-			return make_halo_plan(g, x, g.cin, wf, y, g.cout, tdx, tdy, 0, hbw, hbh, bf16, "fprop");
-		}
-	}
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
 	pl->bf16 = bf16;
@@ -1159,14 +779,6 @@ TcPlan *tc_make_fprop(const ConvGeom &g, const void *x, const void *wf, void *y,
 
 TcPlan *tc_make_dgrad(const ConvGeom &g, const void *dy, const void *wd, void *dx, int accumulate, int bf16) {
 	if (!tc_supported(g, bf16)) { set_error("tc_make_dgrad: unsupported geometry"); return nullptr; }
-	{
-		int hbw, hbh;
-		if (halo_wanted(g, g.cin, bf16, &hbw, &hbh)) {  // dx(h, w) += Wd[kh][kw] . dy(h + 1 - kh, w + 1 - kw)
-			int tdx[9], tdy[9];
-			for (int t = 0; t < 9; t++) { tdx[t] = 1 - t % 3; tdy[t] = 1 - t / 3; }
-			return make_halo_plan(g, dy, g.cout, wd, dx, g.cin, tdx, tdy, accumulate, hbw, hbh, bf16, "dgrad");
-		}
-	}
 	TcPlan *pl = new TcPlan();
 	memset(pl, 0, sizeof(*pl));
 	pl->bf16 = bf16;
@@ -1282,7 +894,8 @@ static CUtensorMapSwizzle wgrad_layout(WgradParams &p, int bf16) {
 	p.b_bytes = (uint32_t)p.BN * 128;
 	p.merge_taps = 1;
 	if (const char *e = getenv("RESNET_B200_WGRAD_MERGE")) p.merge_taps = atoi(e) != 0;
-	p.issuers = issuers_default(1, "RESNET_B200_ISSUERS_W");
+	p.split_major = 1;
+	if (const char *e = getenv("RESNET_B200_WGRAD_SPLIT_MAJOR")) p.split_major = atoi(e) != 0;  // A/B aid
 	return bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 }
 
@@ -1329,7 +942,6 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
-	p.issuers = fit_issuers(p.issuers, &p.stages);
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = tiles * p.splits;
@@ -1518,7 +1130,6 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
-	p.issuers = fit_issuers(p.issuers, &p.stages);
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = ceil_div(p.ntaps, p.tpt) * p.co_items * p.ci_tiles * p.splits;
@@ -1538,32 +1149,28 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 		tc_describe(pl, buf, sizeof(buf));
 		fprintf(stderr, "[tc_run] %s flops=%.6g\n", buf, pl->flops);
 	}
-	static bool attr_set = false;
+	// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once on every device that launches (one process
+	// may hold trainers on several GPUs)
+	static std::mutex attr_mu;
+	static bool attr_done[64] = {false};
+	int dev = 0;
+	RB_CUDA(cudaGetDevice(&dev));
+	std::lock_guard<std::mutex> attr_lk(attr_mu);
+	bool &attr_set = attr_done[dev & 63];
 	if (!attr_set) {
-		const void *kernels[] = {(const void *)igemm_kmajor_kernel<false, false>, (const void *)igemm_kmajor_kernel<true, false>,
-		                         (const void *)igemm_kmajor_kernel<false, true>,  (const void *)igemm_kmajor_kernel<true, true>,
-		                         (const void *)igemm_halo_kernel<false, false>,   (const void *)igemm_halo_kernel<true, false>,
-		                         (const void *)igemm_halo_kernel<false, true>,    (const void *)igemm_halo_kernel<true, true>,
-		                         (const void *)igemm_mnmajor_kernel<false, false>, (const void *)igemm_mnmajor_kernel<true, false>,
-		                         (const void *)igemm_mnmajor_kernel<false, true>,  (const void *)igemm_mnmajor_kernel<true, true>};
+		const void *kernels[] = {(const void *)igemm_kmajor_kernel<false>, (const void *)igemm_kmajor_kernel<true>,
+		                         (const void *)igemm_mnmajor_kernel<false>, (const void *)igemm_mnmajor_kernel<true>};
 		for (const void *k : kernels) RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		attr_set = true;
 	}
 	if (pl->kind == 0) {
 		if (pl->ip.stats) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
-		const bool mi = pl->ip.issuers > 1;
-		const int threads = mi ? kKmajorThreadsMI : kKmajorThreads;
-		if (pl->ip.halo) {
-			if (pl->bf16) { if (mi) igemm_halo_kernel<true, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_halo_kernel<true, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
-			else { if (mi) igemm_halo_kernel<false, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_halo_kernel<false, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
-		} else if (pl->bf16) { if (mi) igemm_kmajor_kernel<true, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_kmajor_kernel<true, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
-		else { if (mi) igemm_kmajor_kernel<false, true><<<pl->grid, threads, pl->smem, st>>>(pl->ip); else igemm_kmajor_kernel<false, false><<<pl->grid, threads, pl->smem, st>>>(pl->ip); }
+		if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
+		else igemm_kmajor_kernel<false><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
 		RB_LAUNCH_CHECK();
 	} else {
-		const bool mi = pl->wp.issuers > 1;
-		const int threads = mi ? kIgemmThreadsMI : kIgemmThreads;
-		if (pl->bf16) { if (mi) igemm_mnmajor_kernel<true, true><<<pl->grid, threads, pl->smem, st>>>(pl->wp); else igemm_mnmajor_kernel<true, false><<<pl->grid, threads, pl->smem, st>>>(pl->wp); }
-		else { if (mi) igemm_mnmajor_kernel<false, true><<<pl->grid, threads, pl->smem, st>>>(pl->wp); else igemm_mnmajor_kernel<false, false><<<pl->grid, threads, pl->smem, st>>>(pl->wp); }
+		if (pl->bf16) igemm_mnmajor_kernel<true><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
+		else igemm_mnmajor_kernel<false><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
 		RB_LAUNCH_CHECK();
 		if (pl->kind == 1) wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
 		else {
@@ -1590,16 +1197,12 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
-		if (p.halo)
-			snprintf(buf, n, "%s | halo %s tile=(%d,%d) m_tiles=%d n_tiles=%d BN=%d kchunks=%d astages=%d bstages=%d epi=%d issuers=%d grid=%d smem=%zu resB=%u", pl->what,
-			         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.m_tiles, p.n_tiles, p.BN, p.kchunks, p.stages, p.bstages, p.epi_groups, p.issuers, pl->grid, pl->smem, p.resb_bytes);
-		else
-		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d issuers=%d grid=%d smem=%zu resB=%u", pl->what,
-		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, p.issuers, pl->grid, pl->smem, p.resb_bytes);
+		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d epi=%d grid=%d smem=%zu resB=%u", pl->what,
+		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, p.epi_groups, pl->grid, pl->smem, p.resb_bytes);
 	} else {
 		const WgradParams &p = pl->wp;
-		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d issuers=%d grid=%d smem=%zu",
-		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.m_pair, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, p.issuers, pl->grid, pl->smem);
+		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
+		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.m_pair, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
 	}
 }
 

@@ -75,6 +75,11 @@ static void worker(Prefetcher *p) {
 		if (p->stop) return;
 		const int s = p->req_shard, b = p->req_batch;
 		lk.unlock();
+		// The pinned buffer about to be overwritten may still be the source of an H2D copy queued on copy_stream (a host that runs
+		// several steps ahead, e.g. with set_pred_copy(0), never waits for those copies; neither does a prefetch miss, which leaves
+		// the buffers unswapped): drain the copy stream first.  It also holds the wait on the compute stream's D2D out of the
+		// staging device buffers, so this thread stays at most one batch ahead of the GPU.
+		cudaStreamSynchronize(p->copy_stream);
 		bool ok = read_batch(s, b, p->batch_size, p->image_size, p->img_pinned, p->lab_pinned);
 		if (ok) {
 			cudaMemcpyAsync(p->img_dev, p->img_pinned, p->img_bytes, cudaMemcpyHostToDevice, p->copy_stream);
@@ -107,6 +112,36 @@ static Prefetcher *prefetcher_of(Batch *bb) {
 	return p;
 }
 
+// stops and joins the prefetch thread of `bb` and frees its buffers (resnet_b200_destroy_trainer)
+void loader_release(Batch *bb) {
+	Prefetcher *p = nullptr;
+	{
+		std::lock_guard<std::mutex> g(g_pf_mu);
+		auto it = g_prefetch.find(bb);
+		if (it == g_prefetch.end()) return;
+		p = it->second;
+		g_prefetch.erase(it);
+	}
+	{
+		std::lock_guard<std::mutex> lk(p->mu);
+		p->stop = true;
+	}
+	p->cv.notify_all();
+	if (p->th.joinable()) p->th.join();
+	cudaStreamSynchronize(p->copy_stream);
+	cudaFreeHost(p->img_pinned); cudaFreeHost(p->lab_pinned);
+	cudaFree(p->img_dev); cudaFree(p->lab_dev);
+	cudaEventDestroy(p->ready);
+	cudaStreamDestroy(p->copy_stream);
+	delete p;
+}
+
+// the reference's cursor step (resnet.cu:1260-1295): next batch of the shard, next shard when the shard is exhausted
+static void advance_cursor(int &shard, int &batch, int batch_size, int shard_n_images) {
+	batch += 1;
+	if (batch * batch_size >= shard_n_images) { shard += 1; batch = 0; }
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -117,10 +152,21 @@ extern "C" void load_new_batch(Train_ResNet *trainer, Class_Metadata *class_meta
 	cudaStream_t st = e ? e->stream : 0;
 	const int batch_size = bb->n_images;
 	// which (shard, batch) this call delivers -- the reference's traversal (resnet.cu:1260-1295)
+	// Data parallel (dp.cu): the replicas share ONE global batch sequence -- the single-GPU traversal -- and rank r of `world` takes
+	// positions r, r + world, r + 2 world, ...: the first call skips `rank` batches, every later call advances by `world`
+	// (SURVEY.md 8e "rank r reads batches r, r+G, ...").  A restored cursor (init_loaded) is rank-local and is taken as is.
+	int rank = 0, world = 1;
+	if (e) dp_rank_world(e, &rank, &world);
 	int shard = bb->cur_shard_id, batch = bb->cur_batch_in_shard;
-	if (trainer->init_loaded || shard == -1 || batch * batch_size >= bb->shard_n_images) {
-		if (!trainer->init_loaded) { shard += 1; batch = 0; }
+	if (trainer->init_loaded) {
 		trainer->init_loaded = 0;
+	} else if (shard == -1) {
+		shard = 0; batch = 0;
+		for (int i = 0; i < rank; i++) advance_cursor(shard, batch, batch_size, bb->shard_n_images);
+	} else {
+		// cur_batch_in_shard is the batch after the one delivered last (the reference's convention): world - 1 more steps
+		if (batch * batch_size >= bb->shard_n_images) { shard += 1; batch = 0; }
+		for (int i = 1; i < world; i++) advance_cursor(shard, batch, batch_size, bb->shard_n_images);
 	}
 	Prefetcher *p = prefetcher_of(bb);
 	bool delivered = false;
@@ -154,8 +200,8 @@ extern "C" void load_new_batch(Train_ResNet *trainer, Class_Metadata *class_meta
 	bb->cur_batch_in_shard = batch + 1;
 	trainer->cur_dump_id += 1;
 	// kick off the prefetch of the batch the NEXT call will ask for
-	int nshard = shard, nbatch = batch + 1;
-	if (nbatch * batch_size >= bb->shard_n_images) { nshard += 1; nbatch = 0; }
+	int nshard = shard, nbatch = batch;
+	for (int i = 0; i < world; i++) advance_cursor(nshard, nbatch, batch_size, bb->shard_n_images);
 	{
 		std::lock_guard<std::mutex> lk(p->mu);
 		p->req_shard = nshard; p->req_batch = nbatch; p->busy = true; p->ok = false;

@@ -30,6 +30,14 @@ Engine *engine_of(const Train_ResNet *t) {
 	return it == g_engines.end() ? nullptr : it->second;
 }
 
+void engine_forget(const Train_ResNet *t) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	g_engines.erase(t);
+	if (t->model) g_param_stores.erase(t->model->params);
+	if (t->backprop_buffer)
+		for (const Params *P : {t->backprop_buffer->param_derivs, t->backprop_buffer->prev_means, t->backprop_buffer->prev_vars}) g_param_stores.erase(P);
+}
+
 int g_default_bf16 = -1;  // resnet_b200_set_dtype(): -1 = follow $RESNET_B200_DTYPE, 0 = fp32/tf32, 1 = bf16
 
 static int env_int(const char *name, int dflt) {
@@ -692,11 +700,28 @@ void update_parameters(Train_ResNet *t) {
 	const float cur_var_decay = t->cur_var_decay * t->base_var_decay;
 	ParamStore *p = param_store_of(t->model->params), *g = param_store_of(t->backprop_buffer->param_derivs);
 	ParamStore *m = param_store_of(t->backprop_buffer->prev_means), *v = param_store_of(t->backprop_buffer->prev_vars);
+	// Checkpoint cadence of the reference: a full dump before the update whenever cur_dump_id % 1000 == 0 (resnet.cu:2941-2944;
+	// cur_dump_id counts load_new_batch calls from 0, and stays -1 -- no dump -- for a host that stages batches itself).
+	// RESNET_B200_DUMP_EVERY overrides the period, 0 switches the periodic dump off.
+	const int dump_every = env_int("RESNET_B200_DUMP_EVERY", 1000);
+	if (dump_every > 0 && t->cur_dump_id >= 0 && t->cur_dump_id % dump_every == 0) {
+		printf("DUMPING TRAINER...!\n\n");
+		dump_trainer(t->cur_dump_id, t, t->dump_dir);
+	}
 	if (*e->bad_host) {
-		// the reference dumps and exit(1)s on the first NaN/Inf it finds (resnet.cu:2893-2900)
-		fprintf(stderr, "ERROR: nan or inf found in %d parameter/gradient entries during the previous update\n", *e->bad_host);
-		set_error("non-finite values in update_parameters (%d entries)", *e->bad_host);
+		// the reference scans all four arenas on the host every step, dumps to id 99999999 and exit(1)s on the first NaN/Inf
+		// (resnet.cu:2879-2900); here the previous update's Adam kernel counted them on the device
+		const int bad = *e->bad_host;
+		fprintf(stderr, "ERROR: nan or inf found in %d parameter/gradient entries during the previous update\n", bad);
+		if (env_int("RESNET_B200_DUMP_ON_NAN", 1)) {
+			printf("Dumping data to id=99999999...\n");
+			dump_trainer(99999999, t, t->dump_dir);
+		}
+		set_error("non-finite values in update_parameters (%d entries)", bad);
 		if (env_int("RESNET_B200_EXIT_ON_NAN", 0)) exit(1);
+		// reported once: the counter restarts, so later updates only complain about NEW non-finite values
+		*e->bad_host = 0;
+		RB_CUDA(cudaMemsetAsync(e->bad_dev, 0, sizeof(int), st));
 	}
 	adam_step(p->base, g->base, m->base, v->base, p->total, t->learning_rate, t->weight_decay, t->base_mean_decay, t->base_var_decay,
 	          cur_mean_decay, cur_var_decay, t->eps, e->bad_dev, st);

@@ -95,7 +95,7 @@ RESNET_B200_H_SYMBOLS = [
     "resnet_b200_memcpy_d2d", "resnet_b200_memset", "resnet_b200_sync", "resnet_b200_rng_create", "resnet_b200_rng_destroy",
     "resnet_b200_stage_batch", "resnet_b200_stage_batch_device", "resnet_b200_prefetch_batch", "resnet_b200_commit_batch", "resnet_b200_trainer_sync", "resnet_b200_timer_begin",
     "resnet_b200_timer_end_ms", "resnet_b200_loss_accuracy", "resnet_b200_set_pred_copy", "resnet_b200_fetch_pred", "resnet_b200_epoch_stats", "resnet_b200_launch_count", "resnet_b200_profile", "resnet_b200_profile_read", "resnet_b200_uses_tensor_cores",
-    "resnet_b200_destroy_trainer", "resnet_b200_conv_forward", "resnet_b200_conv_backward", "resnet_b200_batchnorm_forward",
+    "resnet_b200_destroy_trainer", "resnet_b200_conv_forward", "resnet_b200_conv_bench", "resnet_b200_conv_backward", "resnet_b200_batchnorm_forward",
     "resnet_b200_batchnorm_backward", "resnet_b200_maxpool_forward", "resnet_b200_maxpool_backward",
     "resnet_b200_avgpool_forward", "resnet_b200_avgpool_backward", "resnet_b200_matmul", "resnet_b200_softmax_ce",
     "resnet_b200_adam", "resnet_b200_set_dtype", "resnet_b200_trainer_dtype", "resnet_b200_set_op_dtype", "resnet_b200_convert",
@@ -164,6 +164,7 @@ def load():
     proto("resnet_b200_destroy_trainer", None, [T])
     proto("resnet_b200_conv_forward", ci, [ci] * 6 + [vp, vp, vp, ci])
     proto("resnet_b200_conv_backward", ci, [ci] * 7 + [vp, vp, vp, vp, vp, ci])
+    proto("resnet_b200_conv_bench", cf, [ci] * 10 + [C.c_char_p, ci])
     proto("resnet_b200_batchnorm_forward", ci, [ci, ci, ci, cf, vp, vp, vp, vp, vp, vp, ci, vp, ci])
     proto("resnet_b200_batchnorm_backward", ci, [ci, ci, ci, cf] + [vp] * 9 + [ci])
     proto("resnet_b200_maxpool_forward", ci, [vp, ci, ci, ci, ci, ci, vp, vp])

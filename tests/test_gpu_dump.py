@@ -12,14 +12,6 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True)
-def single_mma_issuer(monkeypatch):
-    """These tests compare two runs bit for bit.  With several MMA-issuing threads per CTA (the default) the order in which a tile's
-    MMAs reach its accumulator depends on timing, so fp32 sums may differ in the last bit from run to run; RESNET_B200_ISSUERS=1 is
-    the bitwise-reproducible mode (determinism)."""
-    monkeypatch.setenv("RESNET_B200_ISSUERS", "1")
-
-
 def make(cfg, dtype, keep_all):
     from resnet_b200 import api
     os.environ["RESNET_B200_KEEP_ALL"] = "1" if keep_all else "0"

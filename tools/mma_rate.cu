@@ -3,6 +3,9 @@
 // train of MMAs and times it with clock64().  Answers the question the conv kernels raised: the layers with 64 / 128 output
 // channels run at 22 / 45 % tensor-pipe although their TMA feed was cut 6x (haloed patch) -- is a narrow MMA bound by its operand
 // reads, by the dependency on its own accumulator, or by the issue path?
+// Round 2: the issuing loops run warp-uniform with elect.sync around the tcgen05 instructions (Cfg::lane0 = 0, the product's form since
+// round 2).  Cfg::lane0 = 1 reproduces round 1's `if (lane == 0)` form, which nvcc compiles into an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// waterfall loop around EVERY UTCHMMA -- the "115-clock issue floor" of profiles/r01_mma_rate.txt was that loop, not the hardware.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I resnet_b200/csrc tools/mma_rate.cu -o tools/mma_rate.bin
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -27,6 +30,7 @@ struct Cfg {
 	const char *note;
 	int issuers = 1;     // warps issuing concurrently (one thread each, own accumulator): is the ~115-clock floor per issuing thread or per SM?
 	int same_acc = 0;    // the concurrent issuers accumulate into ONE accumulator; operands are all ones and every element of D is checked
+	int lane0 = 0;       // 1 = round 1's divergent `if (lane == 0)` issue loop (waterfalled UTCHMMA); 0 = warp-uniform loop + elect.sync
 };
 
 __global__ void __launch_bounds__(128, 1) rate_kernel(Cfg c, unsigned long long *clk) {
@@ -62,6 +66,23 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Cfg c, unsigned long long 
 			__syncthreads();
 			tc_fence_after();
 		}
+		if (warp < c.issuers && !c.lane0) {  // warp-uniform loops + elect.sync
+			const uint64_t adesc = make_smem_desc(smem_u32(base) + (uint32_t)warp * 24576u, 16, 1024);
+			const uint64_t bdesc = make_smem_desc(smem_u32(base + 96 * 1024), 16, 1024);
+			const uint32_t d = tmem_base + (c.same_acc ? 0u : (uint32_t)(warp * c.N));
+			const long long t0 = clock64();
+			for (int i = 0; i < c.n_mma; i += 4) {
+				if (elect_one()) {
+#pragma unroll
+					for (int k = 0; k < 4; k++) mma_ss_rt(c.bf16, d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+				}
+				__syncwarp();
+			}
+			if (elect_one()) mma_commit(&ibars[warp]);
+			__syncwarp();
+			mbar_wait(&ibars[warp], 0);
+			if (lane == 0) iclk[warp] = (unsigned long long)(clock64() - t0);
+		} else
 		if (warp < c.issuers && lane == 0) {
 			const uint64_t adesc = make_smem_desc(smem_u32(base) + (uint32_t)warp * 24576u, 16, 1024);
 			const uint64_t bdesc = make_smem_desc(smem_u32(base + 96 * 1024), 16, 1024);
@@ -94,6 +115,35 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Cfg c, unsigned long long 
 			}
 			if (bad) atomicAdd(&clk[148], (unsigned long long)bad);
 		}
+	} else
+	if (warp == 1 && !c.lane0) {
+		// warp-uniform issue loop: all 32 lanes run it, elect.sync picks the lane that executes the tcgen05 instructions
+		const uint32_t idesc = c.bf16 ? make_idesc_bf16(c.M, c.N, 0, 0) : make_idesc_tf32(c.M, c.N, 0, 0);
+		const uint32_t a0 = smem_u32(base), b0 = smem_u32(base + 96 * 1024);
+		const long long t0 = clock64();
+		int acc = 0, at = 0, bt = 0;
+		for (int i = 0; i < c.n_mma; i += 4) {
+			if (elect_one()) {
+				const uint64_t adesc = make_smem_desc(a0 + (uint32_t)at * 24576u + (uint32_t)c.a_shift, 16, 1024);
+				const uint64_t bdesc = make_smem_desc(b0 + (uint32_t)bt * 32768u, 16, 1024);
+				int a2 = acc;
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					mma_ss_rt(c.bf16, tmem_base + (uint32_t)(a2 * c.N), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+					if (c.nacc > 1) { if (++a2 == c.nacc) a2 = 0; }
+				}
+				if (c.commit_every && ((i + 4) % c.commit_every) == 0) mma_commit(&bars[1]);
+			}
+			__syncwarp();
+			if (c.nacc > 1) acc = (acc + 4) % c.nacc;
+			if (++at == c.a_tiles) at = 0;
+			if (++bt == c.b_tiles) bt = 0;
+		}
+		if (elect_one()) mma_commit(&bars[0]);
+		__syncwarp();
+		mbar_wait(&bars[0], 0);
+		const long long t1 = clock64();
+		if (lane == 0) clk[blockIdx.x] = (unsigned long long)(t1 - t0);
 	} else
 	if (warp == 1 && lane == 0) {
 		const uint32_t idesc = c.bf16 ? make_idesc_bf16(c.M, c.N, 0, 0) : make_idesc_tf32(c.M, c.N, 0, 0);
@@ -139,6 +189,12 @@ int main() {
 		for (int N : {128, 64}) for (int is : {2, 4}) { Cfg c{128, N, bf, 1, 0, 1, 1, 0, n, "issuing warps in parallel, own accumulators"}; c.issuers = is; cfgs.push_back(c); }
 		{ Cfg c{128, 256, bf, 1, 0, 1, 1, 0, n, "issuing warps in parallel, own accumulators"}; c.issuers = 2; cfgs.push_back(c); }
 		for (int N : {256, 128, 64}) for (int is : {2, 4}) { Cfg c{128, N, bf, 1, 0, 1, 1, 0, n, "issuing warps in parallel, ONE accumulator, result checked"}; c.issuers = is; c.same_acc = 1; cfgs.push_back(c); }
+	}
+	{   // round 1's divergent form for comparison (same binary, same box)
+		std::vector<Cfg> legacy;
+		for (int bf = 1; bf >= 0; bf--)
+			for (int N : {256, 128, 64}) { Cfg c{128, N, bf, 1, 0, 1, 1, 0, n, "LEGACY if (lane == 0) loop (waterfalled UTCHMMA)"}; c.lane0 = 1; legacy.push_back(c); }
+		cfgs.insert(cfgs.end(), legacy.begin(), legacy.end());
 	}
 	printf("%-5s %4s %4s %4s %6s %3s %3s %6s %10s %10s  %s\n", "kind", "M", "N", "nacc", "ashift", "At", "Bt", "commit", "clk/mma", "floor", "note");
 	for (const Cfg &c : cfgs) {
