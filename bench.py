@@ -1,9 +1,9 @@
 """bench.py -- ResNet-50 training throughput of the B200-native hot path (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--impl ours|reference|reference_cached] [--batch B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): the reference's ResNet-50 variant (3x3/2 projection shortcuts, 47.6 M parameters,
+Workload (BASELINE.json configs[1] = c2): the reference's ResNet-50 variant (3x3/2 projection shortcuts, 47.6 M parameters,
 39.09 GFLOP / image / training step), full training step = batch in -> forward_pass -> backwards_pass ->
 update_parameters (Adam), batch 256 per GPU, 224x224 synthetic images, fp32 storage, TF32 tensor-core convolutions
 with fp32 accumulation.  N > 1: batch-sharded data parallel, one process per GPU, NCCL gradient allreduce (weak scaling).
@@ -17,9 +17,15 @@ with fp32 accumulation.  N > 1: batch-sharded data parallel, one process per GPU
            of the same step right after the timed region (the event pairs would perturb the headline number).
   cpu_baseline  the host-core C oracle (port of the reference's kernels; the reference has no CPU path) on a bounded
            sample of the same workload.
+  extra    (default c2 run only, --no-extra switches it off) the other BASELINE configurations measured the same way right after
+           the headline, a few steps each: c4 (bf16 training, the data-parallel scaling configuration), c5 (ResNet-152 bf16, batch
+           128 per GPU) at every N, c3 (forward only, bf16, batch 1024) at N = 1.  Each entry: value, ms_per_step, e2e, roofline_all.
   --impl reference  the reference's own resnet_cudnn_fast.cu (oracle/_ref/libref_fast.so, unmodified sources, its own
-           forward_pass/backwards_pass/update_parameters) on the same config on this GPU; falls back to the oracle port
-           on host cores when that library cannot run.
+           forward_pass/backwards_pass/update_parameters) on the same config on this GPU (--config c3: its forward_pass only, batch
+           1024); falls back to the oracle port on host cores when that library cannot run.
+  --impl reference_cached  the same translation unit compiled with a caching cudaMalloc / cudaFree shim (oracle/ref_harness.cu,
+           -DREF_CACHING_ALLOC): the stock build allocates and frees a workspace around every convolution call, so `reference`
+           measures allocator stalls as much as cuDNN 9.10's kernels.  A LABELLED extra arm -- never the driver's baseline.
 """
 import argparse
 import ctypes as C
@@ -151,12 +157,30 @@ def reduce_sum(dist, x):
     return float(t.item())
 
 
+def metric_of(cfg_name):
+    cfg = CONFIGS[cfg_name]
+    return METRIC if cfg_name in ("c2", "c4") else ("ResNet-50 forward img/s" if cfg["fwd_only"] else "ResNet-152 train img/s")
+
+
+def config_dict(cfg_name, batch, world):
+    """`config` of the JSON line: a description of the WORKLOAD only, identical for the product arm and the reference arms (arm-specific
+    detail goes to `impl_detail`)."""
+    cfg = CONFIGS[cfg_name]
+    what = "forward_pass only (batch-statistics BatchNorm: the reference has no inference mode)" if cfg["fwd_only"] else \
+        "full training step (forward_pass + backwards_pass + Adam update_parameters)"
+    return {"workload": "%s (reference variant: 3x3/2 projection shortcuts, %.2f GFLOP/img/step) %s, batch %d per GPU, 224x224 synthetic images"
+                        % (cfg["name"], cfg["gflop"], what, batch),
+            "baseline_config": cfg_name, "global_batch": batch * world, "per_gpu_batch": batch, "parallelism": "dp%d" % world,
+            "l2": "inputs larger than L2 (tens of GB touched per step), no flush needed"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
 def cpu_baseline(batch=4):
     from oracle import oracle as O
+    from resnet_b200.synth import synthetic_batch
     net = O.OracleNet(224, 16, R50_REDUCTIONS, batch=batch)
     net.init_like_reference(0)
-    img, lab = O.synthetic_batch(batch, 224, seed=1234)
+    img, lab = synthetic_batch(batch, 224, seed=1234)
     t0 = time.time()
     net.forward(img, lab)
     net.backward()
@@ -166,30 +190,40 @@ def cpu_baseline(batch=4):
             "sample": "1 full training step (forward, backward, Adam) of the same ResNet-50 at batch %d, oracle/ops.c with OpenMP, %.1f s" % (batch, dt)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank, world):
+# ------------------------------------------------------------------------------------------------ reference arms
+def run_reference(args, rank, world, cached=False):
+    """the reference's own cuDNN build on this GPU (rank 0 only; the reference is single-GPU).  cached: the caching-allocator build."""
     if rank != 0:
         return
-    out = {"impl": "reference", "metric": METRIC, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
-    from oracle import oracle as O
+    cfg = CONFIGS[args.config]
+    fwd_only = cfg["fwd_only"]
+    variant = "fast_cached" if cached else "fast"
+    out = {"impl": "reference_cached" if cached else "reference", "metric": metric_of(args.config), "unit": "img/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
+           "config": config_dict(args.config, args.batch, max(1, args.gpus))}
     from oracle import ref as R
-    img, lab = O.synthetic_batch(args.batch, 224, seed=1234)
+    from resnet_b200.synth import synthetic_batch
+    n_blocks = len(cfg["red"])
     done = False
-    if R.available("fast"):
+    if n_blocks != 16:
+        out["reference_gpu_error"] = "the reference's init_resnet hard-codes ResNet-50's four projection blocks; no ResNet-152 baseline exists"
+    elif R.available(variant):
         try:
+            img, lab = synthetic_batch(args.batch, 224, seed=1234)
             # the reference's cuDNN build, unmodified: its own init_*, forward_pass, backwards_pass, update_parameters
-            r = R.Ref("fast").create(224, 16, R50_REDUCTIONS, args.batch, output=1000, lr=1e-3, seed=1234)
+            r = R.Ref(variant).create(224, 16, cfg["red"], args.batch, output=1000, lr=1e-3, seed=1234)
             r.set_batch(img, lab)
-            ms = r.time_steps(args.warmup, args.steps, e2e=False)
-            ms_e2e = r.time_steps(1, max(2, args.steps // 2), e2e=True)
+            ms = r.time_steps(args.warmup, args.steps, e2e=False, forward_only=fwd_only)
+            ms_e2e = r.time_steps(1, max(2, args.steps // 2), e2e=True, forward_only=fwd_only)
             v = args.batch / (ms / 1e3)
-            out.update({"value": v, "ms_per_step": ms, "dtype": "tf32", "gpu_launches": None,
-                        "config": {"workload": "ResNet-50 (reference variant) full training step, batch %d, 224x224, the reference's resnet_cudnn_fast.cu "
-                                               "(cuDNN 9.10, fp32 NCHW, TENSOR_OP_MATH_ALLOW_CONVERSION) on 1 B200, compiled -O3 --use_fast_math sm_100a" % args.batch,
-                                   "global_batch": args.batch, "inputs": "larger than L2", "note": "reference is single-GPU; runs on GPU 0 for every --gpus"},
+            detail = ("the reference's resnet_cudnn_fast.cu (cuDNN 9.10, fp32 NCHW, TENSOR_OP_MATH_ALLOW_CONVERSION = TF32 tensor-core math), compiled "
+                      "-O3 --use_fast_math sm_100a, its own %s; single-GPU: runs on GPU 0 for every --gpus" %
+                      ("forward_pass" if fwd_only else "forward_pass / backwards_pass / update_parameters"))
+            if cached:
+                detail += "; cudaMalloc / cudaFree inside the step served by a caching shim (-DREF_CACHING_ALLOC): NOT the stock reference"
+            out.update({"value": v, "ms_per_step": ms, "dtype": "tf32", "gpu_launches": None, "impl_detail": detail, "n_gpus_used": 1,
                         "cpu_baseline": {"value": v, "unit": "img/s", "cores": 0, "kind": "reference",
-                                         "sample": "GPU run of oracle/_ref/libref_fast.so (the reference has no CPU path); cuda error: " + r.cuda_error()},
+                                         "sample": "GPU run of oracle/_ref/%s (the reference has no CPU path); cuda error: %s" % (R.VARIANTS[variant], r.cuda_error())},
                         "e2e": {"value": args.batch / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": int(img.nbytes + lab.nbytes),
                                 "d2h_bytes_per_step": int(args.batch * 1000 * 4)}})
             done = np.isfinite(v) and v > 0
@@ -198,36 +232,39 @@ def run_reference(args, rank, world):
     if not done:
         cb = cpu_baseline(batch=4)
         out.update({"value": cb["value"], "ms_per_step": 1e3 * 4 / cb["value"], "dtype": "f32", "gpu_launches": 0, "cpu_baseline": cb,
-                    "config": {"workload": "ResNet-50 (reference variant) full training step, host-core port of the reference's kernels", "global_batch": 4},
+                    "impl_detail": "host-core port of the reference's kernels (oracle/ops.c), one ResNet-50 training step at batch 4",
                     "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's)")
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default c2 = configs[1], the bench line)")
-    ap.add_argument("--impl", default="ours")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    cfg = CONFIGS[args.config]
-    if args.batch is None:
-        args.batch = cfg["batch"]
-    rank, local_rank, world = dist_env()
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+def dp_join(L, api, t, dist, rank, world):
+    """joins trainer `t` to the data-parallel world: NCCL id from rank 0 over the gloo group, then resnet_b200_dp_init"""
+    idbuf = (C.c_char * 128)()
+    if rank == 0:
+        L.resnet_b200_dp_unique_id(idbuf)
+    idbuf = (C.c_char * 128)(*broadcast_bytes(dist, bytes(idbuf), 128))
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION is set in the environment; stdout carries exactly one
+    # JSON line (the driver parses it), so the communicator is created with fd 1 pointing at stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        L.resnet_b200_dp_init(t.t, idbuf, rank, world, 0)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    api.check()
 
-    dist = init_dist(world)
+
+def measure(cfg_name, batch, steps, warmup, dist, rank, local_rank, world, with_clocks=True):
+    """One configuration through the C API; returns the result dict on rank 0 (None elsewhere).  The trainer is destroyed on return."""
     from resnet_b200 import api
+    from resnet_b200.synth import synthetic_batch
     L = api.L()
-    L.resnet_b200_set_device(local_rank)
+    cfg = CONFIGS[cfg_name]
     pk = peaks()
-    N = args.batch
+    N = batch
     t = api.Trainer(input_dim=224, n_blocks=len(cfg["red"]), reductions=cfg["red"], batch=N, output=1000, lr=1e-4, seed=1234, device=local_rank,
                     dtype=cfg["dtype"])
     assert t.uses_tensor_cores(), "bench must run the tcgen05 path"
@@ -235,25 +272,9 @@ def main():
     fwd_only = cfg["fwd_only"]
     flop_per_image = cfg["gflop"] * 1e9
     if world > 1:
-        idbuf = (C.c_char * 128)()
-        if rank == 0:
-            L.resnet_b200_dp_unique_id(idbuf)
-        idbuf = (C.c_char * 128)(*broadcast_bytes(dist, bytes(idbuf), 128))
-        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION is set in the environment; stdout carries exactly one
-        # JSON line (the driver parses it), so the communicator is created with fd 1 pointing at stderr
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            L.resnet_b200_dp_init(t.t, idbuf, rank, world, 0)
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
-        api.check()
+        dp_join(L, api, t, dist, rank, world)
 
-    from oracle import oracle as O  # synthetic batch generator only (shared with the tests)
-    img, lab = O.synthetic_batch(N, 224, seed=1234 + 1000 * rank)
-    npix = img.size
+    img, lab = synthetic_batch(N, 224, seed=1234 + 1000 * rank)
     host_img = L.resnet_b200_malloc_host(img.nbytes)
     host_lab = L.resnet_b200_malloc_host(lab.nbytes)
     C.memmove(host_img, img.ctypes.data, img.nbytes)
@@ -275,7 +296,7 @@ def main():
             L.backwards_pass(t.t)
             L.update_parameters(t.t)
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         step(False)
     t.sync()
     api.check()
@@ -283,10 +304,10 @@ def main():
     # ---- timed region: value (batch resident in HBM)
     barrier(dist)
     t.sync()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None
     launches0 = L.resnet_b200_launch_count()
     L.resnet_b200_timer_begin(t.t)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(False)
     ms = L.resnet_b200_timer_end_ms(t.t)
     t.sync()
@@ -301,7 +322,7 @@ def main():
     L.resnet_b200_prefetch_batch(t.t, host_img, host_lab)   # pipeline fill: step 0's batch
     t.sync()
     L.resnet_b200_timer_begin(t.t)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(True)                                          # commit batch k, start the copy of batch k+1, run the step
     L.resnet_b200_commit_batch(t.t)                         # drain: K host->device copies have completed inside the timed region
     ms_e2e = L.resnet_b200_timer_end_ms(t.t)
@@ -324,13 +345,14 @@ def main():
     L.resnet_b200_profile(0)
     api.check()
 
+    out = None
     if rank == 0:
-        tf32_peak = pk["bf16_tflops_sustained"] / (1.0 if t.bf16 else 2.0)  # tensor peak of the MMA kind in use
+        tensor_peak = pk["bf16_tflops_sustained"] / (1.0 if t.bf16 else 2.0)  # tensor peak of the MMA kind in use
         rl_all = []
         for f in (0, 1, 3):
             if fam[f]["launches"]:
                 ach = fam[f]["work"] / (fam[f]["ms"] * 1e-3) / 1e12
-                peak = tf32_peak if f != 3 else 75.0
+                peak = tensor_peak if f != 3 else 75.0
                 rl_all.append({"kernel": fam[f]["name"], "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                                "ms_per_step": fam[f]["ms"] / prof_steps, "launches_per_step": fam[f]["launches"] / prof_steps,
                                "flops_per_launch": fam[f]["work"] / fam[f]["launches"]})
@@ -341,45 +363,90 @@ def main():
                            "bytes_per_launch": fam[2]["work"] / fam[2]["launches"]})
         dom = max(rl_all, key=lambda r: r["ms_per_step"])
         # DRAM traffic per launch of the dominant family from the committed ncu capture of one step of this configuration's dtype
-        # (profiles/r01_traffic_<dtype>.json, written by tools/ncu_summary.py --json; batch 256 ResNet-50 only)
+        # (profiles/r0N_traffic_<dtype>.json, written by tools/ncu_summary.py --json; batch 256 ResNet-50 only; newest round first)
         traffic, traffic_src = None, None
-        tfile = os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % cfg["dtype"])
-        if os.path.exists(tfile) and args.config in ("c2", "c4") and N == 256:
-            try:
-                tj = json.load(open(tfile))
-                key = "kmajor" if "kmajor" in dom["kernel"] else ("wgrad" if "mnmajor" in dom["kernel"] else "bn_eltwise")
-                traffic = tj[key]["dram_bytes_per_step"] / dom["launches_per_step"]
-                traffic_src = "profiles/r01_traffic_%s.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one step / launches of the family)" % cfg["dtype"]
-            except Exception:
-                traffic = None
+        for rnd in ("r02", "r01"):
+            tfile = os.path.join(ROOT, "profiles", "%s_traffic_%s.json" % (rnd, cfg["dtype"]))
+            if traffic is None and os.path.exists(tfile) and cfg_name in ("c2", "c4") and N == 256:
+                try:
+                    tj = json.load(open(tfile))
+                    key = "kmajor" if "kmajor" in dom["kernel"] else ("wgrad" if "mnmajor" in dom["kernel"] else "bn_eltwise")
+                    traffic = tj[key]["dram_bytes_per_step"] / dom["launches_per_step"]
+                    traffic_src = "profiles/%s_traffic_%s.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of one step / launches of the family)" % (rnd, cfg["dtype"])
+                except Exception:
+                    traffic = None
         roofline = {"bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"], "frac": dom["frac"],
                     "traffic": traffic, "traffic_source": traffic_src, "kernel": dom["kernel"],
                     "peak_source": ("MEASURED_PEAKS.json (%s): " % pk["src"]) + (("bf16_tflops_sustained (kernel timed inside a long step)" if t.bf16 else
                                                                                   "bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate; kernel timed inside a long step)")
                                                                                  if dom["bound"] == "tensor" else "hbm_gbs copy bandwidth"),
                     "how": "CUDA events around every launch of the family on the launching stream, %d instrumented steps after the timed region" % prof_steps}
-        total_img = N * world * args.steps
+        total_img = N * world * steps
         value = total_img / (ms_max * 1e-3)
-        out = {"metric": METRIC if args.config in ("c2", "c4") else ("ResNet-50 forward img/s" if fwd_only else "ResNet-152 train img/s"), "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-               "config": {"workload": "%s (reference variant: 3x3/2 projection shortcuts, %.2f M params, %.2f GFLOP/img/step) %s, batch %d per GPU, 224x224, %s"
-                                      % (cfg["name"], sum(t.sizes) / 1e6, cfg["gflop"],
-                                         "forward_pass only (batch-statistics BatchNorm, as the reference has no inference mode)" if fwd_only else
-                                         "full training step (forward_pass + backwards_pass + Adam update_parameters)", N,
-                                         "bf16 storage NHWC, bf16 tcgen05 convs, fp32 master weights / gradients / Adam" if t.bf16 else
-                                         "fp32 storage NHWC, TF32 tcgen05 convs"),
-                          "baseline_config": args.config, "global_batch": N * world, "per_gpu_batch": N, "parallelism": "dp%d" % world,
-                          "l2": "inputs larger than L2 (tens of GB touched per step), no flush needed",
-                          "step_flops": flop_per_image * N, "achieved_step_tflops_per_gpu": flop_per_image * N / (ms_max / args.steps * 1e-3) / 1e12},
+        config = config_dict(cfg_name, N, world)
+        out = {"metric": metric_of(cfg_name), "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": max(3, warmup),
+               "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+               "config": config,
+               "impl_detail": "libresnet_b200.so through the reference's entry points (ctypes): %s; %.2f M parameters; step FLOPs %.4g; %.1f TFLOP/s per GPU"
+                              % ("bf16 storage NHWC, bf16 tcgen05 convolutions, fp32 master weights / gradients / Adam" if t.bf16 else
+                                 "fp32 storage NHWC, TF32 tcgen05 convolutions", sum(t.sizes) / 1e6, flop_per_image * N,
+                                 flop_per_image * N / (ms_max / steps * 1e-3) / 1e12),
                "e2e": {"value": total_img / (ms_e2e_max * 1e-3), "unit": "img/s", "h2d_bytes_per_step": int(img.nbytes + lab.nbytes),
-                       "d2h_bytes_per_step": int(N * 1000 * 4), "ms_per_step": ms_e2e_max / args.steps},
+                       "d2h_bytes_per_step": int(N * 1000 * 4), "ms_per_step": ms_e2e_max / steps},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_all": rl_all,
                "last_step": {"loss_per_image": loss / N, "n_wrong": nwrong}}
+    barrier(dist)
+    t.close()
+    dev_img.free()
+    dev_lab.free()
+    L.resnet_b200_free_host(host_img)
+    L.resnet_b200_free_host(host_lab)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default c2 = configs[1], the bench line)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cached"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c3 / c4 / c5 measurements that follow the default c2 headline")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    default_run = args.config == "c2" and args.batch is None
+    if args.batch is None:
+        args.batch = cfg["batch"]
+    rank, local_rank, world = dist_env()
+    if args.impl != "ours":
+        run_reference(args, rank, world, cached=(args.impl == "reference_cached"))
+        return
+
+    dist = init_dist(world)
+    from resnet_b200 import api
+    api.L().resnet_b200_set_device(local_rank)
+    out = measure(args.config, args.batch, args.steps, args.warmup, dist, rank, local_rank, world)
+    if default_run and not args.no_extra:
+        # the other BASELINE configurations, a few steps each, so that the driver's N = 1 / 2 / 4 / 8 runs also record the bf16
+        # data-parallel configuration (c4), ResNet-152 (c5) and, on one GPU, forward-only inference (c3)
+        extra = {}
+        for name in (("c4", "c5", "c3") if world == 1 else ("c4", "c5")):
+            try:
+                r = measure(name, CONFIGS[name]["batch"], min(args.steps, 8), 3, dist, rank, local_rank, world, with_clocks=False)
+            except Exception as e:  # noqa: BLE001  (an extra must never take the headline down)
+                r = {"error": repr(e)} if rank == 0 else None
+            if rank == 0 and r is not None:
+                keep = ("metric", "value", "unit", "ms_per_step", "dtype", "config", "e2e", "gpu_launches", "roofline_all", "last_step", "error")
+                extra[name] = {k: r[k] for k in keep if k in r}
+        if rank == 0:
+            out["extra"] = extra
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(batch=4)
         print(json.dumps(out), flush=True)
     barrier(dist)
-    t.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -121,6 +121,14 @@ int resnet_b200_softmax_ce(const float * logits, const int * labels, int batch_s
 int resnet_b200_adam(float * params, float * grads, float * means, float * vars, long long n, float learning_rate, float weight_decay,
                      float base_mean_decay, float base_var_decay, float cur_mean_decay, float cur_var_decay, float eps);
 
+/* ---- in-situ verification (selfcheck.cu) ----------------------------------------------------- */
+/* selfcheck(1): trainers created afterwards re-derive EVERY tensor-core convolution launch of forward_pass / backwards_pass (fprop,
+ * dgrad, accumulating dgrad, wgrad, stem) with the fp32 SIMT restatement of the reference's kernels (resnet.cu:109-281) from the same
+ * input buffers, at the real batch size.  selfcheck_read: family 0 = fprop, 1 = dgrad, 2 = wgrad: the worst max|diff| / max|ref| seen
+ * so far, the number of launches checked and the layer that produced the worst value.  A test aid: slow (fp32 CUDA-core convolutions). */
+int resnet_b200_selfcheck(int enable);
+int resnet_b200_selfcheck_read(Train_ResNet * trainer, int family, float * worst_rel, long long * n_checks, char * where, int where_len);
+
 /* ---- data parallel (new) -------------------------------------------------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and passed to every rank by the launcher (torch.distributed) */
 int resnet_b200_dp_unique_id(void * out_id_128_bytes);

@@ -363,10 +363,10 @@ class OracleNet:
 
 
 def synthetic_batch(batch, input_dim, seed=1234, n_classes=1000):
-    """uniform integers 0..255 minus the per-channel means used by the reference's
-    shard builder (reference: build_training_shards.c:120-134); labels uniform in [0, n_classes)."""
-    rng = np.random.default_rng(seed)
-    img = rng.integers(0, 256, size=(batch, input_dim, input_dim, 3)).astype(np.float32)
-    img -= np.array([103.94, 116.78, 123.68], np.float32)
-    labels = np.random.default_rng(seed + 3087).integers(0, n_classes, size=batch).astype(np.int32)
-    return np.ascontiguousarray(img), labels
+    """SURVEY.md 8(d) synthetic inputs; ONE definition, shared with bench.py's product arm (which must not import the oracle):
+    resnet_b200/synth.py (pure numpy)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_rb_synth", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "resnet_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.synthetic_batch(batch, input_dim, seed=seed, n_classes=n_classes)

@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-VARIANTS = {"naive": "libref_naive.so", "clean": "libref_clean.so", "cudnn": "libref_cudnn.so", "fast": "libref_fast.so"}
+VARIANTS = {"naive": "libref_naive.so", "clean": "libref_clean.so", "cudnn": "libref_cudnn.so", "fast": "libref_fast.so",
+            "fast_cached": "libref_fast_cached.so"}
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int)
 

@@ -23,6 +23,36 @@
 #include <string.h>
 #include <stdio.h>
 
+#ifdef REF_CACHING_ALLOC
+/* Labelled extra arm (bench.py --impl reference_cached; SURVEY.md 8d "optionally also with a caching-allocator shim"): the stock
+ * resnet_cudnn_fast.cu cudaMalloc()s and cudaFree()s a workspace around every convolution call and several temporaries per block
+ * (resnet_cudnn_fast.cu:1324-1331, 1863, 2093), so its step time is dominated by allocator stalls.  With this macro pair the SAME
+ * translation unit is compiled with cudaMalloc / cudaFree served from an exact-size free list (everything runs on the legacy default
+ * stream, so a block handed out again is only touched after the kernels that used it before).  This is NOT the stock reference and is
+ * never used for the driver's baseline ratio. */
+#include <cuda_runtime.h>
+#include <map>
+static std::multimap<size_t, void *> g_cache_free;
+static std::map<void *, size_t> g_cache_live;
+static cudaError_t cached_malloc_impl(void **p, size_t n) {
+	auto it = g_cache_free.find(n);
+	if (it != g_cache_free.end()) { *p = it->second; g_cache_free.erase(it); g_cache_live[*p] = n; return cudaSuccess; }
+	cudaError_t e = (cudaMalloc)(p, n);
+	if (e == cudaSuccess) g_cache_live[*p] = n;
+	return e;
+}
+template <typename T> static cudaError_t cached_malloc(T **p, size_t n) { return cached_malloc_impl((void **)p, n); }
+static cudaError_t cached_free(void *p) {
+	auto it = g_cache_live.find(p);
+	if (it == g_cache_live.end()) return (cudaFree)(p);
+	g_cache_free.insert({it->second, p});
+	g_cache_live.erase(it);
+	return cudaSuccess;
+}
+#define cudaMalloc(p, n) cached_malloc(p, n)
+#define cudaFree(p) cached_free(p)
+#endif
+
 #define main ref_main_unused
 #if REF_VARIANT == 0
 #include "resnet.cu"

@@ -110,8 +110,9 @@ class Trainer:
     """ResNet trainer driven through the reference's entry points."""
 
     def __init__(self, input_dim=224, n_blocks=16, reductions=None, batch=32, output=1000, lr=1e-4, wd=0.0, b1=0.9, b2=0.999,
-                 eps=1e-7, seed=1234, init_filters=64, device=None, shard_n_images=None, dtype=None):
-        """dtype: None = follow $RESNET_B200_DTYPE, "tf32" = fp32 tensors / TF32 MMAs, "bf16" = bf16 tensors (include/resnet_b200.h)"""
+                 eps=1e-7, seed=1234, init_filters=64, device=None, shard_n_images=None, dtype=None, selfcheck=False):
+        """dtype: None = follow $RESNET_B200_DTYPE, "tf32" = fp32 tensors / TF32 MMAs, "bf16" = bf16 tensors (include/resnet_b200.h)
+        selfcheck: every tensor-core convolution launch is re-derived in place by the fp32 SIMT checker (resnet_b200_selfcheck)"""
         lib = L()
         if device is not None:
             lib.resnet_b200_set_device(int(device))
@@ -129,7 +130,9 @@ class Trainer:
         self.batch_struct = lib.init_general_batch(batch, input_dim * input_dim * 3, input_dim, shard_n_images or batch)
         self._dump_dir = b"resnet_b200"
         lib.resnet_b200_set_dtype({None: -1, "tf32": 0, "fp32": 0, "bf16": 1}[dtype])
+        lib.resnet_b200_selfcheck(int(bool(selfcheck)))
         self.t = lib.init_trainer(self.model, self.batch_struct, batch, lr, wd, b1, b2, eps, 1, self._dump_dir)
+        lib.resnet_b200_selfcheck(0)
         lib.resnet_b200_set_dtype(-1)
         check()
         self.bf16 = lib.resnet_b200_trainer_dtype(self.t) == 1
@@ -221,6 +224,16 @@ class Trainer:
         L().resnet_b200_epoch_stats(self.t, C.byref(ls), C.byref(nw), C.byref(ni), int(reset))
         check()
         return ls.value, nw.value, ni.value
+
+    def selfcheck_report(self):
+        """{family: (worst max|diff| / max|ref|, launches checked, where)} for fprop / dgrad / wgrad (Trainer(selfcheck=True))"""
+        out = {}
+        for fam, name in enumerate(("fprop", "dgrad", "wgrad")):
+            w, n, where = C.c_float(), C.c_longlong(), C.create_string_buffer(128)
+            L().resnet_b200_selfcheck_read(self.t, fam, C.byref(w), C.byref(n), where, 128)
+            check()
+            out[name] = (w.value, n.value, where.value.decode())
+        return out
 
     def uses_tensor_cores(self):
         return bool(L().resnet_b200_uses_tensor_cores(self.t))

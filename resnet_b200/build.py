@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libresnet_b200.so")
-SOURCES = ["bw_kernels.cu", "simt_conv.cu", "igemm.cu", "model.cu", "capi.cu", "dp.cu", "prof.cu", "loader.cu", "dump.cu"]
+SOURCES = ["bw_kernels.cu", "simt_conv.cu", "igemm.cu", "model.cu", "capi.cu", "dp.cu", "prof.cu", "loader.cu", "dump.cu", "selfcheck.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
          "-Xcompiler", "-fPIC,-fvisibility=default", "-shared"]

@@ -205,6 +205,7 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 	cudaStreamSynchronize(e->stream);
 	if (t->cur_batch) loader_release(t->cur_batch);  // stops the prefetch thread before its streams / buffers go away
 	dp_release(e);
+	selfcheck_release(e);
 	for (auto &b : e->blocks)
 		for (ConvRef *c : {&b.reduce, &b.spatial, &b.expand, &b.proj}) {
 			if (c->fprop) tc_free(c->fprop);

@@ -96,6 +96,8 @@ struct Engine {
 	cudaEvent_t ev_staged, ev_consumed;
 	// data-parallel hook (dp.cu)
 	void *dp;
+	// in-situ SIMT re-derivation of every tensor-core convolution (selfcheck.cu), NULL unless resnet_b200_selfcheck(1)
+	void *selfcheck;
 	// step timing
 	cudaEvent_t ev0, ev1;
 };
@@ -107,6 +109,13 @@ void dp_rank_world(const Engine *e, int *rank, int *world);  // (0, 1) without d
 void dp_release(Engine *e);                                   // destroys the communicator, stream and events
 // loader.cu
 void loader_release(Batch *bb);
+// selfcheck.cu
+void selfcheck_init(Engine *e, long long max_act_elems, long long max_w_elems);
+void selfcheck_release(Engine *e);
+void selfcheck_fprop(Engine *e, const ConvGeom &g, const float *w, const void *x, bool x_is_fp32_batch, const void *y);
+void selfcheck_dgrad_snapshot(Engine *e, const ConvGeom &g, const void *dx);
+void selfcheck_dgrad(Engine *e, const ConvGeom &g, const float *w, const void *dy, const void *dx, int accumulate);
+void selfcheck_wgrad(Engine *e, const ConvGeom &g, const void *x, bool x_is_fp32_batch, const void *dy, const float *dw);
 // model.cu: drops the side-table entries of a trainer (resnet_b200_destroy_trainer)
 void engine_forget(const Train_ResNet *t);
 void dp_block_done(Engine *e, int block);  // block's gradients are enqueued: issue the buckets that became complete

@@ -125,6 +125,7 @@ struct alignas(64) IgemmParams {
 	int BN, n_tiles, Ncol;
 	int stages;
 	int nstaging;  // epilogue staging tiles PER GROUP (2..4): up to nstaging - 2 TMA stores stay in flight behind the chunk being staged
+	int nprod;       // TMA-producer warps (1, 2 or 4; divides `stages`): warp 0 plus warps 6.. of the idle second epilogue group
 	int epi_groups;  // 1 or 2 groups of four epilogue warps; with 2, the 128-byte column chunks of a CTA alternate between them
 	uint32_t a_bytes, b_bytes, a_tx_bytes;  // smem slot sizes; bytes one A box actually transfers (bw*bh*bn rows)
 	// resident_b: the CTA's whole weight operand (all taps x K chunks of its one N tile, resb_bytes) is loaded ONCE into shared memory
@@ -155,6 +156,7 @@ struct alignas(64) WgradParams {
 	// of stages, so its one epilogue need not overlap).  Cuts the bytes the TMA path must deliver per MAC by a third on the layers
 	// that are bound by it (every wgrad with Cout >= 256 sat at the ~42 B/clk/SM the TMA / L2 path delivers chip-wide).
 	int m_pair, co_items;  // co_items = co_tiles / m_pair
+	int nprod;         // TMA-producer warps: 1, or 2 when the ring depth is even (a slot is always refilled by the same warp)
 	int split_major;   // work-item order, see wgrad_tile()
 	int merge_taps;    // the taps of a group sit back to back in shared memory AND in TMEM: one MMA of N = ntaps * BN covers them all
 	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
@@ -167,7 +169,7 @@ struct alignas(64) WgradParams {
 // (Round 1 carried an experimental mode with 2-4 MMA-issuing warps per CTA.  With the issue loops warp-uniform it measured 1-25 % SLOWER
 // on every layer, profiles/r02_conv_bench_issuers_*.txt -- the kernels are bound by their operand feed and epilogue, not by MMA issue --
 // and it gave up bitwise reproducibility, so it was removed.)
-constexpr int kIgemmThreads = 192;
+constexpr int kIgemmThreads = 224;  // wgrad: warp 0 TMA, 1 MMA, 2-5 epilogue, 6 second TMA producer
 constexpr int kKmajorThreads = 320;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kABytes = 128 * 32 * 4;  // 128 rows x 32 tf32 = 16 KB
@@ -229,10 +231,16 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 	// only around the TMA / tcgen05 instructions themselves.  Round 1 had these loops under `if (lane == 0)`: nvcc then treats the
 	// whole region as divergent and wraps EVERY UTCHMMA / UTMALDG / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop,
 	// which is what made a tcgen05.mma cost ~115 clocks to issue (profiles/r02_mma_rate.txt).
-	if (warp == 0) {
-		int stage = 0;
+	// Several producer warps: one warp needs ~480 clocks per pipeline stage (mbarrier try_wait on the empty slot, elect, expect_tx,
+	// two TMA issues, tap / tile index arithmetic: profiles/r02_ncu_conv_layers.md), more than the 380 / 445 clocks a stage of four
+	// N = 64 / 128 MMAs takes -- the 64- and 128-channel layers were bound by their TMA-issuing warp.  Producer `pi` of `nprod` owns the
+	// ring slots s = pi (mod nprod) (nprod divides the ring depth, so a slot is always refilled by the same warp); the extra producers
+	// are the warps of the second epilogue group (6..8), idle in the long-K plans that need them.
+	const int pi = (warp == 0) ? 0 : ((warp >= 6 && warp - 5 < p.nprod && p.epi_groups == 1) ? warp - 5 : -1);
+	if (pi >= 0) {
+		int stage = 0, turn = 0;  // turn = (stage counter) mod nprod
 		uint32_t phase = 0;
-		if (p.resident_b && (int)blockIdx.x < total_tiles) {  // the weights of this CTA's N tile, once
+		if (pi == 0 && p.resident_b && (int)blockIdx.x < total_tiles) {  // the weights of this CTA's N tile, once
 			const GroupDesc &g = p.groups[0];
 			const int nt = (int)blockIdx.x % p.n_tiles;
 			if (elect_one()) {
@@ -252,14 +260,17 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			for (int t = 0; t < g.ntaps; t++) {
 				const TapDesc tp = g.taps[t];
 				for (int kc = 0; kc < p.kchunks; kc++) {
-					mbar_wait(&empty[stage], phase ^ 1);
-					if (elect_one()) {
-						uint8_t *sa = stage0 + (size_t)stage * stage_bytes;
-						mbar_expect_tx(&full[stage], p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + p.b_bytes);
-						tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * p.kelems, ow0 + tp.dx, oh0 + tp.dy, n0);
-						if (!p.resident_b) tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * p.kelems, nt * p.BN);
+					if (turn == pi) {
+						mbar_wait(&empty[stage], phase ^ 1);
+						if (elect_one()) {
+							uint8_t *sa = stage0 + (size_t)stage * stage_bytes;
+							mbar_expect_tx(&full[stage], p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + p.b_bytes);
+							tma_load_4d(sa, &p.amap[tp.amap], &full[stage], kc * p.kelems, ow0 + tp.dx, oh0 + tp.dy, n0);
+							if (!p.resident_b) tma_load_2d(sa + p.a_bytes, &p.bmap, &full[stage], tp.bcol + kc * p.kelems, nt * p.BN);
+						}
+						__syncwarp();
 					}
-					__syncwarp();
+					if (++turn == p.nprod) turn = 0;
 					if (++stage == p.stages) { stage = 0; phase ^= 1; }
 				}
 			}
@@ -480,7 +491,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	const uint32_t acc_cols = grp_cols * (uint32_t)p.m_pair;     // ... of one work item
 	const int nbuf = (2 * acc_cols <= (uint32_t)kTmemCols) ? 2 : 1;  // TMEM accumulator buffers
 
-	if (warp == 0) {  // all lanes run the loops, one elected lane issues (see igemm_kmajor_kernel)
+	// producer warps: warp 0 and, with nprod = 2, warp 6; producer pi owns the ring slots s = pi (mod nprod) (see igemm_kmajor_kernel)
+	const int pi = (warp == 0) ? 0 : ((warp == 6 && p.nprod == 2) ? 1 : -1);
+	if (pi >= 0) {  // all lanes run the loops, one elected lane issues
 		int stage = 0;
 		uint32_t phase = 0;
 		for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -493,18 +506,20 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			const int kb0 = split * p.boxes_per_split;
 			const int kb1 = min(kb0 + p.boxes_per_split, p.k_boxes);
 			for (int kb = kb0; kb < kb1; kb++) {
-				const int ow0 = (kb % p.tiles_w) * p.bw, oh0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh, n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bn;
-				mbar_wait(&empty[stage], phase ^ 1);
-				if (elect_one()) {
-					uint8_t *sa = base + (size_t)stage * stage_bytes;
-					mbar_expect_tx(&full[stage], p.a_bytes + (uint32_t)ntg * p.b_bytes);
-					tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * p.a_blocks * p.m_pair);  // all [px][128 B of co] boxes in one op
-					for (int t = 0; t < ntg; t++) {
-						const TapDesc tp = p.taps[tap0 + t];
-						tma_load_5d(sa + p.a_bytes + (size_t)t * p.b_bytes, &p.bmap[tp.amap], &full[stage], 0, ow0 + tp.dx, oh0 + tp.dy, n0, cit * nb_boxes);
+				if ((stage & (p.nprod - 1)) == pi) {
+					const int ow0 = (kb % p.tiles_w) * p.bw, oh0 = ((kb / p.tiles_w) % p.tiles_h) * p.bh, n0 = (kb / (p.tiles_w * p.tiles_h)) * p.bn;
+					mbar_wait(&empty[stage], phase ^ 1);
+					if (elect_one()) {
+						uint8_t *sa = base + (size_t)stage * stage_bytes;
+						mbar_expect_tx(&full[stage], p.a_bytes + (uint32_t)ntg * p.b_bytes);
+						tma_load_5d(sa, &p.amap, &full[stage], 0, ow0, oh0, n0, cot * p.a_blocks * p.m_pair);  // all [px][128 B of co] boxes in one op
+						for (int t = 0; t < ntg; t++) {
+							const TapDesc tp = p.taps[tap0 + t];
+							tma_load_5d(sa + p.a_bytes + (size_t)t * p.b_bytes, &p.bmap[tp.amap], &full[stage], 0, ow0 + tp.dx, oh0 + tp.dy, n0, cit * nb_boxes);
+						}
 					}
+					__syncwarp();
 				}
-				__syncwarp();
 				if (++stage == p.stages) { stage = 0; phase ^= 1; }
 			}
 		}
@@ -728,6 +743,12 @@ static void finish_kmajor(TcPlan *pl) {
 	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
 	p.stages = stages > 8 ? 8 : stages;
 	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
+	// A ring slot must always be refilled by the SAME producer warp: a warp that skipped a pass of a slot could find the slot's `empty`
+	// barrier one phase behind and mbarrier.try_wait.parity would report "free" (phase aliasing).  So nprod divides the ring depth.
+	p.nprod = p.epi_groups == 1 ? 2 : 1;
+	if (const char *e = getenv("RESNET_B200_PRODUCERS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) p.nprod = p.epi_groups == 1 ? v : 1; }
+	while (p.nprod > 1 && p.stages < 2 * p.nprod) p.nprod /= 2;
+	p.stages = p.stages / p.nprod * p.nprod;
 	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
 	pl->kind = 0;
 }
@@ -942,6 +963,8 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
+	p.nprod = (p.stages % 2 == 0 && p.stages >= 4) ? 2 : 1;
+	if (const char *e = getenv("RESNET_B200_PRODUCERS")) { if (atoi(e) == 1) p.nprod = 1; }
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = tiles * p.splits;
@@ -1130,6 +1153,8 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
+	p.nprod = (p.stages % 2 == 0 && p.stages >= 4) ? 2 : 1;
+	if (const char *e = getenv("RESNET_B200_PRODUCERS")) { if (atoi(e) == 1) p.nprod = 1; }
 	p.partial = workspace;
 	pl->smem = (size_t)p.stages * stage_bytes + 1024 + 256;
 	const int total = ceil_div(p.ntaps, p.tpt) * p.co_items * p.ci_tiles * p.splits;
@@ -1197,12 +1222,12 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
-		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d epi=%d grid=%d smem=%zu resB=%u", pl->what,
-		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, p.epi_groups, pl->grid, pl->smem, p.resb_bytes);
+		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d epi=%d prod=%d grid=%d smem=%zu resB=%u", pl->what,
+		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, p.epi_groups, p.nprod, pl->grid, pl->smem, p.resb_bytes);
 	} else {
 		const WgradParams &p = pl->wp;
-		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d grid=%d smem=%zu",
-		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.m_pair, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, pl->grid, pl->smem);
+		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d prod=%d grid=%d smem=%zu",
+		         pl->what, pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.k_boxes, p.splits, p.co_tiles, p.m_pair, p.ci_tiles, p.BN, p.ntaps, p.tpt, p.stages, p.nprod, pl->grid, pl->smem);
 	}
 }
 

@@ -449,6 +449,14 @@ static Engine *build_engine(Train_ResNet *t) {
 		}
 	}
 	{
+		long long max_act = std::max(n_x0, (long long)N * S0 * S0 * 3), max_w = e->stem.g.w_elems();
+		for (auto &b : e->blocks) {
+			max_act = std::max(max_act, std::max(b.n_in, std::max(b.n_exp_out, b.n_red_in)));
+			for (ConvRef *c : {&b.reduce, &b.spatial, &b.expand, &b.proj}) if (c->g.cout) max_w = std::max(max_w, c->g.w_elems());
+		}
+		selfcheck_init(e, max_act, max_w);
+	}
+	{
 		std::lock_guard<std::mutex> lk(g_mu);
 		g_engines[t] = e;
 	}
@@ -462,8 +470,11 @@ static void stem_forward(Engine *e, const float *images) {
 	const ConvGeom &g = e->stem.g;
 	stem_pack_weights(e->stem.w, g.cout, e->stem_wfs, e->round_tf32, e->bf16, e->stream);
 	stem_pad_input(images, g.N, g.S, e->stem_xp, e->round_tf32, e->bf16, e->stream);
-	ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
-	tc_run(e->stem_fprop, e->stream);
+	{
+		ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
+		tc_run(e->stem_fprop, e->stream);
+	}
+	if (e->selfcheck) selfcheck_fprop(e, g, e->stem.w, images, true, e->X0);
 }
 static void stem_backward(Engine *e, const float *images) {
 	if (!e->stem_tc) {  // no input gradient (reference: resnet.cu:2243-2245)
@@ -473,8 +484,11 @@ static void stem_backward(Engine *e, const float *images) {
 		return;
 	}
 	const ConvGeom &g = e->stem.g;
-	ProfScope ps(e->stream, PROF_IGEMM_WGRAD, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
-	tc_run(e->stem_wgrad, e->stream);  // reads the padded copy made by this step's forward_pass
+	{
+		ProfScope ps(e->stream, PROF_IGEMM_WGRAD, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
+		tc_run(e->stem_wgrad, e->stream);  // reads the padded copy made by this step's forward_pass
+	}
+	if (e->selfcheck) selfcheck_wgrad(e, g, images, true, e->dX0, e->stem.dw);
 }
 
 // ------------------------------------------------------------------------------------------------ layer helpers
@@ -482,15 +496,25 @@ static void stem_backward(Engine *e, const float *images) {
 static double conv_flops(const ConvGeom &g) { return 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k; }
 
 static void conv_fwd(Engine *e, ConvRef &c, const float *in, float *out) {
-	ProfScope ps(e->stream, c.use_tc ? PROF_IGEMM_KMAJOR : PROF_STEM_SIMT, conv_flops(c.g));
-	if (c.use_tc) tc_run(c.fprop, e->stream);
-	else simt_conv_fprop(c.g, in, c.wf, out, e->stream);
+	{
+		ProfScope ps(e->stream, c.use_tc ? PROF_IGEMM_KMAJOR : PROF_STEM_SIMT, conv_flops(c.g));
+		if (c.use_tc) tc_run(c.fprop, e->stream);
+		else simt_conv_fprop(c.g, in, c.wf, out, e->stream);
+	}
+	if (e->selfcheck && c.use_tc) selfcheck_fprop(e, c.g, c.w, in, false, out);
 }
 static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, float *din, int accumulate) {
 	if (c.use_tc) {
-		if (din) { ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, conv_flops(c.g)); tc_run(c.dgrad, e->stream); }
-		ProfScope ps(e->stream, PROF_IGEMM_WGRAD, conv_flops(c.g));
-		tc_run(c.wgrad, e->stream);
+		if (din) {
+			if (e->selfcheck && accumulate) selfcheck_dgrad_snapshot(e, c.g, din);
+			{ ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, conv_flops(c.g)); tc_run(c.dgrad, e->stream); }
+			if (e->selfcheck) selfcheck_dgrad(e, c.g, c.w, dout, din, accumulate);
+		}
+		{
+			ProfScope ps(e->stream, PROF_IGEMM_WGRAD, conv_flops(c.g));
+			tc_run(c.wgrad, e->stream);
+		}
+		if (e->selfcheck) selfcheck_wgrad(e, c.g, in, false, dout, c.dw);
 	} else {
 		ProfScope ps(e->stream, PROF_STEM_SIMT, conv_flops(c.g) * (din ? 2 : 1));
 		if (din) simt_conv_dgrad(c.g, dout, c.wd, din, accumulate, e->stream);

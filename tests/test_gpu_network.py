@@ -377,3 +377,56 @@ def test_batch_of_one_and_odd_batches(dtype):
             opred = net.forward(img, lab)
             assert np.abs(pred - opred).max() < (2e-2 if dtype == "tf32" else 1e-1)
         t.close()
+
+
+@pytest.mark.parametrize("dtype,tol_act,tol_w", [("tf32", 3e-3, 3e-3), ("bf16", 1e-2, 3e-3)])
+def test_batch256_step_selfcheck(dtype, tol_act, tol_w):
+    """BASELINE configs 2 / 4 as the benchmark runs them: ResNet-50, batch 256, 224 x 224, default (non keep-all) buffers, the reference's
+    own cuRAND initialisation.  One forward + backward with the in-situ checker on: EVERY tensor-core convolution launch of the step
+    (53 fprop incl. the stem, 52 dgrad of which 16 accumulate through the TMA reduce-add, 53 wgrad) is re-derived by the fp32 SIMT
+    restatement of the reference's kernels (resnet.cu:109-281) from the trainer's own input tensors and held to the single-kernel bar:
+    3e-3 (TF32) / 1e-2 (bf16 outputs: one rounding) / 3e-3 (fp32 weight gradients) of the tensor's largest magnitude.  This is what
+    certifies the batch-256 launch plans -- persistent multi-wave tiles, resident weight operand, two epilogue groups, paired co tiles,
+    37-98-way split-K in split-major order -- none of which the small unit-test shapes reach by default.
+    Then the same batch through a second trainer on the fp32 SIMT path (RESNET_B200_CONV=simt, exact fp32 arithmetic): loss close,
+    argmax identical wherever the fp32 top-1 margin is not negligible, and the wrong-prediction count equal up to those near-ties."""
+    from resnet_b200 import api
+    N = 256
+    img, lab = O.synthetic_batch(N, 224, seed=1234)
+    t = api.Trainer(input_dim=224, n_blocks=16, batch=N, output=1000, seed=1234, dtype=dtype, selfcheck=True)
+    assert t.uses_tensor_cores()
+    t.set_batch(img, lab)
+    pred = t.forward()
+    loss, nwrong = t.loss_accuracy()
+    t.backward()
+    t.sync()
+    rep = t.selfcheck_report()
+    t.close()
+    print("selfcheck %s:" % dtype, rep)
+    assert rep["fprop"][1] == 53 and rep["dgrad"][1] == 52 and rep["wgrad"][1] == 53, rep
+    assert rep["fprop"][0] < tol_act, rep["fprop"]
+    assert rep["dgrad"][0] < tol_act, rep["dgrad"]
+    assert rep["wgrad"][0] < tol_w, rep["wgrad"]
+    assert np.isfinite(pred).all()
+    if dtype != "tf32":
+        return
+    os.environ["RESNET_B200_CONV"] = "simt"
+    try:
+        ts = api.Trainer(input_dim=224, n_blocks=16, batch=N, output=1000, seed=1234, dtype="tf32")
+    finally:
+        os.environ.pop("RESNET_B200_CONV", None)
+    assert not ts.uses_tensor_cores()
+    ts.set_batch(img, lab)
+    pred_s = ts.forward()
+    loss_s, nwrong_s = ts.loss_accuracy()
+    ts.close()
+    assert abs(loss - loss_s) / N < 1e-3, (loss, loss_s)
+    top2 = np.sort(pred_s, axis=1)[:, -2:]
+    margin = top2[:, 1] - top2[:, 0]
+    differ = pred.argmax(1) != pred_s.argmax(1)
+    # a freshly initialised network's softmax is almost flat (FC weights ~ N(0, 1e-4)): only near-ties may resolve differently
+    assert (margin[differ] < 2e-4).all(), (int(differ.sum()), margin[differ])
+    assert abs(nwrong - nwrong_s) <= int(differ.sum()), (nwrong, nwrong_s, int(differ.sum()))
+    print("batch-256 TF32 vs fp32 SIMT: loss/img %.6f vs %.6f, argmax differs on %d of %d (all near-ties), softmax max-abs %.2e"
+          % (loss / N, loss_s / N, int(differ.sum()), N, float(np.abs(pred - pred_s).max())))
+

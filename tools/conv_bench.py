@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--only", default="")
+    ap.add_argument("--shape", default="", help="k,stride,cin,cout,S: only this layer (shell-safe form of --only)")
     ap.add_argument("--passes", default="0,1,3")
     ap.add_argument("--variants", default="")
     ap.add_argument("--desc", action="store_true")
@@ -75,6 +76,8 @@ def main():
     for (S, k, cin, cout, stride, dgrad, count) in r50_shapes():
         tag = "%dx%d/%d %d->%d @%d" % (k, k, stride, cin, cout, S)
         if args.only and args.only not in tag:
+            continue
+        if args.shape and [int(v) for v in args.shape.split(",")] != [k, stride, cin, cout, S]:
             continue
         So = S // stride
         fl = 2.0 * args.batch * So * So * cout * cin * k * k

@@ -6,7 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import oracle as O  # noqa: E402  (synthetic batch generator only)
+from resnet_b200 import synth as O  # noqa: E402  (synthetic batch generator)
 from resnet_b200 import api  # noqa: E402
 
 ap = argparse.ArgumentParser()
