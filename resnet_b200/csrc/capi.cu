@@ -215,6 +215,7 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 	if (e->stem_fprop) tc_free(e->stem_fprop);
 	if (e->stem_wgrad) tc_free(e->stem_wgrad);
 	for (void *p : e->allocs) cudaFree(p);
+	arena_close(e->arena);
 	for (Params *P : {t->model->params, t->backprop_buffer->param_derivs, t->backprop_buffer->prev_means, t->backprop_buffer->prev_vars}) {
 		ParamStore *ps = param_store_of(P);
 		if (ps) { cudaFree(ps->base); delete ps; }
@@ -227,6 +228,12 @@ void resnet_b200_destroy_trainer(Train_ResNet *t) {
 	}
 	cudaFreeHost(e->pred_host);
 	cudaFreeHost(e->bad_host);
+	if (e->wstream) {
+		cudaStreamSynchronize(e->wstream);
+		cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join);
+		for (int k = 0; k < 4; k++) cudaEventDestroy(e->ev_rd[k]);
+		cudaStreamDestroy(e->wstream);
+	}
 	cudaEventDestroy(e->ev0);
 	cudaEventDestroy(e->ev1);
 	cudaStreamDestroy(e->stream);

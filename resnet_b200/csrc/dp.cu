@@ -56,7 +56,7 @@ struct DpState {
 	ncclComm_t comm;
 	int rank, world;
 	cudaStream_t comm_stream;
-	cudaEvent_t ready, done;
+	cudaEvent_t ready, ready_w, done;
 	std::vector<Bucket> buckets;  // in issue order (deepest first)
 	size_t next;
 	float *grad_base;
@@ -92,6 +92,10 @@ static void issue_ready(Engine *e, int finished_block) {
 		if (!recorded) {
 			RB_CUDA(cudaEventRecord(s->ready, e->stream));
 			RB_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ready, 0));
+			if (e->wstream) {  // the block's weight gradients are produced on the side stream (Engine::wstream)
+				RB_CUDA(cudaEventRecord(s->ready_w, e->wstream));
+				RB_CUDA(cudaStreamWaitEvent(s->comm_stream, s->ready_w, 0));
+			}
 			recorded = true;
 		}
 		int r = api->AllReduce(s->grad_base + b.off, s->grad_base + b.off, (size_t)b.len, ncclFloat32, ncclSum, s->comm, s->comm_stream);
@@ -113,6 +117,7 @@ void dp_release(Engine *e) {
 	NcclApi *api = nccl();
 	if (api && api->CommDestroy) api->CommDestroy(s->comm);
 	cudaEventDestroy(s->ready);
+	cudaEventDestroy(s->ready_w);
 	cudaEventDestroy(s->done);
 	cudaStreamDestroy(s->comm_stream);
 	delete s;
@@ -164,6 +169,7 @@ int resnet_b200_dp_init(Train_ResNet *t, const void *id_bytes, int rank, int wor
 	if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?"); delete s; return 1; }
 	RB_CUDA(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
 	RB_CUDA(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
+	RB_CUDA(cudaEventCreateWithFlags(&s->ready_w, cudaEventDisableTiming));
 	RB_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
 	ParamStore *g = param_store_of(t->backprop_buffer->param_derivs);
 	s->grad_base = g->base;

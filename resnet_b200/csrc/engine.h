@@ -88,12 +88,21 @@ struct Engine {
 	int n_pack_jobs, pack_max_elems;
 	float *ones, *zeros, *tmp_ab, *tmp_mv;  // keep-all helpers
 	int *bad_dev, *bad_host;
-	std::vector<void *> allocs;
+	std::vector<void *> allocs;  // per-tensor fallback allocations (empty when the arena is in use)
+	void *arena;                 // model.cu Arena: one contiguous activation arena (virtual range + physical granules)
 	// double-buffered host -> device staging of the next batch (resnet_b200_prefetch_batch / commit_batch), created lazily
 	cudaStream_t copy_stream;
 	float *stage_img;
 	int *stage_lab;
 	cudaEvent_t ev_staged, ev_consumed;
+	// Weight gradients on a side stream (RESNET_B200_ASYNC_WGRAD, default on): a layer's wgrad only feeds update_parameters, so it is
+	// forked off right after the BatchNorm backward that produces its dX operand and runs next to the HBM-bound BatchNorm kernels of the
+	// following layers (a persistent wgrad CTA takes the shared memory of an SM but few threads / registers, so BatchNorm blocks share
+	// the SM with it; two convolution kernels never co-reside).  ev_rd[k]: the last wgrad reading role buffer k (0 dXe, 1 dXs, 2 dXr,
+	// 3 dXp) has finished -- awaited by the main stream before the buffer's next writer.  NULL wstream = synchronous.
+	cudaStream_t wstream;
+	cudaEvent_t ev_fork, ev_join, ev_rd[4];
+	bool ev_rd_live[4];
 	// data-parallel hook (dp.cu)
 	void *dp;
 	// in-situ SIMT re-derivation of every tensor-core convolution (selfcheck.cu), NULL unless resnet_b200_selfcheck(1)
@@ -102,6 +111,7 @@ struct Engine {
 	cudaEvent_t ev0, ev1;
 };
 Engine *engine_of(const Train_ResNet *t);
+extern int g_selfcheck;     // selfcheck.cu: trainers created while set verify every conv launch in place
 extern int g_default_bf16;  // storage type of the next init_trainer (resnet_b200_set_dtype)
 
 // dp.cu
@@ -116,7 +126,8 @@ void selfcheck_fprop(Engine *e, const ConvGeom &g, const float *w, const void *x
 void selfcheck_dgrad_snapshot(Engine *e, const ConvGeom &g, const void *dx);
 void selfcheck_dgrad(Engine *e, const ConvGeom &g, const float *w, const void *dy, const void *dx, int accumulate);
 void selfcheck_wgrad(Engine *e, const ConvGeom &g, const void *x, bool x_is_fp32_batch, const void *dy, const float *dw);
-// model.cu: drops the side-table entries of a trainer (resnet_b200_destroy_trainer)
+// model.cu: drops the side-table entries of a trainer (resnet_b200_destroy_trainer); releases the activation arena
+void arena_close(void *arena);
 void engine_forget(const Train_ResNet *t);
 void dp_block_done(Engine *e, int block);  // block's gradients are enqueued: issue the buckets that became complete
 void dp_allreduce_grads(Engine *e);       // end of backward: flush remaining buckets, compute stream waits

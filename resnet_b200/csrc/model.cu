@@ -170,14 +170,109 @@ static Params *make_params(Dims *d, curandGenerator_t *gen) {
 }
 
 // ------------------------------------------------------------------------------------------------ engine
+// One activation arena per trainer (the reference cudaMalloc()s ~1400 buffers one by one): a range of virtual
+// addresses is reserved up front (CUDA virtual memory management), tensors are bump-allocated from it with 256-byte alignment, and
+// physical memory is mapped behind the bump pointer in 512 MB granules -- the arena is contiguous, exactly as large as the trainer
+// needs, and nothing is allocated after init_trainer.  Falls back to one cudaMalloc per tensor if the driver refuses the VMM calls.
+struct Arena {
+	CUdeviceptr base = 0;
+	size_t reserved = 0, mapped = 0, used = 0;
+	std::vector<CUmemGenericAllocationHandle> handles;
+	std::vector<size_t> sizes;
+	CUresult (*reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+	CUresult (*create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+	CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+	CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+	CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+	CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+	CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+	CUresult (*granularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+	CUmemAllocationProp prop;
+	size_t gran = 0;
+	int device = 0;
+	bool ok = false;
+};
+static bool arena_open(Arena *a, size_t reserve_bytes) {
+	auto sym = [](const char *name) -> void * {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+		return p;
+	};
+	a->reserve = (decltype(a->reserve))sym("cuMemAddressReserve");
+	a->create = (decltype(a->create))sym("cuMemCreate");
+	a->map = (decltype(a->map))sym("cuMemMap");
+	a->set_access = (decltype(a->set_access))sym("cuMemSetAccess");
+	a->unmap = (decltype(a->unmap))sym("cuMemUnmap");
+	a->release = (decltype(a->release))sym("cuMemRelease");
+	a->addr_free = (decltype(a->addr_free))sym("cuMemAddressFree");
+	a->granularity = (decltype(a->granularity))sym("cuMemGetAllocationGranularity");
+	if (!a->reserve || !a->create || !a->map || !a->set_access || !a->unmap || !a->release || !a->addr_free || !a->granularity) return false;
+	if (cudaGetDevice(&a->device) != cudaSuccess) return false;
+	memset(&a->prop, 0, sizeof(a->prop));
+	a->prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+	a->prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+	a->prop.location.id = a->device;
+	size_t g = 0;
+	if (a->granularity(&g, &a->prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || g == 0) return false;
+	const size_t chunk = (size_t)512 << 20;
+	a->gran = (chunk + g - 1) / g * g;
+	a->reserved = (reserve_bytes + a->gran - 1) / a->gran * a->gran;
+	if (a->reserve(&a->base, a->reserved, 0, 0, 0) != CUDA_SUCCESS) return false;
+	a->ok = true;
+	return true;
+}
+// maps physical memory so that [base, base + upto) is backed
+static bool arena_back(Arena *a, size_t upto) {
+	while (a->mapped < upto) {
+		if (a->mapped + a->gran > a->reserved) { set_error("activation arena: reserved range of %zu bytes exhausted", a->reserved); return false; }
+		CUmemGenericAllocationHandle h;
+		CUresult r = a->create(&h, a->gran, &a->prop, 0);
+		if (r != CUDA_SUCCESS) { set_error("activation arena: cuMemCreate(%zu) failed (%d) after %zu bytes", a->gran, (int)r, a->mapped); return false; }
+		r = a->map(a->base + a->mapped, a->gran, 0, h, 0);
+		if (r != CUDA_SUCCESS) { a->release(h); set_error("activation arena: cuMemMap failed (%d)", (int)r); return false; }
+		CUmemAccessDesc acc;
+		memset(&acc, 0, sizeof(acc));
+		acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+		acc.location.id = a->device;
+		acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+		r = a->set_access(a->base + a->mapped, a->gran, &acc, 1);
+		if (r != CUDA_SUCCESS) { set_error("activation arena: cuMemSetAccess failed (%d)", (int)r); return false; }
+		a->handles.push_back(h);
+		a->sizes.push_back(a->gran);
+		a->mapped += a->gran;
+	}
+	return true;
+}
+void arena_close(void *arena) {
+	Arena *a = (Arena *)arena;
+	if (!a) return;
+	if (a->ok) {
+		size_t off = 0;
+		for (size_t i = 0; i < a->handles.size(); i++) { a->unmap(a->base + off, a->sizes[i]); a->release(a->handles[i]); off += a->sizes[i]; }
+		a->addr_free(a->base, a->reserved);
+	}
+	delete a;
+}
+
 struct Bump {
 	Engine *e;
 	// activation tensor of n elements in the engine's storage type (fp32 or bf16); the public structs keep float* names
 	float *act(long long n) { return (float *)get<char>((n <= 0 ? 1 : n) * (long long)e->esz); }
 	template <typename T> T *get(long long n) {
 		if (n <= 0) n = 1;
-		void *p = nullptr;
-		RB_CUDA(cudaMalloc(&p, (size_t)align_up(n * (long long)sizeof(T), 256)));
+		const size_t bytes = (size_t)align_up(n * (long long)sizeof(T), 256);
+		Arena *a = (Arena *)e->arena;
+		if (a && a->ok) {
+			if (arena_back(a, a->used + bytes)) {
+				T *p = (T *)(uintptr_t)(a->base + a->used);
+				a->used += bytes;
+				return p;
+			}
+			return nullptr;
+		}
+		void *p = nullptr;  // fallback: one allocation per tensor
+		RB_CUDA(cudaMalloc(&p, bytes));
 		e->allocs.push_back(p);
 		return (T *)p;
 	}
@@ -242,6 +337,21 @@ static Engine *build_engine(Train_ResNet *t) {
 	RB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamDefault));
 	RB_CUDA(cudaEventCreate(&e->ev0));
 	RB_CUDA(cudaEventCreate(&e->ev1));
+	e->wstream = nullptr;
+	if (e->conv_mode == 0 && env_int("RESNET_B200_ASYNC_WGRAD", 1) && !g_selfcheck) {
+		RB_CUDA(cudaStreamCreateWithFlags(&e->wstream, cudaStreamNonBlocking));
+		RB_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+		RB_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+		for (int k = 0; k < 4; k++) { RB_CUDA(cudaEventCreateWithFlags(&e->ev_rd[k], cudaEventDisableTiming)); e->ev_rd_live[k] = false; }
+	}
+	e->arena = nullptr;
+	if (env_int("RESNET_B200_ARENA", 1)) {
+		Arena *a = new Arena();
+		size_t free_b = 0, total_b = 0;
+		RB_CUDA(cudaMemGetInfo(&free_b, &total_b));  // (creates the context before the driver entry points are used)
+		if (arena_open(a, total_b ? total_b : ((size_t)192 << 30))) e->arena = a;  // address space only: reserving the device's size costs nothing
+		else delete a;
+	}
 	Bump B{e};
 	Dims *d = t->model->dims;
 	Params *P = t->model->params;
@@ -361,10 +471,13 @@ static Engine *build_engine(Train_ResNet *t) {
 	e->epoch_images = 0;
 
 	// ---- gradient buffers: per-role scratch (default) or a full mirror (keep-all)
-	float *pp[2] = {nullptr, nullptr}, *T1 = nullptr, *T2 = nullptr, *T3 = nullptr;
+	float *pp[2] = {nullptr, nullptr}, *T1 = nullptr, *T1p = nullptr, *T2 = nullptr, *T3 = nullptr;
 	if (!ka) {
 		pp[0] = B.act(max_exp_out); pp[1] = B.act(max_exp_out);
 		T1 = B.act(max_exp_out); T2 = B.act(max_red_out); T3 = B.act(max_red_in);
+		// the projection branch's dX gets its own buffer when wgrads run on the side stream (it shared T1 with the expansion branch,
+		// whose BatchNorm backward overwrites it right after the projection's convolutions were launched)
+		T1p = e->wstream ? B.act(max_exp_out) : T1;
 	}
 	e->dP0 = DA->init_convblock_input = ka ? B.act(n_p0) : pp[1];  // block 0 writes its input gradient into pp[(0+1)&1]
 	e->dY0 = DA->init_conv_activated = B.act(n_x0);
@@ -388,7 +501,7 @@ static Engine *build_engine(Train_ResNet *t) {
 			db->output = B.act(b.n_exp_out);
 		} else {
 			b.dOA = pp[i & 1];
-			b.dXe = T1; b.dXp = b.has_proj ? T1 : NULL;
+			b.dXe = T1; b.dXp = b.has_proj ? T1p : NULL;
 			b.dYs = b.dXs = T2;
 			b.dYr = b.dXr = T3;
 		}
@@ -484,7 +597,12 @@ static void stem_backward(Engine *e, const float *images) {
 		return;
 	}
 	const ConvGeom &g = e->stem.g;
-	{
+	if (e->wstream && !prof_enabled()) {
+		// same stream as the other weight gradients: they share the split-K workspace
+		RB_CUDA(cudaEventRecord(e->ev_fork, e->stream));
+		RB_CUDA(cudaStreamWaitEvent(e->wstream, e->ev_fork, 0));
+		tc_run(e->stem_wgrad, e->wstream);
+	} else {
 		ProfScope ps(e->stream, PROF_IGEMM_WGRAD, 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k);
 		tc_run(e->stem_wgrad, e->stream);  // reads the padded copy made by this step's forward_pass
 	}
@@ -503,14 +621,27 @@ static void conv_fwd(Engine *e, ConvRef &c, const float *in, float *out) {
 	}
 	if (e->selfcheck && c.use_tc) selfcheck_fprop(e, c.g, c.w, in, false, out);
 }
-static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, float *din, int accumulate) {
+// the main stream is about to overwrite role buffer k (0 dXe, 1 dXs, 2 dXr, 3 dXp): wait for the side-stream wgrad that still reads it
+static void wait_role_readers(Engine *e, int k) {
+	if (e->wstream && e->ev_rd_live[k]) RB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_rd[k], 0));
+}
+// role: which role buffer `dout` is (see Engine::ev_rd), -1 = none (keep-all mode allocates every gradient tensor separately)
+static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, float *din, int accumulate, int role = -1) {
 	if (c.use_tc) {
+		// instrumented passes (bench.py's per-family timing) run the wgrad in line, so that every kernel is timed alone
+		const bool side = e->wstream && !prof_enabled();
+		if (side) {  // dout and in are complete on the main stream here: fork the wgrad before the dgrad is enqueued
+			RB_CUDA(cudaEventRecord(e->ev_fork, e->stream));
+			RB_CUDA(cudaStreamWaitEvent(e->wstream, e->ev_fork, 0));
+			tc_run(c.wgrad, e->wstream);
+			if (role >= 0) { RB_CUDA(cudaEventRecord(e->ev_rd[role], e->wstream)); e->ev_rd_live[role] = true; }
+		}
 		if (din) {
 			if (e->selfcheck && accumulate) selfcheck_dgrad_snapshot(e, c.g, din);
 			{ ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, conv_flops(c.g)); tc_run(c.dgrad, e->stream); }
 			if (e->selfcheck) selfcheck_dgrad(e, c.g, c.w, dout, din, accumulate);
 		}
-		{
+		if (!side) {
 			ProfScope ps(e->stream, PROF_IGEMM_WGRAD, conv_flops(c.g));
 			tc_run(c.wgrad, e->stream);
 		}
@@ -690,18 +821,24 @@ void backwards_pass(Train_ResNet *t) {
 		// identity shortcut: its gradient relu'(OA) * dOA (reference: resnet.cu:2003-2004) is stored by the expansion BatchNorm's
 		// backward, which has it in registers, unless RESNET_B200_FUSE_SHORTCUT=0 asks for the separate pass
 		const bool fuse_short = !b.has_proj && env_int("RESNET_B200_FUSE_SHORTCUT", 1);
+		// (wait_role_readers: in the default buffer plan dXe / dXs / dXr / dXp are one scratch tensor each, shared by all blocks; a
+		// wgrad of the previous block may still be reading it on the side stream)
 		if (b.has_proj) {
+			wait_role_readers(e, 3);
 			bn_backward(e, b.bn_p, b.Xp, b.dOA, b.OA, b.dXp, eps, false, nullptr, b.oa_bits);
-			conv_bwd(e, b.proj, b.x_in, b.dXp, b.dBI, 0);
+			conv_bwd(e, b.proj, b.x_in, b.dXp, b.dBI, 0, 3);
 		} else if (!fuse_short) {
 			relu_backward(e, b.OA, b.dOA, b.n_exp_out, b.dBI);
 		}
+		wait_role_readers(e, 0);
 		bn_backward(e, b.bn_e, b.Xe, b.dOA, b.OA, b.dXe, eps, false, fuse_short ? b.dBI : nullptr, b.oa_bits);
-		conv_bwd(e, b.expand, b.Ys, b.dXe, b.dYs, 0);
+		wait_role_readers(e, 1);  // the expansion's dgrad writes dYs, which shares its tensor with dXs
+		conv_bwd(e, b.expand, b.Ys, b.dXe, b.dYs, 0, 0);
 		bn_backward(e, b.bn_s, b.Xs, b.dYs, b.Ys, b.dXs, eps, true);
-		conv_bwd(e, b.spatial, b.Yr, b.dXs, b.dYr, 0);
+		wait_role_readers(e, 2);  // ... and the 3x3's dgrad writes dYr = dXr's tensor
+		conv_bwd(e, b.spatial, b.Yr, b.dXs, b.dYr, 0, 1);
 		bn_backward(e, b.bn_r, b.Xr, b.dYr, b.Yr, b.dXr, eps, true);
-		conv_bwd(e, b.reduce, b.x_in, b.dXr, b.dBI, 1);
+		conv_bwd(e, b.reduce, b.x_in, b.dXr, b.dBI, 1, 2);
 		dp_block_done(e, i);
 	}
 	const int S1 = d->input / d->init_conv_stride;
@@ -712,6 +849,10 @@ void backwards_pass(Train_ResNet *t) {
 		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bn0.ab, e->bf16);
 	}
 	stem_backward(e, t->cur_batch->images);
+	if (e->wstream) {  // join: every weight gradient is complete before anything later on the main stream (allreduce, Adam, a host read)
+		RB_CUDA(cudaEventRecord(e->ev_join, e->wstream));
+		RB_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+	}
 	dp_allreduce_grads(e);
 }
 
