@@ -174,8 +174,11 @@ constexpr int kKmajorThreads = 320;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kABytes = 128 * 32 * 4;  // 128 rows x 32 tf32 = 16 KB
 
+// 1024-byte aligned start of the dynamic shared memory (the 128-byte swizzle wants 1024).  Plain pointer arithmetic on the __shared__
+// array -- not an integer round trip -- so that the compiler keeps the address space of everything derived from it: the epilogue's
+// staging stores and the statistics loads are then STS / LDS with 32-bit addresses instead of generic ST / LD with 64-bit address math.
 __device__ __forceinline__ uint8_t *align1024(uint8_t *p) {
-	return reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+	return p + ((1024u - (ptx::smem_u32(p) & 1023u)) & 1023u);
 }
 
 // ------------------------------------------------------------------------------------------ fprop / dgrad
