@@ -75,10 +75,13 @@ int resnet_b200_epoch_stats(Train_ResNet * trainer, double * loss_sum, long long
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 long long resnet_b200_launch_count(void);
 /* per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline leg): enable (resets the
- * records), run steps, then read family f: 0 = tcgen05 fprop+dgrad, 1 = tcgen05 wgrad (+ split-K reduce),
+ * records), run steps, then read family f: 0 = tcgen05 fprop+dgrad (3x3 and stem), 1 = tcgen05 wgrad (+ split-K reduce),
  * 2 = BatchNorm / elementwise, 3 = SIMT conv (stem).  work = algorithmic FLOPs (0, 1, 3) or HBM bytes (2). */
 void resnet_b200_profile(int enable);
 int resnet_b200_profile_read(int family, double * ms, long long * launches, double * work);
+/* family 5 = fprop / dgrad of the 1x1 convolutions (HBM-bound; family 0 then holds the 3x3 / stem launches only): work = FLOPs,
+ * work2 = algorithmic HBM bytes (input + output tensor once) */
+int resnet_b200_profile_read2(int family, double * ms, long long * launches, double * work, double * work2);
 /* 1 when conv layers of this trainer run on the tcgen05 path, 0 when on the fp32 SIMT path */
 int resnet_b200_uses_tensor_cores(Train_ResNet * trainer);
 void resnet_b200_destroy_trainer(Train_ResNet * trainer);

@@ -189,6 +189,7 @@ int resnet_b200_epoch_stats(Train_ResNet *t, double *loss_sum, long long *n_wron
 long long resnet_b200_launch_count(void) { return g_launches; }
 void resnet_b200_profile(int enable) { prof_reset(); prof_enable(enable != 0); }
 int resnet_b200_profile_read(int family, double *ms, long long *launches, double *work) { return prof_read(family, ms, launches, work); }
+int resnet_b200_profile_read2(int family, double *ms, long long *launches, double *work, double *work2) { return prof_read(family, ms, launches, work, work2); }
 int resnet_b200_uses_tensor_cores(Train_ResNet *t) {
 	Engine *e = engine_of(t);
 	if (!e) return 0;

@@ -612,10 +612,13 @@ static void stem_backward(Engine *e, const float *images) {
 // ------------------------------------------------------------------------------------------------ layer helpers
 // algorithmic FLOPs of one conv pass: 2 * N * Ho * Wo * Cout * Cin * k^2
 static double conv_flops(const ConvGeom &g) { return 2.0 * g.N * g.So() * g.So() * (double)g.cout * g.cin * g.k * g.k; }
+// fprop / dgrad of a 1x1 convolution move at least their input and output tensor once: the HBM roofline that bounds them
+static double conv_io_bytes(const Engine *e, const ConvGeom &g) { return (double)e->esz * ((double)g.in_elems() + (double)g.out_elems()); }
+static int kmajor_family(const ConvGeom &g) { return g.k == 1 ? PROF_IGEMM_1X1 : PROF_IGEMM_KMAJOR; }
 
 static void conv_fwd(Engine *e, ConvRef &c, const float *in, float *out) {
 	{
-		ProfScope ps(e->stream, c.use_tc ? PROF_IGEMM_KMAJOR : PROF_STEM_SIMT, conv_flops(c.g));
+		ProfScope ps(e->stream, c.use_tc ? kmajor_family(c.g) : PROF_STEM_SIMT, conv_flops(c.g), conv_io_bytes(e, c.g));
 		if (c.use_tc) tc_run(c.fprop, e->stream);
 		else simt_conv_fprop(c.g, in, c.wf, out, e->stream);
 	}
@@ -638,7 +641,7 @@ static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, 
 		}
 		if (din) {
 			if (e->selfcheck && accumulate) selfcheck_dgrad_snapshot(e, c.g, din);
-			{ ProfScope ps(e->stream, PROF_IGEMM_KMAJOR, conv_flops(c.g)); tc_run(c.dgrad, e->stream); }
+			{ ProfScope ps(e->stream, kmajor_family(c.g), conv_flops(c.g), conv_io_bytes(e, c.g)); tc_run(c.dgrad, e->stream); }
 			if (e->selfcheck) selfcheck_dgrad(e, c.g, c.w, dout, din, accumulate);
 		}
 		if (!side) {

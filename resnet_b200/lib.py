@@ -94,7 +94,7 @@ RESNET_B200_H_SYMBOLS = [
     "resnet_b200_malloc_host", "resnet_b200_free_host", "resnet_b200_memcpy_h2d", "resnet_b200_memcpy_d2h",
     "resnet_b200_memcpy_d2d", "resnet_b200_memset", "resnet_b200_sync", "resnet_b200_rng_create", "resnet_b200_rng_destroy",
     "resnet_b200_stage_batch", "resnet_b200_stage_batch_device", "resnet_b200_prefetch_batch", "resnet_b200_commit_batch", "resnet_b200_trainer_sync", "resnet_b200_timer_begin",
-    "resnet_b200_timer_end_ms", "resnet_b200_loss_accuracy", "resnet_b200_set_pred_copy", "resnet_b200_fetch_pred", "resnet_b200_epoch_stats", "resnet_b200_launch_count", "resnet_b200_profile", "resnet_b200_profile_read", "resnet_b200_uses_tensor_cores",
+    "resnet_b200_timer_end_ms", "resnet_b200_loss_accuracy", "resnet_b200_set_pred_copy", "resnet_b200_fetch_pred", "resnet_b200_epoch_stats", "resnet_b200_launch_count", "resnet_b200_profile", "resnet_b200_profile_read", "resnet_b200_profile_read2", "resnet_b200_uses_tensor_cores",
     "resnet_b200_destroy_trainer", "resnet_b200_conv_forward", "resnet_b200_conv_bench", "resnet_b200_conv_backward", "resnet_b200_batchnorm_forward",
     "resnet_b200_batchnorm_backward", "resnet_b200_maxpool_forward", "resnet_b200_maxpool_backward",
     "resnet_b200_avgpool_forward", "resnet_b200_avgpool_backward", "resnet_b200_matmul", "resnet_b200_softmax_ce",
@@ -160,6 +160,7 @@ def load():
     proto("resnet_b200_launch_count", cll, [])
     proto("resnet_b200_profile", None, [ci])
     proto("resnet_b200_profile_read", ci, [ci, C.POINTER(C.c_double), C.POINTER(cll), C.POINTER(C.c_double)])
+    proto("resnet_b200_profile_read2", ci, [ci, C.POINTER(C.c_double), C.POINTER(cll), C.POINTER(C.c_double), C.POINTER(C.c_double)])
     proto("resnet_b200_uses_tensor_cores", ci, [T])
     proto("resnet_b200_destroy_trainer", None, [T])
     proto("resnet_b200_conv_forward", ci, [ci] * 6 + [vp, vp, vp, ci])
