@@ -17,7 +17,7 @@
 //     (1 + 2 + 2 + 4 taps): no multiply by structural zeros.
 //   * B tile = BN weight rows x chunk via a 2-D TMA load.  Both tiles land in 128-byte-swizzled K-major layout,
 //     the canonical operand layout of tcgen05.mma (UMMA) descriptors.
-//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (4 MMAs per stage, K = 8 tf32 / 16 bf16);
+//   * warp 0 (+ 6): TMA producer; warp 1: TMEM allocator + tcgen05.mma issuer (one elected lane, 4 MMAs per stage, K = 8 tf32 / 16 bf16);
 //     warps 2-5 (and 6-9 on short-K layers): epilogue -- tcgen05.ld TMEM -> registers -> swizzled smem staging tile -> TMA
 //     tile store / reduce-add, plus the fused BatchNorm statistics -- overlapped with the next tile's mainloop through a
 //     double-buffered TMEM accumulator (2 x BN <= 512 columns).  Persistent: one CTA per SM.
