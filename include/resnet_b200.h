@@ -139,6 +139,9 @@ int resnet_b200_dp_unique_id(void * out_id_128_bytes);
  * stream, overlapped with backwards_pass; update_parameters waits per bucket.  bucket_bytes <= 0: default. */
 int resnet_b200_dp_init(Train_ResNet * trainer, const void * id_128_bytes, int rank, int world_size, long long bucket_bytes);
 int resnet_b200_dp_world_size(Train_ResNet * trainer);
+/* host-only (no GPU): the (shard, batch) pairs that n_calls consecutive load_new_batch calls deliver on rank `rank` of `world_size`,
+ * from a fresh cursor -- the single-GPU traversal of the reference (resnet.cu:1260-1295) taken with stride world_size */
+int resnet_b200_loader_plan(int rank, int world_size, int batch_size, int shard_n_images, int n_calls, int * out_shard, int * out_batch);
 
 #ifdef __cplusplus
 }

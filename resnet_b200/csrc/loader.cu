@@ -142,9 +142,35 @@ static void advance_cursor(int &shard, int &batch, int batch_size, int shard_n_i
 	if (batch * batch_size >= shard_n_images) { shard += 1; batch = 0; }
 }
 
+// Which (shard, batch) a load_new_batch call delivers, given the cursor the previous call left (the reference's convention:
+// cur_batch_in_shard = batch after the one delivered last; -1 / -1 before the first call) -- pure host logic, shared by
+// load_new_batch and the CPU test hook resnet_b200_loader_plan.
+static void next_delivery(int &shard, int &batch, bool init_loaded, int rank, int world, int batch_size, int shard_n_images) {
+	if (init_loaded) return;  // a restored cursor is rank-local and is taken as is (reference: resnet.cu:1266-1295)
+	if (shard == -1) {
+		shard = 0; batch = 0;
+		for (int i = 0; i < rank; i++) advance_cursor(shard, batch, batch_size, shard_n_images);
+		return;
+	}
+	if (batch * batch_size >= shard_n_images) { shard += 1; batch = 0; }
+	for (int i = 1; i < world; i++) advance_cursor(shard, batch, batch_size, shard_n_images);
+}
+
 }  // namespace rb
 
 using namespace rb;
+
+// host-only view of the traversal for tests: the (shard, batch) pairs `n_calls` consecutive load_new_batch calls deliver on
+// rank `rank` of `world`, starting from a fresh cursor
+extern "C" int resnet_b200_loader_plan(int rank, int world, int batch_size, int shard_n_images, int n_calls, int *out_shard, int *out_batch) {
+	int shard = -1, batch = -1;
+	for (int i = 0; i < n_calls; i++) {
+		next_delivery(shard, batch, false, rank, world, batch_size, shard_n_images);
+		out_shard[i] = shard; out_batch[i] = batch;
+		batch += 1;  // what load_new_batch stores in cur_batch_in_shard
+	}
+	return 0;
+}
 
 extern "C" void load_new_batch(Train_ResNet *trainer, Class_Metadata *class_metadata, Batch *bb) {
 	(void)class_metadata;
@@ -158,16 +184,8 @@ extern "C" void load_new_batch(Train_ResNet *trainer, Class_Metadata *class_meta
 	int rank = 0, world = 1;
 	if (e) dp_rank_world(e, &rank, &world);
 	int shard = bb->cur_shard_id, batch = bb->cur_batch_in_shard;
-	if (trainer->init_loaded) {
-		trainer->init_loaded = 0;
-	} else if (shard == -1) {
-		shard = 0; batch = 0;
-		for (int i = 0; i < rank; i++) advance_cursor(shard, batch, batch_size, bb->shard_n_images);
-	} else {
-		// cur_batch_in_shard is the batch after the one delivered last (the reference's convention): world - 1 more steps
-		if (batch * batch_size >= bb->shard_n_images) { shard += 1; batch = 0; }
-		for (int i = 1; i < world; i++) advance_cursor(shard, batch, batch_size, bb->shard_n_images);
-	}
+	next_delivery(shard, batch, trainer->init_loaded != 0, rank, world, batch_size, bb->shard_n_images);
+	trainer->init_loaded = 0;
 	Prefetcher *p = prefetcher_of(bb);
 	bool delivered = false;
 	{

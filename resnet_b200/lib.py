@@ -99,7 +99,7 @@ RESNET_B200_H_SYMBOLS = [
     "resnet_b200_batchnorm_backward", "resnet_b200_maxpool_forward", "resnet_b200_maxpool_backward",
     "resnet_b200_avgpool_forward", "resnet_b200_avgpool_backward", "resnet_b200_matmul", "resnet_b200_softmax_ce",
     "resnet_b200_adam", "resnet_b200_set_dtype", "resnet_b200_trainer_dtype", "resnet_b200_set_op_dtype", "resnet_b200_convert",
-    "resnet_b200_selfcheck", "resnet_b200_selfcheck_read", "resnet_b200_dp_unique_id", "resnet_b200_dp_init", "resnet_b200_dp_world_size"]
+    "resnet_b200_selfcheck", "resnet_b200_selfcheck_read", "resnet_b200_dp_unique_id", "resnet_b200_dp_init", "resnet_b200_dp_world_size", "resnet_b200_loader_plan"]
 
 _lib = None
 
@@ -184,6 +184,7 @@ def load():
     proto("resnet_b200_dp_unique_id", ci, [vp])
     proto("resnet_b200_dp_init", ci, [T, vp, ci, ci, cll])
     proto("resnet_b200_dp_world_size", ci, [T])
+    proto("resnet_b200_loader_plan", ci, [ci, ci, ci, ci, ci, i32p, i32p])
     proto("resnet_b200_dp_plan", ci, [C.POINTER(cll), ci, cll, i32p, ci, cll, C.POINTER(cll), C.POINTER(cll), i32p, ci])
     _lib = L
     return L

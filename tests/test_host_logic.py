@@ -44,3 +44,36 @@ def test_bench_configs_match_baseline_json():
     assert abs(3 * (f50 + 0.0041) - stem - bench.CONFIGS["c2"]["gflop"]) < 0.05
     f152, _ = conv_gflop(50, bench.R152_REDUCTIONS)
     assert abs(3 * (f152 + 0.0041) - stem - bench.CONFIGS["c5"]["gflop"]) < 0.1
+
+
+def test_loader_traversal_single_and_rank_strided():
+    """load_new_batch's cursor logic without a GPU (resnet_b200_loader_plan): one rank walks the reference's sequence (batches of a
+    shard in order, then the next shard; reference: resnet.cu:1260-1295); under data parallelism rank r of `world` takes positions
+    r, r + world, ... of that same sequence, so the ranks' deliveries are disjoint and their union, in order, is the single-GPU run."""
+    import ctypes as C
+    from resnet_b200 import lib
+    L = lib.load()
+
+    def plan(rank, world, batch, shard_n, n):
+        s, b = (C.c_int * n)(), (C.c_int * n)()
+        assert L.resnet_b200_loader_plan(rank, world, batch, shard_n, n, s, b) == 0
+        return list(zip(list(s), list(b)))
+    single = plan(0, 1, 4, 12, 9)
+    assert single == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2)]
+    for world in (2, 3, 4):
+        per_rank = [plan(r, world, 4, 12, 6) for r in range(world)]
+        merged = [per_rank[i % world][i // world] for i in range(6 * world)]
+        assert merged == plan(0, 1, 4, 12, 6 * world), (world, merged)
+    # a shard size that is not a multiple of the batch: the reference moves on when batch * batch_size >= shard_n_images
+    assert plan(0, 1, 5, 12, 5) == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1)]
+
+
+def test_bench_arms_share_one_config_dict():
+    """the product arm and the reference arms describe the workload with the same `config` dictionary (the driver compares them)"""
+    import bench
+    for name, cfg in bench.CONFIGS.items():
+        a, b = bench.config_dict(name, cfg["batch"], 1), bench.config_dict(name, cfg["batch"], 1)
+        assert a == b and a["baseline_config"] == name and a["global_batch"] == cfg["batch"]
+        assert bench.config_dict(name, cfg["batch"], 8)["global_batch"] == 8 * cfg["batch"]
+    assert bench.metric_of("c2") == bench.metric_of("c4") == bench.METRIC and "forward" in bench.metric_of("c3")
+
