@@ -53,6 +53,18 @@ static EncodeTiledFn get_encode() {
 }
 
 // element type of a tensor map: fp32 (tf32 MMAs) or bf16
+// L2 promotion of the tensor maps: how much L2 fetches from HBM around every 128-byte request of a TMA box.  256 bytes: the next K
+// chunk of the same pixel row comes along (0.5 % on the whole conv set, 3-7 % on the 1x1 dgrads with 4 KB rows;
+// profiles/r02_conv_bench_l2_promotion_f32.txt).  RESNET_B200_L2_PROMO = 0 | 64 | 128 | 256 overrides.
+static CUtensorMapL2promotion map_promo() {
+	if (const char *e = getenv("RESNET_B200_L2_PROMO")) {
+		const int v = atoi(e);
+		if (v == 128) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+		if (v == 64) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+		if (v == 0) return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+	}
+	return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
 static inline CUtensorMapDataType map_dtype(int bf16) { return bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
 static inline size_t esize(int bf16) { return bf16 ? 2 : 4; }
 static inline const void *eptr(const void *base, long long elems, int bf16) { return (const char *)base + elems * (long long)esize(bf16); }
@@ -67,7 +79,7 @@ static bool make_map4(CUtensorMap *m, const void *base, const long long dims[4],
 	for (int i = 0; i < 4; i++) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
 	for (int i = 0; i < 3; i++) gs[i] = (cuuint64_t)strides_elems[i] * esize(bf16);
 	CUresult r = enc(m, map_dtype(bf16), 4, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-	                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                 map_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled(4d) failed: %d dims=(%lld,%lld,%lld,%lld) box=(%d,%d,%d,%d)", (int)r, dims[0], dims[1], dims[2],
 		          dims[3], box[0], box[1], box[2], box[3]);
@@ -89,7 +101,7 @@ static bool make_map5_cblk(CUtensorMap *m, const void *base, const long long dim
 	cuuint32_t bx[5] = {(cuuint32_t)cb, (cuuint32_t)box4[1], (cuuint32_t)box4[2], (cuuint32_t)box4[3], (cuuint32_t)cblk_box}, es[5] = {1, 1, 1, 1, 1};
 	if (C < (long long)cb) gd[0] = (cuuint64_t)C;
 	CUresult r = enc(m, map_dtype(bf16), 5, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-	                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                 map_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled(5d) failed: %d dims=(%lld,%lld,%lld,%lld) box=(%d,%d,%d,%d,%d)", (int)r, dims4[0], dims4[1], dims4[2],
 		          dims4[3], box4[0], box4[1], box4[2], box4[3], cblk_box);
@@ -104,7 +116,7 @@ static bool make_map2(CUtensorMap *m, const void *base, long long cols, long lon
 	cuuint64_t gd[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, gs[1] = {(cuuint64_t)row_stride_elems * esize(bf16)};
 	cuuint32_t bx[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, es[2] = {1, 1};
 	CUresult r = enc(m, map_dtype(bf16), 2, (void *)base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                 CU_TENSOR_MAP_SWIZZLE_128B, map_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d) failed: %d cols=%lld rows=%lld box=(%d,%d)", (int)r, cols, rows, box_cols, box_rows); return false; }
 	return true;
 }
