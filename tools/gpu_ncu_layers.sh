@@ -1,9 +1,9 @@
-# Round 2, ncu --set full captures of representative convolution launches (one launch each, after a plain run of the same command)
+# ncu --set full captures of representative convolution launches (one launch each, after a plain run of the same command)
 mkdir -p gpurun_out
 prof() {  # name dtype only pass
   local cmd="python tools/conv_bench.py --dtype $2 --shape $3 --passes $4 --iters 2 --warmup 1"
-  $cmd > gpurun_out/r2c_plain_$1.log 2>&1 && \
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_ -s 1 -c 1 -f -o gpurun_out/r2c_$1 $cmd > gpurun_out/r2c_ncu_$1.log 2>&1
+  $cmd > gpurun_out/ncu_layer_plain_$1.log 2>&1 && \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_ -s 1 -c 1 -f -o gpurun_out/ncu_layer_$1 $cmd > gpurun_out/ncu_layer_ncu_$1.log 2>&1
   echo "$1 exit $?"
 }
 prof f1x1_256_1024 f32 1,1,256,1024,14 0
