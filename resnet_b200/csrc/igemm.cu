@@ -978,6 +978,7 @@ TcPlan *tc_make_wgrad(const ConvGeom &g, const void *x, const void *dy, float *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
+	if (const char *e = getenv("RESNET_B200_WGRAD_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }  // tuning aid
 	p.nprod = (p.stages % 2 == 0 && p.stages >= 4) ? 2 : 1;
 	if (const char *e = getenv("RESNET_B200_PRODUCERS")) { if (atoi(e) == 1) p.nprod = 1; }
 	p.partial = workspace;
@@ -1168,6 +1169,7 @@ TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *d
 	const uint32_t stage_bytes = p.a_bytes + (uint32_t)p.tpt * p.b_bytes;
 	int stages = (int)((kMaxDynSmem - 2048) / stage_bytes);
 	p.stages = stages > 8 ? 8 : stages;
+	if (const char *e = getenv("RESNET_B200_WGRAD_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }  // tuning aid
 	p.nprod = (p.stages % 2 == 0 && p.stages >= 4) ? 2 : 1;
 	if (const char *e = getenv("RESNET_B200_PRODUCERS")) { if (atoi(e) == 1) p.nprod = 1; }
 	p.partial = workspace;
