@@ -33,6 +33,10 @@ bool trace_on() {
 	static const bool on = getenv("RESNET_B200_TRACE") != nullptr;
 	return on;
 }
+int pdl_mode() {
+	static const int mode = getenv("RESNET_B200_PDL") ? atoi(getenv("RESNET_B200_PDL")) : 3;
+	return mode;
+}
 
 // ------------------------------------------------------------------------------------------- helpers
 constexpr int kThreads = 256;
@@ -141,6 +145,8 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_ker
 	const int Cc = V * VEC;
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) sm[i] = 0.f;
 	__syncthreads();
+	pdl_wait();
+	pdl_trigger();
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	float s[VEC], q[VEC], mu[VEC];
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_ker
 // results (deterministic).  History: one thread per channel over ~1000 partials was latency-bound at 170 us per launch; 32
 // channels x 32 slices still spent 22 us in a 19-deep dependent L2 load chain (profiles/r01_ncu_all_kernels_one_step_summary.txt).
 constexpr int kFinC = 8, kFinS = 128;
-__device__ __forceinline__ bool fold_partials(const float *__restrict__ partials, int nblk, int Cc, double *s_out, double *q_out) {
+__device__ __forceinline__ bool fold_partials(const float *__restrict__ partials, int nblk, int Cc, double *s_out, double *q_out, float *zero = nullptr) {
 	__shared__ double sm[kFinS / 4][2][kFinC];
 	const int cx = threadIdx.x, sy = threadIdx.y, c = blockIdx.x * kFinC + cx;
 	double s = 0, q = 0;
@@ -268,6 +274,9 @@ __device__ __forceinline__ bool fold_partials(const float *__restrict__ partials
 		for (int b = sy; b < nblk; b += kFinS) {
 			s += (double)partials[(size_t)b * 2 * Cc + c];
 			q += (double)partials[(size_t)b * 2 * Cc + Cc + c];
+		}
+		if (zero) {  // every element of the region is read by exactly one thread: that thread clears it
+			for (int b = sy; b < nblk; b += kFinS) { zero[(size_t)b * 2 * Cc + c] = 0.f; zero[(size_t)b * 2 * Cc + Cc + c] = 0.f; }
 		}
 	}
 	// a warp holds 4 consecutive slices x 8 channels: lanes l, l^8, l^16, l^24 share a channel
@@ -285,11 +294,13 @@ __device__ __forceinline__ bool fold_partials(const float *__restrict__ partials
 }
 
 // mean, biased variance, a = gamma*rstd, b = beta - mean*a
-__global__ void bn_finalize_kernel(const float *__restrict__ partials, int nblk, double inv_n, int Cc, const float *__restrict__ gamma,
+__global__ void bn_finalize_kernel(const float *partials, int nblk, double inv_n, int Cc, const float *__restrict__ gamma,
                                    const float *__restrict__ beta, float eps, float *__restrict__ means, float *__restrict__ vars,
-                                   float *__restrict__ ab) {
+                                   float *__restrict__ ab, float *zero) {
 	double s, q;
-	if (!fold_partials(partials, nblk, Cc, &s, &q)) return;
+	pdl_wait();
+	pdl_trigger();
+	if (!fold_partials(partials, nblk, Cc, &s, &q, zero)) return;
 	const int c = blockIdx.x * kFinC + threadIdx.x;
 	const double mean = s * inv_n;
 	double var = q * inv_n - mean * mean;
@@ -319,7 +330,7 @@ static void launch_reduce(bool bwd, const void *x, const void *dy, const void *m
 	if (VEC == 1) fixed = false;
 	const size_t smem = 2 * (size_t)C * sizeof(float);
 #define RB_RED(T_, VEC_, FIX_, BWD_) \
-	bn_reduce_kernel<T_, VEC_, FIX_, BWD_><<<grid, kThreads, smem, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask, means, nvec, V, partials, mab, mask_bits)
+	launch_k(0, bn_reduce_kernel<T_, VEC_, FIX_, BWD_>, grid, kThreads, smem, st, (const T_ *)x, (const T_ *)dy, (const T_ *)mask, means, nvec, V, partials, mab, mask_bits)
 #define RB_RED2(T_, VEC_) \
 	do { \
 		if (fixed) { if (bwd) RB_RED(T_, VEC_, true, true); else RB_RED(T_, VEC_, true, false); } \
@@ -335,9 +346,9 @@ static void launch_reduce(bool bwd, const void *x, const void *dy, const void *m
 	*grid_out = grid;
 }
 
-void bn_finalize(const float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
-                 float *means, float *vars, float *ab, cudaStream_t st) {
-	bn_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, nblk, 1.0 / (double)rows, C, gamma, beta, eps, means, vars, ab);
+void bn_finalize(float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
+                 float *means, float *vars, float *ab, cudaStream_t st, int zero_after) {
+	launch_k(0, bn_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, (const float *)partials, nblk, 1.0 / (double)rows, C, gamma, beta, eps, means, vars, ab, zero_after ? partials : (float *)nullptr);
 	RB_LAUNCH_CHECK();
 }
 
@@ -360,6 +371,8 @@ __global__ void __launch_bounds__(kThreads, 4) bn_apply_kernel(const T *__restri
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	float a[VEC], b[VEC], a2[VEC], b2[VEC];
+	pdl_wait();
+	pdl_trigger();
 	if constexpr (FIXED) {
 		const int c0 = (int)(g % V) * VEC;
 #pragma unroll
@@ -431,7 +444,7 @@ void bn_apply(const void *x, const float *ab, long long rows, int C, int relu, c
 	int grid = flat_grid(nvec, V, kMaxFlatBlocks, &fixed);
 	if (bits_out && !(fixed && VEC >= 4 && nvec % 32 == 0)) { set_error("bn_apply: mask bits need the fixed-column vector path and nvec %% 32 == 0 (rows %lld, C %d)", rows, C); return; }
 #define RB_APPLY(T_, VEC_, FIX_, BITS_) \
-	bn_apply_kernel<T_, VEC_, FIX_, BITS_><<<grid, kThreads, 0, st>>>((const T_ *)x, ab, nvec, V, relu, (const T_ *)res, ab2, (T_ *)y, bf16 ? 0 : rnd, (uint32_t *)bits_out)
+	launch_k(0, bn_apply_kernel<T_, VEC_, FIX_, BITS_>, grid, kThreads, 0, st, (const T_ *)x, ab, nvec, V, relu, (const T_ *)res, ab2, (T_ *)y, bf16 ? 0 : rnd, (uint32_t *)bits_out)
 	if (bf16) { if (bits_out) RB_APPLY(bf16_t, 8, true, true); else if (fixed) RB_APPLY(bf16_t, 8, true, false); else RB_APPLY(bf16_t, 8, false, false); }
 	else if (VEC == 4 && bits_out) RB_APPLY(float, 4, true, true);
 	else if (VEC == 4 && fixed) RB_APPLY(float, 4, true, false);
@@ -450,6 +463,8 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partials, int n
                                        const float *__restrict__ means, const float *__restrict__ vars, float eps,
                                        float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef) {
 	double s1, s2;
+	pdl_wait();
+	pdl_trigger();
 	if (!fold_partials(partials, nblk, Cc, &s1, &s2)) return;
 	const int c = blockIdx.x * kFinC + threadIdx.x;
 	const float rstd = 1.0f / sqrtf(vars[c] + eps);
@@ -475,6 +490,8 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_bwd_dx_ker
 	const bool remask = FIXED && mab != nullptr;
 	const bool rdbits = !remask && mask_bits != nullptr;
 	const bool rdmask = !remask && !rdbits && mask != nullptr;
+	pdl_wait();
+	pdl_trigger();
 	if constexpr (FIXED) {
 		const int c0 = (int)(g % V) * VEC;
 #pragma unroll
@@ -540,7 +557,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
             cudaStream_t st, const float *mab, int bf16, void *masked_out, const uint8_t *mask_bits) {
 	int grid;
 	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab, bf16, mask_bits);
-	bn_bwd_finalize_kernel<<<ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st>>>(partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
+	launch_k(0, bn_bwd_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();
 	const int VEC = vec_of(C, bf16);
 	if (!VEC) return;
@@ -549,7 +566,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 	bool fixed;
 	int g2 = flat_grid(nvec, V, kNumSMs * bn_bwd_blocks_per_sm(bf16) * 2, &fixed);  // two whole waves
 #define RB_DX(T_, VEC_, FIX_) \
-	bn_bwd_dx_kernel<T_, VEC_, FIX_><<<g2, kThreads, 0, st>>>((const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab, (T_ *)masked_out, mask_bits)
+	launch_k(0, bn_bwd_dx_kernel<T_, VEC_, FIX_>, g2, kThreads, 0, st, (const T_ *)x, (const T_ *)dy, (const T_ *)mask_src, coef, nvec, V, (T_ *)dx, bf16 ? 0 : rnd, mab, (T_ *)masked_out, mask_bits)
 	if (bf16) { if (fixed) RB_DX(bf16_t, 8, true); else RB_DX(bf16_t, 8, false); }
 	else if (VEC == 4 && fixed) RB_DX(float, 4, true);
 	else if (VEC == 4) RB_DX(float, 4, false);
@@ -1124,6 +1141,8 @@ __global__ void __launch_bounds__(kWrX * kWrY) wgrad_reduce_lanes_kernel(const f
 	__shared__ float sm[kWrY][kWrX];
 	const long long per = (long long)taps * cout * cin;
 	const int tx = threadIdx.x, ty = threadIdx.y;
+	pdl_wait();
+	pdl_trigger();
 	for (long long base = (long long)blockIdx.x * kWrX; base < per; base += (long long)gridDim.x * kWrX) {
 		const long long i = base + tx;  // indexes partial [tap][co][ci]
 		float s = 0.f;
@@ -1167,6 +1186,8 @@ __global__ void __launch_bounds__(32 * TAPS * GROUPS) wgrad_reduce_vec_kernel(co
 	static_assert(TAPS == 1 || GROUPS == 1, "the shared-memory re-layout is per block");
 	const long long per = cc * TAPS;
 	const int grp = threadIdx.x / (32 * TAPS), tap = (threadIdx.x / 32) % TAPS, quad = threadIdx.x % 32;
+	pdl_wait();
+	pdl_trigger();
 	for (long long p0 = ((long long)blockIdx.x * GROUPS + grp) * kWvPairs; p0 < cc; p0 += (long long)gridDim.x * GROUPS * kWvPairs) {
 		const float4 *src = reinterpret_cast<const float4 *>(partial + (long long)tap * cc + p0) + quad;
 		const long long step = per / 4;
@@ -1201,16 +1222,16 @@ void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps,
 	long long per = (long long)taps * cout * cin;
 	if (splits >= 48) {
 		int grid = (int)((per + kWrX - 1) / kWrX); grid = grid > kNumSMs * 32 ? kNumSMs * 32 : grid;
-		wgrad_reduce_lanes_kernel<<<grid, dim3(kWrX, kWrY), 0, st>>>(partial, splits, cout, cin, taps, dw);
+		launch_k(0, wgrad_reduce_lanes_kernel, grid, dim3(kWrX, kWrY), 0, st, partial, splits, cout, cin, taps, dw);
 	} else if ((taps == 1 || taps == 9) && ((long long)cout * cin) % (8 * kWvPairs) == 0 && (uintptr_t)partial % 16 == 0 && (uintptr_t)dw % 16 == 0 &&
 	           !getenv("RESNET_B200_WGRAD_REDUCE_SCALAR")) {
 		const long long cc = (long long)cout * cin;
 		if (taps == 1) {
 			int grid = (int)(cc / (8 * kWvPairs)); grid = grid > kNumSMs * 8 ? kNumSMs * 8 : grid;
-			wgrad_reduce_vec_kernel<1, 8><<<grid, 256, 0, st>>>(partial, splits, cc, dw);
+			launch_k(0, wgrad_reduce_vec_kernel<1, 8>, grid, 256, 0, st, partial, splits, cc, dw);
 		} else {
 			int grid = (int)(cc / kWvPairs); grid = grid > kNumSMs * 7 ? kNumSMs * 7 : grid;
-			wgrad_reduce_vec_kernel<9, 1><<<grid, 32 * 9, 0, st>>>(partial, splits, cc, dw);
+			launch_k(0, wgrad_reduce_vec_kernel<9, 1>, grid, 32 * 9, 0, st, partial, splits, cc, dw);
 		}
 	} else {
 		int grid = (int)((per + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;

@@ -43,6 +43,39 @@ bool trace_on();
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (round 2).  A step is ~490 (ResNet-50) to ~1100 (ResNet-152) short launches on one stream; between two
+// of them the GPU drains, launches the next grid and runs its prologue (for the convolution kernels: barrier init, TMEM allocation,
+// tensor-map prefetch).  A kernel launched through launch_k with the programmatic-stream-serialization attribute may have its blocks
+// scheduled while the previous kernel of the stream is still running; they run their global-memory-free prologue and then block in
+// pdl_wait() (griddepcontrol.wait) until the previous grid has COMPLETED and its writes are visible -- the data dependency stays the
+// full one of ordinary stream order, only launch latency and prologue move under the predecessor's tail.  Rules: every kernel that
+// can be launched this way calls pdl_wait() in every thread before its first global-memory access (reads AND writes: the predecessor
+// may still be reading what this kernel overwrites); pdl_trigger() lets ITS successor be scheduled.  Without the attribute both
+// instructions are no-ops and the launch is serialized on both sides.
+// Measured (profiles/r02_pdl_ab.txt, same-box A/B): pre-launching the CONVOLUTION kernels under the bandwidth-bound kernel before them
+// is worth 0 / 0.3 / 1.6 % of the ResNet-50 TF32 / bf16 / ResNet-152 step; pre-launching the bandwidth-bound kernels costs 3-5 %
+// (their blocks sit on the SMs next to a running convolution, or land unevenly behind another streaming kernel) -- so the default is
+// mode 3: only the convolution kernels carry the attribute.
+int pdl_mode();  // RESNET_B200_PDL: 0 off, 1 every launch_k kernel, 2 only the bandwidth-bound kernels, 3 only the convolution kernels
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline void launch_k(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	const int mode = pdl_mode();  // cls: 0 = bandwidth-bound kernel, 1 = convolution kernel (one CTA per SM holding ~200 KB of shared memory)
+	cfg.numAttrs = (mode == 1 || (mode == 2 && cls == 0) || (mode == 3 && cls == 1)) ? 1 : 0;
+	RB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
@@ -65,8 +98,9 @@ struct ConvGeom {
 void bn_stats(const void *x, long long rows, int C, const float *gamma, const float *beta, float eps, float *means,
               float *vars, float *ab /* [2][C] */, float *partials, int max_blocks, cudaStream_t st, int bf16 = 0);
 // finalize only (statistics partials already produced, e.g. by a conv epilogue): partials [nblk][2][C]
-void bn_finalize(const float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
-                 float *means, float *vars, float *ab, cudaStream_t st);
+// zero_after: the kernel also clears the partials it folded (the fused-statistics buffer stays all-zero between convolutions)
+void bn_finalize(float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
+                 float *means, float *vars, float *ab, cudaStream_t st, int zero_after = 0);
 // y = act(x*a + b [+ residual]);  residual: res (identity) or res*a2 + b2 (projected, ab2 != NULL)
 // bits_out != NULL: also stores the sign bits of y, one byte per 128-bit vector (bit j = element j of the vector is > 0): the
 // 1-bit ReLU mask BatchNorm backward needs of a residual join's output (bn_bwd mask_bits)

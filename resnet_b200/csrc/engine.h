@@ -79,6 +79,7 @@ struct Engine {
 	long long epoch_images;     // images forwarded since the last reset
 	// workspaces
 	float *bn_partials;
+	float *stats_partials;  // partial sums of the fused conv-epilogue statistics; all-zero between uses (bn_finalize clears what it folds)
 	int bn_max_blocks;
 	float *bn_coef;
 	float *fc_ws;  // split-K planes of the fully-connected GEMMs

@@ -146,6 +146,7 @@ struct alignas(64) IgemmParams {
 	// and sat at the ~10-12 TB/s the TMA / L2 path delivers chip-wide.
 	int resident_b;
 	uint32_t resb_bytes;
+	int pdl_early;  // 1: let the next kernel of the stream be scheduled as soon as this one runs, 0: when its CTAs are done (see tc_run)
 	int debug;  // profiling aid (RESNET_B200_DEBUG_SKIP): bit 0 = issue no MMAs (feed only), bit 1 = epilogue drains TMEM but stores nothing
 	float *out;
 	int OH, OW, os, accumulate;
@@ -173,6 +174,7 @@ struct alignas(64) WgradParams {
 	int merge_taps;    // the taps of a group sit back to back in shared memory AND in TMEM: one MMA of N = ntaps * BN covers them all
 	uint32_t kadv;     // descriptor start-address advance per MMA (16-byte units): 8 tf32 / 16 bf16 pixel rows
 	int stages;
+	int pdl_early;
 	uint32_t a_bytes, b_bytes, lbo, sbo, layout_type;
 	float *partial;
 };
@@ -239,6 +241,9 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
+	// everything above touched shared memory, TMEM and the kernel parameters only; global memory from here on (common.cuh launch_k)
+	pdl_wait();
+	if (p.pdl_early) pdl_trigger();
 
 	const int total_tiles = p.ngroups * p.m_tiles * p.n_tiles;
 
@@ -443,6 +448,7 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 		}
 		if (store_warp) tma_wait_group0();  // shared memory must outlive the last store's reads; global writes complete before exit
 	}
+	pdl_trigger();  // this thread's role loop is finished: the stream's next kernel may be scheduled once every CTA got here
 	tc_fence_before();
 	__syncthreads();
 	if (warp == 1) {
@@ -496,6 +502,9 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
+	// everything above touched shared memory, TMEM and the kernel parameters only; global memory from here on (common.cuh launch_k)
+	pdl_wait();
+	if (p.pdl_early) pdl_trigger();
 
 	// tile = ((tap_group * co_tiles + cot) * ci_tiles + cit) * splits + split; a tap group shares one dY (A) tile per
 	// stage between up to `tpt` filter taps, each with its own BN-column accumulator (tpt * BN <= 256 TMEM columns)
@@ -623,6 +632,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_mnmajor_kernel(const _
 			if (++acc == nbuf) { acc = 0; accphase ^= 1; }
 		}
 	}
+	pdl_trigger();  // this thread's role loop is finished: the stream's next kernel may be scheduled once every CTA got here
 	tc_fence_before();
 	__syncthreads();
 	if (warp == 1) {
@@ -645,6 +655,7 @@ struct TcPlan {
 	// fused BatchNorm statistics (fprop): rows of partial sums and their byte size
 	int stats_rows;
 	size_t stats_bytes;
+	int stats_prezeroed;
 	double flops;  // algorithmic FLOPs of one launch: 2 * N * Ho * Wo * Cout * Cin * k^2
 	char what[40];
 };
@@ -1205,14 +1216,19 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 		for (const void *k : kernels) RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		attr_set = true;
 	}
+	// When may the kernel after this one be scheduled?  Its blocks would sit next to our CTA for our whole run time, blocked in
+	// griddepcontrol.wait -- measured: BatchNorm kernels pre-launched under a convolution cost the step 3-5 % (profiles/r02_pdl_ab.txt),
+	// so by default a convolution releases its successor only when its own CTAs are done.  RESNET_B200_PDL_CONV_EARLY=1: at its start.
+	static const int conv_early = getenv("RESNET_B200_PDL_CONV_EARLY") ? atoi(getenv("RESNET_B200_PDL_CONV_EARLY")) : 0;
+	pl->ip.pdl_early = pl->wp.pdl_early = conv_early;
 	if (pl->kind == 0) {
-		if (pl->ip.stats) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
-		if (pl->bf16) igemm_kmajor_kernel<true><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
-		else igemm_kmajor_kernel<false><<<pl->grid, kKmajorThreads, pl->smem, st>>>(pl->ip);
+		if (pl->ip.stats && !pl->stats_prezeroed) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
+		if (pl->bf16) launch_k(1, igemm_kmajor_kernel<true>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
+		else launch_k(1, igemm_kmajor_kernel<false>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
 		RB_LAUNCH_CHECK();
 	} else {
-		if (pl->bf16) igemm_mnmajor_kernel<true><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
-		else igemm_mnmajor_kernel<false><<<pl->grid, kIgemmThreads, pl->smem, st>>>(pl->wp);
+		if (pl->bf16) launch_k(1, igemm_mnmajor_kernel<true>, pl->grid, kIgemmThreads, pl->smem, st, pl->wp);
+		else launch_k(1, igemm_mnmajor_kernel<false>, pl->grid, kIgemmThreads, pl->smem, st, pl->wp);
 		RB_LAUNCH_CHECK();
 		if (pl->kind == 1) wgrad_reduce(pl->wp.partial, pl->wp.splits, pl->cout, pl->cin, pl->taps, pl->dw, st);
 		else {
@@ -1226,9 +1242,10 @@ void tc_free(TcPlan *pl) { delete pl; }
 
 // Attach BatchNorm statistics to an fprop plan: the epilogue then also produces [rows][2][Cout] partial sums of the
 // conv output (sum, sum of squares) in `partials` (>= tc_stats_floats(cout) floats); returns the row count for bn_finalize.
-int tc_attach_stats(TcPlan *pl, float *partials) {
+int tc_attach_stats(TcPlan *pl, float *partials, int prezeroed) {
 	if (!pl || pl->kind != 0 || pl->ip.ngroups != 1 || !pl->ip.tma_store || pl->ip.accumulate) return 0;
 	pl->ip.stats = partials;
+	pl->stats_prezeroed = prezeroed;
 	pl->stats_rows = pl->grid * 4 * pl->ip.epi_groups;
 	pl->stats_bytes = (size_t)pl->stats_rows * 2 * pl->ip.Ncol * sizeof(float);
 	return pl->stats_rows;

@@ -26,7 +26,9 @@ TcPlan *tc_make_stem_fprop(int N, int S, int cout, const void *xp, const void *w
 size_t tc_stem_wgrad_workspace_bytes(int N, int S, int cout, int bf16);
 TcPlan *tc_make_stem_wgrad(int N, int S, int cout, const void *xp, const void *dy, float *dw, float *workspace, size_t ws_bytes, int bf16);
 // fused BatchNorm statistics in the fprop epilogue: returns the number of partial rows (0 = not available for this plan)
-int tc_attach_stats(TcPlan *pl, float *partials);
+// prezeroed: the caller keeps `partials` all-zero between uses (bn_finalize with zero_after clears exactly what it folded), so tc_run
+// issues no memset in front of the kernel -- a memset node between two kernels also breaks the programmatic launch chain
+int tc_attach_stats(TcPlan *pl, float *partials, int prezeroed = 0);
 size_t tc_stats_floats(int cout);
 void tc_run(TcPlan *pl, cudaStream_t st);
 void tc_free(TcPlan *pl);

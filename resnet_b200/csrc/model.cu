@@ -517,6 +517,8 @@ static Engine *build_engine(Train_ResNet *t) {
 	int maxC = d->final_depth > F ? d->final_depth : F;
 	e->bn_partials = B.get<float>((long long)e->bn_max_blocks * 2 * maxC);
 	e->bn_coef = B.get<float>(4LL * maxC);
+	e->stats_partials = B.get<float>((long long)tc_stats_floats(maxC));
+	RB_CUDA(cudaMemsetAsync(e->stats_partials, 0, tc_stats_floats(maxC) * sizeof(float), e->stream));
 	e->ones = B.get<float>(maxC); e->zeros = B.get<float>(maxC); e->tmp_ab = B.get<float>(2LL * maxC); e->tmp_mv = B.get<float>(2LL * maxC);
 	fill(e->ones, maxC, 1.f, e->stream);
 	fill(e->zeros, maxC, 0.f, e->stream);
@@ -537,7 +539,7 @@ static Engine *build_engine(Train_ResNet *t) {
 	auto plan = [&](ConvRef &c, const float *in, float *out, const float *dout, float *din, int din_accumulate) {
 		if (!c.use_tc) return;
 		c.fprop = tc_make_fprop(c.g, in, c.wf, out, e->bf16);
-		c.stats_rows = fused_stats ? tc_attach_stats(c.fprop, e->bn_partials) : 0;
+		c.stats_rows = fused_stats ? tc_attach_stats(c.fprop, e->stats_partials, 1) : 0;
 		if (din) c.dgrad = tc_make_dgrad(c.g, dout, c.wd, din, din_accumulate, e->bf16);
 		c.wgrad = tc_make_wgrad(c.g, in, dout, c.dw, e->wgrad_ws, e->wgrad_ws_bytes, e->bf16);
 	};
@@ -551,7 +553,7 @@ static Engine *build_engine(Train_ResNet *t) {
 	if (e->stem_tc) {
 		const bool had_error = has_error();
 		e->stem_fprop = tc_make_stem_fprop(N, S0, F, e->stem_xp, e->stem_wfs, e->X0, e->bf16);
-		e->stem.stats_rows = fused_stats ? tc_attach_stats(e->stem_fprop, e->bn_partials) : 0;
+		e->stem.stats_rows = fused_stats ? tc_attach_stats(e->stem_fprop, e->stats_partials, 1) : 0;
 		e->stem_wgrad = tc_make_stem_wgrad(N, S0, F, e->stem_xp, e->dX0, e->stem.dw, e->wgrad_ws, e->wgrad_ws_bytes, e->bf16);
 		if (!e->stem_fprop || !e->stem_wgrad) {
 			// the overlapping-row tensor map was refused by the driver: keep the fp32 SIMT stem (slower, still correct)
@@ -659,10 +661,11 @@ static void conv_bwd(Engine *e, ConvRef &c, const float *in, const float *dout, 
 // statistics 1E; apply 2E (+1E residual); backward reduce 2E (+1E mask) and dx 3E (+1E mask)
 static double bn_bytes(const Engine *e, const BnRef &bn, double passes) { return passes * (double)e->esz * (double)bn.rows * bn.C; }
 
-// stats_rows > 0: the producing conv's epilogue already left [stats_rows][2][C] partial sums in e->bn_partials (fused statistics)
+// stats_rows > 0: the producing conv's epilogue already left [stats_rows][2][C] partial sums in e->stats_partials (fused statistics);
+// the fold clears them again, so the next convolution needs no memset in front of it
 static void bn_forward(Engine *e, BnRef &bn, const float *x, float eps, int stats_rows = 0) {
 	ProfScope ps(e->stream, PROF_BN_ELTWISE, stats_rows ? 0.0 : bn_bytes(e, bn, 1));
-	if (stats_rows) bn_finalize(e->bn_partials, stats_rows, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->stream);
+	if (stats_rows) bn_finalize(e->stats_partials, stats_rows, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->stream, 1);
 	else bn_stats(x, bn.rows, bn.C, bn.gamma, bn.beta, eps, bn.means, bn.vars, bn.ab, e->bn_partials, e->bn_max_blocks, e->stream, e->bf16);
 	if (e->keep_all && bn.cache->normalized) {
 		bn_apply(x, bn.ab, bn.rows, bn.C, 0, nullptr, nullptr, bn.cache->normalized, 0, e->stream, e->bf16);
