@@ -874,6 +874,202 @@ void maxpool_bwd(const int *max_inds, const void *dout, int N, int S, int C, int
 	RB_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------- fused stem tail
+// The stem's BatchNorm + ReLU output (reference: init_conv_activated, N x 112 x 112 x 64 -- the largest tensor of the network, 822 MB
+// in fp32 at batch 256) is read by exactly one consumer, the 3x3/2 max pool, and its gradient by exactly one, the stem BatchNorm's
+// backward.  Unless the trainer keeps every tensor, neither is materialised:
+//   forward   bn_pool_fwd: pooled = maxpool(relu(x * a + b)), argmax indices as before            (X0 in, P0 + max_inds out;
+//             the separate kernels moved 2 E + 1.5 E, this one 1 E + 0.5 E, E = bytes of X0 with 4-byte indices counted at fp32 size)
+//   backward  pool_bn_bwd: the pool's gradient gather (the 2 x 2-block form of maxpool3s2_bwd_block_kernel) feeds the BatchNorm
+//             backward's two passes directly from (dP0, max_inds): reduce reads X0 + 0.5 E, dx reads the same and writes dX0
+//             (separate kernels: 1.5 E + 2 E + 3 E; fused: 1.5 E + 2.5 E).
+// Per element the arithmetic is the one of bn_apply_kernel / maxpool3s2_fwd_kernel / maxpool3s2_bwd_block_kernel / bn_bwd_dx_kernel
+// in the same order (values and indices are bit-identical to the unfused path; only the order of the dgamma / dbeta partial sums differs).
+template <typename T> __device__ __forceinline__ float round_as_stored(float v, int rnd) {
+	if constexpr (sizeof(T) == 2) return bf16_lo(pack_bf16x2(v, 0.f));
+	else return rnd ? round_tf32(v) : v;
+}
+// (32-bit index arithmetic throughout: the host guarantees N * S * S * C < 2^31, as the int32 max_inds already require; the 64-bit
+// divisions of the flat index cost more instructions than the nine compares)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads, VEC == 8 ? 2 : 3) bn_pool_fwd_kernel(const T *__restrict__ x, const float *__restrict__ ab, int N, int S, int C, int rnd,
+                                                                 int *__restrict__ inds, T *__restrict__ out) {
+	using raw_t = typename RawOf<VEC>::type;
+	const int So = S / 2, V = C / VEC;
+	const int total = N * So * So * V;
+	const int cv = (int)(threadIdx.x % V);  // kThreads % V == 0: a thread keeps its channels
+	float a[VEC], b[VEC];
+#pragma unroll
+	for (int j = 0; j < VEC; j++) { a[j] = ab[cv * VEC + j]; b[j] = ab[C + cv * VEC + j]; }
+	for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+		int p = i / V;
+		const int ow = p % So; p /= So;
+		const int oh = p % So;
+		const int n = p / So;
+		raw_t rv[9];
+		bool ok[9];
+		const int base0 = ((n * S + 2 * oh - 1) * S + 2 * ow - 1) * C + cv * VEC;  // window corner (may lie outside: only used with ok[t])
+#pragma unroll
+		for (int t = 0; t < 9; t++) {
+			const int h = 2 * oh + t / 3 - 1, w = 2 * ow + t % 3 - 1;
+			ok[t] = h >= 0 && h < S && w >= 0 && w < S;
+			if (ok[t]) rv[t] = ldraw<T, VEC>(x, (base0 + ((t / 3) * S + t % 3) * C) / VEC);
+		}
+		float mv[VEC]; int mi[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++) { mv[j] = -1024.f; mi[j] = -1024; }
+#pragma unroll
+		for (int t = 0; t < 9; t++) {
+			if (!ok[t]) continue;
+			float v[VEC];
+			unpack<T, VEC>(rv[t], v);
+			const int bt = base0 + ((t / 3) * S + t % 3) * C;  // flat input index (int, as the reference's max_inds)
+#pragma unroll
+			for (int j = 0; j < VEC; j++) {
+				const float y = round_as_stored<T>(fmaxf(fmaf(v[j], a[j], b[j]), 0.f), rnd);
+				if (y > mv[j]) { mv[j] = y; mi[j] = bt + j; }
+			}
+		}
+		stv<T, VEC>(out, i, mv);
+#pragma unroll
+		for (int h = 0; h < VEC / 4; h++) reinterpret_cast<int4 *>(inds)[(long long)i * (VEC / 4) + h] = make_int4(mi[4 * h], mi[4 * h + 1], mi[4 * h + 2], mi[4 * h + 3]);
+	}
+}
+bool bn_pool_fwd_supported(int N, int S, int C, int k, int stride, int bf16) {
+	const int VEC = vec_of(C, bf16);
+	return k == 3 && stride == 2 && S % 2 == 0 && VEC >= 4 && kThreads % (C / VEC) == 0 && (long long)N * S * S * C < (1LL << 31);
+}
+void bn_pool_fwd(const void *x, const float *ab, int N, int S, int C, int rnd, int *max_inds, void *out, cudaStream_t st, int bf16) {
+	const int VEC = vec_of(C, bf16);
+	long long total = (long long)N * (S / 2) * (S / 2) * (C / VEC);
+	int grid = (int)((total + kThreads - 1) / kThreads); grid = grid > kNumSMs * 3 * 4 ? kNumSMs * 3 * 4 : grid;
+	if (bf16) bn_pool_fwd_kernel<bf16_t, 8><<<grid, kThreads, 0, st>>>((const bf16_t *)x, ab, N, S, C, 0, max_inds, (bf16_t *)out);
+	else bn_pool_fwd_kernel<float, 4><<<grid, kThreads, 0, st>>>((const float *)x, ab, N, S, C, rnd, max_inds, (float *)out);
+	RB_LAUNCH_CHECK();
+	RB_TRACE("bn_pool_fwd_kernel", "N=%d S=%d C=%d grid=%d", N, S, C, grid);
+}
+
+// DX = false: partial sums of dy' and dy' (x - mean) per block; DX = true: dx = c1 dy' + c3 x + k.  dy' = relu'(x a + b) * (pool gradient).
+template <typename T, int VEC> __device__ __forceinline__ float elem_of(const typename RawOf<VEC>::type &r, int j) {
+	if constexpr (sizeof(T) == 2) {
+		const uint32_t w = (j >> 1) == 0 ? r.x : ((j >> 1) == 1 ? r.y : ((j >> 1) == 2 ? r.z : r.w));
+		return (j & 1) ? bf16_hi(w) : bf16_lo(w);
+	} else return __uint_as_float(j == 0 ? r.x : (j == 1 ? r.y : (j == 2 ? r.z : r.w)));
+}
+template <typename T, int VEC, bool DX>
+__global__ void __launch_bounds__(kThreads, 2) pool_bn_bwd_kernel(const int *__restrict__ inds, const T *__restrict__ dout, const T *__restrict__ x,
+                                                                 const float *__restrict__ mab, const float *__restrict__ means,
+                                                                 const float *__restrict__ coef, int N, int S, int C, int rnd,
+                                                                 float *__restrict__ partials, T *__restrict__ dx) {
+	using raw_t = typename RawOf<VEC>::type;
+	const int So = S / 2, V = C / VEC;
+	const int total = N * So * So * V;
+	const int cv = (int)(threadIdx.x % V);
+	float ma[VEC], mb[VEC], mu[VEC], c1[VEC], ck[VEC], c3[VEC], s[VEC], q[VEC];
+#pragma unroll
+	for (int j = 0; j < VEC; j++) {
+		const int c = cv * VEC + j;
+		ma[j] = mab[c]; mb[j] = mab[C + c];
+		if constexpr (DX) { c1[j] = coef[c]; ck[j] = coef[C + c]; c3[j] = coef[2 * C + c]; }
+		else { mu[j] = means[c]; s[j] = q[j] = 0.f; }
+	}
+	for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+		int p = i / V;
+		const int b = p % So; p /= So;
+		const int a = p % So;
+		const int n = p / So;
+		raw_t rd[4], rx[4];
+		int4 ri[4][VEC / 4];
+		bool ok[4];
+		const int o0 = ((n * So + a) * So + b) * V + cv;       // pooled vector of window (a, b)
+		const int v0 = ((n * S + 2 * a) * S + 2 * b) * V + cv;  // input vector of pixel (2a, 2b)
+#pragma unroll
+		for (int t = 0; t < 4; t++) {
+			ok[t] = a + (t >> 1) < So && b + (t & 1) < So;
+			if (ok[t]) {
+				const int o = o0 + ((t >> 1) * So + (t & 1)) * V;
+				rd[t] = ldraw<T, VEC>(dout, o);
+#pragma unroll
+				for (int k = 0; k < VEC / 4; k++) ri[t][k] = reinterpret_cast<const int4 *>(inds)[(long long)o * (VEC / 4) + k];
+			}
+			rx[t] = ldraw<T, VEC>(x, v0 + ((t >> 1) * S + (t & 1)) * V);
+		}
+#pragma unroll
+		for (int px = 0; px < 4; px++) {  // pixel (2a + px / 2, 2b + px % 2) collects from windows t with (t / 2 <= px / 2) and (t % 2 <= px % 2)
+			const int vi = v0 + ((px >> 1) * S + (px & 1)) * V;
+			const int me = vi * VEC;
+			float acc[VEC], xv[VEC];
+			unpack<T, VEC>(rx[px], xv);
+#pragma unroll
+			for (int j = 0; j < VEC; j++) acc[j] = 0.f;
+#pragma unroll
+			for (int t = 0; t < 4; t++) {
+				if ((t >> 1) > (px >> 1) || (t & 1) > (px & 1) || !ok[t]) continue;
+#pragma unroll
+				for (int k = 0; k < VEC / 4; k++) {
+					if (ri[t][k].x == me + 4 * k) acc[4 * k] += elem_of<T, VEC>(rd[t], 4 * k);
+					if (ri[t][k].y == me + 4 * k + 1) acc[4 * k + 1] += elem_of<T, VEC>(rd[t], 4 * k + 1);
+					if (ri[t][k].z == me + 4 * k + 2) acc[4 * k + 2] += elem_of<T, VEC>(rd[t], 4 * k + 2);
+					if (ri[t][k].w == me + 4 * k + 3) acc[4 * k + 3] += elem_of<T, VEC>(rd[t], 4 * k + 3);
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < VEC; j++) {
+				// the unfused path stores the pool gradient in T before BatchNorm backward reads it
+				float g = round_as_stored<T>(acc[j], 0);
+				g = fmaf(xv[j], ma[j], mb[j]) > 0.f ? g : 0.f;
+				if constexpr (DX) {
+					const float r = fmaf(c1[j], g, fmaf(c3[j], xv[j], ck[j]));
+					acc[j] = (sizeof(T) == 4 && rnd) ? round_tf32(r) : r;
+				} else {
+					s[j] += g;
+					q[j] += g * (xv[j] - mu[j]);
+				}
+			}
+			if constexpr (DX) stv<T, VEC>(dx, vi, acc);
+		}
+	}
+	if constexpr (!DX) {
+		// deterministic in-block combine, as in bn_reduce_kernel: thread t < V adds the kThreads / V threads of its column in a fixed order
+		__shared__ float red[kThreads][2 * VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][VEC + j] = q[j]; }
+		__syncthreads();
+		if ((int)threadIdx.x < V) {
+			float ss[VEC], qq[VEC];
+#pragma unroll
+			for (int j = 0; j < VEC; j++) ss[j] = qq[j] = 0.f;
+			for (int k = threadIdx.x; k < kThreads; k += V)
+#pragma unroll
+				for (int j = 0; j < VEC; j++) { ss[j] += red[k][j]; qq[j] += red[k][VEC + j]; }
+			float *o = partials + (size_t)blockIdx.x * 2 * C;
+#pragma unroll
+			for (int j = 0; j < VEC; j++) { o[cv * VEC + j] = ss[j]; o[C + cv * VEC + j] = qq[j]; }
+		}
+	}
+}
+// BatchNorm backward of the stem fed by the max pool's gradient gather; mab = the forward's folded scale / shift [2][C]
+void pool_bn_bwd(const int *max_inds, const void *dpool, const void *x, const float *gamma, const float *means, const float *vars, float eps,
+                 const float *mab, int N, int S, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks, float *coef,
+                 int rnd, cudaStream_t st, int bf16) {
+	const int VEC = vec_of(C, bf16);
+	const long long total = (long long)N * (S / 2) * (S / 2) * (C / VEC);
+	const long long blocks = (total + kThreads - 1) / kThreads;
+	int cap = kNumSMs * 2;  // one whole wave of the reduce pass: the fold cost grows with the number of partial blocks
+	if (cap > max_blocks) cap = max_blocks;
+	const int g1 = (int)(blocks > cap ? cap : blocks), g2 = (int)(blocks > kNumSMs * 2 * 4 ? kNumSMs * 2 * 4 : blocks);
+	const long long rows = (long long)N * S * S;
+	if (bf16) pool_bn_bwd_kernel<bf16_t, 8, false><<<g1, kThreads, 0, st>>>(max_inds, (const bf16_t *)dpool, (const bf16_t *)x, mab, means, nullptr, N, S, C, 0, partials, nullptr);
+	else pool_bn_bwd_kernel<float, 4, false><<<g1, kThreads, 0, st>>>(max_inds, (const float *)dpool, (const float *)x, mab, means, nullptr, N, S, C, 0, partials, nullptr);
+	RB_LAUNCH_CHECK();
+	launch_k(0, bn_bwd_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, (const float *)partials, g1, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
+	RB_LAUNCH_CHECK();
+	if (bf16) pool_bn_bwd_kernel<bf16_t, 8, true><<<g2, kThreads, 0, st>>>(max_inds, (const bf16_t *)dpool, (const bf16_t *)x, mab, nullptr, coef, N, S, C, 0, nullptr, (bf16_t *)dx);
+	else pool_bn_bwd_kernel<float, 4, true><<<g2, kThreads, 0, st>>>(max_inds, (const float *)dpool, (const float *)x, mab, nullptr, coef, N, S, C, rnd, nullptr, (float *)dx);
+	RB_LAUNCH_CHECK();
+	RB_TRACE("pool_bn_bwd_kernel", "N=%d S=%d C=%d grids=%d,%d", N, S, C, g1, g2);
+}
+
 // ------------------------------------------------------------------------------------------- average pool
 // activations in T, pooled values and their gradient in fp32 (the FC head stays fp32)
 template <typename T>

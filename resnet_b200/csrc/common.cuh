@@ -118,6 +118,13 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
 void relu_bwd(const void *y, const void *dy, long long n, void *dx, cudaStream_t st, int bf16 = 0);
 void maxpool_fwd(const void *x, int N, int S, int C, int k, int stride, int *max_inds, void *out, cudaStream_t st, int bf16 = 0);
 void maxpool_bwd(const int *max_inds, const void *dout, int N, int S, int C, int k, int stride, void *din, cudaStream_t st, int bf16 = 0);
+// fused stem tail (bw_kernels.cu "fused stem tail"): pooled = maxpool3x3/2(relu(x * a + b)) without materialising the activation, and
+// the stem BatchNorm's backward fed by the pool's gradient gather without materialising the activation's gradient
+bool bn_pool_fwd_supported(int N, int S, int C, int k, int stride, int bf16);
+void bn_pool_fwd(const void *x, const float *ab, int N, int S, int C, int round_tf32, int *max_inds, void *out, cudaStream_t st, int bf16 = 0);
+void pool_bn_bwd(const int *max_inds, const void *dpool, const void *x, const float *gamma, const float *means, const float *vars, float eps,
+                 const float *mab, int N, int S, int C, float *dgamma, float *dbeta, void *dx, float *partials, int max_blocks, float *coef,
+                 int round_tf32, cudaStream_t st, int bf16 = 0);
 // pooled values and their gradient are fp32 in both modes (the FC head is fp32)
 void avgpool_fwd(const void *x, int N, int S, int C, float *out, cudaStream_t st, int bf16 = 0);
 void avgpool_bwd(const float *dpooled, int N, int S, int C, void *din, cudaStream_t st, int bf16 = 0);

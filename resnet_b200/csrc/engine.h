@@ -61,6 +61,7 @@ struct Engine {
 	ConvRef stem;
 	BnRef bn0;
 	float *X0, *Y0, *P0;  // init_conv_applied, init_conv_activated, init_convblock_input
+	bool fuse_stem_tail;  // Y0 and its gradient are not materialised: BatchNorm + ReLU + max pool in one kernel, forward and backward
 	int *max_inds;
 	float *dP0, *dY0, *dX0;
 	// stem on the tensor cores: zero-bordered NHWC4 copy of the batch, packed [Cout][7][8][4] weights, plans

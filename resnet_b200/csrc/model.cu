@@ -394,7 +394,10 @@ static Engine *build_engine(Train_ResNet *t) {
 	}
 	e->X0 = A->init_conv_applied = B.act(n_x0);
 	A->norm_init_conv = mk_cache(B, n_x0, F, ka, true);
-	e->Y0 = A->init_conv_activated = B.act(n_x0);
+	// the stem's activated tensor has one reader, the max pool: unless every tensor is kept it is never written (bw_kernels.cu "fused stem tail")
+	e->fuse_stem_tail = !ka && env_int("RESNET_B200_FUSE_STEM_TAIL", 1) && F % 4 == 0 &&
+	                    bn_pool_fwd_supported(N, S1, F, d->init_maxpool_dim, d->init_maxpool_stride, e->bf16);
+	e->Y0 = A->init_conv_activated = e->fuse_stem_tail ? nullptr : B.act(n_x0);
 	e->max_inds = A->max_inds = B.get<int>(n_p0);
 	e->P0 = A->init_convblock_input = B.act(n_p0);
 	e->bn0 = mk_bnref(B, P->norm_init_conv, G->norm_init_conv, A->norm_init_conv, (long long)N * S1 * S1);
@@ -480,8 +483,8 @@ static Engine *build_engine(Train_ResNet *t) {
 		T1p = e->wstream ? B.act(max_exp_out) : T1;
 	}
 	e->dP0 = DA->init_convblock_input = ka ? B.act(n_p0) : pp[1];  // block 0 writes its input gradient into pp[(0+1)&1]
-	e->dY0 = DA->init_conv_activated = B.act(n_x0);
-	e->dX0 = DA->init_conv_applied = ka ? B.act(n_x0) : e->dY0;
+	e->dY0 = DA->init_conv_activated = e->fuse_stem_tail ? nullptr : B.act(n_x0);
+	e->dX0 = DA->init_conv_applied = (ka || e->fuse_stem_tail) ? B.act(n_x0) : e->dY0;
 	DA->norm_init_conv = mk_cache(B, n_x0, F, false, false);
 	DA->max_inds = NULL;
 	for (int i = 0; i < nb; i++) {
@@ -755,9 +758,15 @@ void forward_pass(Train_ResNet *t) {
 
 	stem_forward(e, t->cur_batch->images);
 	bn_forward(e, e->bn0, e->X0, eps, e->stem.stats_rows);
-	bn_act(e, e->bn0, e->X0, 1, nullptr, nullptr, e->Y0, rnd);
 	const int S1 = d->input / d->init_conv_stride;
-	maxpool_fwd(e->Y0, e->N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->max_inds, e->P0, st, e->bf16);
+	if (e->fuse_stem_tail) {
+		// X0 in, pooled tensor + argmax out: init_conv_activated is never written
+		ProfScope ps(st, PROF_BN_ELTWISE, (double)e->bn0.rows * e->bn0.C * (e->esz + 0.25 * (e->esz + 4)));
+		bn_pool_fwd(e->X0, e->bn0.ab, e->N, S1, d->init_conv_filters, rnd, e->max_inds, e->P0, st, e->bf16);
+	} else {
+		bn_act(e, e->bn0, e->X0, 1, nullptr, nullptr, e->Y0, rnd);
+		maxpool_fwd(e->Y0, e->N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->max_inds, e->P0, st, e->bf16);
+	}
 
 	for (size_t i = 0; i < e->blocks.size(); i++) {
 		BlockRef &b = e->blocks[i];
@@ -848,8 +857,13 @@ void backwards_pass(Train_ResNet *t) {
 		dp_block_done(e, i);
 	}
 	const int S1 = d->input / d->init_conv_stride;
-	maxpool_bwd(e->max_inds, e->dP0, N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->dY0, st, e->bf16);
-	{
+	if (e->fuse_stem_tail) {
+		// two passes over (X0, dP0, max_inds); the second writes dX0: the pool's input gradient is never written
+		ProfScope ps(st, PROF_BN_ELTWISE, (double)e->bn0.rows * e->bn0.C * (3.0 * e->esz + 2 * 0.25 * (e->esz + 4)));
+		pool_bn_bwd(e->max_inds, e->dP0, e->X0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.ab, N, S1, d->init_conv_filters, e->bn0.dgamma,
+		            e->bn0.dbeta, e->dX0, e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bf16);
+	} else {
+		maxpool_bwd(e->max_inds, e->dP0, N, S1, d->init_conv_filters, d->init_maxpool_dim, d->init_maxpool_stride, e->dY0, st, e->bf16);
 		ProfScope ps(st, PROF_BN_ELTWISE, bn_bytes(e, e->bn0, 5));
 		bn_bwd(e->X0, e->dY0, e->Y0, e->bn0.gamma, e->bn0.means, e->bn0.vars, eps, e->bn0.rows, e->bn0.C, e->bn0.dgamma, e->bn0.dbeta, e->dX0,
 		       e->bn_partials, e->bn_max_blocks, e->bn_coef, e->stem_tc ? e->round_tf32 : 0, st, e->bn0.ab, e->bf16);

@@ -56,6 +56,10 @@ def test_dump_layout_and_restore(tmp_path, dtype, keep_all):
         for fname, field in [("init_conv_applied", "init_conv_applied"), ("init_conv_activated", "init_conv_activated"),
                              ("init_convblock_input", "init_convblock_input"), ("final_avg_pool", "final_conv_output_pooled"),
                              ("fc_output", "linear_output")]:
+            if field == "init_conv_activated" and not keep_all:
+                # the stem's BatchNorm + ReLU + max pool are one kernel by default: the activated tensor is not materialised (and not dumped)
+                assert t.activation(field) is None and not (act / (fname + ".buffer")).exists()
+                continue
             np.testing.assert_array_equal(np.fromfile(act / (fname + ".buffer"), np.float32), t.activation(field))
         np.testing.assert_array_equal(np.fromfile(act / "batch_norms" / "init" / "means.buffer", np.float32), t.activation("norm_init_conv.means"))
         blk = {"reduction_applied": "post_reduced", "reduction_activated": "post_reduced_activated", "spatial_applied": "post_spatial",

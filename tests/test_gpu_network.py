@@ -186,6 +186,7 @@ def test_default_mode_aliases_unkept_buffers():
     pred = t.forward()
     assert t.activation("b0.output") is None and t.activation("b0.post_expanded_norm_vals") is None
     assert t.activation("b0.norm_post_reduced.normalized") is None
+    assert t.activation("init_conv_activated") is None  # BatchNorm + ReLU + max pool of the stem are one kernel (test_fused_stem_tail_matches_unfused)
     opred = net.forward(img, lab)
     assert (pred.argmax(1) == opred.argmax(1)).all() and rel_max(pred, opred) < 5e-2
     t.backward()
@@ -377,6 +378,48 @@ def test_batch_of_one_and_odd_batches(dtype):
             opred = net.forward(img, lab)
             assert np.abs(pred - opred).max() < (2e-2 if dtype == "tf32" else 1e-1)
         t.close()
+
+
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+@pytest.mark.parametrize("N,input_dim", [(4, 32), (3, 64)])
+def test_fused_stem_tail_matches_unfused(dtype, N, input_dim):
+    """Default mode never writes init_conv_activated or its gradient: BatchNorm + ReLU + max pool run as one kernel forward
+    (bn_pool_fwd) and the pool's gradient gather feeds the stem BatchNorm's backward directly (pool_bn_bwd).  Against the same
+    trainer with RESNET_B200_FUSE_STEM_TAIL=0 (separate bn_apply / maxpool / bn_bwd kernels): pooled tensor, max_inds and softmax
+    bit-identical; every gradient that does not pass through the stem BatchNorm's sums bit-identical; dgamma / dbeta of the stem
+    BatchNorm, dX0 and the stem's weight gradient equal up to the summation order of two per-channel sums (1e-4)."""
+    from resnet_b200 import api
+    cfg = dict(G.MINI, batch=N, input_dim=input_dim)
+    shapes = O.param_shapes(cfg["input_dim"], cfg["n_blocks"], cfg["reductions"], output=cfg["output"])
+    W = G.mini_weights(shapes)
+    img, lab = G.mini_batch(cfg)
+    res = {}
+    for fuse in ("0", "1"):
+        os.environ["RESNET_B200_FUSE_STEM_TAIL"] = fuse
+        try:
+            t = api.Trainer(input_dim=cfg["input_dim"], n_blocks=cfg["n_blocks"], reductions=cfg["reductions"], batch=N, output=cfg["output"],
+                            lr=cfg["lr"], dtype=dtype)
+        finally:
+            os.environ.pop("RESNET_B200_FUSE_STEM_TAIL", None)
+        t.set_params(W)
+        t.set_batch(img, lab)
+        pred = t.forward()
+        t.backward()
+        res[fuse] = dict(pred=pred.copy(), p0=t.activation("init_convblock_input"), inds=t.activation("max_inds", dtype=np.int32),
+                         y0=t.activation("init_conv_activated"), dx0=t.activation("init_conv_applied", deriv=True), grads=t.get_params(1))
+        t.close()
+    a, b = res["0"], res["1"]
+    assert a["y0"] is not None and b["y0"] is None, "the fused trainer must not materialise init_conv_activated"
+    np.testing.assert_array_equal(a["inds"], b["inds"])
+    np.testing.assert_array_equal(a["p0"], b["p0"])
+    np.testing.assert_array_equal(a["pred"], b["pred"])
+    assert np.isfinite(b["dx0"]).all() and rel_max(b["dx0"], a["dx0"]) < (1e-4 if dtype == "tf32" else 1e-2)
+    # locations[]: 0 = stem weights, 1 / 2 = stem BatchNorm gamma / beta (reference: resnet.cu:839-846); everything after is downstream of P0 only
+    for i, (ga, gb) in enumerate(zip(a["grads"], b["grads"])):
+        if i <= 2:
+            assert rel_l2(gb, ga) < (1e-4 if dtype == "tf32" else 5e-3), i
+        else:
+            np.testing.assert_array_equal(ga, gb, err_msg="location %d" % i)
 
 
 @pytest.mark.parametrize("dtype,tol_act,tol_w", [("tf32", 3e-3, 3e-3), ("bf16", 1e-2, 3e-3)])
