@@ -1095,8 +1095,30 @@ __global__ void avgpool_bwd_kernel(const float *__restrict__ dp, int N, int SS, 
 		st1<T>(din, i, dp[(long long)n * C + c] / (float)SS);
 	}
 }
+// 128-bit stores (the scalar kernel above wrote the 103 MB of the last block's output gradient at 1.3 TB/s); same value per element
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) avgpool_bwd_vec_kernel(const float *__restrict__ dp, int N, int SS, int C, T *__restrict__ din) {
+	const int V = C / VEC, total = N * SS * V;
+	const float inv = (float)SS;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		const int cv = i % V, n = i / (SS * V);
+		float v[VEC];
+#pragma unroll
+		for (int j = 0; j < VEC; j++) v[j] = dp[n * C + cv * VEC + j] / inv;
+		stv<T, VEC>(din, i, v);
+	}
+}
 void avgpool_bwd(const float *dpooled, int N, int S, int C, void *din, cudaStream_t st, int bf16) {
 	long long total = (long long)N * S * S * C;
+	const int VEC = bf16 ? 8 : 4;
+	if (C % VEC == 0 && total < (1LL << 31)) {
+		long long nv = total / VEC;
+		int grid = (int)((nv + 255) / 256); grid = grid > kMaxFlatBlocks ? kMaxFlatBlocks : grid;
+		if (bf16) avgpool_bwd_vec_kernel<bf16_t, 8><<<grid, 256, 0, st>>>(dpooled, N, S * S, C, (bf16_t *)din);
+		else avgpool_bwd_vec_kernel<float, 4><<<grid, 256, 0, st>>>(dpooled, N, S * S, C, (float *)din);
+		RB_LAUNCH_CHECK();
+		return;
+	}
 	int grid = (int)((total + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;
 	if (bf16) avgpool_bwd_kernel<bf16_t><<<grid, 256, 0, st>>>(dpooled, N, S * S, C, (bf16_t *)din);
 	else avgpool_bwd_kernel<float><<<grid, 256, 0, st>>>(dpooled, N, S * S, C, (float *)din);

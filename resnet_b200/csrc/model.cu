@@ -754,6 +754,7 @@ void forward_pass(Train_ResNet *t) {
 	const float eps = t->eps;
 	const int rnd = e->round_tf32;
 	// weights may have been written through locations[] since the last step (update, checkpoint restore): re-pack
+	// (tried in round 2: the re-pack on the side stream next to the stem convolution -- 0.0 / 0.0 / 0.3 % on c2 / c4 / c5, dropped)
 	pack_weights(e->pack_jobs_dev, e->n_pack_jobs, e->pack_max_elems, rnd, st, e->bf16);
 
 	stem_forward(e, t->cur_batch->images);
