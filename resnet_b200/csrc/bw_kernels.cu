@@ -34,7 +34,7 @@ bool trace_on() {
 	return on;
 }
 int pdl_mode() {
-	static const int mode = getenv("RESNET_B200_PDL") ? atoi(getenv("RESNET_B200_PDL")) : 3;
+	static const int mode = getenv("RESNET_B200_PDL") ? atoi(getenv("RESNET_B200_PDL")) : 2;
 	return mode;
 }
 
@@ -146,7 +146,6 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_ker
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) sm[i] = 0.f;
 	__syncthreads();
 	pdl_wait();
-	pdl_trigger();
 	const long long TS = (long long)gridDim.x * kThreads;
 	const long long g = (long long)blockIdx.x * kThreads + threadIdx.x;
 	float s[VEC], q[VEC], mu[VEC];
@@ -256,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, BatchOf<VEC>::kBlocks) bn_reduce_ker
 		}
 	}
 	__syncthreads();
+	pdl_trigger();  // the fold kernel behind this one may be scheduled now (it waits for our completion before it reads)
 	float *out = partials + (size_t)blockIdx.x * 2 * Cc;
 	for (int i = threadIdx.x; i < 2 * Cc; i += kThreads) out[i] = sm[i];
 }
@@ -348,7 +348,7 @@ static void launch_reduce(bool bwd, const void *x, const void *dy, const void *m
 
 void bn_finalize(float *partials, int nblk, long long rows, int C, const float *gamma, const float *beta, float eps,
                  float *means, float *vars, float *ab, cudaStream_t st, int zero_after) {
-	launch_k(0, bn_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, (const float *)partials, nblk, 1.0 / (double)rows, C, gamma, beta, eps, means, vars, ab, zero_after ? partials : (float *)nullptr);
+	launch_k(2, bn_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, (const float *)partials, nblk, 1.0 / (double)rows, C, gamma, beta, eps, means, vars, ab, zero_after ? partials : (float *)nullptr);
 	RB_LAUNCH_CHECK();
 }
 
@@ -557,7 +557,7 @@ void bn_bwd(const void *x, const void *dy, const void *mask_src, const float *ga
             cudaStream_t st, const float *mab, int bf16, void *masked_out, const uint8_t *mask_bits) {
 	int grid;
 	launch_reduce(true, x, dy, mask_src, means, rows, C, partials, max_blocks, &grid, st, mab, bf16, mask_bits);
-	launch_k(0, bn_bwd_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
+	launch_k(2, bn_bwd_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, partials, grid, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();
 	const int VEC = vec_of(C, bf16);
 	if (!VEC) return;
@@ -1062,7 +1062,7 @@ void pool_bn_bwd(const int *max_inds, const void *dpool, const void *x, const fl
 	if (bf16) pool_bn_bwd_kernel<bf16_t, 8, false><<<g1, kThreads, 0, st>>>(max_inds, (const bf16_t *)dpool, (const bf16_t *)x, mab, means, nullptr, N, S, C, 0, partials, nullptr);
 	else pool_bn_bwd_kernel<float, 4, false><<<g1, kThreads, 0, st>>>(max_inds, (const float *)dpool, (const float *)x, mab, means, nullptr, N, S, C, 0, partials, nullptr);
 	RB_LAUNCH_CHECK();
-	launch_k(0, bn_bwd_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, (const float *)partials, g1, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
+	launch_k(2, bn_bwd_finalize_kernel, ceil_div(C, kFinC), dim3(kFinC, kFinS), 0, st, (const float *)partials, g1, 1.0 / (double)rows, C, gamma, means, vars, eps, dgamma, dbeta, coef);
 	RB_LAUNCH_CHECK();
 	if (bf16) pool_bn_bwd_kernel<bf16_t, 8, true><<<g2, kThreads, 0, st>>>(max_inds, (const bf16_t *)dpool, (const bf16_t *)x, mab, nullptr, coef, N, S, C, 0, nullptr, (bf16_t *)dx);
 	else pool_bn_bwd_kernel<float, 4, true><<<g2, kThreads, 0, st>>>(max_inds, (const float *)dpool, (const float *)x, mab, nullptr, coef, N, S, C, rnd, nullptr, (float *)dx);

@@ -57,7 +57,7 @@ constexpr int kNumSMs = 148;  // B200
 // is worth 0 / 0.3 / 1.6 % of the ResNet-50 TF32 / bf16 / ResNet-152 step; pre-launching the bandwidth-bound kernels costs 3-5 %
 // (their blocks sit on the SMs next to a running convolution, or land unevenly behind another streaming kernel) -- so the default is
 // mode 3: only the convolution kernels carry the attribute.
-int pdl_mode();  // RESNET_B200_PDL: 0 off, 1 every launch_k kernel, 2 only the bandwidth-bound kernels, 3 only the convolution kernels
+int pdl_mode();  // RESNET_B200_PDL: bit mask of the kernel classes launched with the attribute -- 1 streaming BatchNorm / reduce kernels, 2 convolutions, 4 the small fold kernels
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
@@ -71,8 +71,8 @@ static inline void launch_k(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 b
 	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	at[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = at;
-	const int mode = pdl_mode();  // cls: 0 = bandwidth-bound kernel, 1 = convolution kernel (one CTA per SM holding ~200 KB of shared memory)
-	cfg.numAttrs = (mode == 1 || (mode == 2 && cls == 0) || (mode == 3 && cls == 1)) ? 1 : 0;
+	// cls: 0 = streaming bandwidth-bound kernel, 1 = convolution kernel (one CTA per SM holding ~200 KB of shared memory), 2 = fold kernel (a few us)
+	cfg.numAttrs = ((pdl_mode() >> cls) & 1) ? 1 : 0;
 	RB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 
