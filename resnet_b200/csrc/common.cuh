@@ -55,8 +55,9 @@ constexpr int kNumSMs = 148;  // B200
 // instructions are no-ops and the launch is serialized on both sides.
 // Measured (profiles/r02_pdl_ab.txt, same-box A/B): pre-launching the CONVOLUTION kernels under the bandwidth-bound kernel before them
 // is worth 0 / 0.3 / 1.6 % of the ResNet-50 TF32 / bf16 / ResNet-152 step; pre-launching the bandwidth-bound kernels costs 3-5 %
-// (their blocks sit on the SMs next to a running convolution, or land unevenly behind another streaming kernel) -- so the default is
-// mode 3: only the convolution kernels carry the attribute.
+// (their blocks sit on the SMs next to a running convolution, or land unevenly behind another streaming kernel); the few-microsecond
+// fold kernels gain 1 % on ResNet-152 and nothing on ResNet-50 -- so the default is mask 2: only the convolution kernels carry the
+// attribute (RESNET_B200_PDL is a bit mask of kernel classes, see pdl_mode).
 int pdl_mode();  // RESNET_B200_PDL: bit mask of the kernel classes launched with the attribute -- 1 streaming BatchNorm / reduce kernels, 2 convolutions, 4 the small fold kernels
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
