@@ -90,7 +90,8 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 if a.json:
     import json
     fam = {"kmajor": ["igemm_kmajor_kernel"], "wgrad": ["igemm_mnmajor_kernel", "wgrad_reduce"],
-           "bn_eltwise": ["bn_apply_kernel", "bn_reduce_kernel", "bn_bwd_dx_kernel", "relu_bwd_kernel", "bn_finalize_kernel", "bn_bwd_finalize_kernel"]}
+           "bn_eltwise": ["bn_apply_kernel", "bn_reduce_kernel", "bn_bwd_dx_kernel", "relu_bwd_kernel", "bn_finalize_kernel", "bn_bwd_finalize_kernel",
+                          "bn_pool_fwd_kernel", "pool_bn_bwd_kernel"]}
     out = {"source": a.csv, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, one step under ncu (cold caches, serialised)"}
     for f, pats in fam.items():
         n, by, us = 0, 0.0, 0.0
@@ -98,7 +99,8 @@ if a.json:
             d = launch[i]
             if any(p in d["kernel"] for p in pats):
                 # the family's launch count follows bench.py's ProfScope granularity: reduces / finalizes ride inside their parent's scope
-                main = any(p in d["kernel"] for p in pats[:1]) if f != "bn_eltwise" else ("finalize" not in d["kernel"] and not ("bn_reduce" in d["kernel"]))
+                main = any(p in d["kernel"] for p in pats[:1]) if f != "bn_eltwise" else ("finalize" not in d["kernel"] and "bn_reduce" not in d["kernel"] and
+                                                                                                not ("pool_bn_bwd" in d["kernel"] and ", 0>" in d["kernel"]))
                 n += 1 if main else 0
                 by += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
                 us += d.get("gpu__time_duration.sum", 0.0) / 1e3
