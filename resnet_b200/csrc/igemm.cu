@@ -687,8 +687,10 @@ static void choose_box(int W, int H, int N, int cap, bool exact, int *bw, int *b
 }
 
 static int pick_bn(int ncol, int bf16) {
+	int cap = 256;
+	if (const char *e = getenv("RESNET_B200_MAX_BN")) { int v = atoi(e); if (v == 128 || v == 64) cap = v; }  // tuning aid: narrower N tiles
 	for (int bn : {256, 128, 64, 32})
-		if (ncol % bn == 0 && bn >= kelems_of(bf16)) return bn;
+		if (bn <= cap && ncol % bn == 0 && bn >= kelems_of(bf16)) return bn;
 	return 0;
 }
 
