@@ -147,6 +147,11 @@ struct alignas(64) IgemmParams {
 	int resident_b;
 	uint32_t resb_bytes;
 	int pdl_early;  // 1: let the next kernel of the stream be scheduled as soon as this one runs, 0: when its CTAs are done (see tc_run)
+	// TMEM columns this CTA allocates: 512 for the one-CTA-per-SM plans; 2 * BN (a power of two >= 32) when two CTAs share an SM
+	// (finish_kmajor `two`): the narrow-N layers are bound by what ONE issuing thread can push into the tensor pipe (~95 clocks per
+	// N = 64 MMA for 32 clocks of pipe time, profiles/r02_mma_rate.txt: two threads issuing side by side reach 62), and a second,
+	// fully independent CTA on the SM is a second issuing thread with its own ring, accumulators and epilogue
+	uint32_t tmem_cols;
 	int debug;  // profiling aid (RESNET_B200_DEBUG_SKIP): bit 0 = issue no MMAs (feed only), bit 1 = epilogue drains TMEM but stores nothing
 	float *out;
 	int OH, OW, os, accumulate;
@@ -205,8 +210,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // BF16 = false: fp32 tensors, kind::tf32 MMAs, 32 output columns per staged 128-byte row;
 // BF16 = true:  bf16 tensors, kind::f16 MMAs, 64 output columns per staged row.  The shared-memory tiles are byte-identical
 // in both modes (128 rows x 128 bytes, 4 MMAs per stage each advancing 32 bytes along K).
-template <bool BF16>
-__global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
+// MINB = 2: the same kernel compiled for two resident CTAs per SM (<= 102 registers per thread)
+template <bool BF16, int MINB>
+__global__ void __launch_bounds__(kKmajorThreads, MINB) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *base = align1024(smem_raw);
 	const uint32_t stage_bytes = p.resident_b ? p.a_bytes : p.a_bytes + p.b_bytes;
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 			fence_barrier_init();
 		}
 		__syncwarp();
-		tmem_alloc(tmem_slot, kTmemCols);
+		tmem_alloc(tmem_slot, p.tmem_cols);
 		tmem_relinquish();
 	}
 	tc_fence_before();
@@ -453,7 +459,7 @@ __global__ void __launch_bounds__(kKmajorThreads, 1) igemm_kmajor_kernel(const _
 	__syncthreads();
 	if (warp == 1) {
 		tc_fence_after();
-		tmem_dealloc(tmem_base, kTmemCols);
+		tmem_dealloc(tmem_base, p.tmem_cols);
 	}
 }
 
@@ -649,6 +655,7 @@ struct TcPlan {
 	WgradParams wp;
 	int grid;
 	size_t smem;
+	int two;  // fprop / dgrad: two CTAs per SM (igemm_kmajor_kernel<., 2>)
 	// wgrad epilogue
 	float *dw;
 	int cout, cin, taps;
@@ -753,22 +760,31 @@ static void finish_kmajor(TcPlan *pl) {
 	p.nstaging = 2;
 	if (const char *e = getenv("RESNET_B200_EPI_GROUPS")) { int v = atoi(e); if (v >= 1 && v <= 2 && p.tma_store) p.epi_groups = v; }
 	if (const char *e = getenv("RESNET_B200_NSTAGING")) { int v = atoi(e); if (v >= 2 && v <= 4) p.nstaging = v; }
-	const size_t staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
 	const int total = p.ngroups * p.m_tiles * p.n_tiles;
-	pl->grid = total < kNumSMs ? total : kNumSMs;
+	// Two CTAs per SM for the narrow-N, long-K layers (the 64- / 128-channel 3x3 convolutions): see IgemmParams::tmem_cols.  Each CTA
+	// gets half of the shared memory (fewer ring slots each, the same number per SM) and 2 * BN TMEM columns.
+	// RESNET_B200_TWO_CTA = largest BN that takes this form (default 64; 0 = never; 128 also the 128-channel layers).
+	int two_max_bn = 64;
+	if (const char *e = getenv("RESNET_B200_TWO_CTA")) two_max_bn = atoi(e);
+	pl->two = p.BN <= two_max_bn && p.BN >= 32 && p.tma_store && max_iters >= 7 && total >= 4 * kNumSMs;
+	if (pl->two) p.epi_groups = 1;  // (the stem: 7 stages per tile would take two epilogue groups; two CTAs bring two groups per SM anyway)
+	const size_t staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
+	const size_t smem_budget = pl->two ? (kMaxDynSmem + 1024) / 2 - 1024 : kMaxDynSmem;  // 228 KB per SM, 1 KB reserved per CTA
+	p.tmem_cols = pl->two ? (uint32_t)(2 * p.BN) : (uint32_t)kTmemCols;
+	pl->grid = pl->two ? (total < 2 * kNumSMs ? total : 2 * kNumSMs) : (total < kNumSMs ? total : kNumSMs);
 	// weights resident in shared memory when they fit next to >= 4 activation stages and every tile of a CTA shares one N tile
 	const size_t resb = (size_t)p.groups[0].ntaps * p.kchunks * p.b_bytes;
 	int want_res = 1;
 	if (const char *e = getenv("RESNET_B200_RESIDENT_B")) want_res = atoi(e);
 	// (RESNET_B200_RESIDENT_B=2 also takes it when a CTA has a single tile: how the unit tests reach this path on small problems)
 	p.resident_b = want_res && p.ngroups == 1 && pl->grid % p.n_tiles == 0 && resb <= 80 * 1024 && (total >= 2 * pl->grid || want_res == 2) &&
-	               kMaxDynSmem - 2048 - staging_bytes - resb >= 4 * (size_t)p.a_bytes;
+	               smem_budget >= 2048 + staging_bytes + resb + 4 * (size_t)p.a_bytes;
 	p.resb_bytes = p.resident_b ? (uint32_t)resb : 0;
 	p.debug = 0;
 	if (const char *e = getenv("RESNET_B200_DEBUG_SKIP")) p.debug = atoi(e);
 	if (const char *e = getenv("RESNET_B200_STAGES")) { int v = atoi(e); if (v >= 1) max_stages_override = v; }
 	const uint32_t pipe_stage = p.resident_b ? p.a_bytes : stage_bytes;
-	int stages = (int)((kMaxDynSmem - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
+	int stages = (int)((smem_budget - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
 	p.stages = stages > 8 ? 8 : stages;
 	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
 	// A ring slot must always be refilled by the SAME producer warp: a warp that skipped a pass of a slot could find the slot's `empty`
@@ -1213,7 +1229,8 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 	std::lock_guard<std::mutex> attr_lk(attr_mu);
 	bool &attr_set = attr_done[dev & 63];
 	if (!attr_set) {
-		const void *kernels[] = {(const void *)igemm_kmajor_kernel<false>, (const void *)igemm_kmajor_kernel<true>,
+		const void *kernels[] = {(const void *)igemm_kmajor_kernel<false, 1>, (const void *)igemm_kmajor_kernel<true, 1>,
+		                         (const void *)igemm_kmajor_kernel<false, 2>, (const void *)igemm_kmajor_kernel<true, 2>,
 		                         (const void *)igemm_mnmajor_kernel<false>, (const void *)igemm_mnmajor_kernel<true>};
 		for (const void *k : kernels) RB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
 		attr_set = true;
@@ -1225,8 +1242,13 @@ void tc_run(TcPlan *pl, cudaStream_t st) {
 	pl->ip.pdl_early = pl->wp.pdl_early = conv_early;
 	if (pl->kind == 0) {
 		if (pl->ip.stats && !pl->stats_prezeroed) RB_CUDA(cudaMemsetAsync(pl->ip.stats, 0, pl->stats_bytes, st));
-		if (pl->bf16) launch_k(1, igemm_kmajor_kernel<true>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
-		else launch_k(1, igemm_kmajor_kernel<false>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
+		if (pl->two) {
+			if (pl->bf16) launch_k(1, igemm_kmajor_kernel<true, 2>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
+			else launch_k(1, igemm_kmajor_kernel<false, 2>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
+		} else {
+			if (pl->bf16) launch_k(1, igemm_kmajor_kernel<true, 1>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
+			else launch_k(1, igemm_kmajor_kernel<false, 1>, pl->grid, kKmajorThreads, pl->smem, st, pl->ip);
+		}
 		RB_LAUNCH_CHECK();
 	} else {
 		if (pl->bf16) launch_k(1, igemm_mnmajor_kernel<true>, pl->grid, kIgemmThreads, pl->smem, st, pl->wp);
@@ -1258,8 +1280,9 @@ void tc_describe(const TcPlan *pl, char *buf, size_t n) {
 	if (!pl) { snprintf(buf, n, "null"); return; }
 	if (pl->kind == 0) {
 		const IgemmParams &p = pl->ip;
-		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d epi=%d prod=%d grid=%d smem=%zu resB=%u", pl->what,
-		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, p.epi_groups, p.nprod, pl->grid, pl->smem, p.resb_bytes);
+		snprintf(buf, n, "%s | kmajor %s box=(%d,%d,%d) m_tiles=%d n_tiles=%d BN=%d groups=%d kchunks=%d stages=%d epi=%d prod=%d grid=%d smem=%zu resB=%u ctas/SM=%d", pl->what,
+		         pl->bf16 ? "bf16" : "tf32", p.bw, p.bh, p.bn, p.m_tiles, p.n_tiles, p.BN, p.ngroups, p.kchunks, p.stages, p.epi_groups, p.nprod, pl->grid, pl->smem, p.resb_bytes,
+		         pl->two ? 2 : 1);
 	} else {
 		const WgradParams &p = pl->wp;
 		snprintf(buf, n, "%s | wgrad %s box=(%d,%d,%d) k_boxes=%d splits=%d co_tiles=%d m_pair=%d ci_tiles=%d BN=%d taps=%d tpt=%d stages=%d prod=%d grid=%d smem=%zu",
