@@ -766,7 +766,9 @@ static void finish_kmajor(TcPlan *pl) {
 	// RESNET_B200_TWO_CTA = largest BN that takes this form (default 64; 0 = never; 128 also the 128-channel layers).
 	int two_max_bn = 64;
 	if (const char *e = getenv("RESNET_B200_TWO_CTA")) two_max_bn = atoi(e);
-	pl->two = p.BN <= two_max_bn && p.BN >= 32 && p.tma_store && max_iters >= 7 && total >= 4 * kNumSMs;
+	int two_min_iters = 7;  // long main loops only: the short-K 1x1 layers are bound by HBM and their epilogue, measured below
+	if (const char *e = getenv("RESNET_B200_TWO_CTA_MINK")) two_min_iters = atoi(e);
+	pl->two = p.BN <= two_max_bn && p.BN >= 32 && p.tma_store && max_iters >= two_min_iters && total >= 4 * kNumSMs;
 	if (pl->two) p.epi_groups = 1;  // (the stem: 7 stages per tile would take two epilogue groups; two CTAs bring two groups per SM anyway)
 	const size_t staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
 	const size_t smem_budget = pl->two ? (kMaxDynSmem + 1024) / 2 - 1024 : kMaxDynSmem;  // 228 KB per SM, 1 KB reserved per CTA
