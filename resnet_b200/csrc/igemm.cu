@@ -768,7 +768,8 @@ static void finish_kmajor(TcPlan *pl) {
 	if (const char *e = getenv("RESNET_B200_TWO_CTA")) two_max_bn = atoi(e);
 	int two_min_iters = 7;  // long main loops only: the short-K 1x1 layers are bound by HBM and their epilogue, measured below
 	if (const char *e = getenv("RESNET_B200_TWO_CTA_MINK")) two_min_iters = atoi(e);
-	pl->two = p.BN <= two_max_bn && p.BN >= 32 && p.tma_store && max_iters >= two_min_iters && total >= 4 * kNumSMs;
+	const bool two_any_size = getenv("RESNET_B200_TWO_CTA_FORCE") != nullptr;  // unit tests: also on problems with a handful of tiles
+	pl->two = p.BN <= two_max_bn && p.BN >= 32 && p.tma_store && max_iters >= two_min_iters && (total >= 4 * kNumSMs || two_any_size);
 	if (pl->two) p.epi_groups = 1;  // (the stem: 7 stages per tile would take two epilogue groups; two CTAs bring two groups per SM anyway)
 	const size_t staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
 	const size_t smem_budget = pl->two ? (kMaxDynSmem + 1024) / 2 - 1024 : kMaxDynSmem;  // 228 KB per SM, 1 KB reserved per CTA

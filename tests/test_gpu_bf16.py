@@ -384,3 +384,36 @@ def test_resident_weight_operand_forced(api, dtype, tol, S, k, cin, cout, stride
     np.testing.assert_array_equal(out["2"][0], out["0"][0])
     if out["2"][1] is not None:
         np.testing.assert_array_equal(out["2"][1], out["0"][1])
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 3e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("S,k,cin,cout,stride,N", [(28, 3, 64, 64, 1, 8), (56, 3, 64, 64, 1, 13), (14, 3, 64, 128, 2, 2), (64, 7, 3, 64, 2, 3)])
+def test_two_ctas_per_sm_forced(api, dtype, tol, S, k, cin, cout, stride, N):
+    """fprop / dgrad of the narrow-N layers with two CTAs per SM (igemm_kmajor_kernel<., 2>: half the shared memory and 2 x BN TMEM
+    columns per CTA, a persistent grid of 296; what the 64-channel 3x3 layers and the stem use at batch 256) forced on small problems
+    with RESNET_B200_TWO_CTA_FORCE=1 -- the 13-image case has 319 tiles, so CTAs really share SMs -- against the oracle, and
+    bit-identical to the one-CTA-per-SM plan (RESNET_B200_TWO_CTA=0): every output element is the same sum in the same order."""
+    rng = np.random.default_rng(S + cin + cout)
+    R = api.bf16_round if dtype == "bf16" else (lambda a: a)
+    x = O.synthetic_batch(N, S, seed=S)[0] if cin == 3 else R(rng.standard_normal((N, S, S, cin)).astype(np.float32))
+    w = R((rng.standard_normal((cout, cin, k, k)) * 0.1).astype(np.float32))
+    dy = R(rng.standard_normal((N, S // stride, S // stride, cout)).astype(np.float32))
+    xr = R(x) if cin == 3 else x
+    out = {}
+    for mode in ("64", "0"):
+        os.environ["RESNET_B200_TWO_CTA"] = mode
+        os.environ["RESNET_B200_TWO_CTA_FORCE"] = "1"
+        try:
+            y = api.conv_forward(x, w, stride, impl=0, dtype=dtype)
+            din = api.conv_backward(x, w, dy, stride, impl=0, dtype=dtype)[0] if cin != 3 else None
+        finally:
+            os.environ.pop("RESNET_B200_TWO_CTA", None)
+            os.environ.pop("RESNET_B200_TWO_CTA_FORCE", None)
+        out[mode] = (y, din)
+    if N <= 8:  # the host oracle on the 13-image case would take a minute; the bit-identity below carries it
+        assert rel_max(out["64"][0], O.conv_fwd(xr, w, stride)) < tol
+        if out["64"][1] is not None:
+            assert rel_max(out["64"][1], O.conv_dgrad(w, dy, S, stride)) < tol
+    np.testing.assert_array_equal(out["64"][0], out["0"][0])
+    if out["64"][1] is not None:
+        np.testing.assert_array_equal(out["64"][1], out["0"][1])
