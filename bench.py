@@ -373,7 +373,14 @@ def measure(cfg_name, batch, steps, warmup, dist, rank, local_rank, world, with_
                            "tflops": fam[5]["work"] / (fam[5]["ms"] * 1e-3) / 1e12})
         # dominant = the kernel family with the largest share of the step (the whole-family kmajor line competes as one entry; its two
         # halves are listed after it for the reader)
-        dom = max([r for r in rl_all if not r["kernel"].startswith("igemm_kmajor_kernel, ")], key=lambda r: r["ms_per_step"])
+        cands = [r for r in rl_all if not r["kernel"].startswith("igemm_kmajor_kernel, ")]
+        dom = max(cands, key=lambda r: r["ms_per_step"])
+        # the tcgen05 fprop + dgrad family and the BatchNorm / elementwise family are within 1 % of each other in the ResNet-50 step
+        # (16.7 ms each): keep the headline on the tensor-core kernel -- the one earlier rounds and reviews quote -- unless another
+        # family leads it by more than 5 %; every family is in roofline_all either way
+        km = [r for r in cands if r["kernel"].startswith("igemm_kmajor_kernel")]
+        if km and km[0]["ms_per_step"] >= 0.95 * dom["ms_per_step"]:
+            dom = km[0]
         # DRAM traffic per launch of the dominant family from the committed ncu capture of one step of this configuration's dtype
         # (profiles/r0N_traffic_<dtype>.json, written by tools/ncu_summary.py --json; batch 256 ResNet-50 only; newest round first)
         traffic, traffic_src = None, None
