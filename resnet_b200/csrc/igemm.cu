@@ -8,7 +8,7 @@
 // Wd[Cin][tap][Cout] (dgrad), both K-major for the GEMM that reads them.  A "K chunk" is one 128-byte swizzle row:
 // 32 tf32 or 64 bf16 elements; the shared-memory tiles are byte-identical in the two modes.
 //
-// fprop / dgrad kernel (igemm_kmajor_kernel<BF16>): D[128 pixels x BN] += A[128 x chunk] * B[BN x chunk]^T per pipeline stage.
+// fprop / dgrad kernel (igemm_kmajor_kernel<BF16, MINB>): D[128 pixels x BN] += A[128 x chunk] * B[BN x chunk]^T per pipeline stage.
 //   * A tile = a (bw x bh x bn) box of output pixels; for filter tap (kh, kw) the SAME box shifted by the tap
 //     offset is fetched by ONE 4-D TMA tiled load {chunk, bw, bh, bn}; out-of-bounds coordinates are zero-filled
 //     by the TMA unit, which is exactly the convolution's zero padding (im2col never exists in memory).
@@ -20,7 +20,9 @@
 //   * warp 0 (+ 6): TMA producer; warp 1: TMEM allocator + tcgen05.mma issuer (one elected lane, 4 MMAs per stage, K = 8 tf32 / 16 bf16);
 //     warps 2-5 (and 6-9 on short-K layers): epilogue -- tcgen05.ld TMEM -> registers -> swizzled smem staging tile -> TMA
 //     tile store / reduce-add, plus the fused BatchNorm statistics -- overlapped with the next tile's mainloop through a
-//     double-buffered TMEM accumulator (2 x BN <= 512 columns).  Persistent: one CTA per SM.
+//     double-buffered TMEM accumulator (2 x BN <= 512 columns).  Persistent: one CTA per SM; the narrow-N, long-K layers (BN <= 64:
+//     the 64-channel 3x3 convolutions and the stem) run TWO independent CTAs per SM -- the <., 2> instantiation, half the shared
+//     memory and 2 x BN TMEM columns each -- because one issuing thread cannot keep the tensor pipe busy with N = 64 MMAs.
 //
 // wgrad kernel (igemm_mnmajor_kernel<BF16>): dW[tap][128 co x BN ci] += dY[px x 128 co]^T * X_tap[px x BN ci], px = 32 (tf32) /
 //   64 (bf16) pixels per stage.  The reduction (GEMM K) runs over pixels, so both operands are MN-major straight out of NHWC
