@@ -215,8 +215,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // MINB = 2: the same kernel compiled for two resident CTAs per SM (<= 102 registers per thread)
 template <bool BF16, int MINB>
 __global__ void __launch_bounds__(kKmajorThreads, MINB) igemm_kmajor_kernel(const __grid_constant__ IgemmParams p) {
-	extern __shared__ uint8_t smem_raw[];
+	extern __shared__ __align__(1024) uint8_t smem_raw[];  // (no static shared memory in this kernel: the dynamic window starts 1024-aligned; align1024 stays as a guard)
 	uint8_t *base = align1024(smem_raw);
+	if (MINB == 2 && base != smem_raw) __trap();  // the two-CTA plans have no spare kilobyte for a misaligned window (see finish_kmajor)
 	const uint32_t stage_bytes = p.resident_b ? p.a_bytes : p.a_bytes + p.b_bytes;
 	uint8_t *resb = base;                                           // resident weight slots [tap * kchunks + kc] (resb_bytes, 0 when unused)
 	uint8_t *stage0 = base + p.resb_bytes;
@@ -368,6 +369,13 @@ __global__ void __launch_bounds__(kKmajorThreads, MINB) igemm_kmajor_kernel(cons
 					float v[CW];
 					if constexpr (BF16) tmem_ld_32x64(taddr + (uint32_t)(c * CW), v);
 					else tmem_ld_32x32(taddr + (uint32_t)(c * CW), v);
+					if (p.nstaging == 1) {
+						// a single staging tile (the two-CTA plans, which trade it for a ring slot): the previous chunk's store must have
+						// read the tile, and everybody must know it, before anyone overwrites it -- one more barrier per chunk, which the
+						// long main loops of these layers hide
+						if (store_warp) tma_wait_group_read<0>();
+						named_barrier_sync(1 + eg, 128);
+					}
 					uint8_t *buf = gstaging + sbuf * kABytes;
 					sbuf = (sbuf + 1 == (uint32_t)p.nstaging ? 0 : sbuf + 1);
 					uint8_t *rowp = buf + row * 128;
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(kKmajorThreads, MINB) igemm_kmajor_kernel(cons
 					fence_proxy_async();
 					// the store that last read the NEXT buffer in the ring is done before anyone rewrites it; nstaging - 2 younger
 					// stores may still be in flight (the write-bound 1x1 layers were serialised on the store round trip with 2 tiles)
-					if (store_warp) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else tma_wait_group_read<0>(); }  // (lanes without bulk groups fall through)
+					if (store_warp) { if (p.nstaging == 4) tma_wait_group_read<2>(); else if (p.nstaging == 3) tma_wait_group_read<1>(); else if (p.nstaging == 2) tma_wait_group_read<0>(); }  // (lanes without bulk groups fall through)
 					named_barrier_sync(1 + eg, 128);
 					if (store_warp) {
 						if (elect_one()) {
@@ -748,6 +756,10 @@ static int tma_store_enabled(int bf16) {
 	return (e && !bf16) ? atoi(e) != 0 : 1;
 }
 
+static int env_two_nstaging() {
+	if (const char *e = getenv("RESNET_B200_TWO_NSTAGING")) { int v = atoi(e); if (v >= 1 && v <= 2) return v; }
+	return 1;
+}
 static void finish_kmajor(TcPlan *pl) {
 	IgemmParams &p = pl->ip;
 	int max_stages_override = 0;  // RESNET_B200_STAGES: profiling aid
@@ -765,14 +777,19 @@ static void finish_kmajor(TcPlan *pl) {
 	const int total = p.ngroups * p.m_tiles * p.n_tiles;
 	// Two CTAs per SM for the narrow-N, long-K layers (the 64- / 128-channel 3x3 convolutions): see IgemmParams::tmem_cols.  Each CTA
 	// gets half of the shared memory (fewer ring slots each, the same number per SM) and 2 * BN TMEM columns.
-	// RESNET_B200_TWO_CTA = largest BN that takes this form (default 64; 0 = never; 128 also the 128-channel layers).
-	int two_max_bn = 64;
+	// RESNET_B200_TWO_CTA = largest BN that takes this form (0 = never).  Default: 128 for the 3x3 layers, 64 for the 1x1 layers (at
+	// N = 128 those are HBM-bound and measured 0-7 % slower with two CTAs; profiles/r02_two_cta.txt).
+	const bool one_tap = p.ngroups == 1 && p.groups[0].ntaps == 1;
+	int two_max_bn = one_tap ? 64 : 128;
 	if (const char *e = getenv("RESNET_B200_TWO_CTA")) two_max_bn = atoi(e);
 	int two_min_iters = 7;  // long main loops only: the short-K 1x1 layers are bound by HBM and their epilogue, measured below
 	if (const char *e = getenv("RESNET_B200_TWO_CTA_MINK")) two_min_iters = atoi(e);
 	const bool two_any_size = getenv("RESNET_B200_TWO_CTA_FORCE") != nullptr;  // unit tests: also on problems with a handful of tiles
 	pl->two = p.BN <= two_max_bn && p.BN >= 32 && p.tma_store && max_iters >= two_min_iters && (total >= 4 * kNumSMs || two_any_size);
-	if (pl->two) p.epi_groups = 1;  // (the stem: 7 stages per tile would take two epilogue groups; two CTAs bring two groups per SM anyway)
+	if (pl->two) {
+		p.epi_groups = 1;  // (the stem: 7 stages per tile would take two epilogue groups; two CTAs bring two groups per SM anyway)
+		p.nstaging = env_two_nstaging();  // one staging tile: the 16 KB buy each CTA a ring slot (4 instead of 3 at BN = 64)
+	}
 	const size_t staging_bytes = (size_t)p.epi_groups * p.nstaging * kABytes;
 	const size_t smem_budget = pl->two ? (kMaxDynSmem + 1024) / 2 - 1024 : kMaxDynSmem;  // 228 KB per SM, 1 KB reserved per CTA
 	p.tmem_cols = pl->two ? (uint32_t)(2 * p.BN) : (uint32_t)kTmemCols;
@@ -789,7 +806,10 @@ static void finish_kmajor(TcPlan *pl) {
 	if (const char *e = getenv("RESNET_B200_DEBUG_SKIP")) p.debug = atoi(e);
 	if (const char *e = getenv("RESNET_B200_STAGES")) { int v = atoi(e); if (v >= 1) max_stages_override = v; }
 	const uint32_t pipe_stage = p.resident_b ? p.a_bytes : stage_bytes;
-	int stages = (int)((smem_budget - 2048 - staging_bytes - p.resb_bytes) / pipe_stage);
+	// bytes kept for the barriers (< 256) and, in the one-CTA plans, for rounding the dynamic window's base up to 1024; the two-CTA plans
+	// count every byte (4 x 24 KB + 16 KB + 256 B fill the half SM exactly) and rely on the 1024-aligned base the kernel declares and checks
+	const size_t reserve = pl->two ? 1024 : 2048, base_pad = pl->two ? 0 : 1024;
+	int stages = (int)((smem_budget - reserve - staging_bytes - p.resb_bytes) / pipe_stage);
 	p.stages = stages > 8 ? 8 : stages;
 	if (max_stages_override > 0 && max_stages_override < p.stages) p.stages = max_stages_override;
 	// A ring slot must always be refilled by the SAME producer warp: a warp that skipped a pass of a slot could find the slot's `empty`
@@ -798,7 +818,7 @@ static void finish_kmajor(TcPlan *pl) {
 	if (const char *e = getenv("RESNET_B200_PRODUCERS")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) p.nprod = p.epi_groups == 1 ? v : 1; }
 	while (p.nprod > 1 && p.stages < 2 * p.nprod) p.nprod /= 2;
 	p.stages = p.stages / p.nprod * p.nprod;
-	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + 1024 + 256;
+	pl->smem = (size_t)p.resb_bytes + (size_t)p.stages * pipe_stage + staging_bytes + base_pad + 256;
 	pl->kind = 0;
 }
 
