@@ -1440,16 +1440,16 @@ void wgrad_reduce(const float *partial, int splits, int cout, int cin, int taps,
 	long long per = (long long)taps * cout * cin;
 	if (splits >= 48) {
 		int grid = (int)((per + kWrX - 1) / kWrX); grid = grid > kNumSMs * 32 ? kNumSMs * 32 : grid;
-		launch_k(0, wgrad_reduce_lanes_kernel, grid, dim3(kWrX, kWrY), 0, st, partial, splits, cout, cin, taps, dw);
+		launch_k(3, wgrad_reduce_lanes_kernel, grid, dim3(kWrX, kWrY), 0, st, partial, splits, cout, cin, taps, dw);
 	} else if ((taps == 1 || taps == 9) && ((long long)cout * cin) % (8 * kWvPairs) == 0 && (uintptr_t)partial % 16 == 0 && (uintptr_t)dw % 16 == 0 &&
 	           !getenv("RESNET_B200_WGRAD_REDUCE_SCALAR")) {
 		const long long cc = (long long)cout * cin;
 		if (taps == 1) {
 			int grid = (int)(cc / (8 * kWvPairs)); grid = grid > kNumSMs * 8 ? kNumSMs * 8 : grid;
-			launch_k(0, wgrad_reduce_vec_kernel<1, 8>, grid, 256, 0, st, partial, splits, cc, dw);
+			launch_k(3, wgrad_reduce_vec_kernel<1, 8>, grid, 256, 0, st, partial, splits, cc, dw);
 		} else {
 			int grid = (int)(cc / kWvPairs); grid = grid > kNumSMs * 7 ? kNumSMs * 7 : grid;
-			launch_k(0, wgrad_reduce_vec_kernel<9, 1>, grid, 32 * 9, 0, st, partial, splits, cc, dw);
+			launch_k(3, wgrad_reduce_vec_kernel<9, 1>, grid, 32 * 9, 0, st, partial, splits, cc, dw);
 		}
 	} else {
 		int grid = (int)((per + 255) / 256); grid = grid > kMaxFlatBlocks * 4 ? kMaxFlatBlocks * 4 : grid;

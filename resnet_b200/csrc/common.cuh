@@ -58,7 +58,7 @@ constexpr int kNumSMs = 148;  // B200
 // (their blocks sit on the SMs next to a running convolution, or land unevenly behind another streaming kernel); the few-microsecond
 // fold kernels gain 1 % on ResNet-152 and nothing on ResNet-50 -- so the default is mask 2: only the convolution kernels carry the
 // attribute (RESNET_B200_PDL is a bit mask of kernel classes, see pdl_mode).
-int pdl_mode();  // RESNET_B200_PDL: bit mask of the kernel classes launched with the attribute -- 1 streaming BatchNorm / reduce kernels, 2 convolutions, 4 the small fold kernels
+int pdl_mode();  // RESNET_B200_PDL: bit mask of the kernel classes launched with the attribute -- 1 streaming BatchNorm kernels, 2 convolutions, 4 the small fold kernels, 8 the split-K reduces of the weight gradients
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
@@ -72,7 +72,8 @@ static inline void launch_k(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 b
 	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	at[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = at;
-	// cls: 0 = streaming bandwidth-bound kernel, 1 = convolution kernel (one CTA per SM holding ~200 KB of shared memory), 2 = fold kernel (a few us)
+	// cls: 0 = streaming bandwidth-bound kernel, 1 = convolution kernel (one CTA per SM holding ~200 KB of shared memory), 2 = fold kernel (a few us),
+	// 3 = split-K reduce behind a weight-gradient kernel
 	cfg.numAttrs = ((pdl_mode() >> cls) & 1) ? 1 : 0;
 	RB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
