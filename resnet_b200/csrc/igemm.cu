@@ -483,6 +483,9 @@ __device__ __forceinline__ void wgrad_tile(const WgradParams &p, int tile, int n
 		const int T = n_groups * p.co_items * p.ci_tiles;
 		split = tile / T;
 		r = tile - split * T;
+		// split_major = 2: pixel ranges from the END of the tensors first -- dY was written front to back by the kernel just before this
+		// one, so its tail is what the 126 MB L2 still holds (the partial sums land in the same workspace planes: results unchanged)
+		if (p.split_major == 2) split = p.splits - 1 - split;
 	} else {
 		split = tile % p.splits;
 		r = tile / p.splits;
@@ -984,8 +987,8 @@ static CUtensorMapSwizzle wgrad_layout(WgradParams &p, int bf16) {
 	p.b_bytes = (uint32_t)p.BN * 128;
 	p.merge_taps = 1;
 	if (const char *e = getenv("RESNET_B200_WGRAD_MERGE")) p.merge_taps = atoi(e) != 0;
-	p.split_major = 1;
-	if (const char *e = getenv("RESNET_B200_WGRAD_SPLIT_MAJOR")) p.split_major = atoi(e) != 0;  // A/B aid
+	p.split_major = 2;  // from the end: 5 same-box A/B pairs, 40.21 40.21 40.55 40.50 40.63 -> 40.24 39.92 40.39 40.49 40.33 ms (c2), identical results
+	if (const char *e = getenv("RESNET_B200_WGRAD_SPLIT_MAJOR")) p.split_major = atoi(e);  // A/B aid: 0 split-fastest, 1 split-major, 2 split-major from the end
 	return bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 }
 
