@@ -77,3 +77,16 @@ def test_bench_arms_share_one_config_dict():
         assert bench.config_dict(name, cfg["batch"], 8)["global_batch"] == 8 * cfg["batch"]
     assert bench.metric_of("c2") == bench.metric_of("c4") == bench.METRIC and "forward" in bench.metric_of("c3")
 
+
+def test_bench_headline_roofline_family():
+    """bench.py pick_dominant: the largest family wins, the sub-family lines of the tcgen05 kernel do not compete, and a near tie
+    (within 5 %) with the tcgen05 fprop + dgrad family is resolved in its favour so that the headline does not flip from run to run."""
+    import bench
+    km = {"kernel": "igemm_kmajor_kernel (tcgen05 fprop+dgrad)", "ms_per_step": 16.5}
+    sub = {"kernel": "igemm_kmajor_kernel, 3x3 + stem fprop/dgrad", "ms_per_step": 30.0}
+    wg = {"kernel": "igemm_mnmajor_kernel (tcgen05 wgrad + split-K reduce)", "ms_per_step": 8.4}
+    bn = {"kernel": "BatchNorm/elementwise", "ms_per_step": 16.7}
+    assert bench.pick_dominant([km, sub, wg, bn]) is km          # 1 % behind: tie, stays on the tensor-core family; `sub` never competes
+    assert bench.pick_dominant([km, wg, dict(bn, ms_per_step=18.0)])["kernel"] == "BatchNorm/elementwise"   # a clear lead wins
+    assert bench.pick_dominant([wg, bn]) is bn                   # forward-only style list without the family
+    assert bench.pick_dominant([dict(km, ms_per_step=20.0), bn])["kernel"].startswith("igemm_kmajor_kernel")
